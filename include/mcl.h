@@ -1,0 +1,193 @@
+/*
+ * mcl.h -- C ABI of libmcl.so, the B200-native Monte-Carlo-localization core.
+ *
+ * The reference (gustavorvillela/mcmh_localization) has no FFI: its hot path is the set of
+ * numba functions in app/scripts/parallel_utils.py ("pu") that the ROS node
+ * app/scripts/amcmh_localizer.py ("node") imports by name at node:13.  Each entry point below
+ * replaces one of those functions (or one block of glue arithmetic in the node) and says which.
+ * A Python maintainer binds them with ctypes (INTEGRATION.md shows the stub);
+ * mcmh_localization_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / CUDA types in the signatures
+ *    (a CUDA stream is passed as void*).
+ *  - pointers named d_* are DEVICE pointers owned by the caller (PyTorch tensors in the Python
+ *    host code); pointers named h_* are HOST pointers.  The library owns only its handle, the
+ *    device copies of map / likelihood table / scan, and reduction scratch.
+ *  - particle state is SoA fp64: x[n], y[n], theta[n]  (the reference keeps an (N,3) fp64 AoS
+ *    array; SoA gives coalesced 8-byte loads).
+ *  - every call returns 0 on success or a negative mcl_status; mcl_last_error() gives the text.
+ *    There is no CPU fallback: without a CUDA device mcl_create fails.
+ *  - calls are asynchronous on the handle's stream unless they return host values
+ *    (mcl_estimate, mcl_softmax_stats, mcl_sync).  One handle = one stream, not thread-safe
+ *    (the node's callbacks run on two threads without a lock, SURVEY 3.3: the Python Localizer
+ *    serialises them).
+ */
+#ifndef MCL_H_
+#define MCL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcl_handle mcl_handle;
+
+typedef enum {
+    MCL_OK = 0,
+    MCL_ERR_ARG = -1,      /* bad argument (null pointer, n < 0, ...) */
+    MCL_ERR_STATE = -2,    /* map / sensor / scan not set yet */
+    MCL_ERR_CUDA = -3,     /* CUDA runtime error (text in mcl_last_error) */
+    MCL_ERR_CAPACITY = -4, /* problem too large for a library limit */
+    MCL_ERR_NOMEM = -5
+} mcl_status;
+
+/* Resampling arithmetic (mcl_resample_indices). */
+enum {
+    MCL_RESAMPLE_REFERENCE_F32 = 0, /* pu:416-446 bit-exact: sequential f32 normalising sum and f32
+                                       running cumulative sum, f64 U = r + m/N */
+    MCL_RESAMPLE_FIXED_POINT = 1    /* production: same walk on 64-bit fixed-point weights (exact,
+                                       associative => identical for any block / rank split) */
+};
+
+/* Philox stream ids (ctr[3] low byte). */
+enum { MCL_STREAM_MOTION = 1, MCL_STREAM_MH = 2, MCL_STREAM_RESAMPLE = 3, MCL_STREAM_INIT = 4,
+       MCL_STREAM_KLD = 5 };
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int mcl_create(mcl_handle **out, int device);
+int mcl_destroy(mcl_handle *h);
+const char *mcl_last_error(const mcl_handle *h);     /* h may be NULL: last create() error */
+const char *mcl_version(void);
+int mcl_set_stream(mcl_handle *h, void *cuda_stream); /* NULL = legacy default stream */
+int mcl_sync(mcl_handle *h);
+int mcl_device_info(mcl_handle *h, int *sm_count, int *smem_per_block_optin, int *cc_major,
+                    int *cc_minor);
+
+/* ---- configuration ---------------------------------------------------------------------- */
+/* node:124-177 load_map: the OccupancyGrid payload (int8, 0 free / 100 occupied / -1 unknown,
+ * row = y, index my*W+mx) and the EDT distance map (f32 metres) computed by the caller
+ * (scipy.ndimage.distance_transform_edt, node:156).  HOST pointers; copied.  Either pointer may be
+ * NULL when only the other half is needed (likelihood needs dist, predict/init need occ). */
+int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_dist, int W, int H,
+                double resolution, double origin_x, double origin_y);
+/* node:52-56 sensor model parameters (amhmcl.yaml: sigma_hit, z_hit, z_rand, max_range, step). */
+int mcl_set_sensor(mcl_handle *h, double sigma_hit, double z_hit, double z_rand, double max_range,
+                   int step);
+/* node:28-33 odometry noise, float32[4] exactly as the node stores it. */
+int mcl_set_motion(mcl_handle *h, const float alpha[4]);
+/* node:341-348 update_scans: ranges f32[M] and per-beam angles f32[M] (np.linspace(angle_min,
+ * angle_max, M, dtype=float32)).  HOST pointers; the valid-beam table is built and uploaded. */
+int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h_angles, int M);
+/* Pre-stage K scans (h_ranges is K x M, one shared angle vector) on the device and switch between
+ * them without any copy: replaying a bag, or a benchmark whose inputs are resident in HBM. */
+int mcl_set_scan_batch(mcl_handle *h, const float *h_ranges, const float *h_angles, int M, int K);
+int mcl_use_scan(mcl_handle *h, int k);
+/* number of beams counted in valid_count (pu:123-124) for the current scan */
+int mcl_scan_valid_count(mcl_handle *h, int *valid_count);
+/* Likelihood-table staging: 0 = auto (shared-memory window when it fits), 1 = force global/L2
+ * gather, 2 = force shared-memory window (error if it does not fit). For measurements. */
+int mcl_set_likelihood_path(mcl_handle *h, int path);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* pu:85-149 compute_likelihoods -> d_score[n] (f32). */
+int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                   int64_t n, float *d_score);
+
+/* node:351-358 convert_scores (softmax).  d_stats (nullable) receives {max, sum exp(s-max)} as
+ * two device doubles; d_weights (nullable) receives exp(s-max)/sum as f32.
+ * ext_stats (nullable, HOST): if given, use these {max, sum} instead of the local ones -- the
+ * multi-GPU path passes the all-reduced values. */
+int mcl_softmax(mcl_handle *h, const float *d_score, int64_t n, float *d_weights, double *d_stats,
+                const double *ext_stats);
+/* blocking read of the two doubles written by mcl_softmax */
+int mcl_softmax_stats(mcl_handle *h, const float *d_score, int64_t n, double h_stats[2]);
+
+/* pu:332-363 apply_motion_model_parallel (+ pu:388-396 is_valid_position).
+ * delta = (rot1, trans, rot2) from node:410-421 compute_motion (see mcl_compute_motion).
+ * d_normals == NULL: Philox4x32-10 draws keyed (seed, step, first_index + i, attempt).
+ * d_normals != NULL: injected standard normals, layout (n, A, 3) f64, attempt t uses row t % A.
+ * d_attempts (nullable): 1-based index of the accepted attempt, 0 = kept old pose (pu:360-361).
+ * Output may alias input. */
+int mcl_predict(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                int64_t n, const double delta[3], uint64_t seed, uint64_t step,
+                uint64_t first_index, const double *d_normals, int A, int max_attempts,
+                double *d_xo, double *d_yo, double *d_thetao, int32_t *d_attempts);
+
+/* node:410-421 compute_motion (host scalar arithmetic, glibc atan2/hypot: within 1 ulp of the
+ * node's NumPy calls; the Python host code uses NumPy itself to stay bit-exact). */
+int mcl_compute_motion(const double odom1[3], const double odom2[3], double delta[3]);
+
+/* pu:208-236 mh_resampling: current = (d_x..), proposal = (d_px..), likelihoods = weights of the
+ * proposal, old_weights = weights of the current.  d_uniforms == NULL: Philox u53 keyed
+ * (seed, step, first_index + i).  Outputs: new poses, new weights, accept flags (nullable). */
+int mcl_mh_accept(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                  const double *d_px, const double *d_py, const double *d_ptheta,
+                  const float *d_likelihoods, const float *d_old_weights, int64_t n,
+                  const double *d_uniforms, uint64_t seed, uint64_t step, uint64_t first_index,
+                  double *d_xo, double *d_yo, double *d_thetao, float *d_weights_out,
+                  uint8_t *d_accept);
+
+/* pu:416-446 low_variance_resample_numba -> source index per output (d_idx[n_out], int32).
+ * r is the single uniform draw in [0, 1/n_out) (see mcl_resample_offset). */
+int mcl_resample_indices(mcl_handle *h, const float *d_weights, int64_t n_in, int64_t n_out,
+                         double r, int mode, int32_t *d_idx);
+/* r = 0 + (1/n_out - 0) * u53(Philox(seed, step, 0, RESAMPLE))  (np.random.uniform(0, 1/N)) */
+double mcl_resample_offset(uint64_t seed, uint64_t step, int64_t n_out);
+/* new_particles[m] = particles[idx[m]] (pu:445), SoA gather; outputs must not alias inputs. */
+int mcl_gather(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+               const int32_t *d_idx, int64_t n_out, double *d_xo, double *d_yo, double *d_thetao);
+
+/* node:586-597 publish_estimate arithmetic.  h_out[16]:
+ *  [0] V1 = sum w  [1] V2 = sum w^2  [2] mean_x  [3] mean_y  [4] mean_theta
+ *  [5..7]  sum w*d  (d = (x-mean_x, y-mean_y, f32(wrap(theta-mean_theta))))
+ *  [8..13] sum w*d_i*d_j  in order xx, xy, xt, yy, yt, tt        [14],[15] reserved
+ * mcl_estimate_moments returns the raw first-pass sums (for the multi-GPU all-reduce):
+ *  h_m[6] = {sum w, sum w^2, sum w x, sum w y, sum w cos, sum w sin}; mcl_estimate_central then
+ *  takes the global means and returns h_c[9] = {sum w d (3), sum w d d (6)}. Blocking calls. */
+int mcl_estimate(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                 const float *d_weights, int64_t n, double h_out[16]);
+/* non-blocking: d_out18 (device) = {6 raw sums, mean_x, mean_y, mean_theta, 9 central sums} */
+int mcl_estimate_async(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                       const float *d_weights, int64_t n, double *d_out18);
+int mcl_estimate_moments(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                         const float *d_weights, int64_t n, double h_m[6]);
+int mcl_estimate_central(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                         const float *d_weights, int64_t n, const double mean[3], double h_c[9]);
+
+/* pu:69-83 normalize_angle_array: out[i] = (float) normalize_angle(angles[i] - mean_angle). */
+int mcl_normalize_angle_array(mcl_handle *h, const double *d_angles, double mean_angle, int64_t n,
+                              float *d_out);
+
+/* pu:450-465 generate_valid_particles (+ pu:398-413 compute_valid_mask).
+ * d_u != NULL: injected uniforms, layout (3, max_trials) f64 = ux | uy | utheta; the first n valid
+ *   trials are kept, in trial order (bit-exact restatement); *h_count returns how many (<= n).
+ * d_u == NULL: per-particle rejection sampling with Philox (seed, first_index + i, attempt);
+ *   the 50M-particle global-localisation config cannot afford 50 N trial vectors. */
+int mcl_init_uniform(mcl_handle *h, int64_t n, const double *d_u, int64_t max_trials, uint64_t seed,
+                     uint64_t first_index, double *d_x, double *d_y, double *d_theta,
+                     int64_t *h_count);
+
+/* AoS (n,3) f64 <-> SoA conversion on the device (the reference's layout at the shim boundary). */
+int mcl_aos_to_soa(mcl_handle *h, const double *d_aos, int64_t n, double *d_x, double *d_y,
+                   double *d_theta);
+int mcl_soa_to_aos(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                   int64_t n, double *d_aos);
+
+/* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */
+/* Random 4-byte gather rate, lookups/s: table_bytes resident in shared memory (where = 0) or in
+ * global memory / L2 (where = 1); n_lookups per launch, iters launches timed with CUDA events. */
+int mcl_bench_gather(mcl_handle *h, int where, int64_t table_bytes, int64_t n_lookups, int iters,
+                     double *lookups_per_s);
+/* launches of library kernels since create (the bench's gpu_launches claim) */
+int64_t mcl_launch_count(const mcl_handle *h);
+/* CUDA-event timing of the library's own launches: accumulate the device time of every
+ * mcl_likelihood launch between start and stop (events on the handle's stream). */
+int mcl_timing_start(mcl_handle *h);
+int mcl_timing_stop(mcl_handle *h, double *likelihood_ms, int64_t *likelihood_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL_H_ */

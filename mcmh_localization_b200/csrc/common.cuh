@@ -1,0 +1,199 @@
+// common.cuh -- handle, error plumbing, warp/block reductions, Philox4x32-10.
+// Internal to libmcl.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mcl.h"
+
+#define MCL_PI 3.141592653589793      // == np.pi
+#define MCL_TWO_PI 6.283185307179586  // == 2*np.pi
+
+struct BeamTable {       // per valid beam, endpoint offset in CELL units (fp64):
+    double bx, by;       //   bx = r cos(a) / res,  by = r sin(a) / res
+};
+
+struct mcl_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sm_count = 0, smem_optin = 0, cc_major = 0, cc_minor = 0;
+    int64_t launches = 0;
+
+    // map (node:124-177)
+    int W = 0, H = 0;
+    double res = 0, ox = 0, oy = 0;
+    int8_t *d_occ = nullptr;
+    float *d_dist = nullptr;
+    // sensor (node:52-56)
+    bool sensor_set = false;
+    double sigma_hit = 0, z_hit = 0, z_rand = 0, max_range = 0;
+    int step = 1;
+    // motion
+    bool motion_set = false;
+    float alpha[4] = {0, 0, 0, 0};
+
+    // likelihood table: logtab[c] = (float) log(max(z_hit*p_hit(dist[c]) + z_rand/max_range, 1e-6))
+    bool tab_dirty = true;
+    float *d_logtab = nullptr;   // W*H
+    float c0 = 0.f;              // table value on dist == 0 cells (everything outside the window)
+    // free-space window [wx0, wx0+ww) x [wy0, wy0+wh): outside it every in-map cell holds c0.
+    // d_win is the packed window with a one-cell c0 border: (wh+2) x (ww+2) floats.
+    int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
+    float *d_win = nullptr;
+    size_t win_bytes = 0;
+    int lik_path = 0;            // 0 auto, 1 global, 2 smem window
+
+    // scan (node:341-348): valid beams with r >= 0 first, then valid beams with r < 0
+    bool scan_set = false;
+    BeamTable *d_beams = nullptr;
+    float *d_neg_r = nullptr;    // unused placeholder (negative ranges handled via beam table)
+    int beams_cap = 0;
+    int n_pos = 0, n_neg = 0;    // valid_count = n_pos + n_neg
+    double rmax_cells = 0;       // max |r|/res over valid beams
+    BeamTable *h_beams = nullptr; // pinned staging
+    // pre-staged scans (mcl_set_scan_batch / mcl_use_scan): K tables of stride batch_stride
+    struct ScanMeta { int n_pos, n_neg; double rmax_cells; };
+    BeamTable *d_batch = nullptr;
+    std::vector<ScanMeta> batch_meta;
+    int batch_stride = 0;
+    const BeamTable *d_beams_active = nullptr;
+
+    // scratch for reductions / scans
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    double *h_pinned = nullptr;  // 64 doubles, pinned, for blocking scalar reads
+
+    // timing of likelihood launches
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lik_events;
+};
+
+extern thread_local std::string g_create_err;
+
+int mcl_fail(mcl_handle *h, int code, const std::string &msg);
+int mcl_ensure_scratch(mcl_handle *h, size_t bytes);
+int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
+
+#define MCL_CUDA(h, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return mcl_fail((h), MCL_ERR_CUDA,                                              \
+                            std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+#define MCL_LAUNCH_CHECK(h)                                                                 \
+    do {                                                                                    \
+        (h)->launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess)                                                             \
+            return mcl_fail((h), MCL_ERR_CUDA, std::string("kernel launch: ") +             \
+                                                   cudaGetErrorString(e__));                \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// pu:62-67 normalize_angle with Python modulo semantics; fmod is exact.
+__device__ __forceinline__ double normalize_angle_dev(double theta) {
+    double r = fmod(__dadd_rn(theta, MCL_PI), MCL_TWO_PI);
+    if (r != 0.0 && r < 0.0) r = __dadd_rn(r, MCL_TWO_PI);
+    return __dadd_rn(r, -MCL_PI);
+}
+
+// Philox4x32-10 (Salmon et al. SC'11).  Same counter layout as oracle/c/mcl_oracle.c draw4().
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 philox_draw4(uint64_t seed, uint64_t step, uint64_t item,
+                                              uint32_t sub, uint32_t stream) {
+    uint4 c;
+    c.x = (uint32_t)item;
+    c.y = (uint32_t)step;
+    c.z = sub;
+    c.w = (stream & 0xffu) | ((uint32_t)(item >> 32) << 8) | ((uint32_t)((step >> 32) & 0xffu) << 24);
+    return philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+// 53-bit uniform in [0,1): same bit recipe as numpy's legacy random_sample.
+__device__ __forceinline__ double u53_from(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+// three standard normals by Box-Muller on 32-bit uniforms (u1 in (0,1], u2 in [0,1)).
+__device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t step, uint64_t item,
+                                                uint32_t attempt, double &z0, double &z1, double &z2) {
+    const uint4 o = philox_draw4(seed, step, item, attempt, MCL_STREAM_MOTION);
+    const double k = 2.3283064365386963e-10;  // 2^-32
+    const double u1 = __dmul_rn(__dadd_rn((double)o.x, 1.0), k), u2 = __dmul_rn((double)o.y, k);
+    const double u3 = __dmul_rn(__dadd_rn((double)o.z, 1.0), k), u4 = __dmul_rn((double)o.w, k);
+    const double r1 = sqrt(__dmul_rn(-2.0, log(u1))), r2 = sqrt(__dmul_rn(-2.0, log(u3)));
+    double s1, c1, s2, c2;
+    sincos(__dmul_rn(MCL_TWO_PI, u2), &s1, &c1);
+    sincos(__dmul_rn(MCL_TWO_PI, u4), &s2, &c2);
+    z0 = __dmul_rn(r1, c1);
+    z1 = __dmul_rn(r1, s1);
+    z2 = __dmul_rn(r2, c2);
+}
+
+// pu:388-396 is_valid_position: trunc-toward-zero cell index, cell == 0 only.
+__device__ __forceinline__ bool is_valid_position_dev(double x, double y, const int8_t *__restrict__ occ,
+                                                      int W, int H, double res, double ox, double oy) {
+    const long long mx = __double2ll_rz(__ddiv_rn(__dadd_rn(x, -ox), res));
+    const long long my = __double2ll_rz(__ddiv_rn(__dadd_rn(y, -oy), res));
+    if (mx >= 0 && mx < W && my >= 0 && my < H) return occ[my * (long long)W + mx] == 0;
+    return false;
+}
+// pu:135-142 evaluated once per map cell (the per-beam value depends only on dist[cell] when
+// 0 <= r <= max_range): logtab = (float) log(max(z_hit * p_hit + z_rand / max_range, 1e-6)).
+// dist ** 2 is an f32 multiply (numba types float32 ** 2 as float32; pinned by the golden vectors).
+__device__ __forceinline__ double cell_p_hit(float d, double sigma_hit, double max_range) {
+    const double dsq = (double)__fmul_rn(d, d);
+    const double s2 = __dmul_rn(sigma_hit, sigma_hit);
+    if ((double)d <= max_range)
+        return __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-0.5, dsq), s2)), sqrt(__dmul_rn(MCL_TWO_PI, s2)));
+    return 0.0;
+}
+__device__ __forceinline__ double cell_logp(float d, double sigma_hit, double z_hit, double z_rand, double max_range,
+                            bool with_rand) {
+    const double p_hit = cell_p_hit(d, sigma_hit, max_range);
+    const double p_rand = with_rand ? __ddiv_rn(1.0, max_range) : 0.0;
+    double p = __dadd_rn(__dmul_rn(z_hit, p_hit), __dmul_rn(z_rand, p_rand));
+    p = p > 1e-6 ? p : 1e-6;
+    return log(p);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,348 @@
+// mcl_core.cu -- handle lifetime, configuration (map / sensor / scan), likelihood-table build.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+thread_local std::string g_create_err;
+
+int mcl_fail(mcl_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+extern "C" const char *mcl_version(void) { return "mcl-b200 0.1 (sm_100a)"; }
+
+extern "C" const char *mcl_last_error(const mcl_handle *h) {
+    return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int mcl_create(mcl_handle **out, int device) {
+    if (!out) return mcl_fail(nullptr, MCL_ERR_ARG, "mcl_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return mcl_fail(nullptr, MCL_ERR_CUDA,
+                        std::string("mcl_create: no CUDA device (") + cudaGetErrorString(e) +
+                            "); libmcl has no CPU fallback");
+    if (device < 0 || device >= count) return mcl_fail(nullptr, MCL_ERR_ARG, "mcl_create: bad device index");
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return mcl_fail(nullptr, MCL_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major < 10)
+        return mcl_fail(nullptr, MCL_ERR_CUDA,
+                        "mcl_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                            ", this library is built for sm_100a only");
+    mcl_handle *h = new mcl_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->cc_major = prop.major;
+    h->cc_minor = prop.minor;
+    if (cudaMallocHost((void **)&h->h_pinned, 64 * sizeof(double)) != cudaSuccess) {
+        delete h;
+        return mcl_fail(nullptr, MCL_ERR_NOMEM, "mcl_create: cudaMallocHost failed");
+    }
+    *out = h;
+    return MCL_OK;
+}
+
+extern "C" int mcl_destroy(mcl_handle *h) {
+    if (!h) return MCL_OK;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
+    cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch);
+    cudaFreeHost(h->h_beams); cudaFreeHost(h->h_pinned);
+    for (auto &p : h->lik_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    delete h;
+    return MCL_OK;
+}
+
+extern "C" int mcl_set_stream(mcl_handle *h, void *s) {
+    if (!h) return MCL_ERR_ARG;
+    h->stream = (cudaStream_t)s;
+    return MCL_OK;
+}
+
+extern "C" int mcl_sync(mcl_handle *h) {
+    if (!h) return MCL_ERR_ARG;
+    DeviceGuard g(h->device);
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MCL_OK;
+}
+
+extern "C" int mcl_device_info(mcl_handle *h, int *sm, int *smem, int *maj, int *min) {
+    if (!h) return MCL_ERR_ARG;
+    if (sm) *sm = h->sm_count;
+    if (smem) *smem = h->smem_optin;
+    if (maj) *maj = h->cc_major;
+    if (min) *min = h->cc_minor;
+    return MCL_OK;
+}
+
+extern "C" int64_t mcl_launch_count(const mcl_handle *h) { return h ? h->launches : 0; }
+
+int mcl_ensure_scratch(mcl_handle *h, size_t bytes) {
+    if (bytes <= h->scratch_bytes) return MCL_OK;
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    want = (want + 255) & ~(size_t)255;
+    MCL_CUDA(h, cudaMalloc(&h->d_scratch, want));
+    h->scratch_bytes = want;
+    return MCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// configuration
+// ------------------------------------------------------------------------------------------
+extern "C" int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_dist, int W, int H,
+                           double res, double ox, double oy) {
+    if (!h) return MCL_ERR_ARG;
+    if ((!h_occ && !h_dist) || W <= 0 || H <= 0 || !(res > 0))
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_set_map: bad argument");
+    if ((int64_t)W * H > ((int64_t)1 << 31) - 1) return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_set_map: map too large");
+    DeviceGuard g(h->device);
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
+    h->d_occ = nullptr; h->d_dist = nullptr; h->d_logtab = nullptr; h->d_win = nullptr;
+    const size_t cells = (size_t)W * H;
+    h->W = W; h->H = H; h->res = res; h->ox = ox; h->oy = oy;
+    h->scan_set = false;
+    if (h_occ) {   // occupancy only needed by predict / init (pu:388-396)
+        MCL_CUDA(h, cudaMalloc((void **)&h->d_occ, cells));
+        MCL_CUDA(h, cudaMemcpy(h->d_occ, h_occ, cells, cudaMemcpyHostToDevice));
+    }
+    if (!h_dist) { h->wx0 = h->wy0 = h->ww = h->wh = 0; h->win_bytes = 0; return MCL_OK; }
+    MCL_CUDA(h, cudaMalloc((void **)&h->d_dist, cells * sizeof(float)));
+    MCL_CUDA(h, cudaMalloc((void **)&h->d_logtab, cells * sizeof(float)));
+    MCL_CUDA(h, cudaMemcpy(h->d_dist, h_dist, cells * sizeof(float), cudaMemcpyHostToDevice));
+    // bounding box of cells with dist > 0 (free space): everywhere else the table is the constant c0
+    int x0 = W, x1 = -1, y0 = H, y1 = -1;
+    for (int y = 0; y < H; ++y) {
+        const float *row = h_dist + (size_t)y * W;
+        int rx0 = -1, rx1 = -1;
+        for (int x = 0; x < W; ++x) if (row[x] != 0.0f) { rx0 = x; break; }
+        if (rx0 < 0) continue;
+        for (int x = W - 1; x >= 0; --x) if (row[x] != 0.0f) { rx1 = x; break; }
+        x0 = std::min(x0, rx0); x1 = std::max(x1, rx1);
+        y0 = std::min(y0, y); y1 = std::max(y1, y);
+    }
+    if (x1 < 0) { h->wx0 = 0; h->wy0 = 0; h->ww = 0; h->wh = 0; }
+    else { h->wx0 = x0; h->wy0 = y0; h->ww = x1 - x0 + 1; h->wh = y1 - y0 + 1; }
+    h->win_bytes = (((size_t)(h->ww + 2) * (h->wh + 2) * sizeof(float)) + 15) & ~(size_t)15;
+    MCL_CUDA(h, cudaMalloc((void **)&h->d_win, h->win_bytes));
+    h->tab_dirty = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_set_sensor(mcl_handle *h, double sigma_hit, double z_hit, double z_rand,
+                              double max_range, int step) {
+    if (!h) return MCL_ERR_ARG;
+    if (!(sigma_hit > 0) || !(max_range > 0) || step < 1)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_set_sensor: need sigma_hit > 0, max_range > 0, step >= 1");
+    h->sigma_hit = sigma_hit; h->z_hit = z_hit; h->z_rand = z_rand; h->max_range = max_range;
+    h->step = step;
+    h->sensor_set = true;
+    h->tab_dirty = true;
+    h->scan_set = false;   // validity of beams depends on max_range / step
+    return MCL_OK;
+}
+
+extern "C" int mcl_set_motion(mcl_handle *h, const float alpha[4]) {
+    if (!h || !alpha) return MCL_ERR_ARG;
+    memcpy(h->alpha, alpha, sizeof(h->alpha));
+    h->motion_set = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_set_likelihood_path(mcl_handle *h, int path) {
+    if (!h || path < 0 || path > 2) return MCL_ERR_ARG;
+    h->lik_path = path;
+    return MCL_OK;
+}
+
+__global__ void k_build_logtab(const float *__restrict__ dist, float *__restrict__ logtab, int64_t cells,
+                               double sigma_hit, double z_hit, double z_rand, double max_range) {
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cells;
+         c += (int64_t)gridDim.x * blockDim.x)
+        logtab[c] = (float)cell_logp(dist[c], sigma_hit, z_hit, z_rand, max_range, true);
+}
+
+__global__ void k_pack_window(const float *__restrict__ logtab, float *__restrict__ win, int W, int wx0,
+                              int wy0, int ww, int wh, float c0) {
+    const int pw = ww + 2, ph = wh + 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pw * ph; i += gridDim.x * blockDim.x) {
+        const int iy = i / pw, ix = i - iy * pw;
+        float v = c0;
+        if (ix >= 1 && ix <= ww && iy >= 1 && iy <= wh)
+            v = logtab[(size_t)(wy0 + iy - 1) * W + (wx0 + ix - 1)];
+        win[i] = v;
+    }
+}
+
+__global__ void k_c0(float *out, double sigma_hit, double z_hit, double z_rand, double max_range) {
+    out[0] = (float)cell_logp(0.0f, sigma_hit, z_hit, z_rand, max_range, true);
+}
+
+int mcl_prepare_table(mcl_handle *h) {
+    if (!h->d_dist) return mcl_fail(h, MCL_ERR_STATE, "map not set (mcl_set_map)");
+    if (!h->sensor_set) return mcl_fail(h, MCL_ERR_STATE, "sensor parameters not set (mcl_set_sensor)");
+    if (!h->tab_dirty) return MCL_OK;
+    const int64_t cells = (int64_t)h->W * h->H;
+    int rc = mcl_ensure_scratch(h, 256);
+    if (rc) return rc;
+    const int blocks = (int)std::min<int64_t>((cells + 255) / 256, (int64_t)h->sm_count * 16);
+    k_build_logtab<<<blocks, 256, 0, h->stream>>>(h->d_dist, h->d_logtab, cells, h->sigma_hit, h->z_hit,
+                                                  h->z_rand, h->max_range);
+    MCL_LAUNCH_CHECK(h);
+    k_c0<<<1, 1, 0, h->stream>>>((float *)h->d_scratch, h->sigma_hit, h->z_hit, h->z_rand, h->max_range);
+    MCL_LAUNCH_CHECK(h);
+    MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scratch, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(&h->c0, h->h_pinned, sizeof(float));
+    const int n = (h->ww + 2) * (h->wh + 2);
+    k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
+        h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->c0);
+    MCL_LAUNCH_CHECK(h);
+    h->tab_dirty = false;
+    return MCL_OK;
+}
+
+// pu:119-129: beams j = 0, step, 2 step, ...; valid iff isfinite(r) and r < max_range.
+// endpoint offset r*(cos a, sin a) with a = (double)angles[j], scaled to cells.
+// Valid beams with r >= 0 first ("0 <= r <= max_range", pu:139), then negative finite ranges (p_rand = 0).
+static void build_beam_table(const mcl_handle *h, const float *h_ranges, const float *h_angles, int M,
+                             BeamTable *out, int &n_pos, int &n_neg, double &rmax) {
+    n_pos = 0; n_neg = 0; rmax = 0;
+    std::vector<BeamTable> neg;
+    for (int j = 0; j < M; j += h->step) {
+        const double r = (double)h_ranges[j];
+        if (!(isfinite(r) && r < h->max_range)) continue;
+        const double a = (double)h_angles[j];
+        BeamTable b;
+        b.bx = r * cos(a) / h->res;
+        b.by = r * sin(a) / h->res;
+        rmax = std::max(rmax, fabs(r) / h->res);
+        if (r >= 0) out[n_pos++] = b;
+        else neg.push_back(b);
+    }
+    for (auto &b : neg) out[n_pos + n_neg++] = b;
+}
+
+extern "C" int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h_angles, int M) {
+    if (!h) return MCL_ERR_ARG;
+    if (M < 0 || (M > 0 && (!h_ranges || !h_angles))) return mcl_fail(h, MCL_ERR_ARG, "mcl_set_scan: bad argument");
+    if (!h->sensor_set || h->W == 0) return mcl_fail(h, MCL_ERR_STATE, "mcl_set_scan: set map and sensor first");
+    DeviceGuard g(h->device);
+    if (M > h->beams_cap) {
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_beams); cudaFreeHost(h->h_beams);
+        h->d_beams = nullptr; h->h_beams = nullptr; h->beams_cap = 0;
+        const int cap = std::max(M, 512);
+        MCL_CUDA(h, cudaMalloc((void **)&h->d_beams, (size_t)cap * sizeof(BeamTable)));
+        MCL_CUDA(h, cudaMallocHost((void **)&h->h_beams, (size_t)cap * sizeof(BeamTable)));
+        h->beams_cap = cap;
+    } else {
+        // the pinned staging buffer may still be the source of an in-flight copy
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    int n_pos = 0, n_neg = 0;
+    double rmax = 0;
+    build_beam_table(h, h_ranges, h_angles, M, h->h_beams, n_pos, n_neg, rmax);
+    h->n_pos = n_pos; h->n_neg = n_neg; h->rmax_cells = rmax;
+    if (n_pos + n_neg > 0)
+        MCL_CUDA(h, cudaMemcpyAsync(h->d_beams, h->h_beams, (size_t)(n_pos + n_neg) * sizeof(BeamTable),
+                                    cudaMemcpyHostToDevice, h->stream));
+    h->d_beams_active = h->d_beams;
+    h->scan_set = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_set_scan_batch(mcl_handle *h, const float *h_ranges, const float *h_angles, int M, int K) {
+    if (!h) return MCL_ERR_ARG;
+    if (M <= 0 || K <= 0 || !h_ranges || !h_angles) return mcl_fail(h, MCL_ERR_ARG, "mcl_set_scan_batch: bad argument");
+    if (!h->sensor_set || h->W == 0) return mcl_fail(h, MCL_ERR_STATE, "mcl_set_scan_batch: set map and sensor first");
+    DeviceGuard g(h->device);
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_batch);
+    h->d_batch = nullptr;
+    h->batch_meta.clear();
+    h->batch_stride = M;
+    std::vector<BeamTable> host((size_t)M * K);
+    for (int k = 0; k < K; ++k) {
+        mcl_handle::ScanMeta m;
+        build_beam_table(h, h_ranges + (size_t)k * M, h_angles, M, host.data() + (size_t)k * M, m.n_pos, m.n_neg,
+                         m.rmax_cells);
+        h->batch_meta.push_back(m);
+    }
+    MCL_CUDA(h, cudaMalloc((void **)&h->d_batch, host.size() * sizeof(BeamTable)));
+    MCL_CUDA(h, cudaMemcpy(h->d_batch, host.data(), host.size() * sizeof(BeamTable), cudaMemcpyHostToDevice));
+    return MCL_OK;
+}
+
+extern "C" int mcl_use_scan(mcl_handle *h, int k) {
+    if (!h) return MCL_ERR_ARG;
+    if (k < 0 || k >= (int)h->batch_meta.size()) return mcl_fail(h, MCL_ERR_ARG, "mcl_use_scan: no such pre-staged scan");
+    h->d_beams_active = h->d_batch + (size_t)k * h->batch_stride;
+    h->n_pos = h->batch_meta[k].n_pos; h->n_neg = h->batch_meta[k].n_neg; h->rmax_cells = h->batch_meta[k].rmax_cells;
+    h->scan_set = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_scan_valid_count(mcl_handle *h, int *valid_count) {
+    if (!h || !valid_count) return MCL_ERR_ARG;
+    if (!h->scan_set) return mcl_fail(h, MCL_ERR_STATE, "scan not set");
+    *valid_count = h->n_pos + h->n_neg;
+    return MCL_OK;
+}
+
+// node:410-421 compute_motion
+extern "C" int mcl_compute_motion(const double o1[3], const double o2[3], double delta[3]) {
+    if (!o1 || !o2 || !delta) return MCL_ERR_ARG;
+    const double dx = o2[0] - o1[0], dy = o2[1] - o1[1];
+    double t = fmod((o2[2] - o1[2]) + MCL_PI, MCL_TWO_PI);
+    if (t != 0.0 && t < 0.0) t += MCL_TWO_PI;
+    const double dtheta = t - MCL_PI;
+    const double rot1 = atan2(dy, dx) - o1[2];
+    delta[0] = rot1;
+    delta[1] = hypot(dx, dy);
+    delta[2] = dtheta - rot1;
+    return MCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// timing of likelihood launches
+// ------------------------------------------------------------------------------------------
+extern "C" int mcl_timing_start(mcl_handle *h) {
+    if (!h) return MCL_ERR_ARG;
+    for (auto &p : h->lik_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    h->lik_events.clear();
+    h->timing = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_timing_stop(mcl_handle *h, double *ms, int64_t *launches) {
+    if (!h) return MCL_ERR_ARG;
+    DeviceGuard g(h->device);
+    h->timing = false;
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    double tot = 0;
+    for (auto &p : h->lik_events) {
+        float t = 0;
+        MCL_CUDA(h, cudaEventElapsedTime(&t, p.first, p.second));
+        tot += t;
+    }
+    if (ms) *ms = tot;
+    if (launches) *launches = (int64_t)h->lik_events.size();
+    for (auto &p : h->lik_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    h->lik_events.clear();
+    return MCL_OK;
+}

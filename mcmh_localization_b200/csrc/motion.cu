@@ -1,0 +1,130 @@
+// motion.cu -- kernel (1): odometry motion-model sample with map rejection,
+// pu:332-363 apply_motion_model_parallel + pu:388-396 is_valid_position.
+//
+// One thread per particle draws attempt 0.  The reference retries up to 1000 times, and the
+// ~2 % of particles facing a wall burn all of them -- serialised inside a warp that
+// would stall 31 finished lanes for 999 iterations.  Because the generator is counter-based
+// (Philox keyed by (seed, step, particle, attempt)) any lane can evaluate any attempt, so the warp
+// retries cooperatively: the 32 lanes evaluate attempts t..t+31 of ONE pending particle at once
+// and the lowest successful attempt wins -- identical to the sequential "first valid attempt"
+// semantics, 32x fewer iterations.  The same code path serves injected draws (parity tests).
+#include <algorithm>
+
+#include "common.cuh"
+
+struct MotionParams {
+    const double *x, *y, *th;
+    int64_t n;
+    double rot1, trans, rot2;
+    double s1, s2, s3;         // pu:345-347 sigmas, computed on the host in the reference's order
+    const int8_t *occ;
+    int W, H;
+    double res, ox, oy;
+    uint64_t seed, step, first_index;
+    const double *normals;     // nullable, (n, A, 3)
+    int A;
+    int max_attempts;
+    double *xo, *yo, *tho;
+    int32_t *attempts;
+};
+
+struct Pose { double x, y, th; };
+
+// one attempt t for a particle at (x,y,th); returns validity and the candidate pose
+__device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i, int t, double x, double y,
+                                               double th, Pose &cand) {
+    double z0, z1, z2;
+    if (p.normals) {
+        const double *z = p.normals + ((size_t)i * p.A + (size_t)(t % p.A)) * 3;
+        z0 = z[0]; z1 = z[1]; z2 = z[2];
+    } else {
+        philox_normals3(p.seed, p.step, p.first_index + (uint64_t)i, (uint32_t)t, z0, z1, z2);
+    }
+    // np.random.normal(0, s) = 0.0 + s*z ; no FMA contraction anywhere (numba does not fuse)
+    const double r1_hat = __dadd_rn(p.rot1, __dadd_rn(0.0, __dmul_rn(p.s1, z0)));
+    const double t_hat = __dadd_rn(p.trans, __dadd_rn(0.0, __dmul_rn(p.s2, z1)));
+    const double r2_hat = __dadd_rn(p.rot2, __dadd_rn(0.0, __dmul_rn(p.s3, z2)));
+    double sn, cs;
+    sincos(__dadd_rn(th, r1_hat), &sn, &cs);
+    cand.x = __dadd_rn(x, __dmul_rn(t_hat, cs));                                  // pu:351
+    cand.y = __dadd_rn(y, __dmul_rn(t_hat, sn));                                  // pu:352
+    cand.th = normalize_angle_dev(__dadd_rn(__dadd_rn(th, r1_hat), r2_hat));      // pu:353
+    return is_valid_position_dev(cand.x, cand.y, p.occ, p.W, p.H, p.res, p.ox, p.oy);
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
+    if (warp_base >= p.n) return;                       // warp-uniform
+    const int64_t i = warp_base + lane;
+    const bool live = i < p.n;
+    double x = 0, y = 0, th = 0;
+    if (live) { x = p.x[i]; y = p.y[i]; th = p.th[i]; }
+    Pose out = {x, y, th};
+    int32_t att = 0;
+    bool done = !live || p.max_attempts <= 0;
+    if (!done) {
+        Pose c;
+        if (motion_attempt(p, i, 0, x, y, th, c)) { out = c; att = 1; done = true; }
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, !done);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        const double sx = shfl_d(x, src), sy = shfl_d(y, src), sth = shfl_d(th, src);
+        const int64_t si = warp_base + src;
+        Pose win = {sx, sy, sth};
+        int watt = 0;
+        for (int t0 = 1; t0 < p.max_attempts; t0 += 32) {
+            const int t = t0 + lane;
+            Pose c = {0, 0, 0};
+            const bool ok = (t < p.max_attempts) && motion_attempt(p, si, t, sx, sy, sth, c);
+            const unsigned okm = __ballot_sync(0xffffffffu, ok);
+            if (okm) {
+                const int w = __ffs(okm) - 1;             // lowest attempt index that is valid
+                win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
+                watt = t0 + w + 1;
+                break;
+            }
+        }
+        if (lane == src) { out = win; att = watt; }       // watt == 0: keep the old pose (pu:360-361)
+        pending &= pending - 1;
+    }
+    if (live) {
+        p.xo[i] = out.x; p.yo[i] = out.y; p.tho[i] = out.th;
+        if (p.attempts) p.attempts[i] = att;
+    }
+}
+
+extern "C" int mcl_predict(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                           int64_t n, const double delta[3], uint64_t seed, uint64_t step,
+                           uint64_t first_index, const double *d_normals, int A, int max_attempts,
+                           double *d_xo, double *d_yo, double *d_thetao, int32_t *d_attempts) {
+    if (!h) return MCL_ERR_ARG;
+    if (n < 0 || !delta || (n > 0 && (!d_x || !d_y || !d_theta || !d_xo || !d_yo || !d_thetao)))
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: bad argument");
+    if (d_normals && A <= 0) return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: injected normals need A > 0");
+    if (!h->d_occ) return mcl_fail(h, MCL_ERR_STATE, "mcl_predict: map not set");
+    if (!h->motion_set) return mcl_fail(h, MCL_ERR_STATE, "mcl_predict: motion noise not set (mcl_set_motion)");
+    if (n == 0) return MCL_OK;
+    DeviceGuard guard(h->device);
+    MotionParams p;
+    p.x = d_x; p.y = d_y; p.th = d_theta; p.n = n;
+    p.rot1 = delta[0]; p.trans = delta[1]; p.rot2 = delta[2];
+    // alpha is float32[4] promoted to f64 inside the reference's compiled code
+    const double a1 = (double)h->alpha[0], a2 = (double)h->alpha[1], a3 = (double)h->alpha[2],
+                 a4 = (double)h->alpha[3];
+    volatile double t1, t2;   // keep the host compiler from contracting a*b+c
+    t1 = a1 * fabs(p.rot1); t2 = a2 * fabs(p.trans); p.s1 = t1 + t2;
+    t1 = a3 * fabs(p.trans); t2 = a4 * (fabs(p.rot1) + fabs(p.rot2)); p.s2 = t1 + t2;
+    t1 = a1 * fabs(p.rot2); t2 = a2 * fabs(p.trans); p.s3 = t1 + t2;
+    p.occ = h->d_occ; p.W = h->W; p.H = h->H; p.res = h->res; p.ox = h->ox; p.oy = h->oy;
+    p.seed = seed; p.step = step; p.first_index = first_index;
+    p.normals = d_normals; p.A = A; p.max_attempts = max_attempts;
+    p.xo = d_xo; p.yo = d_yo; p.tho = d_thetao; p.attempts = d_attempts;
+    const int blocks = (int)((n + 255) / 256);
+    k_motion<<<blocks, 256, 0, h->stream>>>(p);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}

@@ -1,0 +1,311 @@
+// resample.cu -- kernel (4): systematic / low-variance resampling, pu:416-446
+// low_variance_resample_numba, as cumulative sum + vectorised search + SoA gather.
+//
+// The reference walks  "while U_m > c and i < N-1: i++; c += w[i]"  with U_m = r + m/N (f64) and c
+// the running sum of the normalised f32 weights.  Because c_i is non-decreasing the walk is
+//     idx[m] = min( first i with c_i >= U_m , N-1 )
+// i.e. an independent search per output once the cumulative sums exist.
+//   REFERENCE_F32 : c_i reproduces the reference's rounding sequence exactly -- sequential f32
+//                   normalising sum (numba np.sum), f32 divide, sequential f32 running sum.  The
+//                   sequence is produced by ONE warp (loads and divides 32-wide, the additions
+//                   replayed in order through shuffles); the search and gather stay parallel.
+//   FIXED_POINT   : weights quantised to 64-bit fixed point, q_i = trunc(w_i * 2^k); the cumulative
+//                   sum is exact integer arithmetic (associative => any block or rank decomposition
+//                   gives identical indices) computed by a 3-kernel block scan.
+#include <algorithm>
+#include <float.h>
+
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------- reference mode
+// sequential f32 sum of w[0..n): s = ((0 + w0) + w1) + ...   (all lanes redundantly, in order)
+__device__ float seq_sum_f32_warp(const float *__restrict__ w, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    float s = 0.0f;
+    for (int64_t base = 0; base < n; base += 32) {
+        const float v = (base + lane < n) ? w[base + lane] : 0.0f;   // s + 0.0f == s
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, k));
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(32) k_cumsum_ref_f32(const float *__restrict__ w, int64_t n, float *__restrict__ c_out) {
+    const int lane = threadIdx.x & 31;
+    const float sum = seq_sum_f32_warp(w, n);                 // pu:430  np.sum(weights)
+    float c = 0.0f;                                           // 0 + wn[0] == wn[0]  (pu:436)
+    for (int64_t base = 0; base < n; base += 32) {
+        const bool in = base + lane < n;
+        const float wn = in ? __fdiv_rn(w[base + lane], sum) : 0.0f;   // pu:430 weights / sum (f32)
+        float mine = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            c = __fadd_rn(c, __shfl_sync(0xffffffffu, wn, k));         // pu:443 c += weights[i]
+            if (lane == k) mine = c;
+        }
+        if (in) c_out[base + lane] = mine;
+    }
+}
+
+// idx[m] = min(first i in [0, limit] with c_i >= U_m, limit); U_m = r + m*step (two f64 roundings)
+__global__ void k_search_ref_f32(const float *__restrict__ c, int64_t limit, int64_t n_out, double r, double step,
+                                 int32_t *__restrict__ idx) {
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < n_out; m += (int64_t)gridDim.x * blockDim.x) {
+        const double U = __dadd_rn(r, __dmul_rn((double)m, step));     // pu:440
+        int64_t lo = 0, hi = limit;            // invariant: answer in [lo, hi]
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (U > (double)c[mid]) lo = mid + 1; else hi = mid;       // pu:441 "U > c" keeps walking
+        }
+        idx[m] = (int32_t)lo;
+    }
+}
+
+// ----------------------------------------------------------------------------- fixed-point mode
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ uint64_t quantise(float w, double scale) {
+    const double v = __dmul_rn((double)w, scale);
+    return v > 0.0 ? (uint64_t)__double2ull_rz(v) : 0ull;     // negative / NaN weights count as 0
+}
+
+__global__ void __launch_bounds__(256) k_wmax(const float *__restrict__ w, int64_t n, unsigned *counter,
+                                              float *partials, double *out_scale, int64_t n_global) {
+    __shared__ float sh[32];
+    __shared__ bool last;
+    float m = 0.0f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, w[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmaxf(m, sh[k]);
+        partials[blockIdx.x] = m;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        float t = 0.0f;
+        for (unsigned b = 0; b < gridDim.x; ++b) t = fmaxf(t, ((volatile float *)partials)[b]);
+        // scale = 2^(62 - ceil(log2 n_global) - e), 2^e > wmax   (oracle: orc_resample_scale)
+        int e = 0;
+        if (t > 0.0f) frexp((double)t, &e);
+        int lg = 0;
+        while (((int64_t)1 << lg) < n_global) ++lg;
+        out_scale[0] = ldexp(1.0, 62 - lg - e);
+        out_scale[1] = (double)t;
+        *counter = 0;
+    }
+}
+
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// tile sums
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_sums(const float *__restrict__ w, int64_t n,
+                                                           const double *scale_ptr, uint64_t *tile_sums) {
+    __shared__ uint64_t sh[SCAN_THREADS / 32];
+    const double scale = scale_ptr[0];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += quantise(w[i], scale);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) t += sh[k];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile sums (single block, sequential over chunks); writes total to tile_off[nt]
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const uint64_t *tile_sums, int64_t nt, uint64_t *tile_off,
+                                                         uint64_t carry_in) {
+    __shared__ uint64_t sh[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = carry_in;
+    __syncthreads();
+    for (int64_t base = 0; base < nt; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const uint64_t v = i < nt ? tile_sums[i] : 0;
+        uint64_t inc = warp_incl_scan_u64(v);
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0;
+            t = warp_incl_scan_u64(t);
+            sh[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const uint64_t warp_off = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+        const uint64_t c0 = carry;
+        if (i < nt) tile_off[i] = c0 + warp_off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = c0 + warp_off + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_off[nt] = carry;
+}
+
+// inclusive cumulative sums C[i] (uint64), element order: i = base + k*SCAN_THREADS + t is NOT
+// contiguous per thread, so scan item-row by item-row (each row of 256 consecutive elements).
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const float *__restrict__ w, int64_t n,
+                                                           const double *scale_ptr, const uint64_t *tile_off,
+                                                           uint64_t *__restrict__ C) {
+    __shared__ uint64_t sh[SCAN_THREADS / 32];
+    __shared__ uint64_t carry;
+    const double scale = scale_ptr[0];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    if (threadIdx.x == 0) carry = tile_off[blockIdx.x];
+    __syncthreads();
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        const uint64_t v = i < n ? quantise(w[i], scale) : 0;
+        uint64_t inc = warp_incl_scan_u64(v);
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint64_t warp_off = 0;
+        for (int q = 0; q < (int)(threadIdx.x >> 5); ++q) warp_off += sh[q];
+        const uint64_t c0 = carry;
+        const uint64_t mine = c0 + warp_off + inc;
+        if (i < n) C[i] = mine;
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry = mine;
+        __syncthreads();
+    }
+}
+
+// idx[m] = min(first i in [0, limit] with C_i >= T_m, limit), T_m = ceil((r + m*step) * total)
+// m is a GLOBAL output index (m0 + local); C holds GLOBAL cumulative sums of this rank's slice.
+__global__ void k_search_fixed(const uint64_t *__restrict__ C, int64_t limit, int64_t m0, int64_t n_out, double r,
+                               double step, const uint64_t *total_ptr, int32_t *__restrict__ idx) {
+    const double totd = (double)total_ptr[0];
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
+        const double U = __dadd_rn(r, __dmul_rn((double)(m0 + j), step));
+        const double t = ceil(__dmul_rn(U, totd));
+        const uint64_t T = t >= 18446744073709551616.0 ? 0xffffffffffffffffull : (t > 0.0 ? __double2ull_rz(t) : 0ull);
+        int64_t lo = 0, hi = limit;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (T > C[mid]) lo = mid + 1; else hi = mid;
+        }
+        idx[j] = (int32_t)lo;
+    }
+}
+
+extern "C" int mcl_resample_indices(mcl_handle *h, const float *d_w, int64_t n_in, int64_t n_out, double r,
+                                    int mode, int32_t *d_idx) {
+    if (!h) return MCL_ERR_ARG;
+    if (n_in <= 0 || n_out < 0 || !d_w || (n_out > 0 && !d_idx))
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_resample_indices: bad argument");
+    if (n_in > 0x7fffffffLL) return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_resample_indices: n_in exceeds int32 indices");
+    if (n_out == 0) return MCL_OK;
+    DeviceGuard guard(h->device);
+    const double step = 1.0 / (double)n_out;                       // pu:434
+    const int64_t limit = std::min(n_in, n_out) - 1;               // pu:441 "i < N - 1"
+    const int sblocks = (int)std::min<int64_t>((n_out + 255) / 256, (int64_t)h->sm_count * 16);
+    if (mode == MCL_RESAMPLE_REFERENCE_F32) {
+        int rc = mcl_ensure_scratch(h, sizeof(float) * (size_t)n_in);
+        if (rc) return rc;
+        float *c = (float *)h->d_scratch;
+        k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n_in, c);
+        MCL_LAUNCH_CHECK(h);
+        k_search_ref_f32<<<sblocks, 256, 0, h->stream>>>(c, limit, n_out, r, step, d_idx);
+        MCL_LAUNCH_CHECK(h);
+        return MCL_OK;
+    }
+    if (mode != MCL_RESAMPLE_FIXED_POINT) return mcl_fail(h, MCL_ERR_ARG, "mcl_resample_indices: unknown mode");
+    const int64_t nt = (n_in + SCAN_TILE - 1) / SCAN_TILE;
+    const int wblocks = (int)std::min<int64_t>((n_in + 1023) / 1024, (int64_t)h->sm_count * 8);
+    // scratch: [0,64) counter | [64,128) scale(2 doubles) | wmax partials (wblocks floats) | tile_sums nt |
+    //          tile_off nt+1 | C n_in
+    size_t off = 128;
+    const size_t o_part = off; off += ((size_t)wblocks * sizeof(float) + 63) & ~(size_t)63;
+    const size_t o_ts = off; off += ((size_t)nt * 8 + 63) & ~(size_t)63;
+    const size_t o_to = off; off += ((size_t)(nt + 1) * 8 + 63) & ~(size_t)63;
+    const size_t o_c = off; off += (size_t)n_in * 8;
+    int rc = mcl_ensure_scratch(h, off);
+    if (rc) return rc;
+    char *s = (char *)h->d_scratch;
+    unsigned *counter = (unsigned *)s;
+    double *scale = (double *)(s + 64);
+    uint64_t *tile_sums = (uint64_t *)(s + o_ts), *tile_off = (uint64_t *)(s + o_to), *C = (uint64_t *)(s + o_c);
+    MCL_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned), h->stream));
+    k_wmax<<<wblocks, 256, 0, h->stream>>>(d_w, n_in, counter, (float *)(s + o_part), scale, n_in);
+    MCL_LAUNCH_CHECK(h);
+    k_tile_sums<<<(int)nt, SCAN_THREADS, 0, h->stream>>>(d_w, n_in, scale, tile_sums);
+    MCL_LAUNCH_CHECK(h);
+    k_scan_tile_sums<<<1, 1024, 0, h->stream>>>(tile_sums, nt, tile_off, 0ull);
+    MCL_LAUNCH_CHECK(h);
+    k_tile_scan<<<(int)nt, SCAN_THREADS, 0, h->stream>>>(d_w, n_in, scale, tile_off, C);
+    MCL_LAUNCH_CHECK(h);
+    k_search_fixed<<<sblocks, 256, 0, h->stream>>>(C, limit, 0, n_out, r, step, tile_off + nt, d_idx);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// host mirror of oracle u53(Philox(seed, step, item 0, sub 0, RESAMPLE))
+static void philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+extern "C" double mcl_resample_offset(uint64_t seed, uint64_t step, int64_t n_out) {
+    uint32_t ctr[4] = {0u, (uint32_t)step, 0u,
+                       (uint32_t)MCL_STREAM_RESAMPLE | ((uint32_t)((step >> 32) & 0xffu) << 24)};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+    philox_host(ctr, key, o);
+    const double u = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) / 9007199254740992.0;
+    const double hi = 1.0 / (double)n_out;
+    return 0.0 + (hi - 0.0) * u;          // np.random.uniform(0.0, step)
+}
+
+// new_particles[m] = particles[idx[m]] (pu:445)
+__global__ void k_gather(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ th,
+                         const int32_t *__restrict__ idx, int64_t n, double *__restrict__ xo, double *__restrict__ yo,
+                         double *__restrict__ tho) {
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < n; m += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t i = idx[m];
+        xo[m] = x[i]; yo[m] = y[i]; tho[m] = th[i];
+    }
+}
+
+extern "C" int mcl_gather(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                          const int32_t *d_idx, int64_t n_out, double *d_xo, double *d_yo, double *d_thetao) {
+    if (!h) return MCL_ERR_ARG;
+    if (n_out < 0 || (n_out > 0 && (!d_x || !d_y || !d_theta || !d_idx || !d_xo || !d_yo || !d_thetao)))
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_gather: bad argument");
+    if (d_xo == d_x || d_yo == d_y || d_thetao == d_theta)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_gather: outputs must not alias inputs");
+    if (n_out == 0) return MCL_OK;
+    DeviceGuard guard(h->device);
+    const int blocks = (int)std::min<int64_t>((n_out + 255) / 256, (int64_t)h->sm_count * 16);
+    k_gather<<<blocks, 256, 0, h->stream>>>(d_x, d_y, d_theta, d_idx, n_out, d_xo, d_yo, d_thetao);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}

@@ -1,0 +1,324 @@
+"""Stateful, device-resident localizer: the Python-facing surface of the reference's ROS node
+(app/scripts/amcmh_localizer.py, class AMCMHLocalizer) without the ROS message handling.
+
+    node.load_map            (node:124-177)  -> Localizer.load_map
+    rosparam reads           (node:18-58)    -> Localizer.set_params (same keys as amhmcl.yaml)
+    initialize_particles     (node:179-197)  -> init_uniform / init_gaussian / set_particles
+    odom_callback / move_particles (node:379-408) -> predict(odom_xytheta)
+    lidar_callback: update_scans + update_weights + update_particles_mh (node:294-322) -> update(...)
+    publish_estimate math    (node:584-597)  -> estimate()
+    resample_lvr             (node:488-492)  -> resample()
+
+Particles stay on the GPU as SoA fp64 torch tensors; per step the host sends one scan (M floats)
+and one odometry pose and reads back the 3+9 numbers of the estimate.  Every arithmetic step is a
+libmcl.so kernel (include/mcl.h); torch only allocates buffers.  No CPU fallback.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from .maps import GridMap
+from .params import DEFAULT_PARAMS, mode_flags
+
+_pd = C.POINTER(C.c_double)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _dbl3(v):
+    return (C.c_double * 3)(float(v[0]), float(v[1]), float(v[2]))
+
+
+class Localizer:
+    def __init__(self, device=0, params=None, mode=None, seed=0, resample_mode="reference",
+                 max_attempts=1000):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mcmh_localization_b200.Localizer needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", int(device))
+        self.h = _lib.Handle(int(device))
+        self._lock = threading.Lock()      # rospy runs the two callbacks on two threads
+        self.seed = int(seed)
+        self.tick = 0                      # Philox "step": one per stochastic call
+        self.first_index = 0               # global index of local particle 0 (sharded runs)
+        self.max_attempts = int(max_attempts)
+        self.resample_mode = {"reference": _lib.RESAMPLE_REFERENCE_F32,
+                              "fixed": _lib.RESAMPLE_FIXED_POINT}[resample_mode]
+        self.params = dict(DEFAULT_PARAMS)
+        self.map = None
+        self.n = 0
+        self.last_odom = None
+        self.delta = (0.0, 0.0, 0.0)
+        self.cur = self.prev = self.spare = None
+        self.weights_t = None
+        self.set_params(params or {}, mode=mode)
+
+    # ------------------------------------------------------------------ configuration
+    def set_params(self, params, mode=None):
+        """Accepts the keys of app/params/amhmcl.yaml (unknown keys are kept but unused)."""
+        self.params.update(params)
+        if mode is not None:
+            self.params["localization_mode"] = mode
+        p = self.params
+        f = mode_flags(p["localization_mode"])
+        self.use_mh, self.use_adaptive, self.assym = f["use_mh"], f["use_adaptive"], f["assym"]
+        self.alpha = np.array([p["alpha1"], p["alpha2"], p["alpha3"], p["alpha4"]], dtype=np.float32)  # node:28-33
+        self._bind_stream()
+        self.h.call("mcl_set_sensor", float(p["sigma_hit"]), float(p["z_hit"]), float(p["z_rand"]),
+                    float(p["max_range"]), int(p["step"]))
+        self.h.call("mcl_set_motion", self.alpha.ctypes.data_as(C.POINTER(C.c_float)))
+
+    def load_map(self, occ, resolution=None, origin_xy=None):
+        """occ: (H,W) int8 OccupancyGrid payload, or a GridMap (maps.load_map_yaml / map_from_occupancy)."""
+        if isinstance(occ, GridMap):
+            gm = occ
+        else:
+            from .maps import map_from_occupancy
+            gm = map_from_occupancy(occ, resolution, origin_xy[0], origin_xy[1])
+        self.map = gm
+        self._bind_stream()
+        self.h.call("mcl_set_map", C.c_void_p(gm.occ.ctypes.data), C.c_void_p(gm.dist.ctypes.data),
+                    gm.width, gm.height, gm.resolution, gm.origin_x, gm.origin_y)
+
+    def _bind_stream(self):
+        self.h.call("mcl_set_stream", C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+
+    # ------------------------------------------------------------------ particle buffers
+    def _alloc(self, n):
+        mk = lambda: [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3)]
+        self.cur, self.prev, self.spare = mk(), mk(), mk()
+        f32 = lambda: torch.empty(n, dtype=torch.float32, device=self.device)
+        self.score_pre, self.score_post, self.w_pre, self.w_post, self.w_mh = f32(), f32(), f32(), f32(), f32()
+        self.idx = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.weights_t = torch.full((n,), 1.0 / n, dtype=torch.float32, device=self.device)   # node:98
+        self.n = n
+
+    def set_particles(self, particles):
+        """(N,3) float64 host array -> device SoA; also particles_prev (node:95-97)."""
+        p = np.ascontiguousarray(particles, dtype=np.float64)
+        with self._lock:
+            self._bind_stream()
+            self._alloc(p.shape[0])
+            aos = torch.from_numpy(p).to(self.device)
+            self.h.call("mcl_aos_to_soa", _ptr(aos), self.n, *[_ptr(t) for t in self.cur])
+            for a, b in zip(self.prev, self.cur):
+                a.copy_(b)
+            self.last_odom = None
+
+    def init_uniform(self, n, seed=None, uniforms=None):
+        """node:188 generate_valid_particles.  uniforms: optional (3, max(50n,500)) injected draws for
+        the bit-exact restatement; default: per-particle Philox rejection sampling."""
+        with self._lock:
+            self._bind_stream()
+            self._alloc(int(n))
+            cnt = C.c_int64(0)
+            if uniforms is not None:
+                u = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64)).to(self.device)
+                self.h.call("mcl_init_uniform", self.n, _ptr(u), int(u.shape[1]), 0, 0,
+                            *[_ptr(t) for t in self.cur], C.byref(cnt))
+                if cnt.value < self.n:          # pu:462-465 may return fewer than N
+                    k = cnt.value
+                    kept = [t[:k].clone() for t in self.cur]
+                    self._alloc(k)
+                    for a, b in zip(self.cur, kept):
+                        a.copy_(b)
+            else:
+                s = self.seed if seed is None else int(seed)
+                self.h.call("mcl_init_uniform", self.n, None, 0, s, self.first_index,
+                            *[_ptr(t) for t in self.cur], C.byref(cnt))
+            for a, b in zip(self.prev, self.cur):
+                a.copy_(b)
+            self.last_odom = None
+
+    def init_gaussian(self, mean, cov, n, seed=None):
+        """node:183 initialize_gaussian_parallel: N(mean, cov) samples; samples on cells with
+        distance_map >= 1.0 or outside the map are zeroed (pu:594-614).  Host-side, one-off."""
+        rs = np.random.RandomState(self.seed if seed is None else int(seed))
+        s = rs.multivariate_normal(np.asarray(mean, float), np.asarray(cov, float), size=int(n))
+        gm = self.map
+        mx = ((s[:, 0] - gm.origin_x) / gm.resolution).astype(np.int64)
+        my = ((s[:, 1] - gm.origin_y) / gm.resolution).astype(np.int64)
+        ok = (mx >= 0) & (mx < gm.width) & (my >= 0) & (my < gm.height)
+        ok[ok] &= gm.dist[my[ok], mx[ok]] < 1.0
+        s[~ok] = 0.0
+        self.set_particles(s)
+
+    # ------------------------------------------------------------------ predict (odom_callback)
+    def predict(self, odom, normals=None):
+        """node:384-408 move_particles.  odom = (x, y, yaw).  normals: optional injected draws
+        (N, A, 3) (tests); default Philox."""
+        with self._lock:
+            self._bind_stream()
+            cur_odom = np.asarray(odom, dtype=np.float64)
+            if self.last_odom is not None:
+                self.delta = compute_motion(self.last_odom, cur_odom)
+                self._motion(self.cur, self.spare, _dbl3(self.delta), normals)
+                # particles_prev = particles; particles = particles_prop (node:404-405)
+                self.prev, self.cur, self.spare = self.cur, self.spare, self.prev
+            self.last_odom = cur_odom
+
+    def _motion(self, src, dst, delta3, normals=None, attempts=None):
+        if normals is not None:
+            z = normals if torch.is_tensor(normals) else torch.from_numpy(
+                np.ascontiguousarray(normals, dtype=np.float64))
+            z = z.to(self.device)
+            zp, A = _ptr(z), int(z.shape[1])
+        else:
+            zp, A = None, 0
+        self.tick += 1
+        self.h.call("mcl_predict", *[_ptr(t) for t in src], self.n, delta3, self.seed, self.tick,
+                    self.first_index, zp, A, self.max_attempts, *[_ptr(t) for t in dst], _ptr(attempts))
+
+    # ------------------------------------------------------------------ update (lidar_callback)
+    def set_scan(self, ranges, angle_min=None, angle_max=None, angles=None):
+        r = np.ascontiguousarray(ranges, dtype=np.float32)                       # node:343
+        if angles is None:
+            angles = np.linspace(angle_min, angle_max, len(r), dtype=np.float32)  # node:346-348
+        a = np.ascontiguousarray(angles, dtype=np.float32)
+        self._bind_stream()
+        self.h.call("mcl_set_scan", C.c_void_p(r.ctypes.data), C.c_void_p(a.ctypes.data), len(r))
+
+    def _softmax(self, score, w):
+        self.h.call("mcl_softmax", _ptr(score), self.n, _ptr(w), None, None)
+
+    def update(self, ranges, angle_min=None, angle_max=None, angles=None, uniforms=None):
+        """node:296-322: update_scans, update_weights (both particle sets), MH accept by mode."""
+        with self._lock:
+            self.set_scan(ranges, angle_min, angle_max, angles)
+            self._update_core(uniforms)
+
+    def stage_scans(self, ranges_km, angles):
+        """Pre-stage K scans on the device (bag replay / device-resident benchmark inputs)."""
+        r = np.ascontiguousarray(ranges_km, dtype=np.float32)
+        a = np.ascontiguousarray(angles, dtype=np.float32)
+        self._bind_stream()
+        self.h.call("mcl_set_scan_batch", C.c_void_p(r.ctypes.data), C.c_void_p(a.ctypes.data),
+                    int(r.shape[1]), int(r.shape[0]))
+
+    def update_staged(self, k, uniforms=None):
+        """update() on pre-staged scan k: no host->device traffic."""
+        with self._lock:
+            self._bind_stream()
+            self.h.call("mcl_use_scan", int(k))
+            self._update_core(uniforms)
+
+    def estimate_async(self, out18):
+        """Non-blocking estimate into a device tensor of 18 float64 (see include/mcl.h)."""
+        with self._lock:
+            self._bind_stream()
+            self.h.call("mcl_estimate_async", *[_ptr(t) for t in self.cur], _ptr(self.weights_t), self.n,
+                        _ptr(out18))
+
+    def _update_core(self, uniforms=None):
+        if self.assym or self.use_adaptive:
+            raise NotImplementedError(
+                "localization_mode %r: asymmetric-MH / KLD-adaptive modes are SURVEY 8(f) 'next' rows; "
+                "use MCL or MHMCL" % self.params["localization_mode"])
+        self.h.call("mcl_likelihood", *[_ptr(t) for t in self.cur], self.n, _ptr(self.score_post))
+        self._softmax(self.score_post, self.w_post)
+        if not self.use_mh:
+            # MCL: weights = weights_post (node:313). scores_pre is never used in this mode, so it is
+            # not computed (the reference computes and discards it).
+            self.weights_t, self.w_post = self.w_post, self.weights_t
+            return
+        self.h.call("mcl_likelihood", *[_ptr(t) for t in self.prev], self.n, _ptr(self.score_pre))
+        self._softmax(self.score_pre, self.w_pre)
+        up = None
+        if uniforms is not None:
+            u = uniforms if torch.is_tensor(uniforms) else torch.from_numpy(
+                np.ascontiguousarray(uniforms, dtype=np.float64))
+            u = u.to(self.device)
+            up = _ptr(u)
+        self.tick += 1
+        # mh_resampling(particles_prev, particles, weights_post, weights_pre)  (node:363)
+        self.h.call("mcl_mh_accept", *[_ptr(t) for t in self.prev], *[_ptr(t) for t in self.cur],
+                    _ptr(self.w_post), _ptr(self.w_pre), self.n, up, self.seed, self.tick,
+                    self.first_index, *[_ptr(t) for t in self.spare], _ptr(self.w_mh), None)
+        self.cur, self.spare = self.spare, self.cur                       # node:370
+        self.weights_t, self.w_mh = self.w_mh, self.weights_t
+
+    # ------------------------------------------------------------------ estimate / resample
+    def estimate(self):
+        """node:586-597 -> (mean_x, mean_y, mean_theta, cov 3x3) with np.cov(aweights) semantics."""
+        with self._lock:
+            self._bind_stream()
+            out = (C.c_double * 16)()
+            self.h.call("mcl_estimate", *[_ptr(t) for t in self.cur], _ptr(self.weights_t), self.n, out)
+        return assemble_estimate(list(out))
+
+    def resample(self, r=None):
+        """node:488-492 resample_lvr -> low_variance_resample_numba (pu:416-446)."""
+        with self._lock:
+            self._bind_stream()
+            self.tick += 1
+            if r is None:
+                r = self.h.lib.mcl_resample_offset(self.seed, self.tick, self.n)
+            self.h.call("mcl_resample_indices", _ptr(self.weights_t), self.n, self.n, float(r),
+                        self.resample_mode, _ptr(self.idx))
+            self.h.call("mcl_gather", *[_ptr(t) for t in self.cur], _ptr(self.idx), self.n,
+                        *[_ptr(t) for t in self.spare])
+            self.cur, self.spare = self.spare, self.cur
+            # self.weights keeps the pre-resampling values (node:490 discards the uniform weights)
+
+    def step(self, odom, ranges, angle_min=None, angle_max=None, angles=None):
+        """One odom message followed by one scan: predict -> update -> estimate -> resample."""
+        self.predict(odom)
+        self.update(ranges, angle_min, angle_max, angles)
+        est = self.estimate()
+        self.resample()
+        return est
+
+    # ------------------------------------------------------------------ read-back
+    def _aos(self, soa):
+        out = torch.empty((self.n, 3), dtype=torch.float64, device=self.device)
+        self.h.call("mcl_soa_to_aos", *[_ptr(t) for t in soa], self.n, _ptr(out))
+        return out.cpu().numpy()
+
+    def particles(self):
+        with self._lock:
+            self._bind_stream()
+            return self._aos(self.cur)
+
+    def particles_prev(self):
+        with self._lock:
+            self._bind_stream()
+            return self._aos(self.prev)
+
+    def weights(self):
+        return self.weights_t.cpu().numpy()
+
+    def scores(self):
+        return self.score_pre.cpu().numpy(), self.score_post.cpu().numpy()
+
+    def sync(self):
+        self.h.call("mcl_sync")
+
+    def close(self):
+        self.h.close()
+
+
+def compute_motion(odom1, odom2):
+    """node:410-421, host scalars, the node's own NumPy calls (np.arctan2 / np.hypot differ from
+    glibc by an ulp now and then, so this stays NumPy; mcl_compute_motion is the C-host variant)."""
+    dx = odom2[0] - odom1[0]
+    dy = odom2[1] - odom1[1]
+    dtheta = (odom2[2] - odom1[2] + np.pi) % (2 * np.pi) - np.pi      # pu:62-67 normalize_angle
+    rot1 = np.arctan2(dy, dx) - odom1[2]
+    trans = np.hypot(dx, dy)
+    rot2 = dtheta - rot1
+    return float(rot1), float(trans), float(rot2)
+
+
+def assemble_estimate(o):
+    """np.average / np.cov(aweights) from the 16 numbers of mcl_estimate (include/mcl.h)."""
+    v1, v2 = o[0], o[1]
+    mean = np.array([o[2], o[3], o[4]])
+    sd = np.array(o[5:8])
+    sdd = np.array([[o[8], o[9], o[10]], [o[9], o[11], o[12]], [o[10], o[12], o[13]]])
+    fact = v1 - v2 / v1                       # np.cov: w_sum - ddof * sum(w * aweights) / w_sum
+    cov = (sdd - np.outer(sd, sd) / v1) / fact
+    return mean[0], mean[1], mean[2], cov

@@ -1,0 +1,131 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/mcl.h
+declares, the ctypes table covers them all, host-only entry points agree with the oracle, and the
+host logic (maps, params, estimate assembly) matches the reference's semantics."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, YAML_PARAMS as P, golden
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "mcl.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mcmh_localization_b200 import _lib
+    names = _declared()
+    assert len(names) >= 30
+    L = _lib.load()
+    for n in names:
+        assert hasattr(L, n), "libmcl.so does not export %s" % n
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mcmh_localization_b200 import _lib, MclError
+    with pytest.raises(MclError):
+        _lib.Handle(0)
+    from mcmh_localization_b200 import Localizer
+    with pytest.raises(RuntimeError):
+        Localizer()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mcmh_localization_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libmcl_oracle" not in src and "/root/reference" not in src, f
+
+
+def test_compute_motion_matches_oracle():
+    from mcmh_localization_b200 import _lib
+    from oracle import node_glue as ng
+    L = _lib.load()
+    rs = np.random.RandomState(0)
+    for _ in range(200):
+        o1 = rs.uniform(-5, 5, 3)
+        o2 = o1 + rs.normal(0, 0.5, 3)
+        d = (C.c_double * 3)()
+        L.mcl_compute_motion((C.c_double * 3)(*o1), (C.c_double * 3)(*o2), d)
+        ref = tuple(float(v) for v in ng.compute_motion(o1, o2))
+        # the Python host path uses the node's own NumPy calls: bit-exact
+        from mcmh_localization_b200.localizer import compute_motion
+        assert compute_motion(o1, o2) == ref
+        # the C-host variant uses glibc atan2/hypot: within an ulp of NumPy's
+        np.testing.assert_allclose(tuple(d), ref, rtol=0, atol=4e-15)
+
+
+def test_resample_offset_matches_oracle_philox():
+    from mcmh_localization_b200 import _lib
+    from oracle import clib
+    L = _lib.load()
+    for seed, step, n in ((0, 0, 1000), (123456789012345, 7, 1_000_000), (2**63 + 5, 2**33 + 1, 3)):
+        r = L.mcl_resample_offset(seed, step, n)
+        u = clib.uniform53(seed, step, 0, 0, clib.STREAM_RESAMPLE)
+        assert r == 0.0 + (1.0 / n - 0.0) * u and 0 <= r < 1.0 / n
+
+
+def test_map_loader_matches_reference_semantics():
+    from mcmh_localization_b200.maps import load_npz, load_map_yaml
+    from oracle import node_glue as ng
+    for name in ("map_world", "map_house"):
+        gm = load_npz(os.path.join(GOLDEN, name + ".npz"))
+        mp = ng.load_map(gm.occ, gm.resolution, gm.origin_x, gm.origin_y)
+        assert np.array_equal(gm.dist.ravel(), mp["distance_map"])
+        assert np.array_equal(gm.limits, mp["limits"])
+        ref_yaml = os.path.join("/root/reference/app/maps", name + ".yaml")
+        if os.path.exists(ref_yaml):          # build container only
+            gm2 = load_map_yaml(ref_yaml)
+            assert np.array_equal(gm2.occ, gm.occ) and gm2.resolution == 0.05
+            assert (gm2.origin_x, gm2.origin_y) == (-10.0, -10.0)
+    world = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    assert {int(v): int((world.occ == v).sum()) for v in (-1, 0, 100)} == {-1: 138632, 0: 7907, 100: 917}
+
+
+def test_params_keys_and_mode_flags():
+    from mcmh_localization_b200.params import DEFAULT_PARAMS, YAML_PARAMS, load_params, mode_flags
+    assert set(P) <= set(YAML_PARAMS) and all(YAML_PARAMS[k] == v for k, v in P.items())
+    assert load_params(overrides={"sigma_hit": 0.3})["sigma_hit"] == 0.3
+    assert DEFAULT_PARAMS["localization_mode"] == "MHAMCL"
+    assert mode_flags("MCL") == dict(use_mh=False, use_adaptive=False, assym=False)
+    assert mode_flags("MHMCL") == dict(use_mh=True, use_adaptive=False, assym=False)
+    assert mode_flags("AMHAMCL") == dict(use_mh=True, use_adaptive=True, assym=True)
+    assert mode_flags("AMCL") == dict(use_mh=False, use_adaptive=True, assym=False)
+
+
+def test_assemble_estimate_is_np_cov():
+    from mcmh_localization_b200.localizer import assemble_estimate
+    from oracle import node_glue as ng
+    g = golden("mh_map_world.npz")
+    parts, w = g["cur"], g["w_post"].astype(np.float64)
+    rx, ry, rt, rcov = ng.estimate(parts, g["w_post"])
+    d = np.column_stack((parts[:, 0] - rx, parts[:, 1] - ry,
+                         ng.clib.normalize_angle_array(parts[:, 2], rt).astype(np.float64)))
+    o = [w.sum(), (w * w).sum(), rx, ry, rt] + list((w[:, None] * d).sum(0))
+    o += [(w * d[:, i] * d[:, j]).sum() for i, j in ((0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2))] + [0, 0]
+    mx, my, mt, cov = assemble_estimate(o)
+    np.testing.assert_allclose(cov, rcov, rtol=1e-9, atol=1e-15)
+
+
+def test_synthetic_scan_generator_matches_reference_raycast():
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan
+    from oracle import node_glue as ng
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    mp = ng.load_map(gm.occ, gm.resolution, gm.origin_x, gm.origin_y)
+    pose = np.array([-2.0, -0.5, 0.3])
+    r, a = raycast_scan(gm, pose)
+    r2, a2 = ng.synthetic_scan(pose, mp)
+    assert np.array_equal(a, a2) and np.array_equal(r, r2)
