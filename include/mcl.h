@@ -101,6 +101,12 @@ int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const do
  * multi-GPU path passes the all-reduced values. */
 int mcl_softmax(mcl_handle *h, const float *d_score, int64_t n, float *d_weights, double *d_stats,
                 const double *ext_stats);
+/* Staged softmax for sharded particles: max -> [all-reduce MAX on d_stats[0]] -> sumexp (uses
+ * d_stats[0], writes d_stats[1]) -> [all-reduce SUM on d_stats[1]] -> weights.  d_stats: device. */
+int mcl_softmax_max(mcl_handle *h, const float *d_score, int64_t n, double *d_stats);
+int mcl_softmax_sumexp(mcl_handle *h, const float *d_score, int64_t n, double *d_stats);
+int mcl_softmax_weights(mcl_handle *h, const float *d_score, int64_t n, const double *d_stats,
+                        float *d_weights);
 /* blocking read of the two doubles written by mcl_softmax */
 int mcl_softmax_stats(mcl_handle *h, const float *d_score, int64_t n, double h_stats[2]);
 
@@ -133,6 +139,18 @@ int mcl_mh_accept(mcl_handle *h, const double *d_x, const double *d_y, const dou
  * r is the single uniform draw in [0, 1/n_out) (see mcl_resample_offset). */
 int mcl_resample_indices(mcl_handle *h, const float *d_weights, int64_t n_in, int64_t n_out,
                          double r, int mode, int32_t *d_idx);
+/* Global systematic resampling over sharded particles (FIXED_POINT arithmetic):
+ *   mcl_weights_max   -> local max (device f32)            [caller: all-reduce MAX]
+ *   mcl_resample_scan -> local fixed-point cumulative sums with the global scale, local total
+ *                        (device u64)                       [caller: all-gather totals -> offsets]
+ *   mcl_resample_search -> local source index of every global output m in [m0, m0 + n_out_local)
+ *                        that falls into this rank's interval (offset, offset + total].
+ * The cumulative sums stay in the handle's scratch between scan and search. */
+int mcl_weights_max(mcl_handle *h, const float *d_weights, int64_t n, float *d_wmax);
+int mcl_resample_scan(mcl_handle *h, const float *d_weights, int64_t n_in, const float *d_wmax_global,
+                      int64_t n_global, uint64_t *d_total);
+int mcl_resample_search(mcl_handle *h, int64_t n_in, uint64_t offset, uint64_t grand_total, int64_t m0,
+                        int64_t n_out_local, double r, int64_t n_out_global, int32_t *d_idx);
 /* r = 0 + (1/n_out - 0) * u53(Philox(seed, step, 0, RESAMPLE))  (np.random.uniform(0, 1/N)) */
 double mcl_resample_offset(uint64_t seed, uint64_t step, int64_t n_out);
 /* new_particles[m] = particles[idx[m]] (pu:445), SoA gather; outputs must not alias inputs. */
@@ -151,6 +169,14 @@ int mcl_estimate(mcl_handle *h, const double *d_x, const double *d_y, const doub
 /* non-blocking: d_out18 (device) = {6 raw sums, mean_x, mean_y, mean_theta, 9 central sums} */
 int mcl_estimate_async(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                        const float *d_weights, int64_t n, double *d_out18);
+/* staged, non-blocking (sharded particles): d_m9[0..5] raw sums -> [all-reduce SUM] ->
+ * mcl_estimate_means_async fills d_m9[6..8] -> central sums d_c9 -> [all-reduce SUM]. */
+int mcl_estimate_moments_async(mcl_handle *h, const double *d_x, const double *d_y,
+                               const double *d_theta, const float *d_weights, int64_t n, double *d_m9);
+int mcl_estimate_means_async(mcl_handle *h, double *d_m9);
+int mcl_estimate_central_async(mcl_handle *h, const double *d_x, const double *d_y,
+                               const double *d_theta, const float *d_weights, int64_t n,
+                               const double *d_mean3, double *d_c9);
 int mcl_estimate_moments(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                          const float *d_weights, int64_t n, double h_m[6]);
 int mcl_estimate_central(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,

@@ -34,16 +34,25 @@ SIGNATURES = {
     "mcl_set_likelihood_path": (_i, [_vp, _i]),
     "mcl_likelihood": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "mcl_softmax": (_i, [_vp, _vp, _i64, _vp, _vp, _pd]),
+    "mcl_softmax_max": (_i, [_vp, _vp, _i64, _vp]),
+    "mcl_softmax_sumexp": (_i, [_vp, _vp, _i64, _vp]),
+    "mcl_softmax_weights": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "mcl_softmax_stats": (_i, [_vp, _vp, _i64, _pd]),
     "mcl_predict": (_i, [_vp, _vp, _vp, _vp, _i64, _pd, _u64, _u64, _u64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mcl_compute_motion": (_i, [_pd, _pd, _pd]),
     "mcl_mh_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u64,
                            _vp, _vp, _vp, _vp, _vp]),
     "mcl_resample_indices": (_i, [_vp, _vp, _i64, _i64, _d, _i, _vp]),
+    "mcl_weights_max": (_i, [_vp, _vp, _i64, _vp]),
+    "mcl_resample_scan": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "mcl_resample_search": (_i, [_vp, _i64, _u64, _u64, _i64, _i64, _d, _i64, _vp]),
     "mcl_resample_offset": (_d, [_u64, _u64, _i64]),
     "mcl_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mcl_estimate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _pd]),
     "mcl_estimate_async": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "mcl_estimate_moments_async": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "mcl_estimate_means_async": (_i, [_vp, _vp]),
+    "mcl_estimate_central_async": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "mcl_estimate_moments": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _pd]),
     "mcl_estimate_central": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _pd, _pd]),
     "mcl_normalize_angle_array": (_i, [_vp, _vp, _d, _i64, _vp]),

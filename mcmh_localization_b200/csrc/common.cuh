@@ -60,6 +60,7 @@ struct mcl_handle {
     std::vector<ScanMeta> batch_meta;
     int batch_stride = 0;
     const BeamTable *d_beams_active = nullptr;
+    uint64_t scan_gen = 0;       // bumped whenever the active scan table changes
 
     // scratch for reductions / scans
     void *d_scratch = nullptr;

@@ -182,6 +182,43 @@ extern "C" int mcl_estimate_async(mcl_handle *h, const double *d_x, const double
     return MCL_OK;
 }
 
+// staged forms (sharded path): raw sums -> [all-reduce] -> means -> central sums -> [all-reduce]
+extern "C" int mcl_estimate_moments_async(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                                          const float *d_w, int64_t n, double *d_m9) {
+    if (!h || !d_m9) return MCL_ERR_ARG;
+    int rc = check_est_args(h, d_x, d_y, d_theta, d_w, n);
+    if (rc) return rc;
+    DeviceGuard guard(h->device);
+    int nb; unsigned *counter; double *res, *partials;
+    rc = est_setup(h, n, nb, counter, res, partials);
+    if (rc) return rc;
+    MCL_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned), h->stream));
+    k_est_moments<<<nb, EST_THREADS, 0, h->stream>>>(d_x, d_y, d_theta, d_w, n, partials, counter, d_m9);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+extern "C" int mcl_estimate_means_async(mcl_handle *h, double *d_m9) {
+    if (!h || !d_m9) return MCL_ERR_ARG;
+    DeviceGuard guard(h->device);
+    k_est_means<<<1, 1, 0, h->stream>>>(d_m9);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+extern "C" int mcl_estimate_central_async(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                                          const float *d_w, int64_t n, const double *d_mean3, double *d_c9) {
+    if (!h || !d_mean3 || !d_c9) return MCL_ERR_ARG;
+    int rc = check_est_args(h, d_x, d_y, d_theta, d_w, n);
+    if (rc) return rc;
+    DeviceGuard guard(h->device);
+    int nb; unsigned *counter; double *res, *partials;
+    rc = est_setup(h, n, nb, counter, res, partials);
+    if (rc) return rc;
+    MCL_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned), h->stream));
+    k_est_central<<<nb, EST_THREADS, 0, h->stream>>>(d_x, d_y, d_theta, d_w, n, d_mean3, 0, 0, 0, 0, partials, counter, d_c9);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
 extern "C" int mcl_estimate(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                             const float *d_w, int64_t n, double h_out[16]) {
     if (!h || !h_out) return MCL_ERR_ARG;

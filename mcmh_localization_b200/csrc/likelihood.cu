@@ -169,18 +169,132 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// G = 1 (one thread per particle, N large): every lane of a warp evaluates the SAME beam, so the
+// beam constants are warp-uniform and come from the constant bank (no LSU / shared-memory traffic:
+// ncu on the first version showed the shared-memory pipe at 78 % with 40 % of its wavefronts spent on
+// the beam table, and the XU pipe at 66 % on the two F2I.F64 per evaluation).  The cell index is
+// extracted with the round-down magic-number add (FP64 pipe, exact floor for |t| < 2^31) and the
+// window offset + clamp is one VIADDMNMX (__viaddmin_s32_relu).
+// ---------------------------------------------------------------------------------------------
+#define MAX_CBEAMS 2048
+__constant__ BeamTable c_beams[MAX_CBEAMS];
+#define MCL_FLOOR_MAGIC 6755399441055744.0   // 2^52 + 2^51
+
+__device__ __forceinline__ int floor_to_int(double t) {   // exact floor(t) for |t| < 2^31
+    return __double2loint(__dadd_rd(t, MCL_FLOOR_MAGIC));
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood_g1(const LikParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    float *swin = reinterpret_cast<float *>(smem + 16);
+    const int nb = p.n_pos + p.n_neg;
+    if (SMEM) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, p.win_bytes);
+            bulk_g2s_chunked(reinterpret_cast<unsigned char *>(swin), reinterpret_cast<const unsigned char *>(p.win),
+                             p.win_bytes, bar);
+        }
+        mbar_wait(bar, 0);
+    }
+    const int pw = p.ww + 2;
+    const int cx = p.ww + 1, cy = p.wh + 1;
+    const int ofx = 1 - p.wx0, ofy = 1 - p.wy0;
+    const double lo = p.margin, hix = (double)p.W - p.margin, hiy = (double)p.H - p.margin;
+    const int64_t stride = (int64_t)gridDim.x * LIK_THREADS;
+    const int warp_first = threadIdx.x & ~31;
+    for (int64_t base = (int64_t)blockIdx.x * LIK_THREADS; base + warp_first < p.n; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t il = i < p.n ? i : p.n - 1;
+        const double x = p.x[il], y = p.y[il], th = p.th[il];
+        double s, c;
+        sincos(th, &s, &c);
+        const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);
+        const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
+        const bool interior = (px >= lo) && (px <= hix) && (py >= lo) && (py <= hiy);
+        float acc0 = 0.f, acc1 = 0.f;
+        if (SMEM && __all_sync(0xffffffffu, interior)) {
+            // no endpoint can leave the map: coordinates >= 1, floor == trunc, no bounds test
+            int j = 0;
+#pragma unroll 4
+            for (; j + 1 < p.n_pos; j += 2) {
+                const double bx0 = c_beams[j].bx, by0 = c_beams[j].by;
+                const double bx1 = c_beams[j + 1].bx, by1 = c_beams[j + 1].by;
+                const double tx0 = fma(c, bx0, fma(-s, by0, px)), ty0 = fma(s, bx0, fma(c, by0, py));
+                const double tx1 = fma(c, bx1, fma(-s, by1, px)), ty1 = fma(s, bx1, fma(c, by1, py));
+                const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
+                const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
+                const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
+                const int iy1 = __viaddmin_s32_relu(floor_to_int(ty1), ofy, cy);
+                acc0 += swin[iy0 * pw + ix0];
+                acc1 += swin[iy1 * pw + ix1];
+            }
+            if (j < p.n_pos) {
+                const double bx0 = c_beams[j].bx, by0 = c_beams[j].by;
+                const double tx0 = fma(c, bx0, fma(-s, by0, px)), ty0 = fma(s, bx0, fma(c, by0, py));
+                const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
+                const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
+                acc0 += swin[iy0 * pw + ix0];
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < p.n_pos; ++j) {
+                const double bx = c_beams[j].bx, by = c_beams[j].by;
+                const double tx = fma(c, bx, fma(-s, by, px));
+                const double ty = fma(s, bx, fma(c, by, py));
+                const int mx = __double2int_rz(tx), my = __double2int_rz(ty);      // pu:128-129 int()
+                const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
+                float v;
+                if (SMEM) {
+                    const int ix = min(max(mx + ofx, 0), cx), iy = min(max(my + ofy, 0), cy);
+                    v = swin[iy * pw + ix];
+                    v = inmap ? v : 0.f;                                           // pu:131-132
+                } else {
+                    v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0.f;
+                }
+                acc0 += v;
+            }
+        }
+        // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
+        for (int j = p.n_pos; j < nb; ++j) {
+            const double bx = c_beams[j].bx, by = c_beams[j].by;
+            const double tx = fma(c, bx, fma(-s, by, px));
+            const double ty = fma(s, bx, fma(c, by, py));
+            const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
+            if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
+                acc1 += (float)cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
+                                         p.z_rand, p.max_range, false);
+        }
+        if (i < p.n) p.score[i] = (float)((double)(acc0 + acc1) / (double)nb);     // pu:144-145
+    }
+}
+
 __global__ void k_fill_f32(float *out, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = v;
 }
 
-template <int G, bool SMEM>
-static int launch_lik(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
-    auto kern = k_likelihood<G, SMEM>;
-    MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+template <typename K>
+static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t smem_bytes, int G) {
+    // attribute + occupancy queries are cached per (kernel, smem size): they cost tens of microseconds
+    static thread_local const void *c_kern[16];
+    static thread_local size_t c_smem[16];
+    static thread_local int c_occ[16], c_dev[16], c_n = 0;
     int occ = 0;
-    MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LIK_THREADS, smem_bytes));
-    if (occ < 1) return mcl_fail(h, MCL_ERR_CAPACITY, "likelihood kernel does not fit on an SM");
+    for (int k = 0; k < c_n; ++k)
+        if (c_kern[k] == (const void *)kern && c_smem[k] == smem_bytes && c_dev[k] == h->device) occ = c_occ[k];
+    if (occ == 0) {
+        MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LIK_THREADS, smem_bytes));
+        if (occ < 1) return mcl_fail(h, MCL_ERR_CAPACITY, "likelihood kernel does not fit on an SM");
+        const int k = c_n < 16 ? c_n++ : 15;
+        c_kern[k] = (const void *)kern; c_smem[k] = smem_bytes; c_occ[k] = occ; c_dev[k] = h->device;
+    }
     const int64_t groups = LIK_THREADS / G;
     const int64_t need = (p.n + groups - 1) / groups;
     const int blocks = (int)std::min<int64_t>(need, (int64_t)h->sm_count * occ);
@@ -198,6 +312,15 @@ static int launch_lik(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
     }
     return MCL_OK;
 }
+
+template <int G, bool SMEM>
+static int launch_lik(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
+    return launch_lik_kernel(h, k_likelihood<G, SMEM>, p, smem_bytes, G);
+}
+
+// the constant-bank beam table is module-global: re-upload when the active scan (or handle) changed
+static const void *g_cbeams_src = nullptr;
+static uint64_t g_cbeams_gen = 0;
 
 extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                               int64_t n, float *d_score) {
@@ -237,6 +360,16 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     int G = 1;
     const int64_t target = (int64_t)h->sm_count * 2048;
     while (G < 32 && n * G < target) G *= 2;
+    if (G == 1 && nb <= MAX_CBEAMS) {
+        if (g_cbeams_src != (const void *)h->d_beams_active || g_cbeams_gen != h->scan_gen) {
+            MCL_CUDA(h, cudaMemcpyToSymbolAsync(c_beams, h->d_beams_active, beam_bytes, 0, cudaMemcpyDeviceToDevice,
+                                                h->stream));
+            g_cbeams_src = (const void *)h->d_beams_active;
+            g_cbeams_gen = h->scan_gen;
+        }
+        if (use_smem) return launch_lik_kernel(h, k_likelihood_g1<true>, p, 16 + h->win_bytes, 1);
+        return launch_lik_kernel(h, k_likelihood_g1<false>, p, 16, 1);
+    }
 #define LIK_CASE(GV)                                                                   \
     case GV:                                                                           \
         return use_smem ? launch_lik<GV, true>(h, p, smem_win) : launch_lik<GV, false>(h, p, smem_glob);

@@ -262,6 +262,7 @@ extern "C" int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h
         MCL_CUDA(h, cudaMemcpyAsync(h->d_beams, h->h_beams, (size_t)(n_pos + n_neg) * sizeof(BeamTable),
                                     cudaMemcpyHostToDevice, h->stream));
     h->d_beams_active = h->d_beams;
+    h->scan_gen++;
     h->scan_set = true;
     return MCL_OK;
 }
@@ -292,6 +293,7 @@ extern "C" int mcl_use_scan(mcl_handle *h, int k) {
     if (!h) return MCL_ERR_ARG;
     if (k < 0 || k >= (int)h->batch_meta.size()) return mcl_fail(h, MCL_ERR_ARG, "mcl_use_scan: no such pre-staged scan");
     h->d_beams_active = h->d_batch + (size_t)k * h->batch_stride;
+    h->scan_gen++;
     h->n_pos = h->batch_meta[k].n_pos; h->n_neg = h->batch_meta[k].n_neg; h->rmax_cells = h->batch_meta[k].rmax_cells;
     h->scan_set = true;
     return MCL_OK;

@@ -142,6 +142,47 @@ extern "C" int mcl_softmax(mcl_handle *h, const float *d_score, int64_t n, float
     return softmax_impl(h, d_score, n, d_weights, d_stats, ext_stats);
 }
 
+// staged forms for the sharded (multi-GPU) path: the caller all-reduces d_stats between stages
+extern "C" int mcl_softmax_max(mcl_handle *h, const float *d_score, int64_t n, double *d_stats) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_score || !d_stats) return mcl_fail(h, MCL_ERR_ARG, "mcl_softmax_max: bad argument");
+    DeviceGuard guard(h->device);
+    const int nb = red_blocks(h, n);
+    int rc = mcl_ensure_scratch(h, 128 + sizeof(double) * (size_t)nb + 64);
+    if (rc) return rc;
+    RedScratch rs;
+    rs.counter = (unsigned *)h->d_scratch;
+    rs.partials = (double *)((char *)h->d_scratch + 64);
+    MCL_CUDA(h, cudaMemsetAsync(rs.counter, 0, sizeof(unsigned), h->stream));
+    k_max<<<nb, RED_THREADS, 0, h->stream>>>(d_score, n, rs, d_stats);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+extern "C" int mcl_softmax_sumexp(mcl_handle *h, const float *d_score, int64_t n, double *d_stats) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_score || !d_stats) return mcl_fail(h, MCL_ERR_ARG, "mcl_softmax_sumexp: bad argument");
+    DeviceGuard guard(h->device);
+    const int nb = red_blocks(h, n);
+    int rc = mcl_ensure_scratch(h, 128 + sizeof(double) * (size_t)nb + 64);
+    if (rc) return rc;
+    RedScratch rs;
+    rs.counter = (unsigned *)h->d_scratch;
+    rs.partials = (double *)((char *)h->d_scratch + 64);
+    MCL_CUDA(h, cudaMemsetAsync(rs.counter, 0, sizeof(unsigned), h->stream));
+    k_sumexp<<<nb, RED_THREADS, 0, h->stream>>>(d_score, n, rs, d_stats, 0.0, 0);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+extern "C" int mcl_softmax_weights(mcl_handle *h, const float *d_score, int64_t n, const double *d_stats,
+                                   float *d_weights) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_score || !d_stats || !d_weights) return mcl_fail(h, MCL_ERR_ARG, "mcl_softmax_weights: bad argument");
+    DeviceGuard guard(h->device);
+    k_softmax_weights<<<red_blocks(h, n), RED_THREADS, 0, h->stream>>>(d_score, n, d_stats, 0.0, 0.0, 0, d_weights);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
 extern "C" int mcl_softmax_stats(mcl_handle *h, const float *d_score, int64_t n, double h_stats[2]) {
     if (!h) return MCL_ERR_ARG;
     if (n <= 0 || !d_score || !h_stats) return mcl_fail(h, MCL_ERR_ARG, "mcl_softmax_stats: bad argument");

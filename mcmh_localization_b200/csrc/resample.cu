@@ -196,8 +196,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const float *__restr
 // idx[m] = min(first i in [0, limit] with C_i >= T_m, limit), T_m = ceil((r + m*step) * total)
 // m is a GLOBAL output index (m0 + local); C holds GLOBAL cumulative sums of this rank's slice.
 __global__ void k_search_fixed(const uint64_t *__restrict__ C, int64_t limit, int64_t m0, int64_t n_out, double r,
-                               double step, const uint64_t *total_ptr, int32_t *__restrict__ idx) {
-    const double totd = (double)total_ptr[0];
+                               double step, const uint64_t *total_ptr, uint64_t total_val, uint64_t offset,
+                               int32_t *__restrict__ idx) {
+    const double totd = (double)(total_ptr ? total_ptr[0] : total_val);
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_out; j += (int64_t)gridDim.x * blockDim.x) {
         const double U = __dadd_rn(r, __dmul_rn((double)(m0 + j), step));
         const double t = ceil(__dmul_rn(U, totd));
@@ -205,7 +206,7 @@ __global__ void k_search_fixed(const uint64_t *__restrict__ C, int64_t limit, in
         int64_t lo = 0, hi = limit;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            if (T > C[mid]) lo = mid + 1; else hi = mid;
+            if (T > C[mid] + offset) lo = mid + 1; else hi = mid;
         }
         idx[j] = (int32_t)lo;
     }
@@ -257,7 +258,95 @@ extern "C" int mcl_resample_indices(mcl_handle *h, const float *d_w, int64_t n_i
     MCL_LAUNCH_CHECK(h);
     k_tile_scan<<<(int)nt, SCAN_THREADS, 0, h->stream>>>(d_w, n_in, scale, tile_off, C);
     MCL_LAUNCH_CHECK(h);
-    k_search_fixed<<<sblocks, 256, 0, h->stream>>>(C, limit, 0, n_out, r, step, tile_off + nt, d_idx);
+    k_search_fixed<<<sblocks, 256, 0, h->stream>>>(C, limit, 0, n_out, r, step, tile_off + nt, 0ull, 0ull, d_idx);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// ---- staged forms for the sharded (multi-GPU) path --------------------------------------------
+__global__ void k_scale_from_wmax(const float *wmax, int64_t n_global, double *out_scale) {
+    const float t = wmax[0];
+    int e = 0;
+    if (t > 0.0f) frexp((double)t, &e);
+    int lg = 0;
+    while (((int64_t)1 << lg) < n_global) ++lg;
+    out_scale[0] = ldexp(1.0, 62 - lg - e);
+    out_scale[1] = (double)t;
+}
+__global__ void k_store_wmax(const double *scale, float *out) { out[0] = (float)scale[1]; }
+
+struct FixedLayout { size_t o_part, o_ts, o_to, o_c, total; int64_t nt; int wblocks; };
+static FixedLayout fixed_layout(const mcl_handle *h, int64_t n_in) {
+    FixedLayout L;
+    L.nt = (n_in + SCAN_TILE - 1) / SCAN_TILE;
+    L.wblocks = (int)std::min<int64_t>((n_in + 1023) / 1024, (int64_t)h->sm_count * 8);
+    size_t off = 128;
+    L.o_part = off; off += ((size_t)L.wblocks * sizeof(float) + 63) & ~(size_t)63;
+    L.o_ts = off; off += ((size_t)L.nt * 8 + 63) & ~(size_t)63;
+    L.o_to = off; off += ((size_t)(L.nt + 1) * 8 + 63) & ~(size_t)63;
+    L.o_c = off; off += (size_t)n_in * 8;
+    L.total = off;
+    return L;
+}
+
+// local max of the weights -> d_wmax[0] (f32, device); the caller all-reduces it (MAX)
+extern "C" int mcl_weights_max(mcl_handle *h, const float *d_w, int64_t n, float *d_wmax) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_w || !d_wmax) return mcl_fail(h, MCL_ERR_ARG, "mcl_weights_max: bad argument");
+    DeviceGuard guard(h->device);
+    const FixedLayout L = fixed_layout(h, n);
+    int rc = mcl_ensure_scratch(h, L.total);
+    if (rc) return rc;
+    char *s = (char *)h->d_scratch;
+    MCL_CUDA(h, cudaMemsetAsync(s, 0, sizeof(unsigned), h->stream));
+    k_wmax<<<L.wblocks, 256, 0, h->stream>>>(d_w, n, (unsigned *)s, (float *)(s + L.o_part), (double *)(s + 64), n);
+    MCL_LAUNCH_CHECK(h);
+    k_store_wmax<<<1, 1, 0, h->stream>>>((double *)(s + 64), d_wmax);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// fixed-point cumulative sums of this rank's weights (kept in the handle's scratch until the next
+// library call that needs scratch) with the GLOBAL scale; d_total[0] = this rank's total (uint64).
+extern "C" int mcl_resample_scan(mcl_handle *h, const float *d_w, int64_t n_in, const float *d_wmax_global,
+                                 int64_t n_global, uint64_t *d_total) {
+    if (!h) return MCL_ERR_ARG;
+    if (n_in <= 0 || !d_w || !d_wmax_global || !d_total || n_global < n_in)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_resample_scan: bad argument");
+    DeviceGuard guard(h->device);
+    const FixedLayout L = fixed_layout(h, n_in);
+    int rc = mcl_ensure_scratch(h, L.total);
+    if (rc) return rc;
+    char *s = (char *)h->d_scratch;
+    double *scale = (double *)(s + 64);
+    uint64_t *tile_sums = (uint64_t *)(s + L.o_ts), *tile_off = (uint64_t *)(s + L.o_to), *C = (uint64_t *)(s + L.o_c);
+    k_scale_from_wmax<<<1, 1, 0, h->stream>>>(d_wmax_global, n_global, scale);
+    MCL_LAUNCH_CHECK(h);
+    k_tile_sums<<<(int)L.nt, SCAN_THREADS, 0, h->stream>>>(d_w, n_in, scale, tile_sums);
+    MCL_LAUNCH_CHECK(h);
+    k_scan_tile_sums<<<1, 1024, 0, h->stream>>>(tile_sums, L.nt, tile_off, 0ull);
+    MCL_LAUNCH_CHECK(h);
+    k_tile_scan<<<(int)L.nt, SCAN_THREADS, 0, h->stream>>>(d_w, n_in, scale, tile_off, C);
+    MCL_LAUNCH_CHECK(h);
+    MCL_CUDA(h, cudaMemcpyAsync(d_total, tile_off + L.nt, sizeof(uint64_t), cudaMemcpyDeviceToDevice, h->stream));
+    return MCL_OK;
+}
+
+// source index (local) for the global outputs m0 .. m0+n_out_local-1, which the caller has determined
+// to fall into this rank's cumulative-weight interval (offset, offset + local total].
+extern "C" int mcl_resample_search(mcl_handle *h, int64_t n_in, uint64_t offset, uint64_t grand_total, int64_t m0,
+                                   int64_t n_out_local, double r, int64_t n_out_global, int32_t *d_idx) {
+    if (!h) return MCL_ERR_ARG;
+    if (n_in <= 0 || n_out_local < 0 || n_out_global <= 0 || (n_out_local > 0 && !d_idx))
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_resample_search: bad argument");
+    if (n_out_local == 0) return MCL_OK;
+    DeviceGuard guard(h->device);
+    const FixedLayout L = fixed_layout(h, n_in);
+    if (L.total > h->scratch_bytes) return mcl_fail(h, MCL_ERR_STATE, "mcl_resample_search: call mcl_resample_scan first");
+    const uint64_t *C = (const uint64_t *)((char *)h->d_scratch + L.o_c);
+    const int sblocks = (int)std::min<int64_t>((n_out_local + 255) / 256, (int64_t)h->sm_count * 16);
+    k_search_fixed<<<sblocks, 256, 0, h->stream>>>(C, n_in - 1, m0, n_out_local, r, 1.0 / (double)n_out_global, nullptr,
+                                                   grand_total, offset, d_idx);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }

@@ -97,17 +97,23 @@ class Localizer:
         self.weights_t = torch.full((n,), 1.0 / n, dtype=torch.float32, device=self.device)   # node:98
         self.n = n
 
-    def set_particles(self, particles):
-        """(N,3) float64 host array -> device SoA; also particles_prev (node:95-97)."""
+    def set_particles(self, particles, prev=None, keep_odom=False):
+        """(N,3) float64 host array -> device SoA; particles_prev = prev or a copy (node:95-97)."""
         p = np.ascontiguousarray(particles, dtype=np.float64)
         with self._lock:
             self._bind_stream()
-            self._alloc(p.shape[0])
+            if p.shape[0] != self.n or self.cur is None:
+                self._alloc(p.shape[0])
             aos = torch.from_numpy(p).to(self.device)
             self.h.call("mcl_aos_to_soa", _ptr(aos), self.n, *[_ptr(t) for t in self.cur])
-            for a, b in zip(self.prev, self.cur):
-                a.copy_(b)
-            self.last_odom = None
+            if prev is not None:
+                q = torch.from_numpy(np.ascontiguousarray(prev, dtype=np.float64)).to(self.device)
+                self.h.call("mcl_aos_to_soa", _ptr(q), self.n, *[_ptr(t) for t in self.prev])
+            else:
+                for a, b in zip(self.prev, self.cur):
+                    a.copy_(b)
+            if not keep_odom:
+                self.last_odom = None
 
     def init_uniform(self, n, seed=None, uniforms=None):
         """node:188 generate_valid_particles.  uniforms: optional (3, max(50n,500)) injected draws for
