@@ -229,7 +229,7 @@ def run_native(args):
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     for k in range(1, W + 1):
-        loc.predict(poses[k]); loc.update_staged(k); loc.estimate_async(est_buf[k]); loc.resample()
+        loc.step_staged(poses[k], k, est_buf[k])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -241,7 +241,7 @@ def run_native(args):
         k = W + 1 + j
         flush.zero_()
         ev0[j].record()
-        loc.predict(poses[k]); loc.update_staged(k); loc.estimate_async(est_buf[k]); loc.resample()
+        loc.step_staged(poses[k], k, est_buf[k])
         ev1[j].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0

@@ -201,6 +201,32 @@ int mcl_aos_to_soa(mcl_handle *h, const double *d_aos, int64_t n, double *d_x, d
 int mcl_soa_to_aos(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                    int64_t n, double *d_aos);
 
+/* ---- the whole step in one call ------------------------------------------------------------- */
+/* Bind the caller's device buffers once; afterwards each call below enqueues a whole stage of the
+ * node's callbacks on the handle's stream, and the roles of the three pose buffer sets
+ * (particles / particles_prev / spare) rotate inside the library like the node's copies at
+ * node:404-405, node:370 and node:490.  x/y/th: three SoA sets of n fp64; w_a/w_b: the weights
+ * double buffer.  Stochastic stages draw Philox(seed, tick) with tick += 1 per predict, MH accept and
+ * resample -- the same streams as the individual entry points, so results are identical. */
+int mcl_filter_bind(mcl_handle *h, int64_t n, double *const x[3], double *const y[3],
+                    double *const th[3], float *score_pre, float *score_post, float *w_pre,
+                    float *w_post, float *w_a, float *w_b, int32_t *idx, int use_mh, int resample_mode,
+                    uint64_t seed, uint64_t first_index, int max_attempts);
+int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode, uint64_t seed,
+                         uint64_t first_index, int64_t tick /* < 0: keep */);
+/* roles = {particles, particles_prev, spare (indices into x/y/th), weights slot (0 = w_a)} */
+int mcl_filter_roles(mcl_handle *h, int roles[4], uint64_t *tick);
+/* for hosts that sequence the stages themselves (the sharded path interleaves collectives) */
+int mcl_filter_set_roles(mcl_handle *h, const int roles[4], uint64_t tick);
+int mcl_filter_predict(mcl_handle *h, const double delta[3], const double *d_normals, int A);   /* node:384-408 */
+int mcl_filter_update(mcl_handle *h, const double *d_uniforms);                                /* node:296-322 */
+int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]);                   /* node:586-597 */
+int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);                       /* node:488-492 */
+/* odom + scan -> predict (delta != NULL), update on pre-staged scan `scan_slot` (or the current scan
+ * if < 0), estimate (to d_out18 and/or blocking into h_out16; both nullable), resample. */
+int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
+                    double h_out16[16]);
+
 /* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */
 /* Random 4-byte gather rate, lookups/s: table_bytes resident in shared memory (where = 0) or in
  * global memory / L2 (where = 1); n_lookups per launch, iters launches timed with CUDA events. */

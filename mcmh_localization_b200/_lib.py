@@ -59,6 +59,16 @@ SIGNATURES = {
     "mcl_init_uniform": (_i, [_vp, _i64, _vp, _i64, _u64, _u64, _vp, _vp, _vp, C.POINTER(_i64)]),
     "mcl_aos_to_soa": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "mcl_soa_to_aos": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "mcl_filter_bind": (_i, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _i, _i, _u64, _u64, _i]),
+    "mcl_filter_configure": (_i, [_vp, _i, _i, _u64, _u64, _i64]),
+    "mcl_filter_roles": (_i, [_vp, _pi, C.POINTER(_u64)]),
+    "mcl_filter_set_roles": (_i, [_vp, _pi, _u64]),
+    "mcl_filter_predict": (_i, [_vp, _pd, _vp, _i]),
+    "mcl_filter_update": (_i, [_vp, _vp]),
+    "mcl_filter_estimate": (_i, [_vp, _vp, _pd]),
+    "mcl_filter_resample": (_i, [_vp, _d]),
+    "mcl_filter_step": (_i, [_vp, _pd, _i, _vp, _pd]),
     "mcl_bench_gather": (_i, [_vp, _i, _i64, _i64, _i, _pd]),
     "mcl_launch_count": (_i64, [_vp]),
     "mcl_timing_start": (_i, [_vp]),

@@ -66,6 +66,8 @@ struct mcl_handle {
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     double *h_pinned = nullptr;  // 64 doubles, pinned, for blocking scalar reads
+    double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
+    cudaEvent_t ev_est = nullptr;
 
     // timing of likelihood launches
     bool timing = false;
@@ -77,6 +79,7 @@ extern thread_local std::string g_create_err;
 int mcl_fail(mcl_handle *h, int code, const std::string &msg);
 int mcl_ensure_scratch(mcl_handle *h, size_t bytes);
 int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
+void mcl_filter_forget(const mcl_handle *h);
 
 #define MCL_CUDA(h, expr)                                                                   \
     do {                                                                                    \

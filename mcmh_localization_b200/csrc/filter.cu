@@ -1,0 +1,190 @@
+// filter.cu -- the whole filter step sequenced inside the library: one C call enqueues
+// predict -> likelihood x2 -> softmax x2 -> MH accept -> estimate -> resample -> gather on the
+// handle's stream (node:384-408 move_particles + node:294-338 lidar_callback).  The Python host
+// pays one ctypes call per step instead of ~15; buffer roles (particles / particles_prev / spare)
+// rotate inside the handle exactly like the node's copies at node:404-405, node:370 and node:490.
+#include <string.h>
+
+#include "common.cuh"
+
+struct FilterState {
+    bool bound = false;
+    int64_t n = 0;
+    double *x[3] = {nullptr, nullptr, nullptr}, *y[3] = {nullptr, nullptr, nullptr}, *th[3] = {nullptr, nullptr, nullptr};
+    float *score_pre = nullptr, *score_post = nullptr, *w_pre = nullptr, *w_post = nullptr, *w[2] = {nullptr, nullptr};
+    int32_t *idx = nullptr;
+    int cur = 0, prev = 1, spare = 2, wslot = 0;
+    int use_mh = 1, resample_mode = MCL_RESAMPLE_FIXED_POINT, max_attempts = 1000;
+    uint64_t seed = 0, first_index = 0, tick = 0;
+};
+
+// one FilterState per handle, kept out of common.cuh: keyed by handle pointer
+#include <map>
+#include <mutex>
+static std::map<const mcl_handle *, FilterState> g_filters;
+static std::mutex g_filters_mu;
+
+static FilterState *filter_of(mcl_handle *h, bool create) {
+    std::lock_guard<std::mutex> lk(g_filters_mu);
+    auto it = g_filters.find(h);
+    if (it == g_filters.end()) {
+        if (!create) return nullptr;
+        it = g_filters.emplace(h, FilterState()).first;
+    }
+    return &it->second;
+}
+
+void mcl_filter_forget(const mcl_handle *h) {
+    std::lock_guard<std::mutex> lk(g_filters_mu);
+    g_filters.erase(h);
+}
+
+extern "C" int mcl_filter_bind(mcl_handle *h, int64_t n, double *const x[3], double *const y[3], double *const th[3],
+                               float *score_pre, float *score_post, float *w_pre, float *w_post, float *w_a,
+                               float *w_b, int32_t *idx, int use_mh, int resample_mode, uint64_t seed,
+                               uint64_t first_index, int max_attempts) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !x || !y || !th || !score_pre || !score_post || !w_pre || !w_post || !w_a || !w_b || !idx)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_bind: bad argument");
+    FilterState *f = filter_of(h, true);
+    for (int k = 0; k < 3; ++k) {
+        if (!x[k] || !y[k] || !th[k]) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_bind: null pose buffer");
+        f->x[k] = x[k]; f->y[k] = y[k]; f->th[k] = th[k];
+    }
+    f->n = n;
+    f->score_pre = score_pre; f->score_post = score_post; f->w_pre = w_pre; f->w_post = w_post;
+    f->w[0] = w_a; f->w[1] = w_b; f->idx = idx;
+    f->cur = 0; f->prev = 1; f->spare = 2; f->wslot = 0;
+    f->use_mh = use_mh; f->resample_mode = resample_mode; f->seed = seed; f->first_index = first_index;
+    f->max_attempts = max_attempts; f->tick = 0;
+    f->bound = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_filter_roles(mcl_handle *h, int roles[4], uint64_t *tick) {
+    if (!h || !roles) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_roles: no filter bound");
+    roles[0] = f->cur; roles[1] = f->prev; roles[2] = f->spare; roles[3] = f->wslot;
+    if (tick) *tick = f->tick;
+    return MCL_OK;
+}
+
+extern "C" int mcl_filter_set_roles(mcl_handle *h, const int roles[4], uint64_t tick) {
+    if (!h || !roles) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_set_roles: no filter bound");
+    int seen = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (roles[k] < 0 || roles[k] > 2) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_set_roles: bad role");
+        seen |= 1 << roles[k];
+    }
+    if (seen != 7 || roles[3] < 0 || roles[3] > 1) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_set_roles: bad roles");
+    f->cur = roles[0]; f->prev = roles[1]; f->spare = roles[2]; f->wslot = roles[3]; f->tick = tick;
+    return MCL_OK;
+}
+
+extern "C" int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode, uint64_t seed, uint64_t first_index,
+                                    int64_t tick /* < 0: keep */) {
+    if (!h) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_configure: no filter bound");
+    f->use_mh = use_mh; f->resample_mode = resample_mode; f->seed = seed; f->first_index = first_index;
+    if (tick >= 0) f->tick = (uint64_t)tick;
+    return MCL_OK;
+}
+
+#define FILTER_OR_FAIL(name)                                                                          \
+    if (!h) return MCL_ERR_ARG;                                                                       \
+    FilterState *f = filter_of(h, false);                                                             \
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, name ": no filter bound (mcl_filter_bind)");
+
+// node:397-405: particles_prop = motion(particles); particles_prev = particles; particles = particles_prop
+extern "C" int mcl_filter_predict(mcl_handle *h, const double delta[3], const double *d_normals, int A) {
+    FILTER_OR_FAIL("mcl_filter_predict");
+    f->tick++;
+    int rc = mcl_predict(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->n, delta, f->seed, f->tick, f->first_index,
+                         d_normals, A, f->max_attempts, f->x[f->spare], f->y[f->spare], f->th[f->spare], nullptr);
+    if (rc) return rc;
+    const int old_prev = f->prev;
+    f->prev = f->cur; f->cur = f->spare; f->spare = old_prev;
+    return MCL_OK;
+}
+
+// node:252-273 update_weights + node:307-322 (MH by mode); uses the active scan
+extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
+    FILTER_OR_FAIL("mcl_filter_update");
+    int rc = mcl_likelihood(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->n, f->score_post);
+    if (rc) return rc;
+    if (!f->use_mh) {
+        // MCL: weights = weights_post (node:313); scores_pre would be computed and discarded by the reference
+        return mcl_softmax(h, f->score_post, f->n, f->w[f->wslot], nullptr, nullptr);
+    }
+    rc = mcl_softmax(h, f->score_post, f->n, f->w_post, nullptr, nullptr);
+    if (rc) return rc;
+    rc = mcl_likelihood(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->n, f->score_pre);
+    if (rc) return rc;
+    rc = mcl_softmax(h, f->score_pre, f->n, f->w_pre, nullptr, nullptr);
+    if (rc) return rc;
+    f->tick++;
+    // mh_resampling(particles_prev, particles, weights_post, weights_pre)  (node:363)
+    rc = mcl_mh_accept(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur], f->th[f->cur],
+                       f->w_post, f->w_pre, f->n, d_uniforms, f->seed, f->tick, f->first_index, f->x[f->spare],
+                       f->y[f->spare], f->th[f->spare], f->w[f->wslot], nullptr);
+    if (rc) return rc;
+    const int t = f->cur; f->cur = f->spare; f->spare = t;     // self.particles = mh_particles (node:370)
+    return MCL_OK;
+}
+
+extern "C" int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]) {
+    FILTER_OR_FAIL("mcl_filter_estimate");
+    if (h_out16) return mcl_estimate(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->w[f->wslot], f->n, h_out16);
+    if (!d_out18) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_estimate: no output");
+    return mcl_estimate_async(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->w[f->wslot], f->n, d_out18);
+}
+
+// node:488-492 resample_lvr; r < 0: draw r = U(0, 1/N) from Philox(seed, tick)
+extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
+    FILTER_OR_FAIL("mcl_filter_resample");
+    f->tick++;
+    if (r < 0) r = mcl_resample_offset(f->seed, f->tick, f->n);
+    int rc = mcl_resample_indices(h, f->w[f->wslot], f->n, f->n, r, f->resample_mode, f->idx);
+    if (rc) return rc;
+    rc = mcl_gather(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->idx, f->n, f->x[f->spare], f->y[f->spare],
+                    f->th[f->spare]);
+    if (rc) return rc;
+    const int t = f->cur; f->cur = f->spare; f->spare = t;
+    // self.weights keeps its pre-resampling values (node:490 discards the returned uniform weights)
+    return MCL_OK;
+}
+
+// one odom message followed by one scan: predict -> update -> estimate -> resample
+extern "C" int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
+                               double h_out16[16]) {
+    FILTER_OR_FAIL("mcl_filter_step");
+    int rc;
+    if (delta) { rc = mcl_filter_predict(h, delta, nullptr, 0); if (rc) return rc; }
+    if (scan_slot >= 0) { rc = mcl_use_scan(h, scan_slot); if (rc) return rc; }
+    rc = mcl_filter_update(h, nullptr);
+    if (rc) return rc;
+    if (!h_out16) {
+        if (d_out18) { rc = mcl_filter_estimate(h, d_out18, nullptr); if (rc) return rc; }
+        return mcl_filter_resample(h, -1.0);
+    }
+    // host estimate wanted: enqueue the estimate and its read-back, then the resampling kernels, and
+    // wait only for the read-back -- the resampling overlaps the host's handling of the estimate.
+    DeviceGuard guard(h->device);
+    rc = mcl_filter_estimate(h, h->d_est18, nullptr);
+    if (rc) return rc;
+    MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_est18, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCL_CUDA(h, cudaEventRecord(h->ev_est, h->stream));
+    if (d_out18) MCL_CUDA(h, cudaMemcpyAsync(d_out18, h->d_est18, 18 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    rc = mcl_filter_resample(h, -1.0);
+    if (rc) return rc;
+    MCL_CUDA(h, cudaEventSynchronize(h->ev_est));
+    const double *r = h->h_pinned;
+    h_out16[0] = r[0]; h_out16[1] = r[1]; h_out16[2] = r[6]; h_out16[3] = r[7]; h_out16[4] = r[8];
+    for (int k = 0; k < 9; ++k) h_out16[5 + k] = r[9 + k];
+    h_out16[14] = 0; h_out16[15] = 0;
+    return MCL_OK;
+}

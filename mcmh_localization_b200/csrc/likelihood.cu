@@ -289,7 +289,8 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
     for (int k = 0; k < c_n; ++k)
         if (c_kern[k] == (const void *)kern && c_smem[k] == smem_bytes && c_dev[k] == h->device) occ = c_occ[k];
     if (occ == 0) {
-        MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        // opt in to the device maximum once (a later, smaller request must not lower the limit)
+        MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LIK_THREADS, smem_bytes));
         if (occ < 1) return mcl_fail(h, MCL_ERR_CAPACITY, "likelihood kernel does not fit on an SM");
         const int k = c_n < 16 ? c_n++ : 15;

@@ -47,6 +47,12 @@ extern "C" int mcl_create(mcl_handle **out, int device) {
         delete h;
         return mcl_fail(nullptr, MCL_ERR_NOMEM, "mcl_create: cudaMallocHost failed");
     }
+    if (cudaMalloc((void **)&h->d_est18, 32 * sizeof(double)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_est, cudaEventDisableTiming) != cudaSuccess) {
+        cudaFreeHost(h->h_pinned);
+        delete h;
+        return mcl_fail(nullptr, MCL_ERR_NOMEM, "mcl_create: device allocation failed");
+    }
     *out = h;
     return MCL_OK;
 }
@@ -55,6 +61,9 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     if (!h) return MCL_OK;
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
+    mcl_filter_forget(h);
+    cudaFree(h->d_est18);
+    if (h->ev_est) cudaEventDestroy(h->ev_est);
     cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
     cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch);
     cudaFreeHost(h->h_beams); cudaFreeHost(h->h_pinned);

@@ -52,6 +52,39 @@ __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i,
     return is_valid_position_dev(cand.x, cand.y, p.occ, p.W, p.H, p.res, p.ox, p.oy);
 }
 
+// Sound early exit for the particles that would burn all max_attempts (~2 % of a uniform
+// cloud, and whole clusters of duplicates once the filter has converged next to a wall): Box-Muller on
+// 32-bit uniforms bounds every normal by |z| <= sqrt(-2 ln 2^-32) < 6.66, so every candidate of every
+// attempt lies in the annular sector  t in trans +- 6.66 s2,  angle in theta + rot1 +- 6.66 s1.  If all
+// map cells touched by the (slightly inflated) bounding box of that sector are non-free, no attempt
+// can succeed and the particle keeps its pose (pu:360-361) -- the same result the 1000 attempts give.
+// Only used with Philox draws (injected draws are unbounded).
+#define MCL_ZMAX 6.6605
+__device__ bool provably_stuck(const MotionParams &p, double x, double y, double th) {
+    const double dt = MCL_ZMAX * p.s2, da = MCL_ZMAX * p.s1;
+    const double t_lo = p.trans - dt, t_hi = p.trans + dt;
+    if (!(t_lo > 0.0) || !(da < 1.0)) return false;           // sector bound below needs t > 0, small spread
+    double sn, cs;
+    sincos(th + p.rot1, &sn, &cs);
+    const double u_lo = t_lo * cos(da) - 1e-9, u_hi = t_hi + 1e-9;   // along the nominal heading
+    const double v = t_hi * sin(da) + 1e-9;                          // across it
+    // axis-aligned bounding box of the rotated rectangle [u_lo,u_hi] x [-v,v] around (x, y)
+    const double ax = fabs(cs), ay = fabs(sn);
+    const double cxm = 0.5 * (u_lo + u_hi) * cs, cym = 0.5 * (u_lo + u_hi) * sn;
+    const double hx = 0.5 * (u_hi - u_lo) * ax + v * ay + 1e-9, hy = 0.5 * (u_hi - u_lo) * ay + v * ax + 1e-9;
+    const double x0 = x + cxm - hx, x1 = x + cxm + hx, y0 = y + cym - hy, y1 = y + cym + hy;
+    // cell index is monotone in the coordinate (same expression as pu:390-391)
+    const long long mx0 = __double2ll_rz(__ddiv_rn(__dadd_rn(x0, -p.ox), p.res));
+    const long long mx1 = __double2ll_rz(__ddiv_rn(__dadd_rn(x1, -p.ox), p.res));
+    const long long my0 = __double2ll_rz(__ddiv_rn(__dadd_rn(y0, -p.oy), p.res));
+    const long long my1 = __double2ll_rz(__ddiv_rn(__dadd_rn(y1, -p.oy), p.res));
+    if ((mx1 - mx0 + 1) * (my1 - my0 + 1) > 16) return false;        // large region: just run the attempts
+    for (long long my = my0; my <= my1; ++my)
+        for (long long mx = mx0; mx <= mx1; ++mx)
+            if (mx >= 0 && mx < p.W && my >= 0 && my < p.H && p.occ[my * (long long)p.W + mx] == 0) return false;
+    return true;
+}
+
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
@@ -68,6 +101,7 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
     if (!done) {
         Pose c;
         if (motion_attempt(p, i, 0, x, y, th, c)) { out = c; att = 1; done = true; }
+        else if (!p.normals && provably_stuck(p, x, y, th)) done = true;     // att = 0, pose kept
     }
     unsigned pending = __ballot_sync(0xffffffffu, !done);
     while (pending) {

@@ -43,7 +43,6 @@ class Localizer:
         self.h = _lib.Handle(int(device))
         self._lock = threading.Lock()      # rospy runs the two callbacks on two threads
         self.seed = int(seed)
-        self.tick = 0                      # Philox "step": one per stochastic call
         self.first_index = 0               # global index of local particle 0 (sharded runs)
         self.max_attempts = int(max_attempts)
         self.resample_mode = {"reference": _lib.RESAMPLE_REFERENCE_F32,
@@ -53,8 +52,7 @@ class Localizer:
         self.n = 0
         self.last_odom = None
         self.delta = (0.0, 0.0, 0.0)
-        self.cur = self.prev = self.spare = None
-        self.weights_t = None
+        self.sets = None
         self.set_params(params or {}, mode=mode)
 
     # ------------------------------------------------------------------ configuration
@@ -71,6 +69,8 @@ class Localizer:
         self.h.call("mcl_set_sensor", float(p["sigma_hit"]), float(p["z_hit"]), float(p["z_rand"]),
                     float(p["max_range"]), int(p["step"]))
         self.h.call("mcl_set_motion", self.alpha.ctypes.data_as(C.POINTER(C.c_float)))
+        if self.n:
+            self.h.call("mcl_filter_configure", int(self.use_mh), self.resample_mode, self.seed, self.first_index, -1)
 
     def load_map(self, occ, resolution=None, origin_xy=None):
         """occ: (H,W) int8 OccupancyGrid payload, or a GridMap (maps.load_map_yaml / map_from_occupancy)."""
@@ -89,20 +89,48 @@ class Localizer:
 
     # ------------------------------------------------------------------ particle buffers
     def _alloc(self, n):
+        """Allocate the device buffers (torch tensors) and bind them to the library's filter state."""
         mk = lambda: [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3)]
-        self.cur, self.prev, self.spare = mk(), mk(), mk()
+        self.sets = [mk(), mk(), mk()]                      # three SoA pose sets; roles live in the library
         f32 = lambda: torch.empty(n, dtype=torch.float32, device=self.device)
-        self.score_pre, self.score_post, self.w_pre, self.w_post, self.w_mh = f32(), f32(), f32(), f32(), f32()
+        self.score_pre, self.score_post, self.w_pre, self.w_post = f32(), f32(), f32(), f32()
+        self.wbuf = [torch.full((n,), 1.0 / n, dtype=torch.float32, device=self.device), f32()]   # node:98
         self.idx = torch.empty(n, dtype=torch.int32, device=self.device)
-        self.weights_t = torch.full((n,), 1.0 / n, dtype=torch.float32, device=self.device)   # node:98
+        self.est18 = torch.zeros(18, dtype=torch.float64, device=self.device)
         self.n = n
+        arr = lambda k: (C.c_void_p * 3)(*[self.sets[j][k].data_ptr() for j in range(3)])
+        self.h.call("mcl_filter_bind", n, arr(0), arr(1), arr(2), _ptr(self.score_pre), _ptr(self.score_post),
+                    _ptr(self.w_pre), _ptr(self.w_post), _ptr(self.wbuf[0]), _ptr(self.wbuf[1]), _ptr(self.idx),
+                    int(self.use_mh), self.resample_mode, self.seed, self.first_index, self.max_attempts)
+
+    def _roles(self):
+        r = (C.c_int * 4)()
+        t = C.c_uint64(0)
+        self.h.call("mcl_filter_roles", r, C.byref(t))
+        return r[0], r[1], r[2], r[3], t.value
+
+    @property
+    def cur(self):
+        return self.sets[self._roles()[0]]
+
+    @property
+    def prev(self):
+        return self.sets[self._roles()[1]]
+
+    @property
+    def weights_t(self):
+        return self.wbuf[self._roles()[3]]
+
+    @property
+    def tick(self):
+        return self._roles()[4] if self.n else 0
 
     def set_particles(self, particles, prev=None, keep_odom=False):
         """(N,3) float64 host array -> device SoA; particles_prev = prev or a copy (node:95-97)."""
         p = np.ascontiguousarray(particles, dtype=np.float64)
         with self._lock:
             self._bind_stream()
-            if p.shape[0] != self.n or self.cur is None:
+            if p.shape[0] != self.n or self.sets is None:
                 self._alloc(p.shape[0])
             aos = torch.from_numpy(p).to(self.device)
             self.h.call("mcl_aos_to_soa", _ptr(aos), self.n, *[_ptr(t) for t in self.cur])
@@ -162,22 +190,14 @@ class Localizer:
             cur_odom = np.asarray(odom, dtype=np.float64)
             if self.last_odom is not None:
                 self.delta = compute_motion(self.last_odom, cur_odom)
-                self._motion(self.cur, self.spare, _dbl3(self.delta), normals)
-                # particles_prev = particles; particles = particles_prop (node:404-405)
-                self.prev, self.cur, self.spare = self.cur, self.spare, self.prev
+                zp, A = None, 0
+                if normals is not None:
+                    z = normals if torch.is_tensor(normals) else torch.from_numpy(
+                        np.ascontiguousarray(normals, dtype=np.float64))
+                    z = z.to(self.device)
+                    zp, A = _ptr(z), int(z.shape[1])
+                self.h.call("mcl_filter_predict", _dbl3(self.delta), zp, A)
             self.last_odom = cur_odom
-
-    def _motion(self, src, dst, delta3, normals=None, attempts=None):
-        if normals is not None:
-            z = normals if torch.is_tensor(normals) else torch.from_numpy(
-                np.ascontiguousarray(normals, dtype=np.float64))
-            z = z.to(self.device)
-            zp, A = _ptr(z), int(z.shape[1])
-        else:
-            zp, A = None, 0
-        self.tick += 1
-        self.h.call("mcl_predict", *[_ptr(t) for t in src], self.n, delta3, self.seed, self.tick,
-                    self.first_index, zp, A, self.max_attempts, *[_ptr(t) for t in dst], _ptr(attempts))
 
     # ------------------------------------------------------------------ update (lidar_callback)
     def set_scan(self, ranges, angle_min=None, angle_max=None, angles=None):
@@ -187,9 +207,6 @@ class Localizer:
         a = np.ascontiguousarray(angles, dtype=np.float32)
         self._bind_stream()
         self.h.call("mcl_set_scan", C.c_void_p(r.ctypes.data), C.c_void_p(a.ctypes.data), len(r))
-
-    def _softmax(self, score, w):
-        self.h.call("mcl_softmax", _ptr(score), self.n, _ptr(w), None, None)
 
     def update(self, ranges, angle_min=None, angle_max=None, angles=None, uniforms=None):
         """node:296-322: update_scans, update_weights (both particle sets), MH accept by mode."""
@@ -216,36 +233,20 @@ class Localizer:
         """Non-blocking estimate into a device tensor of 18 float64 (see include/mcl.h)."""
         with self._lock:
             self._bind_stream()
-            self.h.call("mcl_estimate_async", *[_ptr(t) for t in self.cur], _ptr(self.weights_t), self.n,
-                        _ptr(out18))
+            self.h.call("mcl_filter_estimate", _ptr(out18), None)
 
     def _update_core(self, uniforms=None):
         if self.assym or self.use_adaptive:
             raise NotImplementedError(
                 "localization_mode %r: asymmetric-MH / KLD-adaptive modes are SURVEY 8(f) 'next' rows; "
                 "use MCL or MHMCL" % self.params["localization_mode"])
-        self.h.call("mcl_likelihood", *[_ptr(t) for t in self.cur], self.n, _ptr(self.score_post))
-        self._softmax(self.score_post, self.w_post)
-        if not self.use_mh:
-            # MCL: weights = weights_post (node:313). scores_pre is never used in this mode, so it is
-            # not computed (the reference computes and discards it, SURVEY Appendix C #5).
-            self.weights_t, self.w_post = self.w_post, self.weights_t
-            return
-        self.h.call("mcl_likelihood", *[_ptr(t) for t in self.prev], self.n, _ptr(self.score_pre))
-        self._softmax(self.score_pre, self.w_pre)
         up = None
         if uniforms is not None:
             u = uniforms if torch.is_tensor(uniforms) else torch.from_numpy(
                 np.ascontiguousarray(uniforms, dtype=np.float64))
             u = u.to(self.device)
             up = _ptr(u)
-        self.tick += 1
-        # mh_resampling(particles_prev, particles, weights_post, weights_pre)  (node:363)
-        self.h.call("mcl_mh_accept", *[_ptr(t) for t in self.prev], *[_ptr(t) for t in self.cur],
-                    _ptr(self.w_post), _ptr(self.w_pre), self.n, up, self.seed, self.tick,
-                    self.first_index, *[_ptr(t) for t in self.spare], _ptr(self.w_mh), None)
-        self.cur, self.spare = self.spare, self.cur                       # node:370
-        self.weights_t, self.w_mh = self.w_mh, self.weights_t
+        self.h.call("mcl_filter_update", up)
 
     # ------------------------------------------------------------------ estimate / resample
     def estimate(self):
@@ -253,30 +254,44 @@ class Localizer:
         with self._lock:
             self._bind_stream()
             out = (C.c_double * 16)()
-            self.h.call("mcl_estimate", *[_ptr(t) for t in self.cur], _ptr(self.weights_t), self.n, out)
+            self.h.call("mcl_filter_estimate", None, out)
         return assemble_estimate(list(out))
 
     def resample(self, r=None):
         """node:488-492 resample_lvr -> low_variance_resample_numba (pu:416-446)."""
         with self._lock:
             self._bind_stream()
-            self.tick += 1
-            if r is None:
-                r = self.h.lib.mcl_resample_offset(self.seed, self.tick, self.n)
-            self.h.call("mcl_resample_indices", _ptr(self.weights_t), self.n, self.n, float(r),
-                        self.resample_mode, _ptr(self.idx))
-            self.h.call("mcl_gather", *[_ptr(t) for t in self.cur], _ptr(self.idx), self.n,
-                        *[_ptr(t) for t in self.spare])
-            self.cur, self.spare = self.spare, self.cur
+            self.h.call("mcl_filter_resample", -1.0 if r is None else float(r))
             # self.weights keeps the pre-resampling values (node:490 discards the uniform weights)
 
     def step(self, odom, ranges, angle_min=None, angle_max=None, angles=None):
-        """One odom message followed by one scan: predict -> update -> estimate -> resample."""
-        self.predict(odom)
-        self.update(ranges, angle_min, angle_max, angles)
-        est = self.estimate()
-        self.resample()
-        return est
+        """One odom message followed by one scan: predict -> update -> estimate -> resample, enqueued by
+        ONE library call; returns the host estimate while the resampling kernels are still running."""
+        with self._lock:
+            cur_odom = np.asarray(odom, dtype=np.float64)
+            d = None
+            if self.last_odom is not None:
+                self.delta = compute_motion(self.last_odom, cur_odom)
+                d = _dbl3(self.delta)
+            self.last_odom = cur_odom
+            self.set_scan(ranges, angle_min, angle_max, angles)
+            if self.assym or self.use_adaptive:
+                raise NotImplementedError("localization_mode %r not supported yet" % self.params["localization_mode"])
+            out = (C.c_double * 16)()
+            self.h.call("mcl_filter_step", d, -1, None, out)
+        return assemble_estimate(list(out))
+
+    def step_staged(self, odom, k, out18=None):
+        """step() on pre-staged scan k with the estimate left on the device (no host<->device traffic)."""
+        with self._lock:
+            self._bind_stream()
+            cur_odom = np.asarray(odom, dtype=np.float64)
+            d = None
+            if self.last_odom is not None:
+                self.delta = compute_motion(self.last_odom, cur_odom)
+                d = _dbl3(self.delta)
+            self.last_odom = cur_odom
+            self.h.call("mcl_filter_step", d, int(k), _ptr(out18 if out18 is not None else self.est18), None)
 
     # ------------------------------------------------------------------ read-back
     def _aos(self, soa):
@@ -296,6 +311,9 @@ class Localizer:
 
     def weights(self):
         return self.weights_t.cpu().numpy()
+
+    def set_weights(self, w):
+        self.weights_t.copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
 
     def scores(self):
         return self.score_pre.cpu().numpy(), self.score_post.cpu().numpy()
