@@ -53,7 +53,7 @@ enum {
 
 /* Philox stream ids (ctr[3] low byte). */
 enum { MCL_STREAM_MOTION = 1, MCL_STREAM_MH = 2, MCL_STREAM_RESAMPLE = 3, MCL_STREAM_INIT = 4,
-       MCL_STREAM_KLD = 5 };
+       MCL_STREAM_KLD = 5, MCL_STREAM_MOTION_RADIUS = 6 };
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int mcl_create(mcl_handle **out, int device);

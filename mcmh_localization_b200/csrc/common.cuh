@@ -157,13 +157,18 @@ __device__ __forceinline__ uint4 philox_draw4(uint64_t seed, uint64_t step, uint
 __device__ __forceinline__ double u53_from(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
-// three standard normals by Box-Muller on 32-bit uniforms (u1 in (0,1], u2 in [0,1)).
-__device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t step, uint64_t item,
-                                                uint32_t attempt, double &z0, double &z1, double &z2) {
-    const uint4 o = philox_draw4(seed, step, item, attempt, MCL_STREAM_MOTION);
+// three standard normals by Box-Muller on 32-bit uniforms (u1 in (0,1], u2 in [0,1)); layout as in
+// oracle/c/mcl_oracle.c normals3(): the radius word of attempt t is word (t & 3) of the MOTION_R block
+// (particle, step, t >> 2), the other uniforms come from the MOTION block (particle, step, t).
+#define MCL_STREAM_MOTION_R 6
+__device__ __forceinline__ uint32_t pick_word(const uint4 &a, uint32_t k) {
+    return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w));
+}
+__device__ __forceinline__ void normals3_from_words(uint32_t w_radius, const uint4 &o, double &z0, double &z1,
+                                                    double &z2) {
     const double k = 2.3283064365386963e-10;  // 2^-32
-    const double u1 = __dmul_rn(__dadd_rn((double)o.x, 1.0), k), u2 = __dmul_rn((double)o.y, k);
-    const double u3 = __dmul_rn(__dadd_rn((double)o.z, 1.0), k), u4 = __dmul_rn((double)o.w, k);
+    const double u1 = __dmul_rn(__dadd_rn((double)w_radius, 1.0), k), u2 = __dmul_rn((double)o.x, k);
+    const double u3 = __dmul_rn(__dadd_rn((double)o.y, 1.0), k), u4 = __dmul_rn((double)o.z, k);
     const double r1 = sqrt(__dmul_rn(-2.0, log(u1))), r2 = sqrt(__dmul_rn(-2.0, log(u3)));
     double s1, c1, s2, c2;
     sincos(__dmul_rn(MCL_TWO_PI, u2), &s1, &c1);
@@ -171,6 +176,12 @@ __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t step, ui
     z0 = __dmul_rn(r1, c1);
     z1 = __dmul_rn(r1, s1);
     z2 = __dmul_rn(r2, c2);
+}
+__device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t step, uint64_t item,
+                                                uint32_t attempt, double &z0, double &z1, double &z2) {
+    const uint4 a = philox_draw4(seed, step, item, attempt >> 2, MCL_STREAM_MOTION_R);
+    const uint4 o = philox_draw4(seed, step, item, attempt, MCL_STREAM_MOTION);
+    normals3_from_words(pick_word(a, attempt & 3u), o, z0, z1, z2);
 }
 
 // pu:388-396 is_valid_position: trunc-toward-zero cell index, cell == 0 only.

@@ -186,8 +186,11 @@ __device__ __forceinline__ int floor_to_int(double t) {   // exact floor(t) for 
     return __double2loint(__dadd_rd(t, MCL_FLOOR_MAGIC));
 }
 
+#define G1_THREADS 256
+#define G1_P 2      // particles per thread: the uniform beam loads and loop overhead are shared
+
 template <bool SMEM>
-__global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood_g1(const LikParams p) {
+__global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     float *swin = reinterpret_cast<float *>(smem + 16);
@@ -206,71 +209,91 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood_g1(const LikParam
     const int cx = p.ww + 1, cy = p.wh + 1;
     const int ofx = 1 - p.wx0, ofy = 1 - p.wy0;
     const double lo = p.margin, hix = (double)p.W - p.margin, hiy = (double)p.H - p.margin;
-    const int64_t stride = (int64_t)gridDim.x * LIK_THREADS;
+    const double2 *cb = reinterpret_cast<const double2 *>(c_beams);
+    const int64_t stride = (int64_t)gridDim.x * (G1_THREADS * G1_P);
     const int warp_first = threadIdx.x & ~31;
-    for (int64_t base = (int64_t)blockIdx.x * LIK_THREADS; base + warp_first < p.n; base += stride) {
-        const int64_t i = base + threadIdx.x;
-        const int64_t il = i < p.n ? i : p.n - 1;
-        const double x = p.x[il], y = p.y[il], th = p.th[il];
-        double s, c;
-        sincos(th, &s, &c);
-        const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);
-        const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
-        const bool interior = (px >= lo) && (px <= hix) && (py >= lo) && (py <= hiy);
-        float acc0 = 0.f, acc1 = 0.f;
+    for (int64_t base = (int64_t)blockIdx.x * (G1_THREADS * G1_P); base + warp_first < p.n; base += stride) {
+        int64_t idx[G1_P];
+        double px[G1_P], py[G1_P], s[G1_P], c[G1_P];
+        bool interior = true;
+#pragma unroll
+        for (int q = 0; q < G1_P; ++q) {
+            idx[q] = base + q * G1_THREADS + threadIdx.x;
+            const int64_t il = idx[q] < p.n ? idx[q] : p.n - 1;
+            const double x = p.x[il], y = p.y[il], th = p.th[il];
+            sincos(th, &s[q], &c[q]);
+            px[q] = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);
+            py[q] = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
+            interior = interior && (px[q] >= lo) && (px[q] <= hix) && (py[q] >= lo) && (py[q] <= hiy);
+        }
+        float acc[G1_P][2];
+#pragma unroll
+        for (int q = 0; q < G1_P; ++q) acc[q][0] = acc[q][1] = 0.f;
         if (SMEM && __all_sync(0xffffffffu, interior)) {
             // no endpoint can leave the map: coordinates >= 1, floor == trunc, no bounds test
             int j = 0;
-#pragma unroll 4
+#pragma unroll 2
             for (; j + 1 < p.n_pos; j += 2) {
-                const double bx0 = c_beams[j].bx, by0 = c_beams[j].by;
-                const double bx1 = c_beams[j + 1].bx, by1 = c_beams[j + 1].by;
-                const double tx0 = fma(c, bx0, fma(-s, by0, px)), ty0 = fma(s, bx0, fma(c, by0, py));
-                const double tx1 = fma(c, bx1, fma(-s, by1, px)), ty1 = fma(s, bx1, fma(c, by1, py));
-                const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
-                const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
-                const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
-                const int iy1 = __viaddmin_s32_relu(floor_to_int(ty1), ofy, cy);
-                acc0 += swin[iy0 * pw + ix0];
-                acc1 += swin[iy1 * pw + ix1];
+                const double2 b0 = cb[j], b1 = cb[j + 1];
+#pragma unroll
+                for (int q = 0; q < G1_P; ++q) {
+                    const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
+                    const double tx1 = fma(c[q], b1.x, fma(-s[q], b1.y, px[q])), ty1 = fma(s[q], b1.x, fma(c[q], b1.y, py[q]));
+                    const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
+                    const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
+                    const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
+                    const int iy1 = __viaddmin_s32_relu(floor_to_int(ty1), ofy, cy);
+                    acc[q][0] += swin[iy0 * pw + ix0];
+                    acc[q][1] += swin[iy1 * pw + ix1];
+                }
             }
             if (j < p.n_pos) {
-                const double bx0 = c_beams[j].bx, by0 = c_beams[j].by;
-                const double tx0 = fma(c, bx0, fma(-s, by0, px)), ty0 = fma(s, bx0, fma(c, by0, py));
-                const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
-                const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
-                acc0 += swin[iy0 * pw + ix0];
+                const double2 b0 = cb[j];
+#pragma unroll
+                for (int q = 0; q < G1_P; ++q) {
+                    const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
+                    const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
+                    const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
+                    acc[q][0] += swin[iy0 * pw + ix0];
+                }
             }
         } else {
-#pragma unroll 2
             for (int j = 0; j < p.n_pos; ++j) {
-                const double bx = c_beams[j].bx, by = c_beams[j].by;
-                const double tx = fma(c, bx, fma(-s, by, px));
-                const double ty = fma(s, bx, fma(c, by, py));
-                const int mx = __double2int_rz(tx), my = __double2int_rz(ty);      // pu:128-129 int()
-                const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
-                float v;
-                if (SMEM) {
-                    const int ix = min(max(mx + ofx, 0), cx), iy = min(max(my + ofy, 0), cy);
-                    v = swin[iy * pw + ix];
-                    v = inmap ? v : 0.f;                                           // pu:131-132
-                } else {
-                    v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0.f;
+                const double2 b = cb[j];
+#pragma unroll
+                for (int q = 0; q < G1_P; ++q) {
+                    const double tx = fma(c[q], b.x, fma(-s[q], b.y, px[q]));
+                    const double ty = fma(s[q], b.x, fma(c[q], b.y, py[q]));
+                    const int mx = __double2int_rz(tx), my = __double2int_rz(ty);      // pu:128-129 int()
+                    const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
+                    float v;
+                    if (SMEM) {
+                        const int ix = min(max(mx + ofx, 0), cx), iy = min(max(my + ofy, 0), cy);
+                        v = swin[iy * pw + ix];
+                        v = inmap ? v : 0.f;                                           // pu:131-132
+                    } else {
+                        v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0.f;
+                    }
+                    acc[q][0] += v;
                 }
-                acc0 += v;
             }
         }
         // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
         for (int j = p.n_pos; j < nb; ++j) {
-            const double bx = c_beams[j].bx, by = c_beams[j].by;
-            const double tx = fma(c, bx, fma(-s, by, px));
-            const double ty = fma(s, bx, fma(c, by, py));
-            const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
-            if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
-                acc1 += (float)cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
-                                         p.z_rand, p.max_range, false);
+            const double2 b = cb[j];
+#pragma unroll
+            for (int q = 0; q < G1_P; ++q) {
+                const double tx = fma(c[q], b.x, fma(-s[q], b.y, px[q]));
+                const double ty = fma(s[q], b.x, fma(c[q], b.y, py[q]));
+                const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
+                if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
+                    acc[q][1] += (float)cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
+                                                  p.z_rand, p.max_range, false);
+            }
         }
-        if (i < p.n) p.score[i] = (float)((double)(acc0 + acc1) / (double)nb);     // pu:144-145
+#pragma unroll
+        for (int q = 0; q < G1_P; ++q)
+            if (idx[q] < p.n) p.score[idx[q]] = (float)((double)(acc[q][0] + acc[q][1]) / (double)nb);   // pu:144-145
     }
 }
 
@@ -280,7 +303,8 @@ __global__ void k_fill_f32(float *out, int64_t n, float v) {
 }
 
 template <typename K>
-static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t smem_bytes, int G) {
+static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t smem_bytes, int G,
+                             int threads = LIK_THREADS, int per_thread = 1) {
     // attribute + occupancy queries are cached per (kernel, smem size): they cost tens of microseconds
     static thread_local const void *c_kern[16];
     static thread_local size_t c_smem[16];
@@ -291,12 +315,12 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
     if (occ == 0) {
         // opt in to the device maximum once (a later, smaller request must not lower the limit)
         MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-        MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LIK_THREADS, smem_bytes));
+        MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem_bytes));
         if (occ < 1) return mcl_fail(h, MCL_ERR_CAPACITY, "likelihood kernel does not fit on an SM");
         const int k = c_n < 16 ? c_n++ : 15;
         c_kern[k] = (const void *)kern; c_smem[k] = smem_bytes; c_occ[k] = occ; c_dev[k] = h->device;
     }
-    const int64_t groups = LIK_THREADS / G;
+    const int64_t groups = (int64_t)threads * per_thread / G;
     const int64_t need = (p.n + groups - 1) / groups;
     const int blocks = (int)std::min<int64_t>(need, (int64_t)h->sm_count * occ);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -305,7 +329,7 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
         MCL_CUDA(h, cudaEventCreate(&e1));
         MCL_CUDA(h, cudaEventRecord(e0, h->stream));
     }
-    kern<<<blocks, LIK_THREADS, smem_bytes, h->stream>>>(p);
+    kern<<<blocks, threads, smem_bytes, h->stream>>>(p);
     MCL_LAUNCH_CHECK(h);
     if (h->timing) {
         MCL_CUDA(h, cudaEventRecord(e1, h->stream));
@@ -368,8 +392,8 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
             g_cbeams_src = (const void *)h->d_beams_active;
             g_cbeams_gen = h->scan_gen;
         }
-        if (use_smem) return launch_lik_kernel(h, k_likelihood_g1<true>, p, 16 + h->win_bytes, 1);
-        return launch_lik_kernel(h, k_likelihood_g1<false>, p, 16, 1);
+        if (use_smem) return launch_lik_kernel(h, k_likelihood_g1<true>, p, 16 + h->win_bytes, 1, G1_THREADS, G1_P);
+        return launch_lik_kernel(h, k_likelihood_g1<false>, p, 16, 1, G1_THREADS, G1_P);
     }
 #define LIK_CASE(GV)                                                                   \
     case GV:                                                                           \

@@ -30,6 +30,9 @@ struct MotionParams {
 
 struct Pose { double x, y, th; };
 
+__device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x, double y, double th, double z0,
+                                                 double z1, double z2, Pose &cand);
+
 // one attempt t for a particle at (x,y,th); returns validity and the candidate pose
 __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i, int t, double x, double y,
                                                double th, Pose &cand) {
@@ -40,6 +43,74 @@ __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i,
     } else {
         philox_normals3(p.seed, p.step, p.first_index + (uint64_t)i, (uint32_t)t, z0, z1, z2);
     }
+    return motion_candidate(p, x, y, th, z0, z1, z2, cand);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact screening of the rejection loop.  A particle facing a wall burns all max_attempts in the
+// reference (~2 % of a uniform cloud, growing to >10 % of a running filter because stuck
+// particles never move).  Every candidate of an attempt whose normals satisfy |z0|, |z1| <= rho lies in
+// the annular sector  t in trans +- rho s2,  angle in theta + rot1 +- rho s1.  region_blocked(rho)
+// proves (separating-axis test against every FREE cell near the sector, everything inflated by 1e-9 m)
+// that this sector touches no free cell.  Since |z0|, |z1| <= R1 = sqrt(-2 ln u1), an attempt whose
+// radius word gives R1 < rho cannot succeed -- an integer compare on the raw Philox word, no log / sqrt /
+// sincos.  The radius words of four consecutive attempts come from one Philox call, so a lane screens
+// four attempts per call and a warp 128 attempts per iteration; only attempts that pass are evaluated in
+// full.  Results are identical to evaluating every attempt in order (tests: vs the oracle's plain loop).
+// ---------------------------------------------------------------------------------------------
+__device__ bool region_blocked(const MotionParams &p, double x, double y, double sn, double cs, double rho) {
+    const double dt = rho * p.s2, da = rho * p.s1;
+    const double t_lo = p.trans - dt, t_hi = p.trans + dt;
+    if (!(t_lo > 0.0) || !(da < 1.0)) return false;           // the sector bound needs t > 0 and a small spread
+    // oriented rectangle containing the sector: along the nominal heading u in [t_lo cos(da), t_hi],
+    // across it |v| <= t_hi sin(da); centre (ccx, ccy), half extents (hu, hv)
+    const double u_lo = t_lo * cos(da) - 1e-9, u_hi = t_hi + 1e-9;
+    const double hv = t_hi * sin(da) + 1e-9, hu = 0.5 * (u_hi - u_lo), um = 0.5 * (u_hi + u_lo);
+    const double ccx = x + um * cs, ccy = y + um * sn;
+    const double ax = fabs(cs), ay = fabs(sn);
+    const double bx = hu * ax + hv * ay + 1e-9, by = hu * ay + hv * ax + 1e-9;     // its axis-aligned half box
+    // cells touched by the box (the cell index is monotone in the coordinate; expression of pu:390-391)
+    const long long mx0 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccx - bx, -p.ox), p.res));
+    const long long mx1 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccx + bx, -p.ox), p.res));
+    const long long my0 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccy - by, -p.oy), p.res));
+    const long long my1 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccy + by, -p.oy), p.res));
+    if (mx0 < 1 || my0 < 1) return false;                             // int() truncation quirk at the map edge
+    if ((mx1 - mx0 + 1) * (my1 - my0 + 1) > 36) return false;         // large region: no claim
+    const double hc = 0.5 * p.res + 1e-9;                             // half cell, inflated
+    for (long long my = my0; my <= my1; ++my)
+        for (long long mx = mx0; mx <= mx1; ++mx) {
+            if (mx >= p.W || my >= p.H || p.occ[my * (long long)p.W + mx] != 0) continue;
+            const double qx = p.ox + ((double)mx + 0.5) * p.res - ccx, qy = p.oy + ((double)my + 0.5) * p.res - ccy;
+            const bool separated = fabs(qx) > bx + hc || fabs(qy) > by + hc ||
+                                   fabs(qx * cs + qy * sn) > hu + hc * (ax + ay) ||
+                                   fabs(-qx * sn + qy * cs) > hv + hc * (ax + ay);
+            if (!separated) return false;
+        }
+    return true;
+}
+
+// Largest screening level whose sector is blocked -> threshold on (radius word + 1):
+// an attempt can only succeed if word + 1 <= T.  T = 2^32 (no screening) .. 0 (provably stuck).
+__device__ unsigned long long screening_threshold(const MotionParams &p, double x, double y, double th) {
+    const double levels[10] = {1.0, 2.0, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.6605};
+    double sn, cs;
+    sincos(th + p.rot1, &sn, &cs);
+    double rho_ok = 0.0;
+    for (int k = 0; k < 10; ++k) {
+        if (!region_blocked(p, x, y, sn, cs, levels[k])) break;
+        rho_ok = levels[k];
+    }
+    if (rho_ok == 0.0) return 1ull << 32;
+    if (rho_ok > 6.66) return 0ull;        // R1 <= sqrt(-2 ln 2^-32) = 6.6604 < 6.6605: nothing can succeed
+    // R1 >= rho  <=>  u1 <= exp(-rho^2/2); keep a relative margin far above the fp64 error of log/sqrt
+    return (unsigned long long)(4294967296.0 * exp(-0.5 * rho_ok * rho_ok) * (1.0 + 1e-9)) + 2ull;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// pose update of pu:350-353 from three normals; returns validity
+__device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x, double y, double th, double z0,
+                                                 double z1, double z2, Pose &cand) {
     // np.random.normal(0, s) = 0.0 + s*z ; no FMA contraction anywhere (numba does not fuse)
     const double r1_hat = __dadd_rn(p.rot1, __dadd_rn(0.0, __dmul_rn(p.s1, z0)));
     const double t_hat = __dadd_rn(p.trans, __dadd_rn(0.0, __dmul_rn(p.s2, z1)));
@@ -52,41 +123,6 @@ __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i,
     return is_valid_position_dev(cand.x, cand.y, p.occ, p.W, p.H, p.res, p.ox, p.oy);
 }
 
-// Sound early exit for the particles that would burn all max_attempts (~2 % of a uniform
-// cloud, and whole clusters of duplicates once the filter has converged next to a wall): Box-Muller on
-// 32-bit uniforms bounds every normal by |z| <= sqrt(-2 ln 2^-32) < 6.66, so every candidate of every
-// attempt lies in the annular sector  t in trans +- 6.66 s2,  angle in theta + rot1 +- 6.66 s1.  If all
-// map cells touched by the (slightly inflated) bounding box of that sector are non-free, no attempt
-// can succeed and the particle keeps its pose (pu:360-361) -- the same result the 1000 attempts give.
-// Only used with Philox draws (injected draws are unbounded).
-#define MCL_ZMAX 6.6605
-__device__ bool provably_stuck(const MotionParams &p, double x, double y, double th) {
-    const double dt = MCL_ZMAX * p.s2, da = MCL_ZMAX * p.s1;
-    const double t_lo = p.trans - dt, t_hi = p.trans + dt;
-    if (!(t_lo > 0.0) || !(da < 1.0)) return false;           // sector bound below needs t > 0, small spread
-    double sn, cs;
-    sincos(th + p.rot1, &sn, &cs);
-    const double u_lo = t_lo * cos(da) - 1e-9, u_hi = t_hi + 1e-9;   // along the nominal heading
-    const double v = t_hi * sin(da) + 1e-9;                          // across it
-    // axis-aligned bounding box of the rotated rectangle [u_lo,u_hi] x [-v,v] around (x, y)
-    const double ax = fabs(cs), ay = fabs(sn);
-    const double cxm = 0.5 * (u_lo + u_hi) * cs, cym = 0.5 * (u_lo + u_hi) * sn;
-    const double hx = 0.5 * (u_hi - u_lo) * ax + v * ay + 1e-9, hy = 0.5 * (u_hi - u_lo) * ay + v * ax + 1e-9;
-    const double x0 = x + cxm - hx, x1 = x + cxm + hx, y0 = y + cym - hy, y1 = y + cym + hy;
-    // cell index is monotone in the coordinate (same expression as pu:390-391)
-    const long long mx0 = __double2ll_rz(__ddiv_rn(__dadd_rn(x0, -p.ox), p.res));
-    const long long mx1 = __double2ll_rz(__ddiv_rn(__dadd_rn(x1, -p.ox), p.res));
-    const long long my0 = __double2ll_rz(__ddiv_rn(__dadd_rn(y0, -p.oy), p.res));
-    const long long my1 = __double2ll_rz(__ddiv_rn(__dadd_rn(y1, -p.oy), p.res));
-    if ((mx1 - mx0 + 1) * (my1 - my0 + 1) > 16) return false;        // large region: just run the attempts
-    for (long long my = my0; my <= my1; ++my)
-        for (long long mx = mx0; mx <= mx1; ++mx)
-            if (mx >= 0 && mx < p.W && my >= 0 && my < p.H && p.occ[my * (long long)p.W + mx] == 0) return false;
-    return true;
-}
-
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
 __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
@@ -97,11 +133,15 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
     if (live) { x = p.x[i]; y = p.y[i]; th = p.th[i]; }
     Pose out = {x, y, th};
     int32_t att = 0;
+    unsigned long long thr = 1ull << 32;
     bool done = !live || p.max_attempts <= 0;
     if (!done) {
         Pose c;
         if (motion_attempt(p, i, 0, x, y, th, c)) { out = c; att = 1; done = true; }
-        else if (!p.normals && provably_stuck(p, x, y, th)) done = true;     // att = 0, pose kept
+        else if (!p.normals) {
+            thr = screening_threshold(p, x, y, th);
+            if (thr == 0ull) done = true;                // provably stuck: att = 0, pose kept (pu:360-361)
+        }
     }
     unsigned pending = __ballot_sync(0xffffffffu, !done);
     while (pending) {
@@ -110,16 +150,54 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
         const int64_t si = warp_base + src;
         Pose win = {sx, sy, sth};
         int watt = 0;
-        for (int t0 = 1; t0 < p.max_attempts; t0 += 32) {
-            const int t = t0 + lane;
-            Pose c = {0, 0, 0};
-            const bool ok = (t < p.max_attempts) && motion_attempt(p, si, t, sx, sy, sth, c);
-            const unsigned okm = __ballot_sync(0xffffffffu, ok);
-            if (okm) {
-                const int w = __ffs(okm) - 1;             // lowest attempt index that is valid
-                win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
-                watt = t0 + w + 1;
-                break;
+        if (p.normals) {
+            // injected draws: the lanes evaluate attempts t0..t0+31 of this particle, lowest valid wins
+            for (int t0 = 1; t0 < p.max_attempts; t0 += 32) {
+                const int t = t0 + lane;
+                Pose c = {0, 0, 0};
+                const bool ok = (t < p.max_attempts) && motion_attempt(p, si, t, sx, sy, sth, c);
+                const unsigned okm = __ballot_sync(0xffffffffu, ok);
+                if (okm) {
+                    const int w = __ffs(okm) - 1;
+                    win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
+                    watt = t0 + w + 1;
+                    break;
+                }
+            }
+        } else {
+            // Philox draws: lane L screens attempts 4g..4g+3 (g = g0 + L) from one radius block
+            const unsigned long long T = __shfl_sync(0xffffffffu, thr, src);
+            const uint64_t item = p.first_index + (uint64_t)si;
+            const int groups = (p.max_attempts + 3) >> 2;
+            for (int g0 = 0; g0 < groups; g0 += 32) {
+                const int g = g0 + lane;
+                int best = 0x7fffffff;
+                Pose c = {0, 0, 0};
+                if (g < groups) {
+                    const uint4 a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int t = 4 * g + k;
+                        const uint32_t w = pick_word(a, k);
+                        if (best == 0x7fffffff && t >= 1 && t < p.max_attempts && (unsigned long long)w + 1ull <= T) {
+                            const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
+                            double z0, z1, z2;
+                            normals3_from_words(w, o, z0, z1, z2);
+                            Pose cc;
+                            if (motion_candidate(p, sx, sy, sth, z0, z1, z2, cc)) { best = t; c = cc; }
+                        }
+                    }
+                }
+                int m = best;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (m != 0x7fffffff) {                     // lowest valid attempt index in this batch of 128
+                    const unsigned who = __ballot_sync(0xffffffffu, best == m);
+                    const int w = __ffs(who) - 1;
+                    win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
+                    watt = m + 1;
+                    break;
+                }
             }
         }
         if (lane == src) { out = win; att = watt; }       // watt == 0: keep the old pose (pu:360-361)

@@ -172,7 +172,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* Stream ids (ctr[3] low byte) -- must match mcmh_localization_b200/csrc/philox.cuh */
 enum { ORC_STREAM_MOTION = 1, ORC_STREAM_MH = 2, ORC_STREAM_RESAMPLE = 3, ORC_STREAM_INIT = 4,
-       ORC_STREAM_KLD = 5 };
+       ORC_STREAM_KLD = 5, ORC_STREAM_MOTION_R = 6 };
 
 static inline void draw4(uint64_t seed, uint64_t step, uint64_t item, uint32_t sub, uint32_t stream,
                          uint32_t out[4]) {
@@ -194,14 +194,20 @@ static inline double u53(uint32_t a, uint32_t b) {
 double orc_uniform53(uint64_t seed, uint64_t step, uint64_t item, uint32_t sub, uint32_t stream) {
     uint32_t o[4]; draw4(seed, step, item, sub, stream, o); return u53(o[0], o[1]);
 }
-/* Three standard normals per (particle, attempt): Box-Muller on 32-bit uniforms,
- * u1 in (0,1], u2 in [0,1).  z0 = R1 cos(2 pi u2), z1 = R1 sin(2 pi u2), z2 = R2 cos(2 pi u4). */
+/* Three standard normals per (particle, attempt t): Box-Muller on 32-bit uniforms, u1 in (0,1],
+ * u2 in [0,1):  z0 = R1 cos(2 pi u2), z1 = R1 sin(2 pi u2), z2 = R2 cos(2 pi u4), R = sqrt(-2 ln u).
+ * The radius word of attempt t is word (t & 3) of the MOTION_R block (particle, step, t >> 2): four
+ * consecutive attempts share one Philox call, which lets the GPU rejection loop screen four attempts
+ * per call (|z0|, |z1| <= R1, so a small R1 cannot leave an all-blocked neighbourhood).  The other
+ * three uniforms come from the MOTION block (particle, step, t). */
 static inline void normals3(uint64_t seed, uint64_t step, uint64_t item, uint32_t attempt, double z[3]) {
-    uint32_t o[4]; draw4(seed, step, item, attempt, ORC_STREAM_MOTION, o);
-    const double u1 = ((double)o[0] + 1.0) * 2.3283064365386963e-10;
-    const double u2 = (double)o[1] * 2.3283064365386963e-10;
-    const double u3 = ((double)o[2] + 1.0) * 2.3283064365386963e-10;
-    const double u4 = (double)o[3] * 2.3283064365386963e-10;
+    uint32_t a[4], o[4];
+    draw4(seed, step, item, attempt >> 2, ORC_STREAM_MOTION_R, a);
+    draw4(seed, step, item, attempt, ORC_STREAM_MOTION, o);
+    const double u1 = ((double)a[attempt & 3u] + 1.0) * 2.3283064365386963e-10;
+    const double u2 = (double)o[0] * 2.3283064365386963e-10;
+    const double u3 = ((double)o[1] + 1.0) * 2.3283064365386963e-10;
+    const double u4 = (double)o[2] * 2.3283064365386963e-10;
     const double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
     const double a1 = 6.283185307179586 * u2, a2 = 6.283185307179586 * u4;
     z[0] = r1 * cos(a1); z[1] = r1 * sin(a1); z[2] = r2 * cos(a2);

@@ -195,6 +195,35 @@ def test_motion_philox_vs_oracle(pu, orc, oracle_map_world):
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12)
 
 
+def test_motion_wall_hugging_cloud_vs_oracle(pu, orc, oracle_map_world):
+    """Soundness of the provably-stuck early exit: 20k particles within 10 cm of a wall, random
+    headings, several odometry increments -- accepted attempt index and pose must equal the oracle's
+    plain rejection loop for every particle."""
+    mp = oracle_map_world
+    rs = np.random.RandomState(2)
+    near = np.flatnonzero((mp["map_data"] == 0) & (mp["distance_map"] <= 0.1001))
+    n = 20000
+    cells = near[rs.randint(0, len(near), n)]
+    my, mx = np.divmod(cells, mp["width"])
+    parts = np.column_stack((mp["origin_np"][0] + (mx + rs.uniform(0, 1, n)) * mp["resolution"],
+                             mp["origin_np"][1] + (my + rs.uniform(0, 1, n)) * mp["resolution"],
+                             rs.uniform(-np.pi, np.pi, n)))
+    alpha = np.array([P["alpha1"], P["alpha2"], P["alpha3"], P["alpha4"]], dtype=np.float32)
+    stuck_total = 0
+    for k, delta in enumerate([(0.0, 0.02, 0.01), (0.3, 0.05, -0.1), (0.0, 0.1, 0.0), (1.0, 0.01, -1.0)]):
+        pu.seed(500 + k)
+        out, att = pu.apply_motion_model_parallel(parts, delta, alpha, mp["map_data"], mp["resolution"],
+                                                  mp["origin_np"][0], mp["origin_np"][1], mp["width"],
+                                                  mp["height"], return_attempts=True)
+        ref, ratt = orc.apply_motion_model_parallel(parts, delta, alpha, mp["map_data"], mp["resolution"],
+                                                    mp["origin_np"][0], mp["origin_np"][1], mp["width"],
+                                                    mp["height"], seed=500 + k, step=1, return_attempts=True)
+        assert np.array_equal(att, ratt), (k, int((att != ratt).sum()))
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12)
+        stuck_total += int((att == 0).sum())
+    assert stuck_total > 1000
+
+
 # --------------------------------------------------------------------------- MH (a5)
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_mh_golden_bitexact(pu, tag):
