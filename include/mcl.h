@@ -95,14 +95,15 @@ int mcl_set_likelihood_path(mcl_handle *h, int path);
 int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                    int64_t n, float *d_score);
 
-/* node:351-358 convert_scores (softmax).  d_stats (nullable) receives {max, sum exp(s-max)} as
- * two device doubles; d_weights (nullable) receives exp(s-max)/sum as f32.
+/* node:351-358 convert_scores (softmax).  d_stats (nullable, room for 4 doubles) receives
+ * {max, sum exp(s-max), the same sum as a 2^-40 fixed-point uint64 bit pattern, unused} on the device; d_weights (nullable) receives exp(s-max)/sum as f32.
  * ext_stats (nullable, HOST): if given, use these {max, sum} instead of the local ones -- the
  * multi-GPU path passes the all-reduced values. */
 int mcl_softmax(mcl_handle *h, const float *d_score, int64_t n, float *d_weights, double *d_stats,
                 const double *ext_stats);
 /* Staged softmax for sharded particles: max -> [all-reduce MAX on d_stats[0]] -> sumexp (uses
- * d_stats[0], writes d_stats[1]) -> [all-reduce SUM on d_stats[1]] -> weights.  d_stats: device. */
+ * d_stats[0], writes d_stats[1] and the exact 2^-40 fixed-point integer d_stats[2]) -> [all-reduce SUM
+ * on the integer, d_stats[1] = integer * 2^-40] -> weights.  d_stats: device, 4 doubles. */
 int mcl_softmax_max(mcl_handle *h, const float *d_score, int64_t n, double *d_stats);
 int mcl_softmax_sumexp(mcl_handle *h, const float *d_score, int64_t n, double *d_stats);
 int mcl_softmax_weights(mcl_handle *h, const float *d_score, int64_t n, const double *d_stats,

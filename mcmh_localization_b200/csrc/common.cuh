@@ -35,14 +35,17 @@ struct mcl_handle {
     bool motion_set = false;
     float alpha[4] = {0, 0, 0, 0};
 
-    // likelihood table: logtab[c] = (float) log(max(z_hit*p_hit(dist[c]) + z_rand/max_range, 1e-6))
+    // likelihood table: logtab[c] = rint(2^25 * log(max(z_hit*p_hit(dist[c]) + z_rand/max_range, 1e-6)))
+    // 2^-25 fixed point (|log p| <= 13.82 fits int32 four times over): sums of table values are exact
+    // integers, so a score does not depend on the order in which beams are accumulated (lanes per
+    // particle, shared vs global path, number of ranks) and carries ~1e-9 error instead of fp32's ~1e-6.
     bool tab_dirty = true;
-    float *d_logtab = nullptr;   // W*H
-    float c0 = 0.f;              // table value on dist == 0 cells (everything outside the window)
+    int32_t *d_logtab = nullptr; // W*H
+    int32_t c0 = 0;              // table value on dist == 0 cells (everything outside the window)
     // free-space window [wx0, wx0+ww) x [wy0, wy0+wh): outside it every in-map cell holds c0.
     // d_win is the packed window with a one-cell c0 border: (wh+2) x (ww+2) floats.
     int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
-    float *d_win = nullptr;
+    int32_t *d_win = nullptr;
     size_t win_bytes = 0;
     int lik_path = 0;            // 0 auto, 1 global, 2 smem window
 
@@ -211,4 +214,6 @@ __device__ __forceinline__ double cell_logp(float d, double sigma_hit, double z_
     return log(p);
 }
 
+#define MCL_LOGP_SCALE 33554432.0   // 2^25
+__device__ __forceinline__ int32_t quantise_logp(double lp) { return __double2int_rn(lp * MCL_LOGP_SCALE); }
 #endif  // __CUDACC__

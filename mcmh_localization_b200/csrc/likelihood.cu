@@ -30,7 +30,8 @@ struct LikParams {
     int n_pos, n_neg;
     double ox, oy, res;
     int W, H;
-    const float *logtab, *dist, *win;
+    const int32_t *logtab, *win;
+    const float *dist;
     int wx0, wy0, ww, wh;
     uint32_t win_bytes;
     double sigma_hit, z_hit, z_rand, max_range;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
     BeamTable *sb = reinterpret_cast<BeamTable *>(smem + 16);
     const int nb = p.n_pos + p.n_neg;
     const uint32_t beam_bytes = (uint32_t)nb * (uint32_t)sizeof(BeamTable);
-    float *swin = reinterpret_cast<float *>(smem + 16 + beam_bytes);
+    int32_t *swin = reinterpret_cast<int32_t *>(smem + 16 + beam_bytes);
 
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
         const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);
         const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
         const bool interior = (px >= lo) && (px <= hix) && (py >= lo) && (py <= hiy);
-        float acc = 0.f;
+        long long acc = 0;
         if (SMEM) {
             if (__all_sync(0xffffffffu, interior)) {
                 // no endpoint can leave the map: coordinates are >= 1, trunc == floor, no bounds test
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
                     const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
                     const int ix = min(max(mx + ofx, 0), cx);
                     const int iy = min(max(my + ofy, 0), cy);
-                    const float v = swin[iy * pw + ix];
-                    acc += inmap ? v : 0.f;                                         // pu:131-132
+                    const int v = swin[iy * pw + ix];
+                    acc += inmap ? v : 0;                                           // pu:131-132
                 }
             }
         } else {
@@ -160,12 +161,12 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
             const double ty = fma(s, b.bx, fma(c, b.by, py));
             const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
             if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
-                acc += (float)cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
-                                        p.z_rand, p.max_range, false);
+                acc += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
+                                               p.z_rand, p.max_range, false));
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (g == 0 && i < p.n) p.score[i] = (float)((double)acc / (double)nb);   // pu:144-145
+        if (g == 0 && i < p.n) p.score[i] = (float)(((double)acc / MCL_LOGP_SCALE) / (double)nb);   // pu:144-145
     }
 }
 
@@ -193,7 +194,7 @@ template <bool SMEM>
 __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    float *swin = reinterpret_cast<float *>(smem + 16);
+    int32_t *swin = reinterpret_cast<int32_t *>(smem + 16);
     const int nb = p.n_pos + p.n_neg;
     if (SMEM) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams
             py[q] = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
             interior = interior && (px[q] >= lo) && (px[q] <= hix) && (py[q] >= lo) && (py[q] <= hiy);
         }
-        float acc[G1_P][2];
+        long long acc[G1_P];
 #pragma unroll
-        for (int q = 0; q < G1_P; ++q) acc[q][0] = acc[q][1] = 0.f;
+        for (int q = 0; q < G1_P; ++q) acc[q] = 0;
         if (SMEM && __all_sync(0xffffffffu, interior)) {
             // no endpoint can leave the map: coordinates >= 1, floor == trunc, no bounds test
             int j = 0;
@@ -243,8 +244,7 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams
                     const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
                     const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
                     const int iy1 = __viaddmin_s32_relu(floor_to_int(ty1), ofy, cy);
-                    acc[q][0] += swin[iy0 * pw + ix0];
-                    acc[q][1] += swin[iy1 * pw + ix1];
+                    acc[q] += swin[iy0 * pw + ix0] + swin[iy1 * pw + ix1];      // two terms fit int32
                 }
             }
             if (j < p.n_pos) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams
                     const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
                     const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
                     const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
-                    acc[q][0] += swin[iy0 * pw + ix0];
+                    acc[q] += swin[iy0 * pw + ix0];
                 }
             }
         } else {
@@ -266,15 +266,15 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams
                     const double ty = fma(s[q], b.x, fma(c[q], b.y, py[q]));
                     const int mx = __double2int_rz(tx), my = __double2int_rz(ty);      // pu:128-129 int()
                     const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
-                    float v;
+                    int v;
                     if (SMEM) {
                         const int ix = min(max(mx + ofx, 0), cx), iy = min(max(my + ofy, 0), cy);
                         v = swin[iy * pw + ix];
-                        v = inmap ? v : 0.f;                                           // pu:131-132
+                        v = inmap ? v : 0;                                             // pu:131-132
                     } else {
-                        v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0.f;
+                        v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
                     }
-                    acc[q][0] += v;
+                    acc[q] += v;
                 }
             }
         }
@@ -287,13 +287,13 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams
                 const double ty = fma(s[q], b.x, fma(c[q], b.y, py[q]));
                 const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
                 if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
-                    acc[q][1] += (float)cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
-                                                  p.z_rand, p.max_range, false);
+                    acc[q] += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
+                                                      p.z_rand, p.max_range, false));
             }
         }
 #pragma unroll
         for (int q = 0; q < G1_P; ++q)
-            if (idx[q] < p.n) p.score[idx[q]] = (float)((double)(acc[q][0] + acc[q][1]) / (double)nb);   // pu:144-145
+            if (idx[q] < p.n) p.score[idx[q]] = (float)(((double)acc[q] / MCL_LOGP_SCALE) / (double)nb);   // pu:144-145
     }
 }
 

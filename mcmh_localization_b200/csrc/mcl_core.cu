@@ -131,7 +131,7 @@ extern "C" int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_di
     }
     if (!h_dist) { h->wx0 = h->wy0 = h->ww = h->wh = 0; h->win_bytes = 0; return MCL_OK; }
     MCL_CUDA(h, cudaMalloc((void **)&h->d_dist, cells * sizeof(float)));
-    MCL_CUDA(h, cudaMalloc((void **)&h->d_logtab, cells * sizeof(float)));
+    MCL_CUDA(h, cudaMalloc((void **)&h->d_logtab, cells * sizeof(int32_t)));
     MCL_CUDA(h, cudaMemcpy(h->d_dist, h_dist, cells * sizeof(float), cudaMemcpyHostToDevice));
     // bounding box of cells with dist > 0 (free space): everywhere else the table is the constant c0
     int x0 = W, x1 = -1, y0 = H, y1 = -1;
@@ -146,7 +146,7 @@ extern "C" int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_di
     }
     if (x1 < 0) { h->wx0 = 0; h->wy0 = 0; h->ww = 0; h->wh = 0; }
     else { h->wx0 = x0; h->wy0 = y0; h->ww = x1 - x0 + 1; h->wh = y1 - y0 + 1; }
-    h->win_bytes = (((size_t)(h->ww + 2) * (h->wh + 2) * sizeof(float)) + 15) & ~(size_t)15;
+    h->win_bytes = (((size_t)(h->ww + 2) * (h->wh + 2) * sizeof(int32_t)) + 15) & ~(size_t)15;
     MCL_CUDA(h, cudaMalloc((void **)&h->d_win, h->win_bytes));
     h->tab_dirty = true;
     return MCL_OK;
@@ -178,27 +178,27 @@ extern "C" int mcl_set_likelihood_path(mcl_handle *h, int path) {
     return MCL_OK;
 }
 
-__global__ void k_build_logtab(const float *__restrict__ dist, float *__restrict__ logtab, int64_t cells,
+__global__ void k_build_logtab(const float *__restrict__ dist, int32_t *__restrict__ logtab, int64_t cells,
                                double sigma_hit, double z_hit, double z_rand, double max_range) {
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < cells;
          c += (int64_t)gridDim.x * blockDim.x)
-        logtab[c] = (float)cell_logp(dist[c], sigma_hit, z_hit, z_rand, max_range, true);
+        logtab[c] = quantise_logp(cell_logp(dist[c], sigma_hit, z_hit, z_rand, max_range, true));
 }
 
-__global__ void k_pack_window(const float *__restrict__ logtab, float *__restrict__ win, int W, int wx0,
-                              int wy0, int ww, int wh, float c0) {
+__global__ void k_pack_window(const int32_t *__restrict__ logtab, int32_t *__restrict__ win, int W, int wx0,
+                              int wy0, int ww, int wh, int32_t c0) {
     const int pw = ww + 2, ph = wh + 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pw * ph; i += gridDim.x * blockDim.x) {
         const int iy = i / pw, ix = i - iy * pw;
-        float v = c0;
+        int32_t v = c0;
         if (ix >= 1 && ix <= ww && iy >= 1 && iy <= wh)
             v = logtab[(size_t)(wy0 + iy - 1) * W + (wx0 + ix - 1)];
         win[i] = v;
     }
 }
 
-__global__ void k_c0(float *out, double sigma_hit, double z_hit, double z_rand, double max_range) {
-    out[0] = (float)cell_logp(0.0f, sigma_hit, z_hit, z_rand, max_range, true);
+__global__ void k_c0(int32_t *out, double sigma_hit, double z_hit, double z_rand, double max_range) {
+    out[0] = quantise_logp(cell_logp(0.0f, sigma_hit, z_hit, z_rand, max_range, true));
 }
 
 int mcl_prepare_table(mcl_handle *h) {
@@ -212,11 +212,11 @@ int mcl_prepare_table(mcl_handle *h) {
     k_build_logtab<<<blocks, 256, 0, h->stream>>>(h->d_dist, h->d_logtab, cells, h->sigma_hit, h->z_hit,
                                                   h->z_rand, h->max_range);
     MCL_LAUNCH_CHECK(h);
-    k_c0<<<1, 1, 0, h->stream>>>((float *)h->d_scratch, h->sigma_hit, h->z_hit, h->z_rand, h->max_range);
+    k_c0<<<1, 1, 0, h->stream>>>((int32_t *)h->d_scratch, h->sigma_hit, h->z_hit, h->z_rand, h->max_range);
     MCL_LAUNCH_CHECK(h);
-    MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scratch, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scratch, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     MCL_CUDA(h, cudaStreamSynchronize(h->stream));
-    memcpy(&h->c0, h->h_pinned, sizeof(float));
+    memcpy(&h->c0, h->h_pinned, sizeof(int32_t));
     const int n = (h->ww + 2) * (h->wh + 2);
     k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
         h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->c0);

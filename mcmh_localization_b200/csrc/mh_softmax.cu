@@ -69,28 +69,47 @@ __global__ void __launch_bounds__(RED_THREADS) k_max(const float *__restrict__ s
 // exponential evaluated in f64 and rounded to f32.
 __device__ __forceinline__ float softmax_num(float s, float m) { return (float)exp((double)__fsub_rn(s, m)); }
 
-// pass 2: sum of the f32 numerators, accumulated in f64 (order-independent to ~1e-16).
+// pass 2: sum of the f32 numerators in 2^-40 fixed point (uint64): exact integer arithmetic, so the
+// sum -- and therefore every weight -- is identical for any block or rank decomposition.  (Numerators
+// below 2^-17 lose the bits under 2^-40: < 1e-6 absolute on a sum that is >= 1.)
+// stats[1] = sum as f64, stats[2] = the raw integer (bit pattern) for the cross-rank all-reduce.
+#define SOFTMAX_FIX 1099511627776.0   // 2^40
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k];
+    __syncthreads();
+    return t;   // valid in thread 0
+}
 __global__ void __launch_bounds__(RED_THREADS) k_sumexp(const float *__restrict__ s, int64_t n, RedScratch rs,
                                                         double *stats, double ext_max, int use_ext) {
-    __shared__ double shd[32];
+    __shared__ unsigned long long shq[32];
     __shared__ bool last;
     const float m = (float)(use_ext ? ext_max : stats[0]);
-    double acc = 0.0;
+    unsigned long long acc = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        acc += (double)softmax_num(s[i], m);
-    acc = block_sum(acc, shd);
+        acc += __double2ull_rz(__dmul_rn((double)softmax_num(s[i], m), SOFTMAX_FIX));
+    acc = block_sum_u64(acc, shq);
     if (threadIdx.x == 0) {
-        rs.partials[blockIdx.x] = acc;
+        ((unsigned long long *)rs.partials)[blockIdx.x] = acc;
         __threadfence();
         last = atomicAdd(rs.counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (last) {
         __threadfence();
-        double t = 0.0;
-        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += ((volatile double *)rs.partials)[b];
-        t = block_sum(t, shd);
-        if (threadIdx.x == 0) { stats[1] = t; *rs.counter = 0; }
+        unsigned long long t = 0;
+        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += ((volatile unsigned long long *)rs.partials)[b];
+        t = block_sum_u64(t, shq);
+        if (threadIdx.x == 0) {
+            stats[1] = (double)t / SOFTMAX_FIX;
+            ((unsigned long long *)stats)[2] = t;
+            *rs.counter = 0;
+        }
     }
 }
 

@@ -107,8 +107,8 @@ class ShardedLocalizer(Localizer):
         super()._alloc(n)
         self.n_global = n * self.world
         d = self.device
-        self.st_post = torch.zeros(2, dtype=torch.float64, device=d)
-        self.st_pre = torch.zeros(2, dtype=torch.float64, device=d)
+        self.st_post = torch.zeros(4, dtype=torch.float64, device=d)   # {max, sum, sum as 2^-40 fixed point, -}
+        self.st_pre = torch.zeros(4, dtype=torch.float64, device=d)
         self.m9 = torch.zeros(9, dtype=torch.float64, device=d)
         self.c9 = torch.zeros(9, dtype=torch.float64, device=d)
         self.wmax = torch.zeros(1, dtype=torch.float32, device=d)
@@ -139,8 +139,10 @@ class ShardedLocalizer(Localizer):
         h.call("mcl_softmax_sumexp", _ptr(self.score_post), n, _ptr(self.st_post))
         if self.use_mh:
             h.call("mcl_softmax_sumexp", _ptr(self.score_pre), n, _ptr(self.st_pre))
-        sm = torch.stack((self.st_post[1], self.st_pre[1]))
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=self.group)
+        # the sums travel as exact 2^-40 fixed-point integers: identical for any number of ranks
+        q = torch.stack((self.st_post.view(torch.int64)[2], self.st_pre.view(torch.int64)[2]))
+        dist.all_reduce(q, op=dist.ReduceOp.SUM, group=self.group)
+        sm = q.to(torch.float64) * (2.0 ** -40)
         self.st_post[1], self.st_pre[1] = sm[0], sm[1]
         if not self.use_mh:
             h.call("mcl_softmax_weights", _ptr(self.score_post), n, _ptr(self.st_post), _ptr(self.wbuf[ws]))
