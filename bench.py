@@ -81,9 +81,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Call at the start of the timed region: only later samples count."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)            # let the sample covering the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -92,7 +97,8 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[getattr(self, "first", 0):] or self.lines[-2:]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -198,6 +204,9 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()             # nvidia-smi needs ~0.5 s to come up: start it before the set-up work
     gm = load_world()
     n = args.particles
     K, W = args.steps, args.warmup
@@ -231,9 +240,7 @@ def run_native(args):
     for k in range(1, W + 1):
         loc.step_staged(poses[k], k, est_buf[k])
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = lib.mcl_launch_count(h)
     lib.mcl_timing_start(h)
     t_wall0 = time.perf_counter()

@@ -16,6 +16,8 @@
 // Mapping: G lanes per particle (G = 1 for large N: beam constants are then warp-uniform shared
 // loads; G up to 32 for small N to fill the machine), beams strided over the G lanes and reduced
 // with __shfl_xor.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -187,11 +189,11 @@ __device__ __forceinline__ int floor_to_int(double t) {   // exact floor(t) for 
     return __double2loint(__dadd_rd(t, MCL_FLOOR_MAGIC));
 }
 
-#define G1_THREADS 256
-#define G1_P 2      // particles per thread: the uniform beam loads and loop overhead are shared
-
-template <bool SMEM>
-__global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams p) {
+// Tunables (chosen by measurement, see profiles/): threads per CTA, particles per thread (the uniform beam
+// loads and loop overhead are shared), minimum CTAs per SM, and MIXED = take the y index with F2I (XU pipe)
+// instead of the magic add (FP64 pipe) to spread the conversions over two pipes.
+template <bool SMEM, int G1_THREADS, int G1_P, int MINB, bool MIXED>
+__global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     int32_t *swin = reinterpret_cast<int32_t *>(smem + 16);
@@ -241,9 +243,9 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_likelihood_g1(const LikParams
                     const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
                     const double tx1 = fma(c[q], b1.x, fma(-s[q], b1.y, px[q])), ty1 = fma(s[q], b1.x, fma(c[q], b1.y, py[q]));
                     const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
-                    const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
+                    const int iy0 = __viaddmin_s32_relu(MIXED ? __double2int_rz(ty0) : floor_to_int(ty0), ofy, cy);
                     const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
-                    const int iy1 = __viaddmin_s32_relu(floor_to_int(ty1), ofy, cy);
+                    const int iy1 = __viaddmin_s32_relu(MIXED ? __double2int_rz(ty1) : floor_to_int(ty1), ofy, cy);
                     acc[q] += swin[iy0 * pw + ix0] + swin[iy1 * pw + ix1];      // two terms fit int32
                 }
             }
@@ -392,8 +394,24 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
             g_cbeams_src = (const void *)h->d_beams_active;
             g_cbeams_gen = h->scan_gen;
         }
-        if (use_smem) return launch_lik_kernel(h, k_likelihood_g1<true>, p, 16 + h->win_bytes, 1, G1_THREADS, G1_P);
-        return launch_lik_kernel(h, k_likelihood_g1<false>, p, 16, 1, G1_THREADS, G1_P);
+        static int variant = -1;
+        if (variant < 0) { const char *e = getenv("MCL_LIK_VARIANT"); variant = e ? atoi(e) : 0; }
+#define G1_CASE(V, T, P, B, M)                                                                              \
+    case V:                                                                                                 \
+        if (use_smem) return launch_lik_kernel(h, k_likelihood_g1<true, T, P, B, M>, p, 16 + h->win_bytes, 1, T, P); \
+        return launch_lik_kernel(h, k_likelihood_g1<false, T, P, B, M>, p, 16, 1, T, P);
+        switch (variant) {
+            G1_CASE(1, 256, 2, 4, false)
+            G1_CASE(2, 512, 1, 2, false)
+            G1_CASE(3, 256, 1, 4, false)
+            G1_CASE(4, 256, 2, 3, true)
+            G1_CASE(5, 128, 2, 6, false)
+            G1_CASE(6, 256, 1, 4, true)
+            G1_CASE(7, 256, 4, 2, false)
+            default:
+            G1_CASE(0, 256, 2, 3, false)
+        }
+#undef G1_CASE
     }
 #define LIK_CASE(GV)                                                                   \
     case GV:                                                                           \

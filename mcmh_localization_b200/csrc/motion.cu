@@ -26,6 +26,11 @@ struct MotionParams {
     int max_attempts;
     double *xo, *yo, *tho;
     int32_t *attempts;
+    // screening levels (warp-uniform, computed on the host): sector bounds for |z| <= rho_k
+    int n_levels;
+    double lv_ulo[10], lv_uhi[10], lv_hv[10];      // along-heading interval and half width of the sector box
+    unsigned long long lv_thr[10];                  // an attempt can only succeed if radius word + 1 <= thr
+    double inv_res;
 };
 
 struct Pose { double x, y, th; };
@@ -58,28 +63,25 @@ __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i,
 // four attempts per call and a warp 128 attempts per iteration; only attempts that pass are evaluated in
 // full.  Results are identical to evaluating every attempt in order (tests: vs the oracle's plain loop).
 // ---------------------------------------------------------------------------------------------
-__device__ bool region_blocked(const MotionParams &p, double x, double y, double sn, double cs, double rho) {
-    const double dt = rho * p.s2, da = rho * p.s1;
-    const double t_lo = p.trans - dt, t_hi = p.trans + dt;
-    if (!(t_lo > 0.0) || !(da < 1.0)) return false;           // the sector bound needs t > 0 and a small spread
-    // oriented rectangle containing the sector: along the nominal heading u in [t_lo cos(da), t_hi],
-    // across it |v| <= t_hi sin(da); centre (ccx, ccy), half extents (hu, hv)
-    const double u_lo = t_lo * cos(da) - 1e-9, u_hi = t_hi + 1e-9;
-    const double hv = t_hi * sin(da) + 1e-9, hu = 0.5 * (u_hi - u_lo), um = 0.5 * (u_hi + u_lo);
+__device__ bool region_blocked(const MotionParams &p, double x, double y, double sn, double cs, int k) {
+    // oriented rectangle containing the sector of level k: along the nominal heading u in [u_lo, u_hi],
+    // across it |v| <= hv (all inflated by 1e-9 m on the host); centre (ccx, ccy), half extents (hu, hv)
+    const double u_lo = p.lv_ulo[k], u_hi = p.lv_uhi[k], hv = p.lv_hv[k];
+    const double hu = 0.5 * (u_hi - u_lo), um = 0.5 * (u_hi + u_lo);
     const double ccx = x + um * cs, ccy = y + um * sn;
     const double ax = fabs(cs), ay = fabs(sn);
     const double bx = hu * ax + hv * ay + 1e-9, by = hu * ay + hv * ax + 1e-9;     // its axis-aligned half box
-    // cells touched by the box (the cell index is monotone in the coordinate; expression of pu:390-391)
-    const long long mx0 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccx - bx, -p.ox), p.res));
-    const long long mx1 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccx + bx, -p.ox), p.res));
-    const long long my0 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccy - by, -p.oy), p.res));
-    const long long my1 = __double2ll_rz(__ddiv_rn(__dadd_rn(ccy + by, -p.oy), p.res));
-    if (mx0 < 1 || my0 < 1) return false;                             // int() truncation quirk at the map edge
+    // cells touched by the box: a conservative superset is enough, so multiply by 1/res (relative error
+    // 1e-16, far inside the 1e-9 m inflation) and widen by one ulp-ish margin instead of dividing
+    const double fx0 = (ccx - bx - p.ox) * p.inv_res - 1e-7, fx1 = (ccx + bx - p.ox) * p.inv_res + 1e-7;
+    const double fy0 = (ccy - by - p.oy) * p.inv_res - 1e-7, fy1 = (ccy + by - p.oy) * p.inv_res + 1e-7;
+    if (!(fx0 >= 1.0) || !(fy0 >= 1.0) || !(fx1 < 2.0e9) || !(fy1 < 2.0e9)) return false;   // int() quirk at the map edge
+    const int mx0 = (int)fx0, mx1 = (int)fx1, my0 = (int)fy0, my1 = (int)fy1;
     if ((mx1 - mx0 + 1) * (my1 - my0 + 1) > 36) return false;         // large region: no claim
     const double hc = 0.5 * p.res + 1e-9;                             // half cell, inflated
-    for (long long my = my0; my <= my1; ++my)
-        for (long long mx = mx0; mx <= mx1; ++mx) {
-            if (mx >= p.W || my >= p.H || p.occ[my * (long long)p.W + mx] != 0) continue;
+    for (int my = my0; my <= my1; ++my)
+        for (int mx = mx0; mx <= mx1; ++mx) {
+            if (mx >= p.W || my >= p.H || p.occ[(size_t)my * p.W + mx] != 0) continue;
             const double qx = p.ox + ((double)mx + 0.5) * p.res - ccx, qy = p.oy + ((double)my + 0.5) * p.res - ccy;
             const bool separated = fabs(qx) > bx + hc || fabs(qy) > by + hc ||
                                    fabs(qx * cs + qy * sn) > hu + hc * (ax + ay) ||
@@ -89,21 +91,21 @@ __device__ bool region_blocked(const MotionParams &p, double x, double y, double
     return true;
 }
 
-// Largest screening level whose sector is blocked -> threshold on (radius word + 1):
-// an attempt can only succeed if word + 1 <= T.  T = 2^32 (no screening) .. 0 (provably stuck).
+// Largest screening level whose sector is blocked -> threshold on (radius word + 1): an attempt can only
+// succeed if word + 1 <= T.  T = 2^32 (no screening) ... 0 (provably stuck: even R1 = 6.6604 stays blocked).
+// blocked(rho) is monotone (a larger sector contains the smaller ones), so test the top level first -- the
+// common outcome for a particle facing a wall -- and bisect otherwise.
 __device__ unsigned long long screening_threshold(const MotionParams &p, double x, double y, double th) {
-    const double levels[10] = {1.0, 2.0, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.6605};
+    if (p.n_levels == 0) return 1ull << 32;
     double sn, cs;
     sincos(th + p.rot1, &sn, &cs);
-    double rho_ok = 0.0;
-    for (int k = 0; k < 10; ++k) {
-        if (!region_blocked(p, x, y, sn, cs, levels[k])) break;
-        rho_ok = levels[k];
+    if (region_blocked(p, x, y, sn, cs, p.n_levels - 1)) return p.lv_thr[p.n_levels - 1];
+    int lo = -1, hi = p.n_levels - 1;          // blocked(lo) (or lo = -1), not blocked(hi)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (region_blocked(p, x, y, sn, cs, mid)) lo = mid; else hi = mid;
     }
-    if (rho_ok == 0.0) return 1ull << 32;
-    if (rho_ok > 6.66) return 0ull;        // R1 <= sqrt(-2 ln 2^-32) = 6.6604 < 6.6605: nothing can succeed
-    // R1 >= rho  <=>  u1 <= exp(-rho^2/2); keep a relative margin far above the fp64 error of log/sqrt
-    return (unsigned long long)(4294967296.0 * exp(-0.5 * rho_ok * rho_ok) * (1.0 + 1e-9)) + 2ull;
+    return lo < 0 ? (1ull << 32) : p.lv_thr[lo];
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -235,6 +237,24 @@ extern "C" int mcl_predict(mcl_handle *h, const double *d_x, const double *d_y, 
     p.seed = seed; p.step = step; p.first_index = first_index;
     p.normals = d_normals; p.A = A; p.max_attempts = max_attempts;
     p.xo = d_xo; p.yo = d_yo; p.tho = d_thetao; p.attempts = d_attempts;
+    // screening levels: every candidate with |z0|, |z1| <= rho has t in trans +- rho s2 and heading within
+    // +- rho s1 of theta + rot1.  Valid only while t stays positive and the spread small; levels are nested.
+    const double levels[10] = {1.0, 2.0, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.6605};
+    p.n_levels = 0;
+    p.inv_res = 1.0 / h->res;
+    for (int k = 0; k < 10 && !d_normals; ++k) {
+        const double rho = levels[k], dt = rho * p.s2, da = rho * p.s1;
+        const double t_lo = p.trans - dt, t_hi = p.trans + dt;
+        if (!(t_lo > 0.0) || !(da < 1.0)) break;
+        p.lv_ulo[k] = t_lo * cos(da) - 1e-9;
+        p.lv_uhi[k] = t_hi + 1e-9;
+        p.lv_hv[k] = t_hi * sin(da) + 1e-9;
+        // R1 >= rho  <=>  u1 <= exp(-rho^2/2); relative margin far above the fp64 error of log/sqrt.
+        // rho = 6.6605 exceeds the largest possible radius sqrt(-2 ln 2^-32) = 6.6604: nothing passes.
+        p.lv_thr[k] = rho > 6.66 ? 0ull
+                                 : (unsigned long long)(4294967296.0 * exp(-0.5 * rho * rho) * (1.0 + 1e-9)) + 2ull;
+        p.n_levels = k + 1;
+    }
     const int blocks = (int)((n + 255) / 256);
     k_motion<<<blocks, 256, 0, h->stream>>>(p);
     MCL_LAUNCH_CHECK(h);

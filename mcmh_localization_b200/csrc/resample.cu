@@ -88,18 +88,25 @@ __global__ void __launch_bounds__(256) k_wmax(const float *__restrict__ w, int64
         last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
         __threadfence();
         float t = 0.0f;
-        for (unsigned b = 0; b < gridDim.x; ++b) t = fmaxf(t, ((volatile float *)partials)[b]);
-        // scale = 2^(62 - ceil(log2 n_global) - e), 2^e > wmax   (oracle: orc_resample_scale)
-        int e = 0;
-        if (t > 0.0f) frexp((double)t, &e);
-        int lg = 0;
-        while (((int64_t)1 << lg) < n_global) ++lg;
-        out_scale[0] = ldexp(1.0, 62 - lg - e);
-        out_scale[1] = (double)t;
-        *counter = 0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t = fmaxf(t, ((volatile float *)partials)[b]);
+        t = warp_max(t);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < (int)(blockDim.x >> 5); ++k) t = fmaxf(t, sh[k]);
+            // scale = 2^(62 - ceil(log2 n_global) - e), 2^e > wmax   (oracle: orc_resample_scale)
+            int e = 0;
+            if (t > 0.0f) frexp((double)t, &e);
+            int lg = 0;
+            while (((int64_t)1 << lg) < n_global) ++lg;
+            out_scale[0] = ldexp(1.0, 62 - lg - e);
+            out_scale[1] = (double)t;
+            *counter = 0;
+        }
     }
 }
 
