@@ -48,6 +48,13 @@ struct mcl_handle {
     int32_t *d_win = nullptr;
     size_t win_bytes = 0;
     int lik_path = 0;            // 0 auto, 1 global, 2 smem window
+    // coded window for maps whose int32 window exceeds shared memory: one byte per cell indexing a
+    // table of the (<= 256) distinct values (the value depends only on dist, and an EDT on a grid takes
+    // few distinct values near walls: 85 on map_world, 242 on map_house)
+    bool coded = false;
+    uint8_t *d_win8 = nullptr;
+    int32_t *d_lut = nullptr;
+    size_t win8_bytes = 0;
 
     // scan (node:341-348): valid beams with r >= 0 first, then valid beams with r < 0
     bool scan_set = false;

@@ -34,6 +34,9 @@ struct LikParams {
     int W, H;
     const int32_t *logtab, *win;
     const float *dist;
+    const uint8_t *win8;       // coded window + table of distinct values (maps whose int32 window is too big)
+    const int32_t *lut;
+    uint32_t win8_bytes;
     int wx0, wy0, ww, wh;
     uint32_t win_bytes;
     double sigma_hit, z_hit, z_rand, max_range;
@@ -192,22 +195,36 @@ __device__ __forceinline__ int floor_to_int(double t) {   // exact floor(t) for 
 // Tunables (chosen by measurement, see profiles/): threads per CTA, particles per thread (the uniform beam
 // loads and loop overhead are shared), minimum CTAs per SM, and MIXED = take the y index with F2I (XU pipe)
 // instead of the magic add (FP64 pipe) to spread the conversions over two pipes.
-template <bool SMEM, int G1_THREADS, int G1_P, int MINB, bool MIXED>
+template <bool SMEM, int G1_THREADS, int G1_P, int MINB, bool MIXED, bool CODED = false>
 __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     int32_t *swin = reinterpret_cast<int32_t *>(smem + 16);
+    // CODED: [16 B barrier][table of distinct values replicated per lane: 256 x 32 int32][uint8 window]
+    int32_t *slut = reinterpret_cast<int32_t *>(smem + 16);
+    const uint8_t *swin8 = smem + 16 + 32768;
     const int nb = p.n_pos + p.n_neg;
+    const int lane = threadIdx.x & 31;
     if (SMEM) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, p.win_bytes);
-            bulk_g2s_chunked(reinterpret_cast<unsigned char *>(swin), reinterpret_cast<const unsigned char *>(p.win),
-                             p.win_bytes, bar);
+            if (CODED) {
+                mbar_expect_tx(bar, p.win8_bytes);
+                bulk_g2s_chunked(smem + 16 + 32768, p.win8, p.win8_bytes, bar);
+            } else {
+                mbar_expect_tx(bar, p.win_bytes);
+                bulk_g2s_chunked(reinterpret_cast<unsigned char *>(swin), reinterpret_cast<const unsigned char *>(p.win),
+                                 p.win_bytes, bar);
+            }
+        }
+        if (CODED) {   // lane-private copies of the value table: slut[code * 32 + lane] is always conflict-free
+            for (int e = threadIdx.x; e < 256 * 32; e += G1_THREADS) slut[e] = __ldg(p.lut + (e >> 5));
+            __syncthreads();
         }
         mbar_wait(bar, 0);
     }
+    auto fetch = [&](int cell) -> int { return CODED ? slut[(int)swin8[cell] * 32 + lane] : swin[cell]; };
     const int pw = p.ww + 2;
     const int cx = p.ww + 1, cy = p.wh + 1;
     const int ofx = 1 - p.wx0, ofy = 1 - p.wy0;
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
                     const int iy0 = __viaddmin_s32_relu(MIXED ? __double2int_rz(ty0) : floor_to_int(ty0), ofy, cy);
                     const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
                     const int iy1 = __viaddmin_s32_relu(MIXED ? __double2int_rz(ty1) : floor_to_int(ty1), ofy, cy);
-                    acc[q] += swin[iy0 * pw + ix0] + swin[iy1 * pw + ix1];      // two terms fit int32
+                    acc[q] += fetch(iy0 * pw + ix0) + fetch(iy1 * pw + ix1);      // two terms fit int32
                 }
             }
             if (j < p.n_pos) {
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
                     const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
                     const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
                     const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
-                    acc[q] += swin[iy0 * pw + ix0];
+                    acc[q] += fetch(iy0 * pw + ix0);
                 }
             }
         } else {
@@ -271,7 +288,7 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
                     int v;
                     if (SMEM) {
                         const int ix = min(max(mx + ofx, 0), cx), iy = min(max(my + ofy, 0), cy);
-                        v = swin[iy * pw + ix];
+                        v = fetch(iy * pw + ix);
                         v = inmap ? v : 0;                                             // pu:131-132
                     } else {
                         v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
@@ -370,6 +387,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     p.beams = h->d_beams_active; p.n_pos = h->n_pos; p.n_neg = h->n_neg;
     p.ox = h->ox; p.oy = h->oy; p.res = h->res; p.W = h->W; p.H = h->H;
     p.logtab = h->d_logtab; p.dist = h->d_dist; p.win = h->d_win;
+    p.win8 = h->d_win8; p.lut = h->d_lut; p.win8_bytes = (uint32_t)h->win8_bytes;
     p.wx0 = h->wx0; p.wy0 = h->wy0; p.ww = h->ww; p.wh = h->wh; p.win_bytes = (uint32_t)h->win_bytes;
     p.sigma_hit = h->sigma_hit; p.z_hit = h->z_hit; p.z_rand = h->z_rand; p.max_range = h->max_range;
     p.margin = h->rmax_cells + 2.0;
@@ -381,7 +399,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     if (smem_glob > smem_limit) return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: too many beams for shared memory");
     bool use_smem = smem_win <= smem_limit;
     if (h->lik_path == 1) use_smem = false;
-    if (h->lik_path == 2 && !use_smem)
+    if (h->lik_path == 2 && !use_smem && !h->coded)
         return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: free-space window does not fit in shared memory");
 
     int G = 1;
@@ -394,6 +412,8 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
             g_cbeams_src = (const void *)h->d_beams_active;
             g_cbeams_gen = h->scan_gen;
         }
+        if (!use_smem && h->coded && h->lik_path != 1)
+            return launch_lik_kernel(h, k_likelihood_g1<true, 512, 2, 1, false, true>, p, 16 + 32768 + h->win8_bytes, 1, 512, 2);
         static int variant = -1;
         if (variant < 0) { const char *e = getenv("MCL_LIK_VARIANT"); variant = e ? atoi(e) : 0; }
 #define G1_CASE(V, T, P, B, M)                                                                              \
@@ -409,7 +429,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
             G1_CASE(6, 256, 1, 4, true)
             G1_CASE(7, 256, 4, 2, false)
             default:
-            G1_CASE(0, 256, 2, 3, false)
+            G1_CASE(0, 256, 2, 4, false)
         }
 #undef G1_CASE
     }

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -65,7 +66,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     cudaFree(h->d_est18);
     if (h->ev_est) cudaEventDestroy(h->ev_est);
     cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
-    cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch);
+    cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch); cudaFree(h->d_win8); cudaFree(h->d_lut);
     cudaFreeHost(h->h_beams); cudaFreeHost(h->h_pinned);
     for (auto &p : h->lik_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete h;
@@ -221,6 +222,30 @@ int mcl_prepare_table(mcl_handle *h) {
     k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
         h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->c0);
     MCL_LAUNCH_CHECK(h);
+    // coded window (uint8 + table of distinct values) when the int32 window does not fit in shared memory
+    cudaFree(h->d_win8); cudaFree(h->d_lut);
+    h->d_win8 = nullptr; h->d_lut = nullptr; h->coded = false; h->win8_bytes = 0;
+    const size_t limit = (size_t)h->smem_optin;
+    if (16 + h->win_bytes > limit && (size_t)n + 16 + 32768 + 64 <= limit) {
+        std::vector<int32_t> win((size_t)n);
+        MCL_CUDA(h, cudaMemcpyAsync(win.data(), h->d_win, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+        std::vector<int32_t> uniq(win);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        if (uniq.size() <= 256) {
+            std::vector<uint8_t> codes((((size_t)n + 15) / 16) * 16, 0);
+            for (int i = 0; i < n; ++i)
+                codes[i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), win[i]) - uniq.begin());
+            uniq.resize(256, 0);
+            MCL_CUDA(h, cudaMalloc((void **)&h->d_win8, codes.size()));
+            MCL_CUDA(h, cudaMalloc((void **)&h->d_lut, 256 * sizeof(int32_t)));
+            MCL_CUDA(h, cudaMemcpy(h->d_win8, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+            MCL_CUDA(h, cudaMemcpy(h->d_lut, uniq.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
+            h->win8_bytes = codes.size();
+            h->coded = true;
+        }
+    }
     h->tab_dirty = false;
     return MCL_OK;
 }

@@ -137,6 +137,34 @@ def test_likelihood_full_size_properties(pu, oracle_map_world):
     assert lik_close(s_smem[sl], ref).all()
 
 
+def test_likelihood_house_coded_window_full_size(pu, oracle_map_house):
+    """map_house: the int32 free-space window (258 KB) exceeds shared memory, so large-N launches stage
+    a uint8-coded window + value table instead.  Must equal the global/L2 path bit-for-bit and the
+    oracle on a slice."""
+    import time
+    from oracle import clib
+    mp = oracle_map_house
+    g = golden("likelihood_map_house.npz")
+    n = 1_000_000
+    rs = np.random.RandomState(77)
+    free = np.flatnonzero(mp["map_data"] == 0)
+    cells = free[rs.randint(0, len(free), n)]
+    my, mx = np.divmod(cells, mp["width"])
+    parts = np.column_stack((mp["origin_np"][0] + (mx + rs.uniform(0, 1, n)) * mp["resolution"],
+                             mp["origin_np"][1] + (my + rs.uniform(0, 1, n)) * mp["resolution"],
+                             rs.uniform(-np.pi, np.pi, n)))
+    parts[:1000, :2] += rs.uniform(-6, 6, (1000, 2))          # some particles far outside free space / the map
+    gg = dict(scan=g["scan"], angles=g["angles"], particles=parts)
+    sensor = (P["sigma_hit"], P["z_hit"], P["z_rand"], P["max_range"], 1)
+    s_auto = _lik(pu, gg, mp, *sensor, path=2)      # shared memory required: only the coded window fits
+    s_glob = _lik(pu, gg, mp, *sensor, path=1)
+    assert np.array_equal(s_auto, s_glob)
+    sl = slice(0, 20_000)
+    ref = clib.compute_likelihoods(g["scan"], g["angles"], parts[sl], mp["distance_map"], mp["resolution"],
+                                   mp["origin_np"], mp["width"], mp["height"], *sensor)
+    assert lik_close(s_auto[sl], ref, rel=2e-6).all()
+
+
 # --------------------------------------------------------------------------- softmax (a2)
 def test_softmax_golden(pu):
     g = golden("mh_map_world.npz")
