@@ -136,6 +136,23 @@ int mcl_mh_accept(mcl_handle *h, const double *d_x, const double *d_y, const dou
                   double *d_xo, double *d_yo, double *d_thetao, float *d_weights_out,
                   uint8_t *d_accept);
 
+/* pu:282-330 motion_model_odometry_parallel: transition density p(cur | prev, delta) per particle
+ * (product of three Gaussians, pu:31-33), d_probs f64[n]; d_sum (nullable, device) receives the population
+ * sum; normalise != 0 divides by it when positive (pu:326-328).  Sharded callers pass normalise = 0,
+ * all-reduce the sum and call mcl_scale_by_sum. */
+int mcl_motion_density(mcl_handle *h, const double *d_px, const double *d_py, const double *d_ptheta,
+                       const double *d_cx, const double *d_cy, const double *d_ctheta, int64_t n,
+                       const double delta[3], double *d_probs, double *d_sum, int normalise);
+int mcl_scale_by_sum(mcl_handle *h, double *d_probs, int64_t n, const double *d_sum);
+/* pu:238-276 assym_mh_resampling (reference quirk kept: alpha = 1 unless log_den > 0). */
+int mcl_assym_mh_accept(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                        const double *d_px, const double *d_py, const double *d_ptheta,
+                        const float *d_likelihoods, const float *d_old_weights,
+                        const double *d_trans_forward, const double *d_trans_backward, int64_t n,
+                        const double *d_uniforms, uint64_t seed, uint64_t step, uint64_t first_index,
+                        double *d_xo, double *d_yo, double *d_thetao, float *d_weights_out,
+                        uint8_t *d_accept);
+
 /* pu:416-446 low_variance_resample_numba -> source index per output (d_idx[n_out], int32).
  * r is the single uniform draw in [0, 1/n_out) (see mcl_resample_offset). */
 int mcl_resample_indices(mcl_handle *h, const float *d_weights, int64_t n_in, int64_t n_out,
@@ -215,6 +232,11 @@ int mcl_filter_bind(mcl_handle *h, int64_t n, double *const x[3], double *const 
                     uint64_t seed, uint64_t first_index, int max_attempts);
 int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode, uint64_t seed,
                          uint64_t first_index, int64_t tick /* < 0: keep */);
+/* asymmetric MH (localization_mode containing "AMH", node:21): update() then runs node:424-439
+ * transition_probability + pu:238-276.  set_transition overrides the increments stored by predict
+ * (delta_b NULL = derive it with node:429-434's formula). */
+int mcl_filter_set_assym(mcl_handle *h, int assym);
+int mcl_filter_set_transition(mcl_handle *h, const double delta[3], const double delta_b[3]);
 /* roles = {particles, particles_prev, spare (indices into x/y/th), weights slot (0 = w_a)} */
 int mcl_filter_roles(mcl_handle *h, int roles[4], uint64_t *tick);
 /* for hosts that sequence the stages themselves (the sharded path interleaves collectives) */

@@ -42,6 +42,10 @@ SIGNATURES = {
     "mcl_compute_motion": (_i, [_pd, _pd, _pd]),
     "mcl_mh_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u64,
                            _vp, _vp, _vp, _vp, _vp]),
+    "mcl_motion_density": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _pd, _vp, _vp, _i]),
+    "mcl_scale_by_sum": (_i, [_vp, _vp, _i64, _vp]),
+    "mcl_assym_mh_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u64,
+                                 _vp, _vp, _vp, _vp, _vp]),
     "mcl_resample_indices": (_i, [_vp, _vp, _i64, _i64, _d, _i, _vp]),
     "mcl_weights_max": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_resample_scan": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
@@ -62,6 +66,8 @@ SIGNATURES = {
     "mcl_filter_bind": (_i, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _i, _i, _u64, _u64, _i]),
     "mcl_filter_configure": (_i, [_vp, _i, _i, _u64, _u64, _i64]),
+    "mcl_filter_set_assym": (_i, [_vp, _i]),
+    "mcl_filter_set_transition": (_i, [_vp, _pd, _pd]),
     "mcl_filter_roles": (_i, [_vp, _pi, C.POINTER(_u64)]),
     "mcl_filter_set_roles": (_i, [_vp, _pi, _u64]),
     "mcl_filter_predict": (_i, [_vp, _pd, _vp, _i]),

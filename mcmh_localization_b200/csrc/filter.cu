@@ -3,6 +3,7 @@
 // handle's stream (node:384-408 move_particles + node:294-338 lidar_callback).  The Python host
 // pays one ctypes call per step instead of ~15; buffer roles (particles / particles_prev / spare)
 // rotate inside the handle exactly like the node's copies at node:404-405, node:370 and node:490.
+#include <math.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -16,6 +17,12 @@ struct FilterState {
     int cur = 0, prev = 1, spare = 2, wslot = 0;
     int use_mh = 1, resample_mode = MCL_RESAMPLE_FIXED_POINT, max_attempts = 1000;
     uint64_t seed = 0, first_index = 0, tick = 0;
+    // asymmetric MH (node:365-367): last odometry increment, the reference's "backward" increment
+    // (node:429-434) and the two transition-density buffers
+    int assym = 0;
+    double delta[3] = {0, 0, 0}, delta_b[3] = {0, 0, 0};
+    double *tf = nullptr, *tb = nullptr;
+    int64_t t_cap = 0;
 };
 
 // one FilterState per handle, kept out of common.cuh: keyed by handle pointer
@@ -36,7 +43,34 @@ static FilterState *filter_of(mcl_handle *h, bool create) {
 
 void mcl_filter_forget(const mcl_handle *h) {
     std::lock_guard<std::mutex> lk(g_filters_mu);
+    auto it = g_filters.find(h);
+    if (it != g_filters.end()) { cudaFree(it->second.tf); cudaFree(it->second.tb); }
     g_filters.erase(h);
+}
+
+// node:429-434: the reference builds the backward increment as if (rot1, trans, rot2) were (dx, dy, dtheta)
+static void backward_delta(const double d[3], double out[3]) {
+    out[0] = -d[0] * cos(d[2]) - d[1] * sin(d[2]);
+    out[1] = d[0] * sin(d[2]) - d[1] * cos(d[2]);
+    out[2] = -d[2];
+}
+
+extern "C" int mcl_filter_set_assym(mcl_handle *h, int assym) {
+    if (!h) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_set_assym: no filter bound");
+    f->assym = assym ? 1 : 0;
+    return MCL_OK;
+}
+
+// delta_b == NULL: computed here with glibc cos/sin (the Python host passes NumPy's, to stay bit-exact)
+extern "C" int mcl_filter_set_transition(mcl_handle *h, const double delta[3], const double delta_b[3]) {
+    if (!h || !delta) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_set_transition: no filter bound");
+    memcpy(f->delta, delta, sizeof(f->delta));
+    if (delta_b) memcpy(f->delta_b, delta_b, sizeof(f->delta_b)); else backward_delta(delta, f->delta_b);
+    return MCL_OK;
 }
 
 extern "C" int mcl_filter_bind(mcl_handle *h, int64_t n, double *const x[3], double *const y[3], double *const th[3],
@@ -102,6 +136,8 @@ extern "C" int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode
 // node:397-405: particles_prop = motion(particles); particles_prev = particles; particles = particles_prop
 extern "C" int mcl_filter_predict(mcl_handle *h, const double delta[3], const double *d_normals, int A) {
     FILTER_OR_FAIL("mcl_filter_predict");
+    memcpy(f->delta, delta, sizeof(f->delta));
+    backward_delta(delta, f->delta_b);
     f->tick++;
     int rc = mcl_predict(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->n, delta, f->seed, f->tick, f->first_index,
                          d_normals, A, f->max_attempts, f->x[f->spare], f->y[f->spare], f->th[f->spare], nullptr);
@@ -127,6 +163,30 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
     rc = mcl_softmax(h, f->score_pre, f->n, f->w_pre, nullptr, nullptr);
     if (rc) return rc;
     f->tick++;
+    if (f->assym) {
+        // node:366-367: transition_probability() then assym_mh_resampling(prev, cur, w_post, w_pre, fwd, bwd)
+        if (f->t_cap < f->n) {
+            DeviceGuard guard(h->device);
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            cudaFree(f->tf); cudaFree(f->tb); f->tf = f->tb = nullptr; f->t_cap = 0;
+            MCL_CUDA(h, cudaMalloc((void **)&f->tf, (size_t)f->n * sizeof(double)));
+            MCL_CUDA(h, cudaMalloc((void **)&f->tb, (size_t)f->n * sizeof(double)));
+            f->t_cap = f->n;
+        }
+        rc = mcl_motion_density(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
+                                f->th[f->cur], f->n, f->delta, f->tf, nullptr, 1);
+        if (rc) return rc;
+        rc = mcl_motion_density(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->x[f->prev], f->y[f->prev],
+                                f->th[f->prev], f->n, f->delta_b, f->tb, nullptr, 1);
+        if (rc) return rc;
+        rc = mcl_assym_mh_accept(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
+                                 f->th[f->cur], f->w_post, f->w_pre, f->tf, f->tb, f->n, d_uniforms, f->seed,
+                                 f->tick, f->first_index, f->x[f->spare], f->y[f->spare], f->th[f->spare],
+                                 f->w[f->wslot], nullptr);
+        if (rc) return rc;
+        const int t = f->cur; f->cur = f->spare; f->spare = t;
+        return MCL_OK;
+    }
     // mh_resampling(particles_prev, particles, weights_post, weights_pre)  (node:363)
     rc = mcl_mh_accept(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur], f->th[f->cur],
                        f->w_post, f->w_pre, f->n, d_uniforms, f->seed, f->tick, f->first_index, f->x[f->spare],

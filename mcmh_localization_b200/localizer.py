@@ -71,6 +71,7 @@ class Localizer:
         self.h.call("mcl_set_motion", self.alpha.ctypes.data_as(C.POINTER(C.c_float)))
         if self.n:
             self.h.call("mcl_filter_configure", int(self.use_mh), self.resample_mode, self.seed, self.first_index, -1)
+            self.h.call("mcl_filter_set_assym", int(self.assym))
 
     def load_map(self, occ, resolution=None, origin_xy=None):
         """occ: (H,W) int8 OccupancyGrid payload, or a GridMap (maps.load_map_yaml / map_from_occupancy)."""
@@ -102,6 +103,7 @@ class Localizer:
         self.h.call("mcl_filter_bind", n, arr(0), arr(1), arr(2), _ptr(self.score_pre), _ptr(self.score_post),
                     _ptr(self.w_pre), _ptr(self.w_post), _ptr(self.wbuf[0]), _ptr(self.wbuf[1]), _ptr(self.idx),
                     int(self.use_mh), self.resample_mode, self.seed, self.first_index, self.max_attempts)
+        self.h.call("mcl_filter_set_assym", int(self.assym))
 
     def _roles(self):
         r = (C.c_int * 4)()
@@ -197,6 +199,7 @@ class Localizer:
                     z = z.to(self.device)
                     zp, A = _ptr(z), int(z.shape[1])
                 self.h.call("mcl_filter_predict", _dbl3(self.delta), zp, A)
+                self._push_transition()
             self.last_odom = cur_odom
 
     # ------------------------------------------------------------------ update (lidar_callback)
@@ -235,11 +238,18 @@ class Localizer:
             self._bind_stream()
             self.h.call("mcl_filter_estimate", _ptr(out18), None)
 
+    def _push_transition(self):
+        """node:429-434 backward increment with the node's own NumPy calls (bit-exact), for AMH modes."""
+        if self.assym:
+            dx, dy, dth = self.delta
+            db = (-dx * np.cos(dth) - dy * np.sin(dth), dx * np.sin(dth) - dy * np.cos(dth), -dth)
+            self.h.call("mcl_filter_set_transition", _dbl3(self.delta), _dbl3(db))
+
     def _update_core(self, uniforms=None):
-        if self.assym or self.use_adaptive:
+        if self.use_adaptive:
             raise NotImplementedError(
-                "localization_mode %r: asymmetric-MH / KLD-adaptive modes are SURVEY 8(f) 'next' rows; "
-                "use MCL or MHMCL" % self.params["localization_mode"])
+                "localization_mode %r: the KLD-adaptive (AMCL) modes are a SURVEY 8(f) 'next' row; "
+                "use MCL, MHMCL or AMHMCL" % self.params["localization_mode"])
         up = None
         if uniforms is not None:
             u = uniforms if torch.is_tensor(uniforms) else torch.from_numpy(
@@ -275,9 +285,13 @@ class Localizer:
                 d = _dbl3(self.delta)
             self.last_odom = cur_odom
             self.set_scan(ranges, angle_min, angle_max, angles)
-            if self.assym or self.use_adaptive:
+            if self.use_adaptive:
                 raise NotImplementedError("localization_mode %r not supported yet" % self.params["localization_mode"])
             out = (C.c_double * 16)()
+            if self.assym and d is not None:       # AMH: predict first so the NumPy backward increment can be pushed
+                self.h.call("mcl_filter_predict", d, None, 0)
+                self._push_transition()
+                d = None
             self.h.call("mcl_filter_step", d, -1, None, out)
         return assemble_estimate(list(out))
 

@@ -159,6 +159,39 @@ def mh_resampling(particles, proposed_particles, likelihoods, old_weights, unifo
     return out + (acc.cpu().numpy(),) if return_accept else out
 
 
+def motion_model_odometry_parallel(particles_prev, particles_curr, delta, alpha):
+    """pu:282-330 -> (N,) float64 transition densities, normalised by their population sum."""
+    c = _ctx()
+    al = np.ascontiguousarray(alpha, dtype=np.float32)
+    c.h.call("mcl_set_motion", al.ctypes.data_as(_pf))
+    px, py, pt = c.soa(particles_prev)
+    cx, cy, ct = c.soa(particles_curr)
+    n = px.shape[0]
+    probs = torch.empty(n, dtype=torch.float64, device=c.device)
+    d = (C.c_double * 3)(float(delta[0]), float(delta[1]), float(delta[2]))
+    c.h.call("mcl_motion_density", _p(px), _p(py), _p(pt), _p(cx), _p(cy), _p(ct), n, d, _p(probs), None, 1)
+    return probs.cpu().numpy()
+
+
+def assym_mh_resampling(particles, proposed_particles, likelihoods, old_weights, trans_forward, trans_backward,
+                        uniforms=None, return_accept=False):
+    """pu:238-276 -> (new_particles, new_weights); the reference's always-accept quirk included."""
+    c = _ctx()
+    n = len(particles)
+    x, y, t = c.soa(particles)
+    px, py, pt = c.soa(proposed_particles)
+    lk, ow = _dev(c, likelihoods, np.float32), _dev(c, old_weights, np.float32)
+    tf, tb = _dev(c, trans_forward, np.float64), _dev(c, trans_backward, np.float64)
+    u = _dev(c, uniforms, np.float64) if uniforms is not None else None
+    xo, yo, to = (torch.empty_like(x) for _ in range(3))
+    wo = torch.empty_like(lk)
+    acc = torch.empty(n, dtype=torch.uint8, device=c.device)
+    c.h.call("mcl_assym_mh_accept", _p(x), _p(y), _p(t), _p(px), _p(py), _p(pt), _p(lk), _p(ow), _p(tf), _p(tb), n,
+             _p(u), _state["seed"], _tick(), 0, _p(xo), _p(yo), _p(to), _p(wo), _p(acc))
+    out = (c.aos(xo, yo, to), wo.cpu().numpy())
+    return out + (acc.cpu().numpy(),) if return_accept else out
+
+
 def apply_motion_model_parallel(particles, delta, alpha, map_data, map_resolution, origin_x, origin_y,
                                 width, height, normals=None, return_attempts=False, max_attempts=1000):
     """pu:332-363 -> (N,3) f64 proposed particles.  normals: optional injected (N, A, 3) draws."""

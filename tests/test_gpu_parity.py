@@ -278,6 +278,51 @@ def test_mh_philox_vs_oracle(pu, orc):
     assert np.array_equal(acc, racc) and np.array_equal(newp, rp) and np.array_equal(neww, rw)
 
 
+# --------------------------------------------------------------------------- asymmetric MH (a6-a8)
+def test_transition_density_and_assym_mh_golden(pu):
+    g = golden("mh_map_world.npz")
+    tf_ = pu.motion_model_odometry_parallel(g["prev"], g["cur"], g["amh_delta"], g["amh_alpha"])
+    tb_ = pu.motion_model_odometry_parallel(g["cur"], g["prev"], -g["amh_delta"], g["amh_alpha"])
+    assert tf_.dtype == np.float64
+    np.testing.assert_allclose(tf_, g["amh_tf"], rtol=1e-11, atol=0)
+    np.testing.assert_allclose(tb_, g["amh_tb"], rtol=1e-11, atol=0)
+    assert abs(tf_.sum() - 1.0) < 1e-12
+    u = np.random.RandomState(int(g["amh_seed"])).random_sample(len(tf_))
+    newp, neww, acc = pu.assym_mh_resampling(g["prev"], g["cur"], g["w_post"], g["w_pre"], g["amh_tf"], g["amh_tb"],
+                                             uniforms=u, return_accept=True)
+    assert np.array_equal(newp, g["amh_particles"]) and np.array_equal(neww, g["amh_weights"])
+    assert acc.all()
+
+
+def test_localizer_amhmcl_step_matches_reference_filter():
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from oracle import node_glue as ng
+    g = golden("filter_run_map_world.npz")
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    mp = ng.load_map(gm.occ, gm.resolution, gm.origin_x, gm.origin_y)
+    n = int(g["n"])
+    loc = Localizer(params=P, mode="AMHMCL", seed=21)
+    loc.load_map(gm)
+    loc.set_particles(g["particles0"])
+    f = ng.ReferenceFilter(mp, P, g["particles0"], mode="AMHMCL")
+    for k in range(3):
+        loc.predict(g["odoms"][k])
+        f.move_particles(g["odoms"][k], seed=21, step=loc.tick)
+        u = np.random.RandomState(k).random_sample(n)
+        loc.update(g["scans"][k], angles=g["angles"], uniforms=u)
+        w_ref = f.update(g["scans"][k], g["angles"], uniforms=u)
+        assert np.abs(loc.particles() - f.particles).max() < 1e-12
+        np.testing.assert_allclose(loc.weights(), w_ref, rtol=2e-6, atol=0)
+        r = (k + 0.5) / (3.0 * n)
+        loc.set_weights(w_ref)
+        loc.resample(r=r); f.resample(r)
+        assert np.abs(loc.particles() - f.particles).max() < 1e-12
+
+
 # --------------------------------------------------------------------------- resampling (a9)
 def test_resample_reference_mode_golden_bitexact(pu):
     g = golden("resample.npz")
