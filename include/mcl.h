@@ -243,6 +243,11 @@ int mcl_filter_roles(mcl_handle *h, int roles[4], uint64_t *tick);
 int mcl_filter_set_roles(mcl_handle *h, const int roles[4], uint64_t tick);
 int mcl_filter_predict(mcl_handle *h, const double delta[3], const double *d_normals, int A);   /* node:384-408 */
 int mcl_filter_update(mcl_handle *h, const double *d_uniforms);                                /* node:296-322 */
+/* update() with `iters` Metropolis-Hastings iterations per scan, one chain per particle (BASELINE
+ * config 4): chain_0 = particles_prev, every iteration proposes a fresh motion sample of particles_prev
+ * (pu:332-363), softmaxes proposal and chain scores separately (node:254-270) and accepts with pu:208-236;
+ * iters = 1 is exactly mcl_filter_update in MHMCL mode.  Uses the increment stored by the last predict. */
+int mcl_filter_update_chain(mcl_handle *h, int iters);
 int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]);                   /* node:586-597 */
 int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);                       /* node:488-492 */
 /* odom + scan -> predict (delta != NULL), update on pre-staged scan `scan_slot` (or the current scan

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mcl_filter_set_roles": (_i, [_vp, _pi, _u64]),
     "mcl_filter_predict": (_i, [_vp, _pd, _vp, _i]),
     "mcl_filter_update": (_i, [_vp, _vp]),
+    "mcl_filter_update_chain": (_i, [_vp, _i]),
     "mcl_filter_estimate": (_i, [_vp, _vp, _pd]),
     "mcl_filter_resample": (_i, [_vp, _d]),
     "mcl_filter_step": (_i, [_vp, _pd, _i, _vp, _pd]),

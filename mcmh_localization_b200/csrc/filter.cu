@@ -6,6 +6,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 struct FilterState {
@@ -193,6 +195,70 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
                        f->y[f->spare], f->th[f->spare], f->w[f->wslot], nullptr);
     if (rc) return rc;
     const int t = f->cur; f->cur = f->spare; f->spare = t;     // self.particles = mh_particles (node:370)
+    return MCL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MH refinement chain (BASELINE config 4: k MH iterations per scan, one chain per particle).
+// Composition of reference primitives (SURVEY 8(a) "MH-chain"): chain_0 = particles_prev; iteration i
+// proposes prop_i = motion(particles_prev, delta) with fresh noise (pu:332-363), weighs proposal and chain
+// by two separately normalised softmaxes (node:254-270) and accepts with pu:208-236.  Iteration 1 is exactly
+// the reference's single accept (the proposal is the predict() output).  The chain's scores are carried
+// (score_chain = accepted ? score_prop : score_chain), which equals re-evaluating compute_likelihoods on
+// the chain because the likelihood is a deterministic function of the pose.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_chain_accept(double *cx, double *cy, double *ct, const double *px, const double *py, const double *pt,
+                               const float *__restrict__ w_prop, const float *__restrict__ w_chain,
+                               float *score_chain, const float *__restrict__ score_prop, int64_t n, uint64_t seed,
+                               uint64_t step, uint64_t first_index, double *ox, double *oy, double *ot, float *w_out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float p_old = w_chain[i], p_new = w_prop[i];
+        double alpha = 1.0;
+        if (p_old > 0.f) {
+            const double q = (double)__fdiv_rn(p_new, p_old);
+            alpha = (q < 1.0) ? q : 1.0;
+        }
+        const uint4 o = philox_draw4(seed, step, first_index + (uint64_t)i, 0u, MCL_STREAM_MH);
+        const bool acc = u53_from(o.x, o.y) < alpha;
+        const double nx = acc ? px[i] : cx[i], ny = acc ? py[i] : cy[i], nt = acc ? pt[i] : ct[i];
+        ox[i] = nx; oy[i] = ny; ot[i] = nt;
+        w_out[i] = acc ? p_new : p_old;
+        if (acc) score_chain[i] = score_prop[i];
+    }
+}
+
+extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
+    FILTER_OR_FAIL("mcl_filter_update_chain");
+    if (iters < 1) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_update_chain: iters < 1");
+    if (!f->use_mh || f->assym) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_update_chain: needs the symmetric MH mode");
+    DeviceGuard guard(h->device);
+    const int blocks = (int)std::min<int64_t>((f->n + 255) / 256, (int64_t)h->sm_count * 16);
+    // roles during the chain: prev = particles_prev (fixed), prop = cur buffer, chain = spare buffer
+    const int prev = f->prev, prop = f->cur, chain = f->spare;
+    float *score_chain = f->score_pre, *score_prop = f->score_post;
+    int rc = mcl_likelihood(h, f->x[prev], f->y[prev], f->th[prev], f->n, score_chain);       // chain_0 = particles_prev
+    if (rc) return rc;
+    for (int it = 0; it < iters; ++it) {
+        if (it > 0) {   // fresh proposal from particles_prev
+            f->tick++;
+            rc = mcl_predict(h, f->x[prev], f->y[prev], f->th[prev], f->n, f->delta, f->seed, f->tick, f->first_index,
+                             nullptr, 0, f->max_attempts, f->x[prop], f->y[prop], f->th[prop], nullptr);
+            if (rc) return rc;
+        }
+        rc = mcl_likelihood(h, f->x[prop], f->y[prop], f->th[prop], f->n, score_prop);
+        if (rc) return rc;
+        rc = mcl_softmax(h, score_prop, f->n, f->w_post, nullptr, nullptr);
+        if (rc) return rc;
+        rc = mcl_softmax(h, score_chain, f->n, f->w_pre, nullptr, nullptr);
+        if (rc) return rc;
+        f->tick++;
+        const int src = it == 0 ? prev : chain;       // iteration 1 reads particles_prev and writes the chain buffer
+        k_chain_accept<<<blocks, 256, 0, h->stream>>>(f->x[src], f->y[src], f->th[src], f->x[prop], f->y[prop], f->th[prop],
+                                                      f->w_post, f->w_pre, score_chain, score_prop, f->n, f->seed, f->tick,
+                                                      f->first_index, f->x[chain], f->y[chain], f->th[chain], f->w[f->wslot]);
+        MCL_LAUNCH_CHECK(h);
+    }
+    f->cur = chain; f->spare = prop;                  // self.particles = chain
     return MCL_OK;
 }
 

@@ -217,6 +217,15 @@ class Localizer:
             self.set_scan(ranges, angle_min, angle_max, angles)
             self._update_core(uniforms)
 
+    def update_chain(self, ranges, angle_min=None, angle_max=None, angles=None, iters=32):
+        """update() with `iters` MH iterations per scan (BASELINE config 4); iters=1 == update() in MHMCL."""
+        with self._lock:
+            if ranges is not None:
+                self.set_scan(ranges, angle_min, angle_max, angles)
+            else:
+                self._bind_stream()
+            self.h.call("mcl_filter_update_chain", int(iters))
+
     def stage_scans(self, ranges_km, angles):
         """Pre-stage K scans on the device (bag replay / device-resident benchmark inputs)."""
         r = np.ascontiguousarray(ranges_km, dtype=np.float32)

@@ -323,6 +323,55 @@ def test_localizer_amhmcl_step_matches_reference_filter():
         assert np.abs(loc.particles() - f.particles).max() < 1e-12
 
 
+def test_mh_chain_equals_composition_of_reference_primitives():
+    """BASELINE config 4 semantics: k MH iterations per scan = the oracle's primitives composed in a
+    Python loop with the same Philox draws; k = 1 equals the plain MHMCL update."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from oracle import clib, node_glue as ng
+    g = golden("filter_run_map_world.npz")
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    mp = ng.load_map(gm.occ, gm.resolution, gm.origin_x, gm.origin_y)
+    alpha = np.array([P["alpha1"], P["alpha2"], P["alpha3"], P["alpha4"]], dtype=np.float32)
+    lik = lambda p, scan: clib.compute_likelihoods(scan, g["angles"], p, mp["distance_map"], mp["resolution"],
+                                                   mp["origin_np"], mp["width"], mp["height"], P["sigma_hit"],
+                                                   P["z_hit"], P["z_rand"], P["max_range"], 1)
+    for iters in (1, 5):
+        loc = Localizer(params=P, mode="MHMCL", seed=31)
+        loc.load_map(gm)
+        loc.set_particles(g["particles0"])
+        loc.predict(g["odoms"][0]); loc.predict(g["odoms"][1])
+        prev, prop = loc.particles_prev(), loc.particles()
+        tick = loc.tick
+        loc.update_chain(g["scans"][1], angles=g["angles"], iters=iters)
+        chain, w = prev.copy(), None
+        for it in range(iters):
+            if it > 0:
+                tick += 1
+                prop = clib.apply_motion_model_parallel(prev, loc.delta, alpha, mp["map_data"], mp["resolution"],
+                                                        mp["origin_np"][0], mp["origin_np"][1], mp["width"],
+                                                        mp["height"], seed=31, step=tick)
+            w_prop = ng.convert_scores(lik(prop, g["scans"][1]))
+            w_chain = ng.convert_scores(lik(chain, g["scans"][1]))
+            tick += 1
+            chain, w = clib.mh_resampling(chain, prop, w_prop, w_chain, seed=31, step=tick)
+        assert loc.tick == tick
+        same = np.isclose(loc.particles(), chain, rtol=0, atol=1e-12).all(axis=1)
+        assert same.mean() >= 0.998, (iters, same.mean())
+        np.testing.assert_allclose(loc.weights()[same], w[same], rtol=3e-6, atol=0)
+    # k = 1 is the plain update
+    a = Localizer(params=P, mode="MHMCL", seed=31); a.load_map(gm); a.set_particles(g["particles0"])
+    b = Localizer(params=P, mode="MHMCL", seed=31); b.load_map(gm); b.set_particles(g["particles0"])
+    for loc_ in (a, b):
+        loc_.predict(g["odoms"][0]); loc_.predict(g["odoms"][1])
+    a.update(g["scans"][1], angles=g["angles"])
+    b.update_chain(g["scans"][1], angles=g["angles"], iters=1)
+    assert np.array_equal(a.particles(), b.particles()) and np.array_equal(a.weights(), b.weights())
+
+
 # --------------------------------------------------------------------------- resampling (a9)
 def test_resample_reference_mode_golden_bitexact(pu):
     g = golden("resample.npz")
