@@ -108,6 +108,9 @@ int mcl_softmax_max(mcl_handle *h, const float *d_score, int64_t n, double *d_st
 int mcl_softmax_sumexp(mcl_handle *h, const float *d_score, int64_t n, double *d_stats);
 int mcl_softmax_weights(mcl_handle *h, const float *d_score, int64_t n, const double *d_stats,
                         float *d_weights);
+/* node:276-278 update_acml_weights: d_w /= sum(d_w) (f32 divide by the f32-rounded exact sum);
+ * h_out (nullable) = {sum before, mean of the normalised weights (node:284)}.  Blocking if h_out. */
+int mcl_weights_normalize(mcl_handle *h, float *d_weights, int64_t n, double h_out[2]);
 /* blocking read of the two doubles written by mcl_softmax */
 int mcl_softmax_stats(mcl_handle *h, const float *d_score, int64_t n, double h_stats[2]);
 
@@ -169,6 +172,17 @@ int mcl_resample_scan(mcl_handle *h, const float *d_weights, int64_t n_in, const
                       int64_t n_global, uint64_t *d_total);
 int mcl_resample_search(mcl_handle *h, int64_t n_in, uint64_t offset, uint64_t grand_total, int64_t m0,
                         int64_t n_out_local, double r, int64_t n_out_global, int32_t *d_idx);
+/* pu:529-591 kld_sampling_amcl: KLD-adaptive systematic resampling with Gaussian jitter.
+ * weights are used as given (node:276-278 normalises them first).  r in [0, 1/max_samples).
+ * d_normals != NULL: injected standard normals (max_samples, 3); NULL: Philox(seed, step, sample index).
+ * mode: MCL_RESAMPLE_REFERENCE_F32 (sequential f32 running sum, bit-exact) or MCL_RESAMPLE_FIXED_POINT.
+ * Outputs hold max_samples poses (f32-rounded like the reference's buffer); *h_count = how many are valid.
+ * Blocking (the caller needs the count). */
+int mcl_kld_resample(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                     const float *d_weights, int64_t n_in, int64_t max_samples, int64_t min_particles,
+                     double bin_size_xy, double bin_size_theta, double epsilon, double z, double r,
+                     const double *d_normals, uint64_t seed, uint64_t step, int mode, double *d_xo,
+                     double *d_yo, double *d_thetao, int64_t *h_count);
 /* r = 0 + (1/n_out - 0) * u53(Philox(seed, step, 0, RESAMPLE))  (np.random.uniform(0, 1/N)) */
 double mcl_resample_offset(uint64_t seed, uint64_t step, int64_t n_out);
 /* new_particles[m] = particles[idx[m]] (pu:445), SoA gather; outputs must not alias inputs. */
@@ -238,6 +252,7 @@ int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode, uint64_t 
 int mcl_filter_set_assym(mcl_handle *h, int assym);
 int mcl_filter_set_transition(mcl_handle *h, const double delta[3], const double delta_b[3]);
 /* roles = {particles, particles_prev, spare (indices into x/y/th), weights slot (0 = w_a)} */
+int mcl_filter_set_n(mcl_handle *h, int64_t n);   /* KLD-adaptive modes: n changes, buffers keep capacity */
 int mcl_filter_roles(mcl_handle *h, int roles[4], uint64_t *tick);
 /* for hosts that sequence the stages themselves (the sharded path interleaves collectives) */
 int mcl_filter_set_roles(mcl_handle *h, const int roles[4], uint64_t tick);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mcl_softmax_max": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_softmax_sumexp": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_softmax_weights": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "mcl_weights_normalize": (_i, [_vp, _vp, _i64, _pd]),
     "mcl_softmax_stats": (_i, [_vp, _vp, _i64, _pd]),
     "mcl_predict": (_i, [_vp, _vp, _vp, _vp, _i64, _pd, _u64, _u64, _u64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mcl_compute_motion": (_i, [_pd, _pd, _pd]),
@@ -50,6 +51,8 @@ SIGNATURES = {
     "mcl_weights_max": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_resample_scan": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "mcl_resample_search": (_i, [_vp, _i64, _u64, _u64, _i64, _i64, _d, _i64, _vp]),
+    "mcl_kld_resample": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _d, _d, _d, _d, _d, _vp, _u64, _u64, _i,
+                              _vp, _vp, _vp, C.POINTER(_i64)]),
     "mcl_resample_offset": (_d, [_u64, _u64, _i64]),
     "mcl_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mcl_estimate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _pd]),
@@ -68,6 +71,7 @@ SIGNATURES = {
     "mcl_filter_configure": (_i, [_vp, _i, _i, _u64, _u64, _i64]),
     "mcl_filter_set_assym": (_i, [_vp, _i]),
     "mcl_filter_set_transition": (_i, [_vp, _pd, _pd]),
+    "mcl_filter_set_n": (_i, [_vp, _i64]),
     "mcl_filter_roles": (_i, [_vp, _pi, C.POINTER(_u64)]),
     "mcl_filter_set_roles": (_i, [_vp, _pi, _u64]),
     "mcl_filter_predict": (_i, [_vp, _pd, _vp, _i]),

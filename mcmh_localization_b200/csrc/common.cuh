@@ -76,6 +76,8 @@ struct mcl_handle {
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     double *h_pinned = nullptr;  // 64 doubles, pinned, for blocking scalar reads
+    void *d_kld = nullptr;       // KLD-sampling work buffers (kld.cu)
+    size_t kld_bytes = 0;
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;
 
@@ -90,6 +92,7 @@ int mcl_fail(mcl_handle *h, int code, const std::string &msg);
 int mcl_ensure_scratch(mcl_handle *h, size_t bytes);
 int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
 void mcl_filter_forget(const mcl_handle *h);
+int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c);
 
 #define MCL_CUDA(h, expr)                                                                   \
     do {                                                                                    \

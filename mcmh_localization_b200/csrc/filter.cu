@@ -120,6 +120,16 @@ extern "C" int mcl_filter_set_roles(mcl_handle *h, const int roles[4], uint64_t 
     return MCL_OK;
 }
 
+// KLD-adaptive modes change the particle count every scan (node:496-527); the buffers keep their capacity
+extern "C" int mcl_filter_set_n(mcl_handle *h, int64_t n) {
+    if (!h) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_set_n: no filter bound");
+    if (n <= 0) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_set_n: n <= 0");
+    f->n = n;
+    return MCL_OK;
+}
+
 extern "C" int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode, uint64_t seed, uint64_t first_index,
                                     int64_t tick /* < 0: keep */) {
     if (!h) return MCL_ERR_ARG;

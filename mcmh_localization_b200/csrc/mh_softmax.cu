@@ -268,3 +268,63 @@ extern "C" int mcl_mh_accept(mcl_handle *h, const double *d_x, const double *d_y
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }
+
+// node:276-278 update_acml_weights: weights = weights / np.sum(weights).  The sum is taken in 2^-40 fixed
+// point (exact, decomposition-independent) and rounded to f32 like NumPy's f32 sum; h_out = {sum before,
+// mean of the normalised weights (node:284 w_avg)}.  Blocking.
+__global__ void __launch_bounds__(RED_THREADS) k_wsum_fixed(const float *__restrict__ w, int64_t n, RedScratch rs,
+                                                            double *out) {
+    __shared__ unsigned long long shq[32];
+    __shared__ bool last;
+    unsigned long long acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = __dmul_rn((double)w[i], SOFTMAX_FIX);
+        acc += v > 0.0 ? __double2ull_rz(v) : 0ull;
+    }
+    acc = block_sum_u64(acc, shq);
+    if (threadIdx.x == 0) {
+        ((unsigned long long *)rs.partials)[blockIdx.x] = acc;
+        __threadfence();
+        last = atomicAdd(rs.counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        unsigned long long t = 0;
+        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += ((volatile unsigned long long *)rs.partials)[b];
+        t = block_sum_u64(t, shq);
+        if (threadIdx.x == 0) { out[0] = (double)t / SOFTMAX_FIX; *rs.counter = 0; }
+    }
+}
+__global__ void k_wdiv(float *w, int64_t n, const double *sum) {
+    const float s = (float)sum[0];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        w[i] = __fdiv_rn(w[i], s);
+}
+
+extern "C" int mcl_weights_normalize(mcl_handle *h, float *d_w, int64_t n, double h_out[2]) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_w) return mcl_fail(h, MCL_ERR_ARG, "mcl_weights_normalize: bad argument");
+    DeviceGuard guard(h->device);
+    const int nb = red_blocks(h, n);
+    int rc = mcl_ensure_scratch(h, 128 + sizeof(double) * (size_t)nb + 64);
+    if (rc) return rc;
+    RedScratch rs;
+    rs.counter = (unsigned *)h->d_scratch;
+    rs.partials = (double *)((char *)h->d_scratch + 64);
+    double *out = (double *)((char *)h->d_scratch + 64 + sizeof(double) * (size_t)nb);
+    MCL_CUDA(h, cudaMemsetAsync(rs.counter, 0, sizeof(unsigned), h->stream));
+    k_wsum_fixed<<<nb, RED_THREADS, 0, h->stream>>>(d_w, n, rs, out);
+    MCL_LAUNCH_CHECK(h);
+    k_wdiv<<<nb, RED_THREADS, 0, h->stream>>>(d_w, n, out);
+    MCL_LAUNCH_CHECK(h);
+    k_wsum_fixed<<<nb, RED_THREADS, 0, h->stream>>>(d_w, n, rs, out + 1);
+    MCL_LAUNCH_CHECK(h);
+    if (h_out) {
+        MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+        h_out[0] = h->h_pinned[0];
+        h_out[1] = h->h_pinned[1] / (double)n;
+    }
+    return MCL_OK;
+}

@@ -30,9 +30,10 @@ __device__ float seq_sum_f32_warp(const float *__restrict__ w, int64_t n) {
     return s;
 }
 
-__global__ void __launch_bounds__(32) k_cumsum_ref_f32(const float *__restrict__ w, int64_t n, float *__restrict__ c_out) {
+__global__ void __launch_bounds__(32) k_cumsum_ref_f32(const float *__restrict__ w, int64_t n, float *__restrict__ c_out,
+                                                       int normalise) {
     const int lane = threadIdx.x & 31;
-    const float sum = seq_sum_f32_warp(w, n);                 // pu:430  np.sum(weights)
+    const float sum = normalise ? seq_sum_f32_warp(w, n) : 1.0f;   // pu:430  np.sum(weights); x / 1.0f == x
     float c = 0.0f;                                           // 0 + wn[0] == wn[0]  (pu:436)
     for (int64_t base = 0; base < n; base += 32) {
         const bool in = base + lane < n;
@@ -234,7 +235,7 @@ extern "C" int mcl_resample_indices(mcl_handle *h, const float *d_w, int64_t n_i
         int rc = mcl_ensure_scratch(h, sizeof(float) * (size_t)n_in);
         if (rc) return rc;
         float *c = (float *)h->d_scratch;
-        k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n_in, c);
+        k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n_in, c, 1);
         MCL_LAUNCH_CHECK(h);
         k_search_ref_f32<<<sblocks, 256, 0, h->stream>>>(c, limit, n_out, r, step, d_idx);
         MCL_LAUNCH_CHECK(h);
@@ -354,6 +355,13 @@ extern "C" int mcl_resample_search(mcl_handle *h, int64_t n_in, uint64_t offset,
     const int sblocks = (int)std::min<int64_t>((n_out_local + 255) / 256, (int64_t)h->sm_count * 16);
     k_search_fixed<<<sblocks, 256, 0, h->stream>>>(C, n_in - 1, m0, n_out_local, r, 1.0 / (double)n_out_global, nullptr,
                                                    grand_total, offset, d_idx);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// sequential f32 running sum of the weights as given (pu:555-563 kld_sampling_amcl does not renormalise)
+int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c) {
+    k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n, d_c, 0);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }

@@ -53,6 +53,10 @@ class Localizer:
         self.last_odom = None
         self.delta = (0.0, 0.0, 0.0)
         self.sets = None
+        self.w_slow = 1e-3                 # node:86-87
+        self.w_fast = 1e-3
+        self.num_particles = 0             # node:26 / node:520 (lags one scan behind in the KLD modes)
+        self.capacity = 0
         self.set_params(params or {}, mode=mode)
 
     # ------------------------------------------------------------------ configuration
@@ -99,6 +103,8 @@ class Localizer:
         self.idx = torch.empty(n, dtype=torch.int32, device=self.device)
         self.est18 = torch.zeros(18, dtype=torch.float64, device=self.device)
         self.n = n
+        self.capacity = n
+        self.num_particles = n
         arr = lambda k: (C.c_void_p * 3)(*[self.sets[j][k].data_ptr() for j in range(3)])
         self.h.call("mcl_filter_bind", n, arr(0), arr(1), arr(2), _ptr(self.score_pre), _ptr(self.score_post),
                     _ptr(self.w_pre), _ptr(self.w_post), _ptr(self.wbuf[0]), _ptr(self.wbuf[1]), _ptr(self.idx),
@@ -255,10 +261,6 @@ class Localizer:
             self.h.call("mcl_filter_set_transition", _dbl3(self.delta), _dbl3(db))
 
     def _update_core(self, uniforms=None):
-        if self.use_adaptive:
-            raise NotImplementedError(
-                "localization_mode %r: the KLD-adaptive (AMCL) modes are a SURVEY 8(f) 'next' row; "
-                "use MCL, MHMCL or AMHMCL" % self.params["localization_mode"])
         up = None
         if uniforms is not None:
             u = uniforms if torch.is_tensor(uniforms) else torch.from_numpy(
@@ -266,6 +268,56 @@ class Localizer:
             u = u.to(self.device)
             up = _ptr(u)
         self.h.call("mcl_filter_update", up)
+        if self.use_adaptive:
+            self._update_acml_weights()
+
+    # ------------------------------------------------------------------ KLD-adaptive modes (AMCL family)
+    def _update_acml_weights(self):
+        """node:276-286: normalise the weights, then the slow / fast running averages of w_avg."""
+        out = (C.c_double * 2)()
+        self.h.call("mcl_weights_normalize", _ptr(self.weights_t), self.n, out)
+        w_avg = float(np.float32(out[1]))                     # np.mean of a float32 array
+        self.w_slow += self.params["alpha_slow"] * (w_avg - self.w_slow)
+        self.w_fast += self.params["alpha_fast"] * (w_avg - self.w_fast)
+
+    def _resample_amcl_kld(self, r=None, normals=None):
+        """node:496-527 resample_amcl_kld: KLD-adaptive systematic resampling (pu:529-591) of
+        N - N_random particles plus N_random uniformly re-initialised ones (pu:450-465); N changes."""
+        p = self.params
+        p_random = max(0.0, 1.0 - self.w_fast / (self.w_slow + 1e-9))            # node:497
+        N = self.num_particles
+        n_random = min(int(p_random * N), self.capacity)
+        n_resampled = N - n_random
+        cur, prev, spare, ws, tick = self._roles()
+        tick += 1
+        if r is None and n_resampled > 0:
+            r = self.h.lib.mcl_resample_offset(self.seed, tick, n_resampled)
+        zp = None
+        if normals is not None:
+            z = torch.from_numpy(np.ascontiguousarray(normals, dtype=np.float64)).to(self.device)
+            zp = _ptr(z)
+        S = self.sets
+        off = lambda t, k: C.c_void_p(t.data_ptr() + 8 * k)
+        cnt = C.c_int64(0)
+        if n_resampled > 0:
+            self.h.call("mcl_kld_resample", *[_ptr(t) for t in S[cur]], _ptr(self.wbuf[ws]), self.n, n_resampled,
+                        int(p["min_particles"]), float(p["kld_bin_size_xy"]), float(p["kld_bin_size_theta"]),
+                        float(p["kld_epsilon"]), float(p["kld_z"]), float(r), zp, self.seed, tick, self.resample_mode,
+                        *[off(t, n_random) for t in S[spare]], C.byref(cnt))
+        if n_random > 0:                                                         # node:515-516
+            c2 = C.c_int64(0)
+            self.h.call("mcl_init_uniform", n_random, None, 0, self.seed ^ (tick << 20), self.first_index,
+                        *[_ptr(t) for t in S[spare]], C.byref(c2))
+        new_n = n_random + cnt.value
+        self.num_particles = self.n                                              # node:520 (before the reassignment)
+        self.h.call("mcl_filter_set_roles", (C.c_int * 4)(spare, prev, cur, ws), int(tick))
+        self.n = new_n
+        self.h.call("mcl_filter_set_n", new_n)
+        self.wbuf[ws][:new_n].fill_(1.0 / new_n)                                  # node:522
+        # particles_prev keeps the old length in the reference until the next odom message (node:404); keep
+        # the two sets the same length here so that an update without a predict in between stays defined
+        for a, b in zip(S[prev], S[spare]):
+            a[:new_n].copy_(b[:new_n])
 
     # ------------------------------------------------------------------ estimate / resample
     def estimate(self):
@@ -280,6 +332,9 @@ class Localizer:
         """node:488-492 resample_lvr -> low_variance_resample_numba (pu:416-446)."""
         with self._lock:
             self._bind_stream()
+            if self.use_adaptive:                                                 # node:329-331
+                self._resample_amcl_kld(r)
+                return
             self.h.call("mcl_filter_resample", -1.0 if r is None else float(r))
             # self.weights keeps the pre-resampling values (node:490 discards the uniform weights)
 
@@ -294,8 +349,15 @@ class Localizer:
                 d = _dbl3(self.delta)
             self.last_odom = cur_odom
             self.set_scan(ranges, angle_min, angle_max, angles)
-            if self.use_adaptive:
-                raise NotImplementedError("localization_mode %r not supported yet" % self.params["localization_mode"])
+            if self.use_adaptive:                 # N changes per scan: sequence the stages from the host
+                if d is not None:
+                    self.h.call("mcl_filter_predict", d, None, 0)
+                    self._push_transition()
+                self._update_core()
+                out = (C.c_double * 16)()
+                self.h.call("mcl_filter_estimate", None, out)
+                self._resample_amcl_kld()
+                return assemble_estimate(list(out))
             out = (C.c_double * 16)()
             if self.assym and d is not None:       # AMH: predict first so the NumPy backward increment can be pushed
                 self.h.call("mcl_filter_predict", d, None, 0)
@@ -333,13 +395,13 @@ class Localizer:
             return self._aos(self.prev)
 
     def weights(self):
-        return self.weights_t.cpu().numpy()
+        return self.weights_t[:self.n].cpu().numpy()
 
     def set_weights(self, w):
-        self.weights_t.copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
+        self.weights_t[:self.n].copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
 
     def scores(self):
-        return self.score_pre.cpu().numpy(), self.score_post.cpu().numpy()
+        return self.score_pre[:self.n].cpu().numpy(), self.score_post[:self.n].cpu().numpy()
 
     def sync(self):
         self.h.call("mcl_sync")

@@ -230,6 +230,28 @@ def low_variance_resample_numba(particles, weights, N, r=None, mode=_lib.RESAMPL
     return particles[idx].copy(), np.full(int(N), 1.0 / N, dtype=np.float32)
 
 
+def kld_sampling_amcl(particles, weights, bin_size_xy, bin_size_theta, epsilon, z, max_samples, min_particles,
+                      r=None, normals=None, mode=_lib.RESAMPLE_REFERENCE_F32):
+    """pu:529-591 -> (count, 3) float32 sampled particles.  r / normals: optional injected draws."""
+    c = _ctx()
+    x, y, t = c.soa(particles)
+    w = _dev(c, weights, np.float32)
+    ms = int(max_samples)
+    if ms == 0:
+        return np.zeros((0, 3), np.float32)
+    zz = _dev(c, normals, np.float64) if normals is not None else None
+    tick = _tick()
+    if r is None:
+        r = c.h.lib.mcl_resample_offset(_state["seed"], tick, ms)
+    xo, yo, to = (torch.empty(ms, dtype=torch.float64, device=c.device) for _ in range(3))
+    cnt = C.c_int64(0)
+    c.h.call("mcl_kld_resample", _p(x), _p(y), _p(t), _p(w), x.shape[0], ms, int(min_particles), float(bin_size_xy),
+             float(bin_size_theta), float(epsilon), float(z), float(r), _p(zz), _state["seed"], tick, int(mode),
+             _p(xo), _p(yo), _p(to), C.byref(cnt))
+    k = cnt.value
+    return c.aos(xo[:k].contiguous(), yo[:k].contiguous(), to[:k].contiguous()).astype(np.float32)
+
+
 def generate_valid_particles(num_particles, map_data, map_resolution, origin_x, origin_y, width, height,
                              uniforms=None):
     """pu:450-465.  uniforms: optional injected (3, max(50 N, 500)) draws (ux | uy | utheta) for the

@@ -400,3 +400,52 @@ void orc_systematic_resample_q(const float *weights, int64_t n_in, int64_t N, do
         idx[m] = (int32_t)i;
     }
 }
+
+/* pu:529-591 kld_sampling_amcl with injected draws: r (the one uniform) and normals (max_samples, 3)
+ * standard normals (np.random.normal(0, s) = 0 + s*z, three per sample, in order).
+ * weights are used as given (node:276-278 normalises them before); c accumulates in f32.
+ * The Python set of bin triples is restated as an open-addressing hash set.
+ * Returns the number of samples; out is (max_samples, 3) f32 like the reference's buffer. */
+int64_t orc_kld_sampling(const double *particles, const float *weights, int64_t n, double bin_xy,
+                         double bin_theta, double epsilon, double z, int64_t max_samples,
+                         int64_t min_particles, double r, const double *normals, float *out) {
+    const double noise_std[3] = {0.001, 0.001, 0.02};                  /* pu:552 */
+    int64_t cap = 16;
+    while (cap < 4 * (max_samples + 1)) cap <<= 1;
+    int64_t *keys = (int64_t *)malloc((size_t)cap * 3 * sizeof(int64_t));
+    unsigned char *used = (unsigned char *)calloc((size_t)cap, 1);
+    int64_t nbins = 0, count = 0, i = 0;
+    float c = weights[0];                                               /* pu:555 */
+    while (count < max_samples) {
+        const double u = r + (double)count / (double)max_samples;       /* pu:560 */
+        while (u > (double)c && i < n - 1) { i += 1; c += weights[i]; } /* pu:561-563 */
+        double noisy[3];
+        for (int j = 0; j < 3; ++j)
+            noisy[j] = particles[3 * i + j] + (0.0 + noise_std[j] * normals[3 * count + j]);   /* pu:570 */
+        const int64_t xb = (int64_t)(noisy[0] / bin_xy), yb = (int64_t)(noisy[1] / bin_xy),
+                      tb = (int64_t)(noisy[2] / bin_theta);             /* pu:573-575 int() truncation */
+        uint64_t hsh = (uint64_t)xb * 0x9E3779B97F4A7C15ull ^ (uint64_t)yb * 0xC2B2AE3D27D4EB4Full ^
+                       (uint64_t)tb * 0x165667B19E3779F9ull;
+        int64_t slot = (int64_t)(hsh & (uint64_t)(cap - 1));
+        int found = 0;
+        while (used[slot]) {
+            if (keys[3 * slot] == xb && keys[3 * slot + 1] == yb && keys[3 * slot + 2] == tb) { found = 1; break; }
+            slot = (slot + 1) & (cap - 1);
+        }
+        if (!found) {                                                   /* pu:578-586 */
+            used[slot] = 1; keys[3 * slot] = xb; keys[3 * slot + 1] = yb; keys[3 * slot + 2] = tb;
+            nbins += 1;
+            const int64_t k = nbins;
+            if (k > 1 && count >= min_particles) {
+                const double km1 = (double)(k - 1);
+                const double a = 1.0 - 2.0 / (9.0 * km1) + sqrt(2.0 / (9.0 * km1)) * z;
+                const double chi2 = km1 * (a * a * a);
+                if ((double)count > chi2 / (2.0 * epsilon)) break;      /* breaks BEFORE storing this sample */
+            }
+        }
+        out[3 * count] = (float)noisy[0]; out[3 * count + 1] = (float)noisy[1]; out[3 * count + 2] = (float)noisy[2];
+        count += 1;
+    }
+    free(keys); free(used);
+    return count;
+}

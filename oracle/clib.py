@@ -235,6 +235,23 @@ def systematic_resample_q(weights, N, r, scale=None):
     return idx
 
 
+def kld_sampling_amcl(particles, weights, bin_size_xy, bin_size_theta, epsilon, z, max_samples, min_particles,
+                      r, normals):
+    """pu:529-591 with injected draws (r, normals (max_samples, 3)) -> (count, 3) float32."""
+    p = _f64(particles)
+    w = _f32(weights)
+    zz = _f64(normals)
+    assert zz.shape[0] >= max_samples and zz.shape[1] == 3
+    out = np.zeros((int(max_samples), 3), np.float32)
+    L = lib()
+    L.orc_kld_sampling.restype = C.c_int64
+    cnt = L.orc_kld_sampling(_p(p, C.c_double), _p(w, C.c_float), C.c_int64(p.shape[0]), C.c_double(float(bin_size_xy)),
+                             C.c_double(float(bin_size_theta)), C.c_double(float(epsilon)), C.c_double(float(z)),
+                             C.c_int64(int(max_samples)), C.c_int64(int(min_particles)), C.c_double(float(r)),
+                             _p(zz, C.c_double), _p(out, C.c_float))
+    return out[:cnt]
+
+
 def philox4x32_10(ctr, key):
     c = np.ascontiguousarray(ctr, np.uint32)
     k = np.ascontiguousarray(key, np.uint32)

@@ -258,6 +258,31 @@ def gen_mh_and_resample():
     print("resample cases", list(cases))
 
 
+def gen_kld():
+    """pu:529-591 kld_sampling_amcl on weights from a real update (yaml KLD parameters)."""
+    g = np.load(os.path.join(OUT, "mh_map_world.npz"))
+    out = {}
+    cases = {"spread": (g["mh_particles_a"], g["mh_weights_a"] / np.sum(g["mh_weights_a"]), 2000, 100),
+             "minpart": (g["mh_particles_a"], g["mh_weights_a"] / np.sum(g["mh_weights_a"]), 1500, 1200)}
+    rs = np.random.RandomState(3)
+    tight = np.column_stack((rs.normal(-2.0, 0.03, 3000), rs.normal(-0.5, 0.03, 3000), rs.normal(0.3, 0.02, 3000)))
+    wt = rs.uniform(0.5, 1.0, 3000).astype(np.float32)
+    cases["tight"] = (tight, (wt / np.sum(wt)).astype(np.float32), 3000, 100)
+    for k, (tag, (parts, w, max_samples, min_particles)) in enumerate(cases.items()):
+        seed = 300 + k
+        seed_reference(seed)
+        res = pu.kld_sampling_amcl(np.ascontiguousarray(parts), w.astype(np.float32), 0.20, 0.1745, 0.03, 2,
+                                   max_samples, min_particles)
+        out["p_" + tag] = parts
+        out["w_" + tag] = w.astype(np.float32)
+        out["max_" + tag] = max_samples
+        out["min_" + tag] = min_particles
+        out["seed_" + tag] = seed
+        out["out_" + tag] = res
+        print("kld", tag, "->", res.shape, res.dtype)
+    np.savez_compressed(os.path.join(OUT, "kld.npz"), **out)
+
+
 def gen_init():
     occ, res, ox, oy = load_ref_map("map_world")
     mp = ng.load_map(occ, res, ox, oy)
@@ -326,6 +351,7 @@ def main():
     gen_motion()
     gen_mh_and_resample()
     gen_init()
+    gen_kld()
     gen_filter_run()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes", tot)

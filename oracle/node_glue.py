@@ -146,7 +146,11 @@ class ReferenceFilter:
         self.p = dict(params)
         self.mode = mode
         self.use_mh = "MH" in mode                 # node:19
+        self.use_adaptive = "AMCL" in mode         # node:20
         self.assym = "AMH" in mode                 # node:21
+        self.w_slow = 1e-3                         # node:86-87
+        self.w_fast = 1e-3
+        self.num_particles = len(particles)
         self.alpha = np.array([params["alpha1"], params["alpha2"], params["alpha3"],
                                params["alpha4"]], dtype=np.float32)     # node:28-33
         self.particles = np.array(particles, dtype=np.float64)
@@ -197,11 +201,33 @@ class ReferenceFilter:
                     uniforms)
         else:
             weights = weights_post                                           # node:313
+        if self.use_adaptive:                                                # node:316-318 -> node:276-286
+            self.weights = weights / np.sum(weights)
+            w_avg = np.mean(self.weights)
+            self.w_slow += self.p["alpha_slow"] * (w_avg - self.w_slow)
+            self.w_fast += self.p["alpha_fast"] * (w_avg - self.w_fast)
+            return self.weights
         self.weights = weights                                               # node:322
         return weights
 
     def estimate(self):
         return estimate(self.particles, self.weights)
+
+    def resample_amcl_kld(self, r, normals, random_particles):
+        """node:496-527 with injected draws; random_particles: callable(N_random) -> (N_random, 3)
+        standing in for generate_valid_particles (node:515-516)."""
+        p_random = max(0.0, 1.0 - self.w_fast / (self.w_slow + 1e-9))
+        N = self.num_particles
+        N_random = int(p_random * N)
+        N_resampled = N - N_random
+        resampled = clib.kld_sampling_amcl(self.particles, self.weights, self.p["kld_bin_size_xy"],
+                                           self.p["kld_bin_size_theta"], self.p["kld_epsilon"], self.p["kld_z"],
+                                           N_resampled, self.p["min_particles"], r, normals)
+        rnd = np.asarray(random_particles(N_random), dtype=np.float64).reshape(-1, 3)
+        self.num_particles = len(self.particles)                             # node:520
+        self.particles = np.vstack((rnd, resampled))                         # node:521 (f32 values in an f64 array)
+        self.weights = np.full(len(self.particles), 1.0 / len(self.particles))
+        return N_random, len(resampled)
 
     def resample(self, r):
         n = len(self.particles)

@@ -415,6 +415,100 @@ def test_resample_all_zero_weights(pu):
         assert np.all(idx == 0)        # reference: 0/0 = NaN, "U > NaN" is false, the walk never moves
 
 
+# --------------------------------------------------------------------------- KLD sampling (a13)
+def test_kld_sampling_golden_bitexact(pu):
+    g = golden("kld.npz")
+    for tag in ("spread", "minpart", "tight"):
+        ms = int(g["max_" + tag])
+        rs = np.random.RandomState(int(g["seed_" + tag]))
+        r = rs.uniform(0, 1.0 / ms)
+        z = rs.normal(0, 1, (ms, 3))
+        out = pu.kld_sampling_amcl(g["p_" + tag], g["w_" + tag], 0.20, 0.1745, 0.03, 2, ms, int(g["min_" + tag]),
+                                   r=r, normals=z)
+        ref = g["out_" + tag]
+        assert out.dtype == np.float32 and out.shape == ref.shape, (tag, out.shape, ref.shape)
+        assert np.array_equal(out, ref), tag
+    assert g["out_tight"].shape[0] < int(g["max_tight"])          # the stop rule fired
+
+
+def test_kld_sampling_large_vs_oracle(pu, orc):
+    rs = np.random.RandomState(9)
+    n = 200000
+    parts = np.column_stack((rs.normal(1.0, 0.4, n), rs.normal(-2.0, 0.3, n), rs.uniform(-np.pi, np.pi, n)))
+    w = rs.uniform(0, 1, n).astype(np.float32)
+    w = (w / w.sum()).astype(np.float32)
+    ms = n
+    r = rs.uniform(0, 1.0 / ms)
+    z = rs.normal(0, 1, (ms, 3))
+    out = pu.kld_sampling_amcl(parts, w, 0.20, 0.1745, 0.03, 2, ms, 100, r=r, normals=z)
+    ref = orc.kld_sampling_amcl(parts, w, 0.20, 0.1745, 0.03, 2, ms, 100, r, z)
+    assert out.shape == ref.shape and 100 < len(ref) < ms
+    assert np.array_equal(out, ref)
+
+
+def test_localizer_adaptive_modes_lockstep_with_oracle():
+    """AMCL / MHAMCL (KLD-adaptive, node:315-333): the particle count changes every scan.  Lock-step with the
+    oracle's restatement of update_acml_weights + resample_amcl_kld on injected draws."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN, YAML_PARAMS
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.params import YAML_PARAMS as FULL
+    from oracle import node_glue as ng
+    g = golden("filter_run_map_world.npz")
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    mp = ng.load_map(gm.occ, gm.resolution, gm.origin_x, gm.origin_y)
+    params = dict(FULL)
+    for mode in ("AMCL", "MHAMCL"):
+        loc = Localizer(params=params, mode=mode, seed=41)
+        loc.load_map(gm)
+        loc.set_particles(g["particles0"])
+        f = ng.ReferenceFilter(mp, params, g["particles0"], mode=mode)
+        counts = []
+        for k in range(6):
+            if k == 3:      # a converged cloud (tight cluster at the true pose): now the KLD bound stops early
+                rs_c = np.random.RandomState(5)
+                tight = np.column_stack((g["odoms"][k - 1][0] + rs_c.normal(0, 0.03, loc.n),
+                                         g["odoms"][k - 1][1] + rs_c.normal(0, 0.03, loc.n),
+                                         g["odoms"][k - 1][2] + rs_c.normal(0, 0.02, loc.n)))
+                loc.set_particles(tight, keep_odom=True)
+                f.particles = tight.copy(); f.particles_prev = tight.copy()
+            loc.predict(g["odoms"][k])
+            f.move_particles(g["odoms"][k], seed=41, step=loc.tick)
+            if f.last_odom is not None and k > 0:
+                assert np.abs(loc.particles() - f.particles).max() < 1e-12
+            n = loc.n
+            u = np.random.RandomState(100 + k).random_sample(n)
+            loc.update(g["scans"][k], angles=g["angles"], uniforms=u)
+            w_ref = f.update(g["scans"][k], g["angles"], uniforms=u)
+            assert np.abs(loc.particles() - f.particles).max() < 1e-12
+            np.testing.assert_allclose(loc.weights(), w_ref, rtol=3e-6, atol=0)
+            assert abs(loc.w_slow - f.w_slow) < 1e-9 and abs(loc.w_fast - f.w_fast) < 1e-9
+            mx, my, mt, cov = loc.estimate()
+            rx, ry, rt, rcov = f.estimate()
+            np.testing.assert_allclose([mx, my], [rx, ry], rtol=0, atol=1e-6)
+            # teacher-force the weights so both resample the same distribution, then compare bit-for-bit
+            loc.set_weights(w_ref.astype(np.float32))
+            f.weights = w_ref.astype(np.float32)
+            loc.w_slow, loc.w_fast = f.w_slow, f.w_fast
+            N_res = loc.num_particles - int(max(0.0, 1.0 - f.w_fast / (f.w_slow + 1e-9)) * loc.num_particles)
+            rs = np.random.RandomState(200 + k)
+            r = rs.uniform(0, 1.0 / max(N_res, 1))
+            z = rs.normal(0, 1, (max(N_res, 1), 3))
+            with loc._lock:
+                loc._bind_stream()
+                loc._resample_amcl_kld(r=r, normals=z)
+            got = loc.particles()
+            n_random, n_res = f.resample_amcl_kld(r, z, lambda m: got[:m])      # random part: taken from the GPU
+            assert loc.n == n_random + n_res == len(f.particles)
+            assert np.array_equal(got, f.particles)
+            assert loc.num_particles == f.num_particles
+            counts.append(loc.n)
+            f.particles_prev = f.particles.copy()
+        assert min(counts) < len(g["particles0"])        # the adaptive rule actually shrank the set
+
+
 # --------------------------------------------------------------------------- estimate (a10)
 def test_estimate_vs_numpy(pu):
     from oracle import node_glue as ng
