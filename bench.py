@@ -345,10 +345,15 @@ def run_native(args):
                "sample": "%d of %d particles x %d beams, %d full MHMCL steps (%.1f s), oracle C port (OpenMP, all "
                          "host cores) + NumPy glue" % (ns, n, args.beams, cdone, cms * cdone / 1e3)}
 
+    cfg = workload_config(args, gm)
+    if world > 1:
+        cfg["parallelism"] = "particles sharded over %d ranks (weak scaling), map replicated" % world
+        cfg["resample_exchange"] = ("peer-push over NVLink symmetric memory (gather fused with the exchange)"
+                                    if getattr(loc, "symm", None) is not None else "NCCL all-to-all")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, gm),
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "step_ms_median": float(np.median(step_ms)), "step_ms_min": float(step_ms.min()),
         "host_wall_ms_per_step": 1e3 * t_wall / K,
         "valid_beams_mean": mv, "likelihood_kernel_evals_per_s": n * mv / (lik_launch_ms * 1e-3),

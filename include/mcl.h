@@ -183,6 +183,13 @@ int mcl_kld_resample(mcl_handle *h, const double *d_x, const double *d_y, const 
                      double bin_size_xy, double bin_size_theta, double epsilon, double z, double r,
                      const double *d_normals, uint64_t seed, uint64_t step, int mode, double *d_xo,
                      double *d_yo, double *d_thetao, int64_t *h_count);
+/* Peer-push variant of the search + exchange: after mcl_resample_scan and the all-gather of the totals
+ * (d_totals_all, world u64 on the device) every rank stores its offspring directly into the destination
+ * ranks' pose buffers through peer (NVLink) pointers: d_peer_ptrs = device array [3][world] of the x, y, theta
+ * destination base pointers of every rank.  No host round trip; follow with a cross-rank barrier. */
+int mcl_resample_push(mcl_handle *h, int64_t n_in, const uint64_t *d_totals_all, int rank, int world, double r,
+                      int64_t n_global, int64_t n_per_rank, const double *d_x, const double *d_y,
+                      const double *d_theta, const uint64_t *d_peer_ptrs);
 /* r = 0 + (1/n_out - 0) * u53(Philox(seed, step, 0, RESAMPLE))  (np.random.uniform(0, 1/N)) */
 double mcl_resample_offset(uint64_t seed, uint64_t step, int64_t n_out);
 /* new_particles[m] = particles[idx[m]] (pu:445), SoA gather; outputs must not alias inputs. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mcl_resample_search": (_i, [_vp, _i64, _u64, _u64, _i64, _i64, _d, _i64, _vp]),
     "mcl_kld_resample": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _d, _d, _d, _d, _d, _vp, _u64, _u64, _i,
                               _vp, _vp, _vp, C.POINTER(_i64)]),
+    "mcl_resample_push": (_i, [_vp, _i64, _vp, _i, _i, _d, _i64, _i64, _vp, _vp, _vp, _vp]),
     "mcl_resample_offset": (_d, [_u64, _u64, _i64]),
     "mcl_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mcl_estimate": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _pd]),

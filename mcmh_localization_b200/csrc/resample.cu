@@ -366,6 +366,90 @@ int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c) {
     return MCL_OK;
 }
 
+// ---- peer-push global resampling: gather fused with the all-to-all over NVLink peer memory --------------
+// Every rank emits the offspring whose thresholds fall into its own cumulative-weight interval and stores each
+// one DIRECTLY into the destination rank's particle buffer (P2P stores through NVLink / NVSwitch), so there are no
+// send buffers, no split sizes and no host round trip: the interval, the output range and the destinations are
+// all computed on the device from the all-gathered totals.  The caller follows with a barrier.
+struct PushPlan { uint64_t offset, grand; long long m_lo, m_hi; };
+
+__device__ __forceinline__ uint64_t push_threshold(long long m, double r, double step, double totd) {
+    const double U = __dadd_rn(r, __dmul_rn((double)m, step));
+    const double t = ceil(__dmul_rn(U, totd));
+    return t >= 18446744073709551616.0 ? 0xffffffffffffffffull : (t > 0.0 ? __double2ull_rz(t) : 0ull);
+}
+__device__ long long count_thresholds_le_dev(uint64_t x, double r, double step, double totd, long long n_out) {
+    long long lo = 0, hi = n_out;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (push_threshold(mid, r, step, totd) <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// same partition as sharded.plan_resample (host): ranks without weight emit nothing, rank 0 starts at 0,
+// the last rank ends at n_out
+__global__ void k_push_plan(const uint64_t *totals, int rank, int world, double r, long long n_out, PushPlan *plan) {
+    uint64_t off[17];
+    uint64_t acc = 0;
+    for (int k = 0; k < world; ++k) { off[k] = acc; acc += totals[k]; }
+    off[world] = acc;
+    const double step = 1.0 / (double)n_out, totd = (double)acc;
+    long long prev_hi = 0, my_lo = 0, my_hi = 0;
+    for (int k = 0; k < world; ++k) {
+        long long lo = k == 0 ? 0 : count_thresholds_le_dev(off[k], r, step, totd, n_out);
+        long long hi = k == world - 1 ? n_out : count_thresholds_le_dev(off[k + 1], r, step, totd, n_out);
+        if (hi < lo) hi = lo;
+        if (k > 0) { if (lo < prev_hi) lo = prev_hi; if (hi < lo) hi = lo; }
+        if (k == world - 1) hi = n_out;
+        if (k == rank) { my_lo = lo; my_hi = hi; }
+        prev_hi = hi;
+    }
+    plan->offset = off[rank]; plan->grand = acc; plan->m_lo = my_lo; plan->m_hi = my_hi;
+}
+
+__global__ void k_push(const uint64_t *__restrict__ C, int64_t limit, const PushPlan *plan, double r, long long n_out,
+                       long long n_per_rank, int world, const double *__restrict__ x, const double *__restrict__ y,
+                       const double *__restrict__ th, const unsigned long long *peers /* [3][world] */) {
+    const PushPlan pl = *plan;
+    const double step = 1.0 / (double)n_out, totd = (double)pl.grand;
+    for (long long m = pl.m_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; m < pl.m_hi;
+         m += (long long)gridDim.x * blockDim.x) {
+        const uint64_t T = push_threshold(m, r, step, totd);
+        int64_t lo = 0, hi = limit;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (T > C[mid] + pl.offset) lo = mid + 1; else hi = mid;
+        }
+        long long d = m / n_per_rank;
+        if (d > world - 1) d = world - 1;
+        const long long j = m - d * n_per_rank;
+        reinterpret_cast<double *>(peers[d])[j] = x[lo];
+        reinterpret_cast<double *>(peers[world + d])[j] = y[lo];
+        reinterpret_cast<double *>(peers[2 * world + d])[j] = th[lo];
+    }
+    __threadfence_system();
+}
+
+extern "C" int mcl_resample_push(mcl_handle *h, int64_t n_in, const uint64_t *d_totals_all, int rank, int world,
+                                 double r, int64_t n_global, int64_t n_per_rank, const double *d_x, const double *d_y,
+                                 const double *d_theta, const uint64_t *d_peer_ptrs) {
+    if (!h) return MCL_ERR_ARG;
+    if (n_in <= 0 || !d_totals_all || world < 1 || world > 16 || rank < 0 || rank >= world || n_global <= 0 ||
+        n_per_rank <= 0 || !d_x || !d_y || !d_theta || !d_peer_ptrs)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_resample_push: bad argument");
+    DeviceGuard guard(h->device);
+    const FixedLayout L = fixed_layout(h, n_in);
+    if (L.total > h->scratch_bytes) return mcl_fail(h, MCL_ERR_STATE, "mcl_resample_push: call mcl_resample_scan first");
+    const uint64_t *C = (const uint64_t *)((char *)h->d_scratch + L.o_c);
+    PushPlan *plan = (PushPlan *)((char *)h->d_scratch + 64 + 32);      // after the scale slot
+    k_push_plan<<<1, 1, 0, h->stream>>>(d_totals_all, rank, world, r, (long long)n_global, plan);
+    MCL_LAUNCH_CHECK(h);
+    k_push<<<h->sm_count * 8, 256, 0, h->stream>>>(C, n_in - 1, plan, r, (long long)n_global, (long long)n_per_rank, world,
+                                                   d_x, d_y, d_theta, (const unsigned long long *)d_peer_ptrs);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
 // host mirror of oracle u53(Philox(seed, step, item 0, sub 0, RESAMPLE))
 static void philox_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];

@@ -95,8 +95,7 @@ class Localizer:
     # ------------------------------------------------------------------ particle buffers
     def _alloc(self, n):
         """Allocate the device buffers (torch tensors) and bind them to the library's filter state."""
-        mk = lambda: [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3)]
-        self.sets = [mk(), mk(), mk()]                      # three SoA pose sets; roles live in the library
+        self.sets = self._make_sets(n)                      # three SoA pose sets; roles live in the library
         f32 = lambda: torch.empty(n, dtype=torch.float32, device=self.device)
         self.score_pre, self.score_post, self.w_pre, self.w_post = f32(), f32(), f32(), f32()
         self.wbuf = [torch.full((n,), 1.0 / n, dtype=torch.float32, device=self.device), f32()]   # node:98
@@ -110,6 +109,10 @@ class Localizer:
                     _ptr(self.w_pre), _ptr(self.w_post), _ptr(self.wbuf[0]), _ptr(self.wbuf[1]), _ptr(self.idx),
                     int(self.use_mh), self.resample_mode, self.seed, self.first_index, self.max_attempts)
         self.h.call("mcl_filter_set_assym", int(self.assym))
+
+    def _make_sets(self, n):
+        mk = lambda: [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3)]
+        return [mk(), mk(), mk()]
 
     def _roles(self):
         r = (C.c_int * 4)()

@@ -92,16 +92,39 @@ class ShardedLocalizer(Localizer):
     """Localizer whose particle set is the union over ranks of equally sized shards."""
 
     def __init__(self, device=0, params=None, mode=None, seed=0, resample_mode="fixed", max_attempts=1000,
-                 group=None):
+                 group=None, peer_push=True):
         if resample_mode != "fixed":
             raise ValueError("sharded resampling uses the fixed-point arithmetic (decomposition-independent)")
         self.group = group
+        self.use_peer_push = peer_push
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         super().__init__(device=device, params=params, mode=mode, seed=seed, resample_mode="fixed",
                          max_attempts=max_attempts)
 
     # -- buffers -----------------------------------------------------------------------------
+    def _make_sets(self, n):
+        """Pose buffers in symmetric memory (every rank can store into every other rank's buffers over
+        NVLink): lets resampling push offspring straight to their destination.  Falls back to private
+        buffers + NCCL all-to-all when symmetric memory is unavailable."""
+        self.symm = None
+        self.peer_tab = None
+        if self.use_peer_push:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(9 * n, dtype=torch.float64, device=self.device)
+                hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                tab = torch.tensor([[[ptrs[d] + (3 * j + k) * n * 8 for d in range(self.world)] for k in range(3)]
+                                    for j in range(3)], dtype=torch.int64)
+                self.peer_tab = tab.to(self.device)                      # [set][component][rank]
+                self.symm, self.symm_buf = hdl, buf
+                return [[buf[(3 * j + k) * n:(3 * j + k + 1) * n] for k in range(3)] for j in range(3)]
+            except Exception as e:      # noqa: BLE001 -- any failure means: use the all-to-all path
+                self.symm_error = repr(e)
+                self.symm = None
+        return super()._make_sets(n)
+
     def _alloc(self, n):
         self.first_index = self.rank * n
         super()._alloc(n)
@@ -201,6 +224,13 @@ class ShardedLocalizer(Localizer):
             dist.all_reduce(self.wmax, op=dist.ReduceOp.MAX, group=self.group)
             h.call("mcl_resample_scan", _ptr(w), n, _ptr(self.wmax), self.n_global, _ptr(self.total))
             dist.all_gather_into_tensor(self.totals_all, self.total, group=self.group)
+            if self.symm is not None:
+                # fused gather + exchange: offspring are stored straight into the destination ranks' spare set
+                h.call("mcl_resample_push", n, _ptr(self.totals_all), self.rank, W, float(r), self.n_global, n,
+                       *[_ptr(t) for t in S[cur]], C.c_void_p(self.peer_tab[spare].data_ptr()))
+                self.symm.barrier()
+                self._set_roles(spare, prev, cur, ws, tick)
+                return
             totals = [int(t) for t in self.totals_all.cpu().tolist()]              # sync: the plan is host logic
             offsets, grand, m_lo, m_hi, send = plan_resample(totals, float(r), self.n_global, W)
             k = self.rank

@@ -650,8 +650,9 @@ def test_sharded_two_gpus_equals_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from conftest import ROOT
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533",
-                        os.path.join(ROOT, "scripts", "dist_check.py"), "20000"],
-                       capture_output=True, text=True, timeout=600)
-    assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for push in ("1", "0"):      # peer-push over symmetric memory, and the NCCL all-to-all fallback
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", "2953" + push,
+                            os.path.join(ROOT, "scripts", "dist_check.py"), "20000"],
+                           capture_output=True, text=True, timeout=600, env=dict(os.environ, MCL_PEER_PUSH=push))
+        assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
