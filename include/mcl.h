@@ -282,6 +282,10 @@ int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double 
  * global memory / L2 (where = 1); n_lookups per launch, iters launches timed with CUDA events. */
 int mcl_bench_gather(mcl_handle *h, int where, int64_t table_bytes, int64_t n_lookups, int iters,
                      double *lookups_per_s);
+/* test hook: the sequential-f32 running sums c_i = fl32(c_{i-1} + w_i) that MCL_RESAMPLE_REFERENCE_F32
+ * searches (normalise: of w_i / seq_sum(w), pu:430; else of w_i as given, pu:555-563), produced by the
+ * exact parallel scan (serial = 0) or by the one-warp in-order replay (serial = 1). */
+int mcl_debug_seq_cumsum(mcl_handle *h, const float *d_weights, int64_t n, int normalise, int serial, float *d_c);
 /* launches of library kernels since create (the bench's gpu_launches claim) */
 int64_t mcl_launch_count(const mcl_handle *h);
 /* CUDA-event timing of the library's own launches: accumulate the device time of every

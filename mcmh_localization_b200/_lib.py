@@ -82,6 +82,7 @@ SIGNATURES = {
     "mcl_filter_resample": (_i, [_vp, _d]),
     "mcl_filter_step": (_i, [_vp, _pd, _i, _vp, _pd]),
     "mcl_bench_gather": (_i, [_vp, _i, _i64, _i64, _i, _pd]),
+    "mcl_debug_seq_cumsum": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "mcl_launch_count": (_i64, [_vp]),
     "mcl_timing_start": (_i, [_vp]),
     "mcl_timing_stop": (_i, [_vp, _pd, C.POINTER(_i64)]),

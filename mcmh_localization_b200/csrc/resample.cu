@@ -12,6 +12,8 @@
 //   FIXED_POINT   : weights quantised to 64-bit fixed point, q_i = trunc(w_i * 2^k); the cumulative
 //                   sum is exact integer arithmetic (associative => any block or rank decomposition
 //                   gives identical indices) computed by a 3-kernel block scan.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <float.h>
 
@@ -46,6 +48,187 @@ __global__ void __launch_bounds__(32) k_cumsum_ref_f32(const float *__restrict__
         }
         if (in) c_out[base + lane] = mine;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact PARALLEL emulation of the sequential f32 accumulation  c_i = fl32(c_{i-1} + w_i)  (w_i >= 0).
+//
+// While c stays inside one binade [2^e, 2^(e+1)) it is an integer multiple K of u = 2^(e-23), and adding w
+// is integer arithmetic: with w / u = a0 + f (a0 integer, 0 <= f < 1), round-to-nearest-even gives
+//     K' = K + a0            if f < 1/2
+//     K' = K + a0 + 1        if f > 1/2
+//     K' = K + a0 + ((K + a0) & 1)   if f == 1/2            (ties to even)
+// i.e. every element is a map  K -> K + A(K & 1)  given by the pair (A(0), A(1)); such maps compose
+// associatively (the parity after one map selects the branch of the next), so a block scan over the pairs
+// reproduces the sequential rounding sequence exactly.  The scan is valid up to the first element that pushes
+// K to 2^24 (the sum leaves the binade); that one addition is done with a real f32 add and the scan restarts
+// from there with the new unit.  One CTA streams over the array tile by tile (the sum is monotone, so there
+// are at most ~25-150 restarts in total), replacing 1M dependent additions by ~130 tile scans.
+// ---------------------------------------------------------------------------------------------
+#define SEQ_THREADS 1024
+#define SEQ_ITEMS 8
+#define SEQ_TILE (SEQ_THREADS * SEQ_ITEMS)
+
+struct Pair64 { long long a0, a1; };     // increment if the incoming K is even / odd
+
+__device__ __forceinline__ Pair64 pair_compose(const Pair64 &f1, const Pair64 &f2) {   // first f1, then f2
+    Pair64 r;
+    r.a0 = f1.a0 + ((f1.a0 & 1) ? f2.a1 : f2.a0);
+    r.a1 = f1.a1 + (((1 + f1.a1) & 1) ? f2.a1 : f2.a0);
+    return r;
+}
+__device__ __forceinline__ Pair64 pair_shfl_up(const Pair64 &v, int o) {
+    Pair64 r;
+    r.a0 = __shfl_up_sync(0xffffffffu, v.a0, o);
+    r.a1 = __shfl_up_sync(0xffffffffu, v.a1, o);
+    return r;
+}
+// element map for weight w when the running sum has unit exponent e (u = 2^(e-23), e >= -126)
+__device__ __forceinline__ Pair64 seq_decode(float w, int e) {
+    const unsigned b = __float_as_uint(w);
+    const unsigned ef = (b >> 23) & 0xffu, mf = b & 0x7fffffu;
+    Pair64 r; r.a0 = 0; r.a1 = 0;
+    if ((b & 0x7fffffffu) == 0u) return r;
+    const long long M = ef ? (long long)(mf | 0x800000u) : (long long)mf;
+    const int Ew = ef ? (int)ef - 127 : -126;
+    const int sh = e - Ew;
+    if (sh <= 0) {
+        const long long a = (-sh > 38) ? (1ll << 62) : (M << (-sh));
+        r.a0 = a; r.a1 = a;
+    } else if (sh <= 24) {
+        const long long a = M >> sh, rem = M & ((1ll << sh) - 1), half = 1ll << (sh - 1);
+        if (rem < half) { r.a0 = a; r.a1 = a; }
+        else if (rem > half) { r.a0 = a + 1; r.a1 = a + 1; }
+        else { r.a0 = a + (a & 1); r.a1 = a + ((1 + a) & 1); }
+    }   // sh >= 25: w < u/2, the sum does not move
+    return r;
+}
+__device__ __forceinline__ int seq_exponent(float c) {      // unit exponent of c (denormals share e = -126)
+    const unsigned ef = (__float_as_uint(c) >> 23) & 0xffu;
+    return ef ? (int)ef - 127 : -126;
+}
+__device__ __forceinline__ long long seq_K(float c) {        // c = K * 2^(e-23)
+    const unsigned b = __float_as_uint(c);
+    const unsigned ef = (b >> 23) & 0xffu, mf = b & 0x7fffffu;
+    return ef ? (long long)(mf | 0x800000u) : (long long)mf;
+}
+__device__ __forceinline__ float seq_value(long long K, int e) {   // K < 2^24
+    return __uint_as_float((unsigned)(((long long)(e + 126) << 23) + K));
+}
+
+// w_eff[i] = divide ? w[i] / *div : w[i];  c_out (nullable) receives every partial sum, *total_out the last one
+__global__ void __launch_bounds__(SEQ_THREADS) k_seq_accumulate_exact(const float *__restrict__ w, int64_t n,
+                                                                      const float *div, float *__restrict__ c_out,
+                                                                      float *total_out) {
+    __shared__ Pair64 warp_tot[32];
+    __shared__ float s_c;
+    __shared__ long long s_cross;
+    __shared__ int64_t s_seg0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float dv = div ? div[0] : 1.0f;
+    if (threadIdx.x == 0) { s_c = 0.0f; s_seg0 = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += SEQ_TILE) {
+        float wv[SEQ_ITEMS];
+        const int64_t first = base + (int64_t)threadIdx.x * SEQ_ITEMS;
+#pragma unroll
+        for (int k = 0; k < SEQ_ITEMS; ++k) {
+            const int64_t i = first + k;
+            float v = i < n ? w[i] : 0.0f;
+            if (div && i < n) v = __fdiv_rn(v, dv);
+            wv[k] = v;
+        }
+        while (true) {
+            const float c0 = s_c;
+            const int64_t seg0 = s_seg0;            // first index of this tile not yet finalised
+            const int e = seq_exponent(c0);
+            const long long K0 = seq_K(c0);
+            // thread-local inclusive prefixes of the element maps (identity for finished / out-of-range slots)
+            Pair64 loc[SEQ_ITEMS];
+            Pair64 run; run.a0 = 0; run.a1 = 0;
+#pragma unroll
+            for (int k = 0; k < SEQ_ITEMS; ++k) {
+                const int64_t i = first + k;
+                Pair64 m; m.a0 = 0; m.a1 = 0;
+                if (i >= seg0 && i < n) m = seq_decode(wv[k], e);
+                run = pair_compose(run, m);
+                loc[k] = run;
+            }
+            // exclusive scan of the per-thread totals across the block
+            Pair64 inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const Pair64 t = pair_shfl_up(inc, o);
+                if (lane >= o) inc = pair_compose(t, inc);
+            }
+            if (lane == 31) warp_tot[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                Pair64 t = warp_tot[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const Pair64 u2 = pair_shfl_up(t, o);
+                    if (lane >= o) t = pair_compose(u2, t);
+                }
+                warp_tot[lane] = t;               // inclusive over warps
+            }
+            if (threadIdx.x == 0) s_cross = 0x7fffffffffffffffll;
+            __syncthreads();
+            Pair64 excl = pair_shfl_up(inc, 1);
+            if (lane == 0) { excl.a0 = 0; excl.a1 = 0; }
+            if (warp > 0) excl = pair_compose(warp_tot[warp - 1], excl);
+            const int p0 = (int)(K0 & 1);
+            long long Kprev = K0 + (p0 ? excl.a1 : excl.a0);      // K just before this thread's first element
+            long long Ks[SEQ_ITEMS];
+            long long my_cross = 0x7fffffffffffffffll;
+#pragma unroll
+            for (int k = 0; k < SEQ_ITEMS; ++k) {
+                const Pair64 q = pair_compose(excl, loc[k]);
+                Ks[k] = K0 + (p0 ? q.a1 : q.a0);
+                const int64_t i = first + k;
+                if (i >= seg0 && i < n && (Ks[k] >= (1ll << 24) || Ks[k] < 0) && my_cross == 0x7fffffffffffffffll) my_cross = i;
+            }
+            if (my_cross != 0x7fffffffffffffffll) atomicMin((unsigned long long *)&s_cross, (unsigned long long)my_cross);
+            __syncthreads();
+            const long long cross = s_cross;
+            const int64_t end = cross == 0x7fffffffffffffffll ? (base + SEQ_TILE < n ? base + SEQ_TILE : n) : (int64_t)cross;
+            // finalise [seg0, end)
+            float last_val = c0;
+            bool have_last = false;
+#pragma unroll
+            for (int k = 0; k < SEQ_ITEMS; ++k) {
+                const int64_t i = first + k;
+                if (i >= seg0 && i < end) {
+                    const float v = seq_value(Ks[k], e);
+                    if (c_out) c_out[i] = v;
+                    if (i == end - 1) { last_val = v; have_last = true; }
+                }
+            }
+            __syncthreads();
+            if (cross == 0x7fffffffffffffffll) {
+                if (have_last) s_c = last_val;            // exactly one thread owns index end-1 (if the segment is non-empty)
+                if (threadIdx.x == 0) s_seg0 = end;
+                __syncthreads();
+                break;                                    // next tile
+            }
+            // the addition at index `cross` leaves the binade: do it for real and restart behind it
+#pragma unroll
+            for (int k = 0; k < SEQ_ITEMS; ++k) {
+                const int64_t i = first + k;
+                if (i == cross) {
+                    const long long Kb = k == 0 ? Kprev : Ks[k - 1];
+                    const float cb = (cross == seg0) ? c0 : seq_value(Kb, e);
+                    const float cn = __fadd_rn(cb, wv[k]);
+                    if (c_out) c_out[i] = cn;
+                    s_c = cn;
+                    s_seg0 = cross + 1;
+                }
+            }
+            __syncthreads();
+            if (s_seg0 >= (base + SEQ_TILE < n ? base + SEQ_TILE : n)) break;
+        }
+    }
+    if (threadIdx.x == 0 && total_out) total_out[0] = s_c;
 }
 
 // idx[m] = min(first i in [0, limit] with c_i >= U_m, limit); U_m = r + m*step (two f64 roundings)
@@ -232,11 +415,21 @@ extern "C" int mcl_resample_indices(mcl_handle *h, const float *d_w, int64_t n_i
     const int64_t limit = std::min(n_in, n_out) - 1;               // pu:441 "i < N - 1"
     const int sblocks = (int)std::min<int64_t>((n_out + 255) / 256, (int64_t)h->sm_count * 16);
     if (mode == MCL_RESAMPLE_REFERENCE_F32) {
-        int rc = mcl_ensure_scratch(h, sizeof(float) * (size_t)n_in);
+        int rc = mcl_ensure_scratch(h, 64 + sizeof(float) * (size_t)n_in);
         if (rc) return rc;
-        float *c = (float *)h->d_scratch;
-        k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n_in, c, 1);
-        MCL_LAUNCH_CHECK(h);
+        float *c = (float *)((char *)h->d_scratch + 64);
+        float *sum = (float *)h->d_scratch;
+        static int serial = -1;
+        if (serial < 0) { const char *e = getenv("MCL_REF_SERIAL"); serial = (e && atoi(e)) ? 1 : 0; }
+        if (serial) {        // the one-warp replay of the additions (kept as the cross-check of the parallel scan)
+            k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n_in, c, 1);
+            MCL_LAUNCH_CHECK(h);
+        } else {
+            k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n_in, nullptr, nullptr, sum);     // pu:430 np.sum
+            MCL_LAUNCH_CHECK(h);
+            k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n_in, sum, c, nullptr);           // pu:430, 436-443
+            MCL_LAUNCH_CHECK(h);
+        }
         k_search_ref_f32<<<sblocks, 256, 0, h->stream>>>(c, limit, n_out, r, step, d_idx);
         MCL_LAUNCH_CHECK(h);
         return MCL_OK;
@@ -361,7 +554,7 @@ extern "C" int mcl_resample_search(mcl_handle *h, int64_t n_in, uint64_t offset,
 
 // sequential f32 running sum of the weights as given (pu:555-563 kld_sampling_amcl does not renormalise)
 int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c) {
-    k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n, d_c, 0);
+    k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, nullptr, d_c, nullptr);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }
@@ -446,6 +639,29 @@ extern "C" int mcl_resample_push(mcl_handle *h, int64_t n_in, const uint64_t *d_
     MCL_LAUNCH_CHECK(h);
     k_push<<<h->sm_count * 8, 256, 0, h->stream>>>(C, n_in - 1, plan, r, (long long)n_global, (long long)n_per_rank, world,
                                                    d_x, d_y, d_theta, (const unsigned long long *)d_peer_ptrs);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// test hook: the running f32 sums themselves (normalise != 0: of w / seq_sum(w), else of w as given);
+// serial != 0 uses the one-warp replay instead of the parallel scan
+extern "C" int mcl_debug_seq_cumsum(mcl_handle *h, const float *d_w, int64_t n, int normalise, int serial, float *d_c) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_w || !d_c) return mcl_fail(h, MCL_ERR_ARG, "mcl_debug_seq_cumsum: bad argument");
+    DeviceGuard guard(h->device);
+    int rc = mcl_ensure_scratch(h, 64);
+    if (rc) return rc;
+    float *sum = (float *)h->d_scratch;
+    if (serial) {
+        k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n, d_c, normalise);
+        MCL_LAUNCH_CHECK(h);
+        return MCL_OK;
+    }
+    if (normalise) {
+        k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, nullptr, nullptr, sum);
+        MCL_LAUNCH_CHECK(h);
+    }
+    k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, normalise ? sum : nullptr, d_c, nullptr);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }

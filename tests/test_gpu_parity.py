@@ -165,6 +165,31 @@ def test_likelihood_house_coded_window_full_size(pu, oracle_map_house):
     assert lik_close(s_auto[sl], ref, rel=2e-6).all()
 
 
+def test_likelihood_large_tiled_map_vs_oracle(pu):
+    """BASELINE config 5 in miniature: map_house tiled to 2048 x 2048 (table 16 MB: global/L2 path),
+    particles spread over the whole map, against the oracle."""
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200.maps import load_npz, tiled_map
+    from mcmh_localization_b200.synth import free_space_particles, raycast_scan
+    from oracle import clib
+    gm = tiled_map(load_npz(os.path.join(GOLDEN, "map_house.npz")), 6, 6, 2048, 2048)
+    assert gm.occ.shape == (2048, 2048)
+    n = 300_000
+    parts = free_space_particles(gm, n, seed=8)
+    scan, angles = raycast_scan(gm, parts[0])
+    args = (scan, angles, parts, gm.dist.ravel(), gm.resolution, np.array([gm.origin_x, gm.origin_y]), gm.width,
+            gm.height, P["sigma_hit"], P["z_hit"], P["z_rand"], P["max_range"], 1)
+    got = pu.compute_likelihoods(*args)
+    sl = slice(0, 30_000)
+    ref = clib.compute_likelihoods(scan, angles, parts[sl], *args[3:])
+    assert lik_close(got[sl], ref, rel=2e-6).all()
+    # uniform initialisation by per-particle rejection sampling on the big map
+    p0 = pu.generate_valid_particles(100_000, gm.occ.ravel(), gm.resolution, gm.origin_x, gm.origin_y, gm.width, gm.height)
+    assert p0.shape == (100_000, 3)
+    assert clib.compute_valid_mask(p0, gm.occ.ravel(), gm.width, gm.height, gm.resolution, gm.origin_x, gm.origin_y).all()
+
+
 # --------------------------------------------------------------------------- softmax (a2)
 def test_softmax_golden(pu):
     g = golden("mh_map_world.npz")
@@ -406,6 +431,58 @@ def test_resample_fixed_point_vs_oracle_bitexact(pu, orc, n):
     expect = n * w.astype(np.float64) / w.astype(np.float64).sum()
     assert np.abs(cnt - expect).max() < 1.0 + 1e-3
     assert np.all(cnt[w == 0] == 0) or n == 1
+
+
+def _seq_cumsum_numpy(w, normalise):
+    w = np.asarray(w, np.float32)
+    if normalise:
+        s = np.float32(0)
+        for v in w:
+            s = np.float32(s + v)
+        w = (w / s).astype(np.float32)
+    c = np.empty_like(w)
+    acc = np.float32(0)
+    for i, v in enumerate(w):
+        acc = np.float32(acc + v)
+        c[i] = acc
+    return c
+
+
+def test_sequential_f32_sum_exact_parallel_emulation(pu):
+    """The parallel scan that emulates c_i = fl32(c_{i-1} + w_i) must reproduce the sequential rounding
+    sequence bit-for-bit: adversarial weight sets (exact ties, powers of two, denormals, huge dynamic range,
+    zeros) against a NumPy float32 loop and against the one-warp in-order replay."""
+    import ctypes as C
+    import torch
+    c = pu._ctx()
+    rs = np.random.RandomState(12)
+    sets = {
+        "ties_pow2": np.full(70000, 2.0 ** -10, np.float32),
+        "ties_3x": (3.0 * 2.0 ** rs.randint(-30, -8, 60000)).astype(np.float32),
+        "uniform": rs.uniform(0, 1, 50000).astype(np.float32),
+        "softmax_like": np.exp(rs.normal(0, 3, 80000)).astype(np.float32),
+        "range": (rs.uniform(0.5, 1, 40000) * 2.0 ** rs.randint(-60, 0, 40000)).astype(np.float32),
+        "denormal": (rs.randint(0, 2 ** 22, 30000).astype(np.float64) * 2.0 ** -149).astype(np.float32),
+        "zeros_mixed": np.where(rs.uniform(0, 1, 50000) < 0.7, 0, rs.uniform(0, 1, 50000)).astype(np.float32),
+        "big_then_small": np.concatenate([[1e6], rs.uniform(0, 1e-3, 30000)]).astype(np.float32),
+        "one": np.array([0.3], np.float32),
+    }
+    for tag, w in sets.items():
+        wd = torch.from_numpy(w).to(c.device)
+        for normalise in (0, 1):
+            out = torch.empty_like(wd)
+            c.h.call("mcl_debug_seq_cumsum", C.c_void_p(wd.data_ptr()), len(w), normalise, 0, C.c_void_p(out.data_ptr()))
+            got = out.cpu().numpy()
+            ref = _seq_cumsum_numpy(w, normalise)
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (tag, normalise, int((got != ref).sum()))
+    # 1M weights: parallel scan == in-order replay
+    w = np.exp(rs.normal(0, 2, 1_000_000)).astype(np.float32)
+    wd = torch.from_numpy(w).to(c.device)
+    a, b = torch.empty_like(wd), torch.empty_like(wd)
+    for normalise in (0, 1):
+        c.h.call("mcl_debug_seq_cumsum", C.c_void_p(wd.data_ptr()), len(w), normalise, 0, C.c_void_p(a.data_ptr()))
+        c.h.call("mcl_debug_seq_cumsum", C.c_void_p(wd.data_ptr()), len(w), normalise, 1, C.c_void_p(b.data_ptr()))
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
 
 
 def test_resample_all_zero_weights(pu):
