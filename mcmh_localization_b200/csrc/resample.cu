@@ -69,12 +69,17 @@ __global__ void __launch_bounds__(32) k_cumsum_ref_f32(const float *__restrict__
 #define SEQ_ITEMS 8
 #define SEQ_TILE (SEQ_THREADS * SEQ_ITEMS)
 
-struct Pair64 { long long a0, a1; };     // increment if the incoming K is even / odd
+// increment if the incoming K is even / odd.  Increments saturate at SEQ_SAT (>= 2^25 > any in-binade K):
+// a saturated value means "the sum has left the binade", which is absorbing, so the composition stays
+// associative while everything fits in 32 bits (half the shuffles and registers of a 64-bit scan).
+#define SEQ_SAT 0x40000000u
+struct Pair64 { unsigned a0, a1; };
 
+__device__ __forceinline__ unsigned sat_add(unsigned a, unsigned b) { return min(a + b, SEQ_SAT); }   // a, b <= SEQ_SAT
 __device__ __forceinline__ Pair64 pair_compose(const Pair64 &f1, const Pair64 &f2) {   // first f1, then f2
     Pair64 r;
-    r.a0 = f1.a0 + ((f1.a0 & 1) ? f2.a1 : f2.a0);
-    r.a1 = f1.a1 + (((1 + f1.a1) & 1) ? f2.a1 : f2.a0);
+    r.a0 = sat_add(f1.a0, (f1.a0 & 1u) ? f2.a1 : f2.a0);
+    r.a1 = sat_add(f1.a1, ((1u + f1.a1) & 1u) ? f2.a1 : f2.a0);
     return r;
 }
 __device__ __forceinline__ Pair64 pair_shfl_up(const Pair64 &v, int o) {
@@ -93,13 +98,13 @@ __device__ __forceinline__ Pair64 seq_decode(float w, int e) {
     const int Ew = ef ? (int)ef - 127 : -126;
     const int sh = e - Ew;
     if (sh <= 0) {
-        const long long a = (-sh > 38) ? (1ll << 62) : (M << (-sh));
+        const unsigned a = (-sh > 6) ? SEQ_SAT : (unsigned)min((long long)SEQ_SAT, M << (-sh));
         r.a0 = a; r.a1 = a;
     } else if (sh <= 24) {
-        const long long a = M >> sh, rem = M & ((1ll << sh) - 1), half = 1ll << (sh - 1);
+        const unsigned a = (unsigned)(M >> sh), rem = (unsigned)(M & ((1ll << sh) - 1)), half = 1u << (sh - 1);
         if (rem < half) { r.a0 = a; r.a1 = a; }
         else if (rem > half) { r.a0 = a + 1; r.a1 = a + 1; }
-        else { r.a0 = a + (a & 1); r.a1 = a + ((1 + a) & 1); }
+        else { r.a0 = a + (a & 1u); r.a1 = a + ((1u + a) & 1u); }
     }   // sh >= 25: w < u/2, the sum does not move
     return r;
 }
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_seq_accumulate_exact(const floa
                 const Pair64 q = pair_compose(excl, loc[k]);
                 Ks[k] = K0 + (p0 ? q.a1 : q.a0);
                 const int64_t i = first + k;
-                if (i >= seg0 && i < n && (Ks[k] >= (1ll << 24) || Ks[k] < 0) && my_cross == 0x7fffffffffffffffll) my_cross = i;
+                if (i >= seg0 && i < n && Ks[k] >= (1ll << 24) && my_cross == 0x7fffffffffffffffll) my_cross = i;
             }
             if (my_cross != 0x7fffffffffffffffll) atomicMin((unsigned long long *)&s_cross, (unsigned long long)my_cross);
             __syncthreads();
