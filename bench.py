@@ -350,6 +350,8 @@ def run_native(args):
         cfg["parallelism"] = "particles sharded over %d ranks (weak scaling), map replicated" % world
         cfg["resample_exchange"] = ("peer-push over NVLink symmetric memory (gather fused with the exchange)"
                                     if getattr(loc, "symm", None) is not None else "NCCL all-to-all")
+        cfg["scalar_exchanges"] = ("libmcl kernels over NVLink peer memory (mailbox all-gather)"
+                                   if getattr(loc, "native", False) else "NCCL via torch.distributed")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

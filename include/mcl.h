@@ -277,6 +277,18 @@ int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);        
 int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
                     double h_out16[16]);
 
+/* Sharded operation, one process per GPU (call after mcl_filter_bind on every rank): the per-step scalar
+ * exchanges (softmax max / sum, estimate sums, resampling scale and totals) and the resampling exchange then run
+ * over NVLink peer memory inside the library's own kernels -- every mcl_filter_* call above becomes collective.
+ *   d_mailbox        this rank's mailbox, >= 8 KiB of zero-initialised symmetric (peer-mapped) memory
+ *   h_peer_mailbox   host array[world]: the address of every rank's mailbox as mapped in THIS process
+ *   h_peer_pose      host array[3][3][world]: peer-mapped base address of pose set s, component c (x, y, theta)
+ * Particle indices for the random streams become global (first_index = rank * n).  mcl_comm_status reports
+ * whether an exchange timed out (a peer died). */
+int mcl_comm_init(mcl_handle *h, int rank, int world, void *d_mailbox, const uint64_t *h_peer_mailbox,
+                  const uint64_t *h_peer_pose);
+int mcl_comm_status(mcl_handle *h, int *err);
+
 /* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */
 /* Random 4-byte gather rate, lookups/s: table_bytes resident in shared memory (where = 0) or in
  * global memory / L2 (where = 1); n_lookups per launch, iters launches timed with CUDA events. */

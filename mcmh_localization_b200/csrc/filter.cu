@@ -25,6 +25,17 @@ struct FilterState {
     double delta[3] = {0, 0, 0}, delta_b[3] = {0, 0, 0};
     double *tf = nullptr, *tb = nullptr;
     int64_t t_cap = 0;
+    // sharded operation (one process per GPU): peer-memory mailboxes for the small exchanges and peer
+    // pointers of every rank's pose buffers for the resampling push
+    bool comm = false;
+    int rank = 0, world = 1;
+    int64_t n_global = 0;
+    unsigned long long *mailbox = nullptr;           // local mailbox (symmetric memory)
+    unsigned long long peer_mailbox[16] = {0};
+    uint64_t *d_peer_pose = nullptr;                  // device [3 sets][3 comps][world]
+    uint64_t epoch = 0;
+    double *d_x8 = nullptr;                           // device staging for exchange payloads / results (64 doubles)
+    int *d_comm_err = nullptr;
 };
 
 // one FilterState per handle, kept out of common.cuh: keyed by handle pointer
@@ -46,7 +57,10 @@ static FilterState *filter_of(mcl_handle *h, bool create) {
 void mcl_filter_forget(const mcl_handle *h) {
     std::lock_guard<std::mutex> lk(g_filters_mu);
     auto it = g_filters.find(h);
-    if (it != g_filters.end()) { cudaFree(it->second.tf); cudaFree(it->second.tb); }
+    if (it != g_filters.end()) {
+        cudaFree(it->second.tf); cudaFree(it->second.tb); cudaFree(it->second.d_peer_pose);
+        cudaFree(it->second.d_x8); cudaFree(it->second.d_comm_err);
+    }
     g_filters.erase(h);
 }
 
@@ -140,6 +154,157 @@ extern "C" int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode
     return MCL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small all-gathers over NVLink peer memory.  The per-step exchanges are a handful of scalars (softmax
+// max / sum, estimate sums, resampling scale and totals), latency-bound through NCCL (20-50 us each with 8
+// ranks).  Here every rank stores its payload straight into every peer's mailbox (symmetric memory), raises
+// a flag with system-scope release, and spins with acquire on its own flags until all peers have written:
+// one ~5 us kernel, no host involvement, and the reduction is done locally in rank order (deterministic).
+// Mailbox (u64 units): flags[2][16] | slots[2][16][16]; two parities so that a fast rank's exchange k+2
+// cannot overwrite what a slow rank is still reading from exchange k (a rank cannot finish k+1 before every
+// peer has entered k+1, i.e. finished k).
+// ---------------------------------------------------------------------------------------------
+enum { XCH_SUM_F64 = 0, XCH_MAX_F64 = 1, XCH_SUM_U64 = 2, XCH_GATHER = 3 };
+#define XCH_MAXV 16
+
+struct XchArgs {
+    unsigned long long *mailbox;
+    unsigned long long peers[16];
+    int rank, world;
+    unsigned long long epoch;
+    int *err;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(32) k_exchange(const XchArgs a, const unsigned long long *payload, int nvals, int op,
+                                                 unsigned long long *out) {
+    const int t = threadIdx.x;
+    const int par = (int)(a.epoch & 1ull);
+    if (t < a.world) {
+        unsigned long long *peer = reinterpret_cast<unsigned long long *>(a.peers[t]);
+        unsigned long long *slot = peer + 32 + ((size_t)par * 16 + a.rank) * XCH_MAXV;
+        for (int v = 0; v < nvals; ++v) slot[v] = payload[v];
+        __threadfence_system();
+        st_release_sys(peer + par * 16 + a.rank, a.epoch);
+    }
+    bool ok = true;
+    if (t < a.world) {
+        const unsigned long long *flag = a.mailbox + par * 16 + t;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) < a.epoch) {
+            if (clock64() - t0 > 8000000000ll) { ok = false; break; }      // ~4 s: a peer died; do not hang the GPU
+        }
+    }
+    if (!__all_sync(0xffffffffu, ok)) { if (t == 0) *a.err = 1; return; }
+    if (t < nvals) {
+        const unsigned long long *slots = a.mailbox + 32 + (size_t)par * 16 * XCH_MAXV;
+        if (op == XCH_GATHER) {
+            for (int d = 0; d < a.world; ++d) out[d * nvals + t] = ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
+        } else if (op == XCH_SUM_U64) {
+            unsigned long long acc = 0;
+            for (int d = 0; d < a.world; ++d) acc += ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
+            out[t] = acc;
+        } else {
+            double acc = __longlong_as_double((long long)((volatile const unsigned long long *)slots)[t]);
+            for (int d = 1; d < a.world; ++d) {
+                const double v = __longlong_as_double((long long)((volatile const unsigned long long *)slots)[d * XCH_MAXV + t]);
+                acc = op == XCH_MAX_F64 ? fmax(acc, v) : acc + v;            // rank order: deterministic
+            }
+            out[t] = (unsigned long long)__double_as_longlong(acc);
+        }
+    }
+}
+
+static int comm_exchange(mcl_handle *h, FilterState *f, const void *d_payload, int nvals, int op, void *d_out) {
+    if (nvals > XCH_MAXV) return mcl_fail(h, MCL_ERR_ARG, "comm_exchange: payload too large");
+    XchArgs a;
+    a.mailbox = f->mailbox;
+    for (int d = 0; d < 16; ++d) a.peers[d] = f->peer_mailbox[d];
+    a.rank = f->rank; a.world = f->world; a.epoch = ++f->epoch; a.err = f->d_comm_err;
+    k_exchange<<<1, 32, 0, h->stream>>>(a, (const unsigned long long *)d_payload, nvals, op, (unsigned long long *)d_out);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// helpers on the staging buffer d_x8: [0..15] payload, [16..47] result
+__global__ void k_pack2(const double *a, int ia, const double *b, int ib, double *out) { out[0] = a[ia]; out[1] = b ? b[ib] : 0.0; }
+__global__ void k_unpack_max(const double *in, double *a, double *b) { a[0] = in[0]; if (b) b[0] = in[1]; }
+__global__ void k_unpack_qsum(const unsigned long long *in, double *a, double *b) {
+    a[1] = (double)in[0] / 1099511627776.0; ((unsigned long long *)a)[2] = in[0];
+    if (b) { b[1] = (double)in[1] / 1099511627776.0; ((unsigned long long *)b)[2] = in[1]; }
+}
+__global__ void k_f32_to_f64(const float *in, double *out) { out[0] = (double)in[0]; }
+__global__ void k_f64_to_f32(const double *in, float *out) { out[0] = (float)in[0]; }
+
+// mcl_comm_init: see include/mcl.h
+extern "C" int mcl_comm_init(mcl_handle *h, int rank, int world, void *d_mailbox, const uint64_t *h_peer_mailbox,
+                             const uint64_t *h_peer_pose /* [3][3][world] */) {
+    if (!h) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_comm_init: bind the filter first");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || !d_mailbox || !h_peer_mailbox || !h_peer_pose)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_comm_init: bad argument");
+    DeviceGuard guard(h->device);
+    f->rank = rank; f->world = world; f->n_global = f->n * world;
+    f->mailbox = (unsigned long long *)d_mailbox;
+    for (int d = 0; d < world; ++d) f->peer_mailbox[d] = h_peer_mailbox[d];
+    if (!f->d_peer_pose) MCL_CUDA(h, cudaMalloc((void **)&f->d_peer_pose, 9 * 16 * sizeof(uint64_t)));
+    if (!f->d_x8) MCL_CUDA(h, cudaMalloc((void **)&f->d_x8, 64 * sizeof(double)));
+    if (!f->d_comm_err) { MCL_CUDA(h, cudaMalloc((void **)&f->d_comm_err, sizeof(int))); MCL_CUDA(h, cudaMemset(f->d_comm_err, 0, sizeof(int))); }
+    MCL_CUDA(h, cudaMemcpy(f->d_peer_pose, h_peer_pose, (size_t)9 * world * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    f->first_index = (uint64_t)rank * (uint64_t)f->n;
+    f->epoch = 0;
+    f->comm = true;
+    return MCL_OK;
+}
+
+extern "C" int mcl_comm_status(mcl_handle *h, int *err) {
+    if (!h || !err) return MCL_ERR_ARG;
+    FilterState *f = filter_of(h, false);
+    *err = 0;
+    if (!f || !f->comm) return MCL_OK;
+    DeviceGuard guard(h->device);
+    MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, f->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(err, h->h_pinned, sizeof(int));
+    return MCL_OK;
+}
+
+// softmax of both score sets with the two global statistics exchanged over peer memory
+static int sharded_softmax(mcl_handle *h, FilterState *f, bool both) {
+    double *st_post = f->d_x8 + 48, *st_pre = f->d_x8 + 52;          // 4 doubles each
+    int rc = mcl_softmax_max(h, f->score_post, f->n, st_post);
+    if (rc) return rc;
+    if (both) { rc = mcl_softmax_max(h, f->score_pre, f->n, st_pre); if (rc) return rc; }
+    k_pack2<<<1, 1, 0, h->stream>>>(st_post, 0, both ? st_pre : nullptr, 0, f->d_x8);
+    MCL_LAUNCH_CHECK(h);
+    rc = comm_exchange(h, f, f->d_x8, 2, XCH_MAX_F64, f->d_x8 + 16);
+    if (rc) return rc;
+    k_unpack_max<<<1, 1, 0, h->stream>>>(f->d_x8 + 16, st_post, both ? st_pre : nullptr);
+    MCL_LAUNCH_CHECK(h);
+    rc = mcl_softmax_sumexp(h, f->score_post, f->n, st_post);
+    if (rc) return rc;
+    if (both) { rc = mcl_softmax_sumexp(h, f->score_pre, f->n, st_pre); if (rc) return rc; }
+    k_pack2<<<1, 1, 0, h->stream>>>(st_post, 2, both ? st_pre : nullptr, 2, f->d_x8);     // the exact 2^-40 integers
+    MCL_LAUNCH_CHECK(h);
+    rc = comm_exchange(h, f, f->d_x8, 2, XCH_SUM_U64, f->d_x8 + 16);
+    if (rc) return rc;
+    k_unpack_qsum<<<1, 1, 0, h->stream>>>((const unsigned long long *)(f->d_x8 + 16), st_post, both ? st_pre : nullptr);
+    MCL_LAUNCH_CHECK(h);
+    rc = mcl_softmax_weights(h, f->score_post, f->n, st_post, both ? f->w_post : f->w[f->wslot]);
+    if (rc) return rc;
+    if (both) rc = mcl_softmax_weights(h, f->score_pre, f->n, st_pre, f->w_pre);
+    return rc;
+}
+
 #define FILTER_OR_FAIL(name)                                                                          \
     if (!h) return MCL_ERR_ARG;                                                                       \
     FilterState *f = filter_of(h, false);                                                             \
@@ -166,15 +331,24 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
     if (rc) return rc;
     if (!f->use_mh) {
         // MCL: weights = weights_post (node:313); scores_pre would be computed and discarded by the reference
+        if (f->comm) return sharded_softmax(h, f, false);
         return mcl_softmax(h, f->score_post, f->n, f->w[f->wslot], nullptr, nullptr);
     }
-    rc = mcl_softmax(h, f->score_post, f->n, f->w_post, nullptr, nullptr);
-    if (rc) return rc;
-    rc = mcl_likelihood(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->n, f->score_pre);
-    if (rc) return rc;
-    rc = mcl_softmax(h, f->score_pre, f->n, f->w_pre, nullptr, nullptr);
-    if (rc) return rc;
+    if (f->comm) {
+        rc = mcl_likelihood(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->n, f->score_pre);
+        if (rc) return rc;
+        rc = sharded_softmax(h, f, true);
+        if (rc) return rc;
+    } else {
+        rc = mcl_softmax(h, f->score_post, f->n, f->w_post, nullptr, nullptr);
+        if (rc) return rc;
+        rc = mcl_likelihood(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->n, f->score_pre);
+        if (rc) return rc;
+        rc = mcl_softmax(h, f->score_pre, f->n, f->w_pre, nullptr, nullptr);
+        if (rc) return rc;
+    }
     f->tick++;
+    if (f->assym && f->comm) return mcl_fail(h, MCL_ERR_STATE, "asymmetric MH is not available on sharded particles yet");
     if (f->assym) {
         // node:366-367: transition_probability() then assym_mh_resampling(prev, cur, w_post, w_pre, fwd, bwd)
         if (f->t_cap < f->n) {
@@ -241,6 +415,7 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
     FILTER_OR_FAIL("mcl_filter_update_chain");
     if (iters < 1) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_update_chain: iters < 1");
     if (!f->use_mh || f->assym) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_update_chain: needs the symmetric MH mode");
+    if (f->comm) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_update_chain: not available on sharded particles yet");
     DeviceGuard guard(h->device);
     const int blocks = (int)std::min<int64_t>((f->n + 255) / 256, (int64_t)h->sm_count * 16);
     // roles during the chain: prev = particles_prev (fixed), prop = cur buffer, chain = spare buffer
@@ -274,6 +449,30 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
 
 extern "C" int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]) {
     FILTER_OR_FAIL("mcl_filter_estimate");
+    if (f->comm) {
+        // raw sums -> rank-ordered sum over peers -> means -> central sums -> rank-ordered sum
+        DeviceGuard guard(h->device);
+        double *o = d_out18 ? d_out18 : h->d_est18;
+        int rc = mcl_estimate_moments_async(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->w[f->wslot], f->n, f->d_x8);
+        if (rc) return rc;
+        rc = comm_exchange(h, f, f->d_x8, 6, XCH_SUM_F64, o);
+        if (rc) return rc;
+        rc = mcl_estimate_means_async(h, o);
+        if (rc) return rc;
+        rc = mcl_estimate_central_async(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->w[f->wslot], f->n, o + 6, f->d_x8);
+        if (rc) return rc;
+        rc = comm_exchange(h, f, f->d_x8, 9, XCH_SUM_F64, o + 9);
+        if (rc) return rc;
+        if (h_out16) {
+            MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, o, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            const double *r = h->h_pinned;
+            h_out16[0] = r[0]; h_out16[1] = r[1]; h_out16[2] = r[6]; h_out16[3] = r[7]; h_out16[4] = r[8];
+            for (int k = 0; k < 9; ++k) h_out16[5 + k] = r[9 + k];
+            h_out16[14] = 0; h_out16[15] = 0;
+        }
+        return MCL_OK;
+    }
     if (h_out16) return mcl_estimate(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->w[f->wslot], f->n, h_out16);
     if (!d_out18) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_estimate: no output");
     return mcl_estimate_async(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->w[f->wslot], f->n, d_out18);
@@ -283,6 +482,32 @@ extern "C" int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out1
 extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
     FILTER_OR_FAIL("mcl_filter_resample");
     f->tick++;
+    if (f->comm) {
+        // global systematic resampling (fixed-point arithmetic): scale from the global weight maximum, local
+        // cumulative sums, all-gather of the totals, offspring pushed into the destination ranks' spare set
+        DeviceGuard guard(h->device);
+        if (r < 0) r = mcl_resample_offset(f->seed, f->tick, f->n_global);
+        float *wmax = (float *)(f->d_x8 + 56);
+        int rc = mcl_weights_max(h, f->w[f->wslot], f->n, wmax);
+        if (rc) return rc;
+        k_f32_to_f64<<<1, 1, 0, h->stream>>>(wmax, f->d_x8);
+        MCL_LAUNCH_CHECK(h);
+        rc = comm_exchange(h, f, f->d_x8, 1, XCH_MAX_F64, f->d_x8 + 16);
+        if (rc) return rc;
+        k_f64_to_f32<<<1, 1, 0, h->stream>>>(f->d_x8 + 16, wmax);
+        MCL_LAUNCH_CHECK(h);
+        rc = mcl_resample_scan(h, f->w[f->wslot], f->n, wmax, f->n_global, (uint64_t *)f->d_x8);
+        if (rc) return rc;
+        rc = comm_exchange(h, f, f->d_x8, 1, XCH_GATHER, f->d_x8 + 16);          // totals of every rank
+        if (rc) return rc;
+        rc = mcl_resample_push(h, f->n, (const uint64_t *)(f->d_x8 + 16), f->rank, f->world, r, f->n_global, f->n,
+                               f->x[f->cur], f->y[f->cur], f->th[f->cur], f->d_peer_pose + (size_t)f->spare * 3 * f->world);
+        if (rc) return rc;
+        rc = comm_exchange(h, f, f->d_x8, 0, XCH_GATHER, f->d_x8 + 16);          // barrier: all pushes have landed
+        if (rc) return rc;
+        const int t = f->cur; f->cur = f->spare; f->spare = t;
+        return MCL_OK;
+    }
     if (r < 0) r = mcl_resample_offset(f->seed, f->tick, f->n);
     int rc = mcl_resample_indices(h, f->w[f->wslot], f->n, f->n, r, f->resample_mode, f->idx);
     if (rc) return rc;

@@ -92,11 +92,12 @@ class ShardedLocalizer(Localizer):
     """Localizer whose particle set is the union over ranks of equally sized shards."""
 
     def __init__(self, device=0, params=None, mode=None, seed=0, resample_mode="fixed", max_attempts=1000,
-                 group=None, peer_push=True):
+                 group=None, peer_push=True, native_comm=True):
         if resample_mode != "fixed":
             raise ValueError("sharded resampling uses the fixed-point arithmetic (decomposition-independent)")
         self.group = group
         self.use_peer_push = peer_push
+        self.use_native_comm = native_comm and peer_push
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         super().__init__(device=device, params=params, mode=mode, seed=seed, resample_mode="fixed",
@@ -129,6 +130,13 @@ class ShardedLocalizer(Localizer):
         self.first_index = self.rank * n
         super()._alloc(n)
         self.n_global = n * self.world
+        self.native = False
+        if self.symm is not None and self.use_native_comm:
+            try:
+                self._init_native_comm(n)
+            except Exception as e:      # noqa: BLE001 -- fall back to NCCL through torch.distributed
+                self.symm_error = repr(e)
+                self.native = False
         d = self.device
         self.st_post = torch.zeros(4, dtype=torch.float64, device=d)   # {max, sum, sum as 2^-40 fixed point, -}
         self.st_pre = torch.zeros(4, dtype=torch.float64, device=d)
@@ -140,13 +148,39 @@ class ShardedLocalizer(Localizer):
         self.send_cap = 0
         self.send = None
 
+    def _init_native_comm(self, n):
+        """Hand the peer-mapped mailboxes and pose buffers to the library: from here on every exchange of the
+        step runs inside libmcl's own kernels over NVLink peer memory (mcl_comm_init), and the whole sharded
+        step is sequenced by the same C calls as the single-GPU one."""
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.mail = symm_mem.empty(2048, dtype=torch.int64, device=self.device)
+        self.mail.zero_()
+        self.mail_hdl = symm_mem.rendezvous(self.mail, grp)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)                                   # every mailbox is zeroed before first use
+        W = self.world
+        peers = (C.c_uint64 * W)(*[int(p) for p in self.mail_hdl.buffer_ptrs])
+        ptrs = [int(p) for p in self.symm.buffer_ptrs]
+        pose = (C.c_uint64 * (9 * W))(*[ptrs[d] + (3 * j + k) * n * 8 for j in range(3) for k in range(3) for d in range(W)])
+        self.h.call("mcl_comm_init", self.rank, W, C.c_void_p(self.mail.data_ptr()), peers, pose)
+        self.native = True
+
+    def comm_error(self):
+        e = C.c_int(0)
+        self.h.call("mcl_comm_status", C.byref(e))
+        return e.value
+
     def _set_roles(self, cur, prev, spare, ws, tick):
         self.h.call("mcl_filter_set_roles", (C.c_int * 4)(cur, prev, spare, ws), int(tick))
 
     # -- update ------------------------------------------------------------------------------
     def _update_core(self, uniforms=None):
         if self.assym or self.use_adaptive:
-            raise NotImplementedError("localization_mode %r not supported yet" % self.params["localization_mode"])
+            raise NotImplementedError("localization_mode %r is not available on sharded particles yet"
+                                      % self.params["localization_mode"])
+        if self.native:
+            return Localizer._update_core(self, uniforms)
         cur, prev, spare, ws, tick = self._roles()
         S, n, h = self.sets, self.n, self.h
         h.call("mcl_likelihood", *[_ptr(t) for t in S[cur]], n, _ptr(self.score_post))
@@ -196,6 +230,8 @@ class ShardedLocalizer(Localizer):
         dist.all_reduce(self.c9, op=dist.ReduceOp.SUM, group=self.group)
 
     def estimate(self):
+        if self.native:
+            return Localizer.estimate(self)
         with self._lock:
             self._bind_stream()
             self._estimate_sums()
@@ -204,6 +240,8 @@ class ShardedLocalizer(Localizer):
         return assemble_estimate([m[0], m[1], m[6], m[7], m[8]] + list(c) + [0, 0])
 
     def estimate_async(self, out18):
+        if self.native:
+            return Localizer.estimate_async(self, out18)
         with self._lock:
             self._bind_stream()
             self._estimate_sums()
@@ -212,6 +250,8 @@ class ShardedLocalizer(Localizer):
 
     # -- resample ----------------------------------------------------------------------------
     def resample(self, r=None):
+        if self.native:
+            return Localizer.resample(self, r)
         with self._lock:
             self._bind_stream()
             cur, prev, spare, ws, tick = self._roles()
@@ -254,6 +294,8 @@ class ShardedLocalizer(Localizer):
 
     # -- whole step ---------------------------------------------------------------------------
     def step(self, odom, ranges, angle_min=None, angle_max=None, angles=None):
+        if self.native:
+            return Localizer.step(self, odom, ranges, angle_min, angle_max, angles)
         self.predict(odom)
         self.update(ranges, angle_min, angle_max, angles)
         est = self.estimate()
@@ -261,6 +303,8 @@ class ShardedLocalizer(Localizer):
         return est
 
     def step_staged(self, odom, k, out18=None):
+        if self.native:
+            return Localizer.step_staged(self, odom, k, out18)
         self.predict(odom)
         self.update_staged(k)
         self.estimate_async(out18 if out18 is not None else self.est18)

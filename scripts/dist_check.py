@@ -23,8 +23,9 @@ def main():
     poses = bench.trajectory(steps + 1)
     scans, angles = bench.make_scans(gm, poses, 360)
     parts = free_space_particles(gm, n, seed=5)
-    peer_push = os.environ.get("MCL_PEER_PUSH", "1") != "0"
-    sh = ShardedLocalizer(device=local, params=P, mode="MHMCL", seed=99, peer_push=peer_push)
+    mode = os.environ.get("MCL_EXCHANGE", "native")      # native | push | nccl
+    sh = ShardedLocalizer(device=local, params=P, mode="MHMCL", seed=99, peer_push=mode != "nccl",
+                          native_comm=mode == "native")
     sh.load_map(gm)
     sh.set_particles(parts[rank * n_local:(rank + 1) * n_local])
     ref = None
@@ -34,8 +35,8 @@ def main():
         ref.set_particles(parts)
     ok = True
     if rank == 0:
-        print("exchange:", "peer-push over symmetric memory" if sh.symm is not None else
-              "NCCL all-to-all (%s)" % getattr(sh, "symm_error", "peer push disabled"), flush=True)
+        print("exchange:", ("native peer-memory exchanges + peer-push" if sh.native else "NCCL scalars + peer-push")
+              if sh.symm is not None else "NCCL all-to-all (%s)" % getattr(sh, "symm_error", "peer push disabled"), flush=True)
     for k in range(steps):
         est = sh.step(poses[k], scans[k], angles=angles)
         allp = sh.gather_particles()

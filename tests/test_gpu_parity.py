@@ -727,9 +727,11 @@ def test_sharded_two_gpus_equals_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from conftest import ROOT
-    for push in ("1", "0"):      # peer-push over symmetric memory, and the NCCL all-to-all fallback
+    # native: every exchange inside libmcl over NVLink peer memory; push: NCCL scalars + peer-push
+    # resampling; nccl: NCCL scalars + all-to-all
+    for k, mode in enumerate(("native", "push", "nccl")):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                            "--master-addr", "127.0.0.1", "--master-port", "2953" + push,
+                            "--master-addr", "127.0.0.1", "--master-port", str(29533 + k),
                             os.path.join(ROOT, "scripts", "dist_check.py"), "20000"],
-                           capture_output=True, text=True, timeout=600, env=dict(os.environ, MCL_PEER_PUSH=push))
-        assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+                           capture_output=True, text=True, timeout=600, env=dict(os.environ, MCL_EXCHANGE=mode))
+        assert "DIST_CHECK OK" in r.stdout, (mode, r.stdout[-2000:] + r.stderr[-2000:])
