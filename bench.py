@@ -287,6 +287,22 @@ def run_native(args):
         e2e_t = float(t.item())
     e2e_value = evals / e2e_t
 
+    # ---- the same step with the reference's own resampling arithmetic (sequential-f32 sums, bit-exact) ---
+    ref_mode_ms = None
+    if world == 1 and args.resample == "fixed" and not args.quick:
+        from mcmh_localization_b200 import RESAMPLE_REFERENCE_F32, RESAMPLE_FIXED_POINT
+        loc.h.call("mcl_filter_configure", 1, RESAMPLE_REFERENCE_F32, loc.seed, 0, -1)
+        ts = []
+        for j in range(min(K, 30)):
+            k = W + 1 + j
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            a.record(); loc.step_staged(poses[k], k, est_buf[k]); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        ref_mode_ms = float(np.median(ts[3:])) if len(ts) > 3 else float(np.median(ts))
+        loc.h.call("mcl_filter_configure", 1, RESAMPLE_FIXED_POINT, loc.seed, 0, -1)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,6 +374,7 @@ def run_native(args):
         "dtype": "f64", "data": "synthetic", "config": cfg,
         "step_ms_median": float(np.median(step_ms)), "step_ms_min": float(step_ms.min()),
         "host_wall_ms_per_step": 1e3 * t_wall / K,
+        "step_ms_reference_resampling": ref_mode_ms,
         "valid_beams_mean": mv, "likelihood_kernel_evals_per_s": n * mv / (lik_launch_ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_t / K,

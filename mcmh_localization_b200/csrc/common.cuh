@@ -76,6 +76,8 @@ struct mcl_handle {
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     double *h_pinned = nullptr;  // 64 doubles, pinned, for blocking scalar reads
+    void *d_seq = nullptr;       // work buffers of the exact sequential-f32 scan (resample.cu)
+    size_t seq_bytes = 0;
     void *d_kld = nullptr;       // KLD-sampling work buffers (kld.cu)
     size_t kld_bytes = 0;
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)

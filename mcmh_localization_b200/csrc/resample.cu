@@ -236,6 +236,294 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_seq_accumulate_exact(const floa
     if (threadIdx.x == 0 && total_out) total_out[0] = s_c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-CTA version of the exact emulation (large n).  The element maps depend on the binade of the running
+// sum, which a tile only knows once every earlier tile is done -- but almost every tile lies entirely inside
+// the binade an APPROXIMATE (fp64) prefix predicts.  So:
+//   A  per-tile fp64 sums                      (parallel)        B  their prefix -> speculated exponent per tile
+//   C  per-tile aggregate map under that exponent (parallel; a saturated map = "the sum leaves the binade here")
+//   D  one CTA walks the tiles in order: where the exact incoming sum has the speculated exponent and the
+//      aggregate does not leave the binade, the outgoing sum is one integer add (thread 0, no barrier);
+//      otherwise the CTA scans that tile exactly (with binade restarts).  Records the exact incoming sum of
+//      every tile.  ~25-40 slow tiles per pass.
+//   E  every tile, now knowing its exact incoming sum, writes its running sums (parallel, with restarts).
+// ---------------------------------------------------------------------------------------------
+#define MT_THREADS 256
+#define MT_ITEMS 8
+#define MT_TILE (MT_THREADS * MT_ITEMS)
+
+struct MtShared {
+    Pair64 warp_tot[MT_THREADS / 32];
+    float c;
+    long long cross;
+    int64_t seg0;
+};
+
+__device__ __forceinline__ void mt_load(const float *__restrict__ w, int64_t n, const float *div, int64_t base,
+                                        float (&wv)[MT_ITEMS]) {
+    const float dv = div ? div[0] : 1.0f;
+    const int64_t first = base + (int64_t)threadIdx.x * MT_ITEMS;
+#pragma unroll
+    for (int k = 0; k < MT_ITEMS; ++k) {
+        const int64_t i = first + k;
+        float v = i < n ? w[i] : 0.0f;
+        if (div && i < n) v = __fdiv_rn(v, dv);
+        wv[k] = v;
+    }
+}
+
+// block-wide exclusive scan of per-thread maps; also returns the block aggregate
+__device__ __forceinline__ Pair64 mt_block_exclusive(const Pair64 &mine, MtShared &sh, Pair64 &aggregate) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Pair64 inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Pair64 t = pair_shfl_up(inc, o);
+        if (lane >= o) inc = pair_compose(t, inc);
+    }
+    if (lane == 31) sh.warp_tot[warp] = inc;
+    __syncthreads();
+    Pair64 excl = pair_shfl_up(inc, 1);
+    if (lane == 0) { excl.a0 = 0; excl.a1 = 0; }
+    Pair64 pre; pre.a0 = 0; pre.a1 = 0;
+    Pair64 tot; tot.a0 = 0; tot.a1 = 0;
+#pragma unroll
+    for (int q = 0; q < MT_THREADS / 32; ++q) {
+        if (q == warp) pre = tot;
+        tot = pair_compose(tot, sh.warp_tot[q]);
+    }
+    aggregate = tot;
+    __syncthreads();
+    return pair_compose(pre, excl);
+}
+
+// exact running sums of one tile starting from c_start (binade restarts inside); returns the outgoing sum
+template <bool WRITE>
+__device__ float mt_tile_exact(const float (&wv)[MT_ITEMS], int64_t base, int64_t n, float c_start, float *c_out,
+                               MtShared &sh) {
+    const int64_t first = base + (int64_t)threadIdx.x * MT_ITEMS;
+    const int64_t tile_end = base + MT_TILE < n ? base + MT_TILE : n;
+    if (threadIdx.x == 0) { sh.c = c_start; sh.seg0 = base; }
+    __syncthreads();
+    while (true) {
+        const float c0 = sh.c;
+        const int64_t seg0 = sh.seg0;
+        const int e = seq_exponent(c0);
+        const long long K0 = seq_K(c0);
+        Pair64 loc[MT_ITEMS];
+        Pair64 run; run.a0 = 0; run.a1 = 0;
+#pragma unroll
+        for (int k = 0; k < MT_ITEMS; ++k) {
+            const int64_t i = first + k;
+            Pair64 m; m.a0 = 0; m.a1 = 0;
+            if (i >= seg0 && i < n) m = seq_decode(wv[k], e);
+            run = pair_compose(run, m);
+            loc[k] = run;
+        }
+        if (threadIdx.x == 0) sh.cross = 0x7fffffffffffffffll;
+        Pair64 agg;
+        const Pair64 excl = mt_block_exclusive(run, sh, agg);
+        const int p0 = (int)(K0 & 1);
+        const long long Kprev = K0 + (p0 ? excl.a1 : excl.a0);
+        long long Ks[MT_ITEMS];
+        long long my_cross = 0x7fffffffffffffffll;
+#pragma unroll
+        for (int k = 0; k < MT_ITEMS; ++k) {
+            const Pair64 q = pair_compose(excl, loc[k]);
+            Ks[k] = K0 + (p0 ? q.a1 : q.a0);
+            const int64_t i = first + k;
+            if (i >= seg0 && i < n && Ks[k] >= (1ll << 24) && my_cross == 0x7fffffffffffffffll) my_cross = i;
+        }
+        if (my_cross != 0x7fffffffffffffffll) atomicMin((unsigned long long *)&sh.cross, (unsigned long long)my_cross);
+        __syncthreads();
+        const long long cross = sh.cross;
+        const int64_t end = cross == 0x7fffffffffffffffll ? tile_end : (int64_t)cross;
+        float last_val = c0;
+        bool have_last = false;
+#pragma unroll
+        for (int k = 0; k < MT_ITEMS; ++k) {
+            const int64_t i = first + k;
+            if (i >= seg0 && i < end) {
+                const float v = seq_value(Ks[k], e);
+                if (WRITE) c_out[i] = v;
+                if (i == end - 1) { last_val = v; have_last = true; }
+            }
+        }
+        __syncthreads();
+        if (cross == 0x7fffffffffffffffll) {
+            if (have_last) sh.c = last_val;
+            __syncthreads();
+            break;
+        }
+#pragma unroll
+        for (int k = 0; k < MT_ITEMS; ++k) {
+            const int64_t i = first + k;
+            if (i == cross) {
+                const long long Kb = k == 0 ? Kprev : Ks[k - 1];
+                const float cb = (cross == seg0) ? c0 : seq_value(Kb, e);
+                const float cn = __fadd_rn(cb, wv[k]);
+                if (WRITE) c_out[i] = cn;
+                sh.c = cn;
+                sh.seg0 = cross + 1;
+            }
+        }
+        __syncthreads();
+        if (sh.seg0 >= tile_end) break;
+    }
+    const float r = sh.c;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_mt_tilesum(const float *__restrict__ w, int64_t n, const float *div,
+                                                           double *tsum) {
+    __shared__ double shd[MT_THREADS / 32];
+    float wv[MT_ITEMS];
+    mt_load(w, n, div, (int64_t)blockIdx.x * MT_TILE, wv);
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < MT_ITEMS; ++k) s += (double)wv[k];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) shd[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int q = 0; q < MT_THREADS / 32; ++q) t += shd[q];
+        tsum[blockIdx.x] = t;
+    }
+}
+
+// exclusive fp64 prefix of the tile sums -> speculated unit exponent of the sum entering each tile
+__global__ void __launch_bounds__(1024) k_mt_speculate(const double *tsum, int64_t nt, int *e_spec) {
+    __shared__ double sh[32];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < nt; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const double v = i < nt ? tsum[i] : 0.0;
+        double inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) sh[warp] = inc;
+        __syncthreads();
+        double off = 0;
+        for (int q = 0; q < warp; ++q) off += sh[q];
+        const double excl = carry + off + inc - v;
+        if (i < nt) e_spec[i] = seq_exponent((float)excl);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = carry + off + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_mt_aggregate(const float *__restrict__ w, int64_t n, const float *div,
+                                                             const int *e_spec, uint2 *agg) {
+    __shared__ MtShared sh;
+    float wv[MT_ITEMS];
+    const int64_t base = (int64_t)blockIdx.x * MT_TILE;
+    mt_load(w, n, div, base, wv);
+    const int e = e_spec[blockIdx.x];
+    Pair64 run; run.a0 = 0; run.a1 = 0;
+    const int64_t first = base + (int64_t)threadIdx.x * MT_ITEMS;
+#pragma unroll
+    for (int k = 0; k < MT_ITEMS; ++k) {
+        Pair64 m; m.a0 = 0; m.a1 = 0;
+        if (first + k < n) m = seq_decode(wv[k], e);
+        run = pair_compose(run, m);
+    }
+    Pair64 a;
+    mt_block_exclusive(run, sh, a);
+    if (threadIdx.x == 0) agg[blockIdx.x] = make_uint2(a.a0, a.a1);
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_mt_walk(const float *__restrict__ w, int64_t n, const float *div,
+                                                        const int *__restrict__ e_spec, const uint2 *__restrict__ agg,
+                                                        int64_t nt, float *c_in, float *total_out) {
+    __shared__ MtShared sh;
+    __shared__ float s_cur;
+    __shared__ int64_t s_tile;
+    if (threadIdx.x == 0) { s_cur = 0.0f; s_tile = 0; }
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x == 0) {
+            // fast walk: one integer add per tile while the speculation holds
+            float c = s_cur;
+            int64_t j = s_tile;
+            while (j < nt) {
+                const int e = seq_exponent(c);
+                const uint2 a = agg[j];
+                const long long K = seq_K(c) + ((seq_K(c) & 1) ? a.y : a.x);
+                if (e != e_spec[j] || K >= (1ll << 24)) break;        // mis-speculated or leaves the binade: slow tile
+                c_in[j] = c;
+                c = seq_value(K, e);
+                ++j;
+            }
+            s_cur = c; s_tile = j;
+            if (j < nt) c_in[j] = c;
+        }
+        __syncthreads();
+        const int64_t j = s_tile;
+        if (j >= nt) break;
+        float wv[MT_ITEMS];
+        mt_load(w, n, div, j * MT_TILE, wv);
+        const float c = mt_tile_exact<false>(wv, j * MT_TILE, n, s_cur, nullptr, sh);
+        if (threadIdx.x == 0) { s_cur = c; s_tile = j + 1; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) total_out[0] = s_cur;
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_mt_write(const float *__restrict__ w, int64_t n, const float *div,
+                                                         const float *__restrict__ c_in, float *__restrict__ c_out) {
+    __shared__ MtShared sh;
+    float wv[MT_ITEMS];
+    const int64_t base = (int64_t)blockIdx.x * MT_TILE;
+    mt_load(w, n, div, base, wv);
+    mt_tile_exact<true>(wv, base, n, c_in[blockIdx.x], c_out, sh);
+}
+
+// exact sequential-f32 accumulation of w (or of w / *d_div): running sums to d_c (nullable), total to d_total
+// (nullable).  Small inputs: one streaming CTA; large inputs: the multi-CTA pipeline above.
+static int seq_accumulate(mcl_handle *h, const float *d_w, int64_t n, const float *d_div, float *d_c, float *d_total) {
+    static int force_single = -1;
+    if (force_single < 0) { const char *e = getenv("MCL_SEQ_SINGLE_CTA"); force_single = (e && atoi(e)) ? 1 : 0; }
+    if (n <= 4 * MT_TILE || force_single) {
+        k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, d_div, d_c, d_total);
+        MCL_LAUNCH_CHECK(h);
+        return MCL_OK;
+    }
+    const int64_t nt = (n + MT_TILE - 1) / MT_TILE;
+    // work buffers in the KLD arena (separate from the reduction scratch the callers use)
+    const size_t need = (size_t)nt * (8 + 4 + 8 + 4) + 256;
+    if (need > h->seq_bytes) {
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_seq); h->d_seq = nullptr; h->seq_bytes = 0;
+        MCL_CUDA(h, cudaMalloc(&h->d_seq, need * 2));
+        h->seq_bytes = need * 2;
+    }
+    char *s = (char *)h->d_seq;
+    const int64_t cap = (int64_t)((h->seq_bytes - 256) / 24);
+    double *tsum = (double *)s;
+    uint2 *agg = (uint2 *)(s + (size_t)cap * 8);
+    int *e_spec = (int *)(s + (size_t)cap * 16);
+    float *c_in = (float *)(s + (size_t)cap * 20);
+    k_mt_tilesum<<<(int)nt, MT_THREADS, 0, h->stream>>>(d_w, n, d_div, tsum);
+    MCL_LAUNCH_CHECK(h);
+    k_mt_speculate<<<1, 1024, 0, h->stream>>>(tsum, nt, e_spec);
+    MCL_LAUNCH_CHECK(h);
+    k_mt_aggregate<<<(int)nt, MT_THREADS, 0, h->stream>>>(d_w, n, d_div, e_spec, agg);
+    MCL_LAUNCH_CHECK(h);
+    k_mt_walk<<<1, MT_THREADS, 0, h->stream>>>(d_w, n, d_div, e_spec, agg, nt, c_in, d_total);
+    MCL_LAUNCH_CHECK(h);
+    if (d_c) {
+        k_mt_write<<<(int)nt, MT_THREADS, 0, h->stream>>>(d_w, n, d_div, c_in, d_c);
+        MCL_LAUNCH_CHECK(h);
+    }
+    return MCL_OK;
+}
+
 // idx[m] = min(first i in [0, limit] with c_i >= U_m, limit); U_m = r + m*step (two f64 roundings)
 __global__ void k_search_ref_f32(const float *__restrict__ c, int64_t limit, int64_t n_out, double r, double step,
                                  int32_t *__restrict__ idx) {
@@ -430,10 +718,10 @@ extern "C" int mcl_resample_indices(mcl_handle *h, const float *d_w, int64_t n_i
             k_cumsum_ref_f32<<<1, 32, 0, h->stream>>>(d_w, n_in, c, 1);
             MCL_LAUNCH_CHECK(h);
         } else {
-            k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n_in, nullptr, nullptr, sum);     // pu:430 np.sum
-            MCL_LAUNCH_CHECK(h);
-            k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n_in, sum, c, nullptr);           // pu:430, 436-443
-            MCL_LAUNCH_CHECK(h);
+            rc = seq_accumulate(h, d_w, n_in, nullptr, nullptr, sum);     // pu:430 np.sum
+            if (rc) return rc;
+            rc = seq_accumulate(h, d_w, n_in, sum, c, nullptr);           // pu:430 divide, pu:436-443 running sum
+            if (rc) return rc;
         }
         k_search_ref_f32<<<sblocks, 256, 0, h->stream>>>(c, limit, n_out, r, step, d_idx);
         MCL_LAUNCH_CHECK(h);
@@ -559,9 +847,7 @@ extern "C" int mcl_resample_search(mcl_handle *h, int64_t n_in, uint64_t offset,
 
 // sequential f32 running sum of the weights as given (pu:555-563 kld_sampling_amcl does not renormalise)
 int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c) {
-    k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, nullptr, d_c, nullptr);
-    MCL_LAUNCH_CHECK(h);
-    return MCL_OK;
+    return seq_accumulate(h, d_w, n, nullptr, d_c, nullptr);
 }
 
 // ---- peer-push global resampling: gather fused with the all-to-all over NVLink peer memory --------------
@@ -663,12 +949,10 @@ extern "C" int mcl_debug_seq_cumsum(mcl_handle *h, const float *d_w, int64_t n, 
         return MCL_OK;
     }
     if (normalise) {
-        k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, nullptr, nullptr, sum);
-        MCL_LAUNCH_CHECK(h);
+        rc = seq_accumulate(h, d_w, n, nullptr, nullptr, sum);
+        if (rc) return rc;
     }
-    k_seq_accumulate_exact<<<1, SEQ_THREADS, 0, h->stream>>>(d_w, n, normalise ? sum : nullptr, d_c, nullptr);
-    MCL_LAUNCH_CHECK(h);
-    return MCL_OK;
+    return seq_accumulate(h, d_w, n, normalise ? sum : nullptr, d_c, nullptr);
 }
 
 // host mirror of oracle u53(Philox(seed, step, item 0, sub 0, RESAMPLE))
