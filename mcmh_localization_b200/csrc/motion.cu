@@ -125,7 +125,10 @@ __device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x
     return is_valid_position_dev(cand.x, cand.y, p.occ, p.W, p.H, p.res, p.ox, p.oy);
 }
 
+#define MOTION_Q 192     // >= 31 leftover + 128 new candidates per screening round
 __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
+    __shared__ unsigned short q_att[8][MOTION_Q];
+    __shared__ unsigned q_word[8][MOTION_Q];
     const int lane = threadIdx.x & 31;
     const int64_t warp_base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
     if (warp_base >= p.n) return;                       // warp-uniform
@@ -167,39 +170,79 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
                 }
             }
         } else {
-            // Philox draws: lane L screens attempts 4g..4g+3 (g = g0 + L) from one radius block
+            // Philox draws.  Screening: lane L reads the radius words of attempts 4g..4g+3 (g = g0 + L) from one
+            // Philox block and queues, in attempt order, the attempts whose word passes the threshold.  Full
+            // evaluation (log, sqrt, sincos, map lookup: ~1000 instructions) then takes 32 queued attempts at a
+            // time, lowest index first -- evaluating a passing attempt inside the screening loop would run it
+            // with one or two active lanes.
             const unsigned long long T = __shfl_sync(0xffffffffu, thr, src);
             const uint64_t item = p.first_index + (uint64_t)si;
             const int groups = (p.max_attempts + 3) >> 2;
-            for (int g0 = 0; g0 < groups; g0 += 32) {
-                const int g = g0 + lane;
-                int best = 0x7fffffff;
-                Pose c = {0, 0, 0};
-                if (g < groups) {
-                    const uint4 a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
+            unsigned short *qt = q_att[threadIdx.x >> 5];
+            unsigned *qw = q_word[threadIdx.x >> 5];
+            int qlen = 0, qhead = 0, g0 = 0;
+            bool found = false;
+            while (!found && (g0 < groups || qhead < qlen)) {
+                // fewer than 32 candidates left: move them to the front of the queue before screening more
+                if (qhead > 0 && g0 < groups && qlen - qhead < 32) {
+                    const int left = qlen - qhead;
+                    unsigned short ta = 0; unsigned tw = 0;
+                    if (lane < left) { ta = qt[qhead + lane]; tw = qw[qhead + lane]; }
+                    __syncwarp();
+                    if (lane < left) { qt[lane] = ta; qw[lane] = tw; }
+                    __syncwarp();
+                    qlen = left; qhead = 0;
+                }
+                // screen until 32 candidates are queued (or the attempts are exhausted)
+                while (g0 < groups && qlen - qhead < 32) {
+                    const int g = g0 + lane;
+                    unsigned wv[4];
+                    int cnt = 0;
+                    bool pass[4] = {false, false, false, false};
+                    if (g < groups) {
+                        const uint4 a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
+                        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int t = 4 * g + k;
-                        const uint32_t w = pick_word(a, k);
-                        if (best == 0x7fffffff && t >= 1 && t < p.max_attempts && (unsigned long long)w + 1ull <= T) {
-                            const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
-                            double z0, z1, z2;
-                            normals3_from_words(w, o, z0, z1, z2);
-                            Pose cc;
-                            if (motion_candidate(p, sx, sy, sth, z0, z1, z2, cc)) { best = t; c = cc; }
+                        for (int k = 0; k < 4; ++k) {
+                            const int t = 4 * g + k;
+                            pass[k] = t >= 1 && t < p.max_attempts && (unsigned long long)wv[k] + 1ull <= T;
+                            cnt += pass[k];
                         }
                     }
-                }
-                int m = best;
+                    int pre = cnt;                                   // exclusive prefix over lanes -> queue order = attempt order
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if (m != 0x7fffffff) {                     // lowest valid attempt index in this batch of 128
-                    const unsigned who = __ballot_sync(0xffffffffu, best == m);
-                    const int w = __ffs(who) - 1;
-                    win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
-                    watt = m + 1;
-                    break;
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+                    const int total = __shfl_sync(0xffffffffu, pre, 31);
+                    int pos = qlen + pre - cnt;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (pass[k]) { qt[pos] = (unsigned short)(4 * g + k); qw[pos] = wv[k]; ++pos; }
+                    qlen += total;
+                    g0 += 32;
+                    __syncwarp();
                 }
+                // evaluate up to 32 queued attempts, lowest attempt index first
+                const int e = qhead + lane;
+                Pose c = {0, 0, 0};
+                bool ok = false;
+                int t = 0;
+                if (e < qlen) {
+                    t = qt[e];
+                    const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
+                    double z0, z1, z2;
+                    normals3_from_words(qw[e], o, z0, z1, z2);
+                    ok = motion_candidate(p, sx, sy, sth, z0, z1, z2, c);
+                }
+                const unsigned okm = __ballot_sync(0xffffffffu, ok);
+                if (okm) {
+                    const int w = __ffs(okm) - 1;                    // queue order = attempt order: lowest valid attempt
+                    win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
+                    watt = __shfl_sync(0xffffffffu, t, w) + 1;
+                    found = true;
+                }
+                qhead += 32;
+                if (qhead >= qlen) { qhead = 0; qlen = 0; }          // queue drained: reuse it from the start
+                __syncwarp();
             }
         }
         if (lane == src) { out = win; att = watt; }       // watt == 0: keep the old pose (pu:360-361)
