@@ -735,3 +735,36 @@ def test_sharded_two_gpus_equals_single_gpu():
                             os.path.join(ROOT, "scripts", "dist_check.py"), "20000"],
                            capture_output=True, text=True, timeout=600, env=dict(os.environ, MCL_EXCHANGE=mode))
         assert "DIST_CHECK OK" in r.stdout, (mode, r.stdout[-2000:] + r.stderr[-2000:])
+
+
+def test_c_abi_error_behaviour():
+    """Every export returns a negative mcl_status with a message instead of crashing (SURVEY 8(b) errors)."""
+    _need_gpu()
+    import ctypes as C
+    import torch
+    from mcmh_localization_b200 import _lib, MclError
+    h = _lib.Handle(0)
+    x = torch.zeros(8, dtype=torch.float64, device="cuda")
+    s = torch.zeros(8, dtype=torch.float32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with pytest.raises(MclError) as e:      # scan / map not set
+        h.call("mcl_likelihood", p(x), p(x), p(x), 8, p(s))
+    assert e.value.code == -2
+    with pytest.raises(MclError) as e:      # null pointer
+        h.call("mcl_likelihood", None, p(x), p(x), 8, p(s))
+    assert e.value.code == -1
+    with pytest.raises(MclError) as e:
+        h.call("mcl_set_sensor", -1.0, 0.5, 0.5, 5.0, 1)
+    assert e.value.code == -1
+    with pytest.raises(MclError) as e:      # predict without a map
+        d = (C.c_double * 3)(0, 0.1, 0)
+        h.call("mcl_predict", p(x), p(x), p(x), 8, d, 0, 0, 0, None, 0, 1000, p(x), p(x), p(x), None)
+    assert e.value.code == -2
+    with pytest.raises(MclError) as e:      # no filter bound
+        h.call("mcl_filter_resample", -1.0)
+    assert e.value.code == -2
+    with pytest.raises(MclError):
+        h.call("mcl_resample_indices", p(s), 0, 8, 0.01, 0, p(x))
+    with pytest.raises(MclError):
+        _lib.Handle(10_000)                 # no such device
+    h.close()
