@@ -95,6 +95,7 @@ int mcl_ensure_scratch(mcl_handle *h, size_t bytes);
 int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
 void mcl_filter_forget(const mcl_handle *h);
 int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c);
+int mcl_softmax_pair(mcl_handle *h, const float *s0, float *w0, const float *s1, float *w1, int64_t n);
 
 #define MCL_CUDA(h, expr)                                                                   \
     do {                                                                                    \

@@ -88,8 +88,14 @@ __global__ void __launch_bounds__(EST_THREADS) k_est_central(const double *__res
                                                              double mt_, int use_args, double *partials,
                                                              unsigned *counter, double *out) {
     __shared__ double sh[9 * 32];
-    const double mx = use_args ? mx_ : mean_ptr[0], my = use_args ? my_ : mean_ptr[1],
-                 mt = use_args ? mt_ : mean_ptr[2];
+    // use_args = 2: mean_ptr points at the six raw sums; derive the means here (saves the k_est_means launch)
+    double mx, my, mt;
+    if (use_args == 2) {
+        mx = mean_ptr[2] / mean_ptr[0]; my = mean_ptr[3] / mean_ptr[0]; mt = atan2(mean_ptr[5], mean_ptr[4]);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { out[-3] = mx; out[-2] = my; out[-1] = mt; }
+    } else {
+        mx = use_args ? mx_ : mean_ptr[0]; my = use_args ? my_ : mean_ptr[1]; mt = use_args ? mt_ : mean_ptr[2];
+    }
     double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double wi = (double)w[i];
@@ -174,9 +180,8 @@ extern "C" int mcl_estimate_async(mcl_handle *h, const double *d_x, const double
     MCL_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(unsigned), h->stream));
     k_est_moments<<<nb, EST_THREADS, 0, h->stream>>>(d_x, d_y, d_theta, d_w, n, partials, counter, d_out18);
     MCL_LAUNCH_CHECK(h);
-    k_est_means<<<1, 1, 0, h->stream>>>(d_out18);
-    MCL_LAUNCH_CHECK(h);
-    k_est_central<<<nb, EST_THREADS, 0, h->stream>>>(d_x, d_y, d_theta, d_w, n, d_out18 + 6, 0, 0, 0, 0, partials, counter,
+    // means derived inside the central pass from the raw sums (written to d_out18[6..8] by block 0)
+    k_est_central<<<nb, EST_THREADS, 0, h->stream>>>(d_x, d_y, d_theta, d_w, n, d_out18, 0, 0, 0, 2, partials, counter,
                                                      d_out18 + 9);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;

@@ -340,11 +340,9 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
         rc = sharded_softmax(h, f, true);
         if (rc) return rc;
     } else {
-        rc = mcl_softmax(h, f->score_post, f->n, f->w_post, nullptr, nullptr);
-        if (rc) return rc;
         rc = mcl_likelihood(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->n, f->score_pre);
         if (rc) return rc;
-        rc = mcl_softmax(h, f->score_pre, f->n, f->w_pre, nullptr, nullptr);
+        rc = mcl_softmax_pair(h, f->score_post, f->w_post, f->score_pre, f->w_pre, f->n);    // node:261, 270
         if (rc) return rc;
     }
     f->tick++;
@@ -432,9 +430,7 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
         }
         rc = mcl_likelihood(h, f->x[prop], f->y[prop], f->th[prop], f->n, score_prop);
         if (rc) return rc;
-        rc = mcl_softmax(h, score_prop, f->n, f->w_post, nullptr, nullptr);
-        if (rc) return rc;
-        rc = mcl_softmax(h, score_chain, f->n, f->w_pre, nullptr, nullptr);
+        rc = mcl_softmax_pair(h, score_prop, f->w_post, score_chain, f->w_pre, f->n);
         if (rc) return rc;
         f->tick++;
         const int src = it == 0 ? prev : chain;       // iteration 1 reads particles_prev and writes the chain buffer

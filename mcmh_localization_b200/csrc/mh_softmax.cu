@@ -328,3 +328,100 @@ extern "C" int mcl_weights_normalize(mcl_handle *h, float *d_w, int64_t n, doubl
     }
     return MCL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Both softmaxes of an MH update (scores of particles and of particles_prev, node:254-270) in three launches
+// instead of six: blockIdx.y selects the score set.  Same arithmetic as k_max / k_sumexp / k_softmax_weights.
+// ---------------------------------------------------------------------------------------------
+struct Softmax2 {
+    const float *s[2];
+    float *w[2];
+    double *stats[2];
+    unsigned *counter[2];
+    double *partials[2];
+};
+
+__global__ void __launch_bounds__(RED_THREADS) k_max2(const Softmax2 a, int64_t n) {
+    __shared__ float shf[32];
+    __shared__ bool last;
+    const int y = blockIdx.y;
+    const float *s = a.s[y];
+    float m = -FLT_MAX;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, s[i]);
+    m = block_max(m, shf);
+    if (threadIdx.x == 0) {
+        a.partials[y][blockIdx.x] = (double)m;
+        __threadfence();
+        last = atomicAdd(a.counter[y], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        float t = -FLT_MAX;
+        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t = fmaxf(t, (float)((volatile double *)a.partials[y])[b]);
+        t = block_max(t, shf);
+        if (threadIdx.x == 0) { a.stats[y][0] = (double)t; *a.counter[y] = 0; }
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_sumexp2(const Softmax2 a, int64_t n) {
+    __shared__ unsigned long long shq[32];
+    __shared__ bool last;
+    const int y = blockIdx.y;
+    const float *s = a.s[y];
+    const float m = (float)a.stats[y][0];
+    unsigned long long acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += __double2ull_rz(__dmul_rn((double)softmax_num(s[i], m), SOFTMAX_FIX));
+    acc = block_sum_u64(acc, shq);
+    if (threadIdx.x == 0) {
+        ((unsigned long long *)a.partials[y])[blockIdx.x] = acc;
+        __threadfence();
+        last = atomicAdd(a.counter[y], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        unsigned long long t = 0;
+        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += ((volatile unsigned long long *)a.partials[y])[b];
+        t = block_sum_u64(t, shq);
+        if (threadIdx.x == 0) {
+            a.stats[y][1] = (double)t / SOFTMAX_FIX;
+            ((unsigned long long *)a.stats[y])[2] = t;
+            *a.counter[y] = 0;
+        }
+    }
+}
+
+__global__ void k_softmax_weights2(const Softmax2 a, int64_t n) {
+    const int y = blockIdx.y;
+    const float *s = a.s[y];
+    float *w = a.w[y];
+    const float m = (float)a.stats[y][0], sum = (float)a.stats[y][1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        w[i] = __fdiv_rn(softmax_num(s[i], m), sum);
+}
+
+// internal (filter.cu): softmax of two score sets of equal length
+int mcl_softmax_pair(mcl_handle *h, const float *s0, float *w0, const float *s1, float *w1, int64_t n) {
+    const int nb = red_blocks(h, n);
+    // scratch: [0,64) counters | 2 x partials | 2 x 4 stats doubles
+    int rc = mcl_ensure_scratch(h, 128 + 2 * sizeof(double) * (size_t)nb + 128);
+    if (rc) return rc;
+    char *sc = (char *)h->d_scratch;
+    Softmax2 a;
+    a.s[0] = s0; a.s[1] = s1; a.w[0] = w0; a.w[1] = w1;
+    a.counter[0] = (unsigned *)sc; a.counter[1] = (unsigned *)(sc + 16);
+    a.partials[0] = (double *)(sc + 64); a.partials[1] = a.partials[0] + nb;
+    a.stats[0] = a.partials[1] + nb; a.stats[1] = a.stats[0] + 4;
+    MCL_CUDA(h, cudaMemsetAsync(sc, 0, 32, h->stream));
+    const dim3 grid(nb, 2);
+    k_max2<<<grid, RED_THREADS, 0, h->stream>>>(a, n);
+    MCL_LAUNCH_CHECK(h);
+    k_sumexp2<<<grid, RED_THREADS, 0, h->stream>>>(a, n);
+    MCL_LAUNCH_CHECK(h);
+    k_softmax_weights2<<<grid, RED_THREADS, 0, h->stream>>>(a, n);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
