@@ -180,17 +180,8 @@ class Localizer:
             self.last_odom = None
 
     def init_gaussian(self, mean, cov, n, seed=None):
-        """node:183 initialize_gaussian_parallel: N(mean, cov) samples; samples on cells with
-        distance_map >= 1.0 or outside the map are zeroed (pu:594-614).  Host-side, one-off."""
-        rs = np.random.RandomState(self.seed if seed is None else int(seed))
-        s = rs.multivariate_normal(np.asarray(mean, float), np.asarray(cov, float), size=int(n))
-        gm = self.map
-        mx = ((s[:, 0] - gm.origin_x) / gm.resolution).astype(np.int64)
-        my = ((s[:, 1] - gm.origin_y) / gm.resolution).astype(np.int64)
-        ok = (mx >= 0) & (mx < gm.width) & (my >= 0) & (my < gm.height)
-        ok[ok] &= gm.dist[my[ok], mx[ok]] < 1.0
-        s[~ok] = 0.0
-        self.set_particles(s)
+        """node:183 initialize_gaussian_parallel (pu:594-614).  Host-side, one-off."""
+        self.set_particles(gaussian_particles(mean, cov, n, self.map, self.seed if seed is None else int(seed)))
 
     # ------------------------------------------------------------------ predict (odom_callback)
     def predict(self, odom, normals=None):
@@ -411,6 +402,21 @@ class Localizer:
 
     def close(self):
         self.h.close()
+
+
+def gaussian_particles(mean, cov, n, gm, seed):
+    """pu:594-614 initialize_gaussian_parallel + validate_samples: N(mean, cov) samples from NumPy's legacy
+    generator (np.random.multivariate_normal after np.random.seed(seed)); a sample is kept if its cell
+    (int() truncation, no lower-bound quirk: 0 <= mx) lies in the map and distance_map < 1.0, otherwise it is
+    replaced by (0, 0, 0) like the reference does."""
+    rs = np.random.RandomState(int(seed))
+    s = rs.multivariate_normal(np.asarray(mean, float), np.asarray(cov, float), size=int(n))
+    mx = np.trunc((s[:, 0] - gm.origin_x) / gm.resolution).astype(np.int64)
+    my = np.trunc((s[:, 1] - gm.origin_y) / gm.resolution).astype(np.int64)
+    ok = (mx >= 0) & (mx < gm.width) & (my >= 0) & (my < gm.height)
+    ok[ok] &= gm.dist[my[ok], mx[ok]] < 1.0
+    s[~ok] = 0.0
+    return s
 
 
 def compute_motion(odom1, odom2):

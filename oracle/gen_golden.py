@@ -258,6 +258,21 @@ def gen_mh_and_resample():
     print("resample cases", list(cases))
 
 
+def gen_gaussian_init():
+    """pu:594-614 initialize_gaussian_parallel (node:183), seeded through NumPy's global legacy generator."""
+    occ, res, ox, oy = load_ref_map("map_world")
+    mp = ng.load_map(occ, res, ox, oy)
+    out = {}
+    for k, (mean, cov) in enumerate((([-2.0, -0.5, 0.0], np.diag([0.05, 0.05, 0.1])),      # node:49 initial_cov
+                                     ([-9.8, 9.0, 1.0], np.diag([0.5, 0.5, 0.3])))):
+        np.random.seed(400 + k)
+        p = pu.initialize_gaussian_parallel(np.array(mean), cov, 500, mp["distance_map"].reshape(mp["height"], mp["width"]),
+                                            mp["resolution"], mp["origin_np"])
+        out["mean_%d" % k] = np.array(mean); out["cov_%d" % k] = cov; out["seed_%d" % k] = 400 + k; out["out_%d" % k] = p
+        print("gaussian init", k, p.shape, int((p == 0).all(axis=1).sum()), "zeroed")
+    np.savez_compressed(os.path.join(OUT, "init_gaussian.npz"), **out)
+
+
 def gen_kld():
     """pu:529-591 kld_sampling_amcl on weights from a real update (yaml KLD parameters)."""
     g = np.load(os.path.join(OUT, "mh_map_world.npz"))
@@ -351,6 +366,7 @@ def main():
     gen_motion()
     gen_mh_and_resample()
     gen_init()
+    gen_gaussian_init()
     gen_kld()
     gen_filter_run()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

@@ -129,3 +129,15 @@ def test_synthetic_scan_generator_matches_reference_raycast():
     r, a = raycast_scan(gm, pose)
     r2, a2 = ng.synthetic_scan(pose, mp)
     assert np.array_equal(a, a2) and np.array_equal(r, r2)
+
+
+def test_gaussian_init_matches_reference():
+    """Localizer.init_gaussian's host routine vs the reference's initialize_gaussian_parallel (golden)."""
+    from mcmh_localization_b200.localizer import gaussian_particles
+    from mcmh_localization_b200.maps import load_npz
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    g = golden("init_gaussian.npz")
+    for k in (0, 1):
+        p = gaussian_particles(g["mean_%d" % k], g["cov_%d" % k], 500, gm, int(g["seed_%d" % k]))
+        assert np.array_equal(p, g["out_%d" % k])
+    assert (g["out_1"] == 0).all(axis=1).sum() > 0
