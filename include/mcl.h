@@ -95,6 +95,15 @@ int mcl_set_likelihood_path(mcl_handle *h, int path);
 int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                    int64_t n, float *d_score);
 
+/* pu:151-201 compute_likelihoods_raycast (+ pu:4-29 raycast, pu:36-58 p_hit / p_rand): the reference's
+ * alternative beam model by ray marching (hard-coded sigma 0.05, z_hit 0.8, z_rand 0.1, max_range 10).  Not
+ * reached from the node's callbacks; provided for completeness of the parallel_utils surface.
+ * h_blocked: (H, W) bytes, non-zero where the reference's grid_map > 0.5; x_min / y_min = limits[0] / limits[2]. */
+int mcl_set_raycast_grid(mcl_handle *h, const uint8_t *h_blocked, int W, int H, double resolution, double x_min,
+                         double y_min);
+int mcl_likelihood_raycast(mcl_handle *h, const float *h_ranges, const float *h_angles, int M, const double *d_x,
+                           const double *d_y, const double *d_theta, int64_t n, float *d_score);
+
 /* node:351-358 convert_scores (softmax).  d_stats (nullable, room for 4 doubles) receives
  * {max, sum exp(s-max), the same sum as a 2^-40 fixed-point uint64 bit pattern, unused} on the device; d_weights (nullable) receives exp(s-max)/sum as f32.
  * ext_stats (nullable, HOST): if given, use these {max, sum} instead of the local ones -- the

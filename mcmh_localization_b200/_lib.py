@@ -33,6 +33,8 @@ SIGNATURES = {
     "mcl_scan_valid_count": (_i, [_vp, _pi]),
     "mcl_set_likelihood_path": (_i, [_vp, _i]),
     "mcl_likelihood": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "mcl_set_raycast_grid": (_i, [_vp, _vp, _i, _i, _d, _d, _d]),
+    "mcl_likelihood_raycast": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _vp]),
     "mcl_softmax": (_i, [_vp, _vp, _i64, _vp, _vp, _pd]),
     "mcl_softmax_max": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_softmax_sumexp": (_i, [_vp, _vp, _i64, _vp]),

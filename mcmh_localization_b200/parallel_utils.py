@@ -132,6 +132,28 @@ def compute_likelihoods(scan_ranges, angles, particles, distance_map, map_resolu
     return score.cpu().numpy()
 
 
+def compute_likelihoods_raycast(scan_ranges, angles, particles, grid_map, map_resolution, limits):
+    """pu:151-201 (ray-marching beam model, the reference's hard-coded parameters)."""
+    c = _ctx()
+    g = np.asarray(grid_map)
+    blocked = np.ascontiguousarray(g > 0.5, dtype=np.uint8)
+    key = (g.shape, float(map_resolution), float(limits[0]), float(limits[2]), zlib.adler32(blocked))
+    if getattr(c, "rc_key", None) != key:
+        c.h.call("mcl_set_raycast_grid", C.c_void_p(blocked.ctypes.data), int(g.shape[1]), int(g.shape[0]),
+                 float(map_resolution), float(limits[0]), float(limits[2]))
+        c.rc_key = key
+    r = np.ascontiguousarray(scan_ranges, dtype=np.float32)
+    a = np.ascontiguousarray(angles, dtype=np.float32)
+    n = len(particles)
+    if n == 0:
+        return np.zeros(0, np.float32)
+    x, y, t = c.soa(particles)
+    score = torch.empty(n, dtype=torch.float32, device=c.device)
+    c.h.call("mcl_likelihood_raycast", C.c_void_p(r.ctypes.data), C.c_void_p(a.ctypes.data), len(r), _p(x), _p(y), _p(t),
+             n, _p(score))
+    return score.cpu().numpy()
+
+
 def convert_scores(scores):
     """node:351-358 softmax of the scores (float32)."""
     c = _ctx()

@@ -449,3 +449,35 @@ int64_t orc_kld_sampling(const double *particles, const float *weights, int64_t 
     free(keys); free(used);
     return count;
 }
+
+/* pu:151-201 compute_likelihoods_raycast (+ pu:36-58 p_hit / p_rand): beam model by ray marching, hard-coded
+ * sigma_hit 0.05, z_hit 0.8, z_rand 0.1, max_range 10.  grid is (H, W) f64 (row = y), occupied where > 0.5;
+ * limits = [x_min, x_max, y_min, y_max].  No valid beam -> -inf (pu:199). */
+void orc_compute_likelihoods_raycast(const float *scan, const float *angles, int M, const double *particles,
+                                     int64_t N, const double *grid, int W, int H, double res,
+                                     const double *limits, float *scores) {
+    const double sigma_hit = 0.05, z_hit = 0.8, z_rand = 0.1, max_range = 10.0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < N; ++i) {
+        const double x = particles[3 * i], y = particles[3 * i + 1], theta = particles[3 * i + 2];
+        double log_score = 0.0;
+        int64_t valid_count = 0;
+        for (int j = 0; j < M; ++j) {
+            const double r_meas = (double)scan[j];
+            if (isfinite(r_meas) && r_meas < max_range) {
+                valid_count += 1;
+                const double r_pred = orc_raycast(x, y, theta + (double)angles[j], max_range, limits, res, grid, W, H);
+                double prob_hit = 0.0;                                         /* pu:36-41 */
+                if (0 <= r_meas && r_meas <= max_range) {
+                    const double q = (r_meas - r_pred) / sigma_hit;
+                    prob_hit = (1 / (sqrt(2 * ORC_PI) * sigma_hit)) * exp(-0.5 * (q * q));
+                }
+                const double prob_rand = (0 <= r_meas && r_meas <= max_range) ? 1.0 / max_range : 0.0;   /* pu:55-58 */
+                double p = z_hit * prob_hit + z_rand * prob_rand;
+                p = p > 1e-6 ? p : 1e-6;
+                log_score += log(p);
+            }
+        }
+        scores[i] = valid_count > 0 ? (float)(log_score / (double)valid_count) : -INFINITY;
+    }
+}

@@ -104,6 +104,19 @@ def raycast(pose, angle, max_range, limits, resolution, grid_map, grid_width, gr
         _p(g, C.c_double), C.c_int(int(grid_width)), C.c_int(int(grid_height))))
 
 
+def compute_likelihoods_raycast(scan_ranges, angles, particles, grid_map, map_resolution, limits):
+    """pu:151-201."""
+    scan, ang, p = _f32(scan_ranges), _f32(angles), _f64(particles)
+    g = _f64(grid_map)
+    lim = _f64(limits)
+    out = np.zeros(p.shape[0], np.float32)
+    lib().orc_compute_likelihoods_raycast(_p(scan, C.c_float), _p(ang, C.c_float), C.c_int(scan.shape[0]),
+                                          _p(p, C.c_double), C.c_int64(p.shape[0]), _p(g, C.c_double),
+                                          C.c_int(g.shape[1]), C.c_int(g.shape[0]), C.c_double(float(map_resolution)),
+                                          _p(lim, C.c_double), _p(out, C.c_float))
+    return out
+
+
 def compute_valid_mask(particles, map_data, width, height, resolution, origin_x, origin_y):
     p = _f64(particles)
     m = np.ascontiguousarray(map_data, np.int8)

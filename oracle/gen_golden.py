@@ -258,6 +258,31 @@ def gen_mh_and_resample():
     print("resample cases", list(cases))
 
 
+def gen_raycast_likelihood():
+    """pu:151-201 compute_likelihoods_raycast + pu:4-29 raycast on both maps."""
+    for name in ("map_world", "map_house"):
+        occ, res, ox, oy = load_ref_map(name)
+        mp = ng.load_map(occ, res, ox, oy)
+        rs = np.random.RandomState(55)
+        grid = (occ != 0).astype(np.float64)
+        start = free_particles(mp, 1, rs)[0]
+        scan, angles = ng.synthetic_scan(start, mp, 360, 3.5, noise=rs.normal(0, 0.01, 360))
+        scan[5] = np.nan; scan[6] = -0.2; scan[7] = 9.99; scan[8] = 10.0; scan[9] = 0.0
+        pa = free_particles(mp, 600, rs)
+        W, H = mp["width"], mp["height"]
+        pb = np.column_stack((rs.uniform(ox - 1, ox + W * res + 1, 150), rs.uniform(oy - 1, oy + H * res + 1, 150),
+                              rs.uniform(-4 * np.pi, 4 * np.pi, 150)))
+        particles = np.ascontiguousarray(np.vstack((pa, pb)))
+        scores = pu.compute_likelihoods_raycast(scan, angles, particles, grid, mp["resolution"], mp["limits"])
+        blind = pu.compute_likelihoods_raycast(np.full(360, np.inf, np.float32), angles, particles[:8], grid,
+                                               mp["resolution"], mp["limits"])
+        rays = np.array([pu.raycast(particles[k, :2], particles[k, 2] + 0.3 * k, 10.0, mp["limits"], mp["resolution"],
+                                    grid, W, H) for k in range(200)])
+        np.savez_compressed(os.path.join(OUT, "raycast_%s.npz" % name), scan=scan, angles=angles, particles=particles,
+                            scores=scores, blind=blind, rays=rays)
+        print("raycast", name, float(np.nanmin(scores)), float(np.nanmax(scores)), blind[:2])
+
+
 def gen_gaussian_init():
     """pu:594-614 initialize_gaussian_parallel (node:183), seeded through NumPy's global legacy generator."""
     occ, res, ox, oy = load_ref_map("map_world")
@@ -367,6 +392,7 @@ def main():
     gen_mh_and_resample()
     gen_init()
     gen_gaussian_init()
+    gen_raycast_likelihood()
     gen_kld()
     gen_filter_run()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

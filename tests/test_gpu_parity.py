@@ -190,6 +190,31 @@ def test_likelihood_large_tiled_map_vs_oracle(pu):
     assert clib.compute_valid_mask(p0, gm.occ.ravel(), gm.width, gm.height, gm.resolution, gm.origin_x, gm.origin_y).all()
 
 
+@pytest.mark.parametrize("name", ["map_world", "map_house"])
+def test_raycast_likelihood_golden(pu, orc, name):
+    """pu:151-201 compute_likelihoods_raycast (ray-marching beam model) against the reference's outputs."""
+    m = golden(name + ".npz")
+    g = golden("raycast_%s.npz" % name)
+    grid = (m["occ"] != 0).astype(np.float64)
+    res = float(m["resolution"])
+    ox, oy = float(m["origin"][0]), float(m["origin"][1])
+    H, W = grid.shape
+    limits = np.array([ox, ox + W * res, oy, oy + H * res])
+    s = pu.compute_likelihoods_raycast(g["scan"], g["angles"], g["particles"], grid, res, limits)
+    assert s.dtype == np.float32
+    ok = lik_close(s, g["scores"], rel=1e-4)
+    assert ok.all(), (int((~ok).sum()), s[~ok][:5], g["scores"][~ok][:5])
+    assert np.abs(s.astype(np.float64) - g["scores"]).max() < 2e-6
+    blind = pu.compute_likelihoods_raycast(np.full(360, np.inf, np.float32), g["angles"], g["particles"][:8], grid, res, limits)
+    assert np.all(np.isneginf(blind)) and np.array_equal(blind, g["blind"])
+    # larger seeded set against the oracle
+    rs = np.random.RandomState(4)
+    parts = np.column_stack((rs.uniform(ox + 5, ox + 14, 20000), rs.uniform(oy + 5, oy + 14, 20000), rs.uniform(-np.pi, np.pi, 20000)))
+    got = pu.compute_likelihoods_raycast(g["scan"], g["angles"], parts, grid, res, limits)
+    ref = orc.compute_likelihoods_raycast(g["scan"], g["angles"], parts, grid, res, limits)
+    assert lik_close(got, ref, rel=1e-4).all()
+
+
 # --------------------------------------------------------------------------- softmax (a2)
 def test_softmax_golden(pu):
     g = golden("mh_map_world.npz")
