@@ -72,6 +72,11 @@ int mcl_device_info(mcl_handle *h, int *sm_count, int *smem_per_block_optin, int
  * NULL when only the other half is needed (likelihood needs dist, predict/init need occ). */
 int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_dist, int W, int H,
                 double resolution, double origin_x, double origin_y);
+/* Same, with the distance map computed on the device: an exact Euclidean distance transform of the free
+ * cells in integers, bit-identical to scipy.ndimage.distance_transform_edt(map == 0) * resolution as f32
+ * (node:153-157).  h_dist_out (nullable, W*H floats) receives it. */
+int mcl_set_map_edt(mcl_handle *h, const int8_t *h_occ, int W, int H, double resolution, double origin_x,
+                    double origin_y, float *h_dist_out);
 /* node:52-56 sensor model parameters (amhmcl.yaml: sigma_hit, z_hit, z_rand, max_range, step). */
 int mcl_set_sensor(mcl_handle *h, double sigma_hit, double z_hit, double z_rand, double max_range,
                    int step);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mcl_sync": (_i, [_vp]),
     "mcl_device_info": (_i, [_vp, _pi, _pi, _pi, _pi]),
     "mcl_set_map": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d]),
+    "mcl_set_map_edt": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _vp]),
     "mcl_set_sensor": (_i, [_vp, _d, _d, _d, _d, _i]),
     "mcl_set_motion": (_i, [_vp, C.POINTER(C.c_float)]),
     "mcl_set_scan": (_i, [_vp, _vp, _vp, _i]),

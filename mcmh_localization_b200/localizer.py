@@ -77,10 +77,19 @@ class Localizer:
             self.h.call("mcl_filter_configure", int(self.use_mh), self.resample_mode, self.seed, self.first_index, -1)
             self.h.call("mcl_filter_set_assym", int(self.assym))
 
-    def load_map(self, occ, resolution=None, origin_xy=None):
-        """occ: (H,W) int8 OccupancyGrid payload, or a GridMap (maps.load_map_yaml / map_from_occupancy)."""
+    def load_map(self, occ, resolution=None, origin_xy=None, gpu_edt=False):
+        """occ: (H,W) int8 OccupancyGrid payload, or a GridMap (maps.load_map_yaml / map_from_occupancy).
+        gpu_edt: compute the distance map (node:153-157) on the device instead of with SciPy (bit-identical)."""
         if isinstance(occ, GridMap):
             gm = occ
+        elif gpu_edt:
+            o = np.ascontiguousarray(occ, dtype=np.int8)
+            dist = np.empty(o.shape, np.float32)
+            self._bind_stream()
+            self.h.call("mcl_set_map_edt", C.c_void_p(o.ctypes.data), int(o.shape[1]), int(o.shape[0]), float(resolution),
+                        float(origin_xy[0]), float(origin_xy[1]), C.c_void_p(dist.ctypes.data))
+            self.map = GridMap(o, dist, float(resolution), float(origin_xy[0]), float(origin_xy[1]))
+            return
         else:
             from .maps import map_from_occupancy
             gm = map_from_occupancy(occ, resolution, origin_xy[0], origin_xy[1])

@@ -793,3 +793,30 @@ def test_c_abi_error_behaviour():
     with pytest.raises(MclError):
         _lib.Handle(10_000)                 # no such device
     h.close()
+
+
+def test_gpu_edt_bit_identical_to_scipy():
+    """node:153-157 load_map: the device distance transform equals SciPy's (exact integers -> same sqrt)."""
+    _need_gpu()
+    import os
+    import time
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz, tiled_map
+    for name in ("map_world", "map_house"):
+        gm = load_npz(os.path.join(GOLDEN, name + ".npz"))
+        loc = Localizer(params=P, mode="MCL")
+        loc.load_map(gm.occ, gm.resolution, (gm.origin_x, gm.origin_y), gpu_edt=True)
+        assert loc.map.dist.dtype == np.float32 and np.array_equal(loc.map.dist, gm.dist), name
+    big = tiled_map(load_npz(os.path.join(GOLDEN, "map_house.npz")), 6, 6, 2048, 2048)
+    loc = Localizer(params=P, mode="MCL")
+    t0 = time.time()
+    loc.load_map(big.occ, big.resolution, (big.origin_x, big.origin_y), gpu_edt=True)
+    assert np.array_equal(loc.map.dist, big.dist)
+    rs = np.random.RandomState(1)            # a map with large open areas (long searches) and a few obstacles
+    occ = np.zeros((300, 500), np.int8)
+    occ[rs.randint(0, 300, 12), rs.randint(0, 500, 12)] = 100
+    from mcmh_localization_b200.maps import map_from_occupancy
+    ref = map_from_occupancy(occ, 0.05, 0.0, 0.0)
+    loc.load_map(occ, 0.05, (0.0, 0.0), gpu_edt=True)
+    assert np.array_equal(loc.map.dist, ref.dist)
