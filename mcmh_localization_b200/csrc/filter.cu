@@ -279,29 +279,37 @@ extern "C" int mcl_comm_status(mcl_handle *h, int *err) {
 }
 
 // softmax of both score sets with the two global statistics exchanged over peer memory
+static int sharded_softmax_arrays(mcl_handle *h, FilterState *f, const float *s_post, float *w_post, const float *s_pre,
+                                  float *w_pre);
 static int sharded_softmax(mcl_handle *h, FilterState *f, bool both) {
+    return sharded_softmax_arrays(h, f, f->score_post, both ? f->w_post : f->w[f->wslot], both ? f->score_pre : nullptr,
+                                  both ? f->w_pre : nullptr);
+}
+static int sharded_softmax_arrays(mcl_handle *h, FilterState *f, const float *s_post, float *w_post, const float *s_pre,
+                                  float *w_pre) {
+    const bool both = s_pre != nullptr;
     double *st_post = f->d_x8 + 48, *st_pre = f->d_x8 + 52;          // 4 doubles each
-    int rc = mcl_softmax_max(h, f->score_post, f->n, st_post);
+    int rc = mcl_softmax_max(h, s_post, f->n, st_post);
     if (rc) return rc;
-    if (both) { rc = mcl_softmax_max(h, f->score_pre, f->n, st_pre); if (rc) return rc; }
+    if (both) { rc = mcl_softmax_max(h, s_pre, f->n, st_pre); if (rc) return rc; }
     k_pack2<<<1, 1, 0, h->stream>>>(st_post, 0, both ? st_pre : nullptr, 0, f->d_x8);
     MCL_LAUNCH_CHECK(h);
     rc = comm_exchange(h, f, f->d_x8, 2, XCH_MAX_F64, f->d_x8 + 16);
     if (rc) return rc;
     k_unpack_max<<<1, 1, 0, h->stream>>>(f->d_x8 + 16, st_post, both ? st_pre : nullptr);
     MCL_LAUNCH_CHECK(h);
-    rc = mcl_softmax_sumexp(h, f->score_post, f->n, st_post);
+    rc = mcl_softmax_sumexp(h, s_post, f->n, st_post);
     if (rc) return rc;
-    if (both) { rc = mcl_softmax_sumexp(h, f->score_pre, f->n, st_pre); if (rc) return rc; }
+    if (both) { rc = mcl_softmax_sumexp(h, s_pre, f->n, st_pre); if (rc) return rc; }
     k_pack2<<<1, 1, 0, h->stream>>>(st_post, 2, both ? st_pre : nullptr, 2, f->d_x8);     // the exact 2^-40 integers
     MCL_LAUNCH_CHECK(h);
     rc = comm_exchange(h, f, f->d_x8, 2, XCH_SUM_U64, f->d_x8 + 16);
     if (rc) return rc;
     k_unpack_qsum<<<1, 1, 0, h->stream>>>((const unsigned long long *)(f->d_x8 + 16), st_post, both ? st_pre : nullptr);
     MCL_LAUNCH_CHECK(h);
-    rc = mcl_softmax_weights(h, f->score_post, f->n, st_post, both ? f->w_post : f->w[f->wslot]);
+    rc = mcl_softmax_weights(h, s_post, f->n, st_post, w_post);
     if (rc) return rc;
-    if (both) rc = mcl_softmax_weights(h, f->score_pre, f->n, st_pre, f->w_pre);
+    if (both) rc = mcl_softmax_weights(h, s_pre, f->n, st_pre, w_pre);
     return rc;
 }
 
@@ -346,7 +354,6 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
         if (rc) return rc;
     }
     f->tick++;
-    if (f->assym && f->comm) return mcl_fail(h, MCL_ERR_STATE, "asymmetric MH is not available on sharded particles yet");
     if (f->assym) {
         // node:366-367: transition_probability() then assym_mh_resampling(prev, cur, w_post, w_pre, fwd, bwd)
         if (f->t_cap < f->n) {
@@ -357,12 +364,28 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
             MCL_CUDA(h, cudaMalloc((void **)&f->tb, (size_t)f->n * sizeof(double)));
             f->t_cap = f->n;
         }
-        rc = mcl_motion_density(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
-                                f->th[f->cur], f->n, f->delta, f->tf, nullptr, 1);
-        if (rc) return rc;
-        rc = mcl_motion_density(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->x[f->prev], f->y[f->prev],
-                                f->th[f->prev], f->n, f->delta_b, f->tb, nullptr, 1);
-        if (rc) return rc;
+        if (f->comm) {
+            // pu:326-328 normalises by the sum over the WHOLE population: local sums, rank-ordered sum over peers
+            rc = mcl_motion_density(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
+                                    f->th[f->cur], f->n, f->delta, f->tf, f->d_x8, 0);
+            if (rc) return rc;
+            rc = mcl_motion_density(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->x[f->prev], f->y[f->prev],
+                                    f->th[f->prev], f->n, f->delta_b, f->tb, f->d_x8 + 1, 0);
+            if (rc) return rc;
+            rc = comm_exchange(h, f, f->d_x8, 2, XCH_SUM_F64, f->d_x8 + 16);
+            if (rc) return rc;
+            rc = mcl_scale_by_sum(h, f->tf, f->n, f->d_x8 + 16);
+            if (rc) return rc;
+            rc = mcl_scale_by_sum(h, f->tb, f->n, f->d_x8 + 17);
+            if (rc) return rc;
+        } else {
+            rc = mcl_motion_density(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
+                                    f->th[f->cur], f->n, f->delta, f->tf, nullptr, 1);
+            if (rc) return rc;
+            rc = mcl_motion_density(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->x[f->prev], f->y[f->prev],
+                                    f->th[f->prev], f->n, f->delta_b, f->tb, nullptr, 1);
+            if (rc) return rc;
+        }
         rc = mcl_assym_mh_accept(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
                                  f->th[f->cur], f->w_post, f->w_pre, f->tf, f->tb, f->n, d_uniforms, f->seed,
                                  f->tick, f->first_index, f->x[f->spare], f->y[f->spare], f->th[f->spare],
@@ -413,7 +436,7 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
     FILTER_OR_FAIL("mcl_filter_update_chain");
     if (iters < 1) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_update_chain: iters < 1");
     if (!f->use_mh || f->assym) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_update_chain: needs the symmetric MH mode");
-    if (f->comm) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_update_chain: not available on sharded particles yet");
+
     DeviceGuard guard(h->device);
     const int blocks = (int)std::min<int64_t>((f->n + 255) / 256, (int64_t)h->sm_count * 16);
     // roles during the chain: prev = particles_prev (fixed), prop = cur buffer, chain = spare buffer
@@ -430,7 +453,8 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
         }
         rc = mcl_likelihood(h, f->x[prop], f->y[prop], f->th[prop], f->n, score_prop);
         if (rc) return rc;
-        rc = mcl_softmax_pair(h, score_prop, f->w_post, score_chain, f->w_pre, f->n);
+        rc = f->comm ? sharded_softmax_arrays(h, f, score_prop, f->w_post, score_chain, f->w_pre)
+                     : mcl_softmax_pair(h, score_prop, f->w_post, score_chain, f->w_pre, f->n);
         if (rc) return rc;
         f->tick++;
         const int src = it == 0 ? prev : chain;       // iteration 1 reads particles_prev and writes the chain buffer

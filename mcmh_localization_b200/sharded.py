@@ -176,11 +176,12 @@ class ShardedLocalizer(Localizer):
 
     # -- update ------------------------------------------------------------------------------
     def _update_core(self, uniforms=None):
-        if self.assym or self.use_adaptive:
-            raise NotImplementedError("localization_mode %r is not available on sharded particles yet"
-                                      % self.params["localization_mode"])
+        if self.use_adaptive:
+            raise NotImplementedError("the KLD-adaptive (AMCL) modes are single-GPU: %r" % self.params["localization_mode"])
         if self.native:
             return Localizer._update_core(self, uniforms)
+        if self.assym:
+            raise NotImplementedError("asymmetric MH on sharded particles needs the native exchange path")
         cur, prev, spare, ws, tick = self._roles()
         S, n, h = self.sets, self.n, self.h
         h.call("mcl_likelihood", *[_ptr(t) for t in S[cur]], n, _ptr(self.score_post))
@@ -309,6 +310,11 @@ class ShardedLocalizer(Localizer):
         self.update_staged(k)
         self.estimate_async(out18 if out18 is not None else self.est18)
         self.resample()
+
+    def update_chain(self, ranges, angle_min=None, angle_max=None, angles=None, iters=32):
+        if not self.native:
+            raise NotImplementedError("the MH chain on sharded particles needs the native exchange path")
+        return Localizer.update_chain(self, ranges, angle_min, angle_max, angles, iters)
 
     def gather_particles(self):
         """(n_global, 3) on every rank (tests / visualisation)."""
