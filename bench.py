@@ -237,8 +237,20 @@ def run_native(args):
     loc.predict(poses[0])
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    iters = max(1, args.mh_iters)
+
+    def staged_step(k):
+        if iters == 1:
+            loc.step_staged(poses[k], k, est_buf[k])
+        else:       # config 4: k MH iterations per scan
+            loc.predict(poses[k])
+            loc.h.call("mcl_use_scan", int(k))
+            loc.update_chain(None, iters=iters)
+            loc.estimate_async(est_buf[k])
+            loc.resample()
+
     for k in range(1, W + 1):
-        loc.step_staged(poses[k], k, est_buf[k])
+        staged_step(k)
     barrier()
     sampler.mark()
     launches0 = lib.mcl_launch_count(h)
@@ -248,7 +260,7 @@ def run_native(args):
         k = W + 1 + j
         flush.zero_()
         ev0[j].record()
-        loc.step_staged(poses[k], k, est_buf[k])
+        staged_step(k)
         ev1[j].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -266,7 +278,8 @@ def run_native(args):
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
-    evals = float(np.sum(valid[W + 1:W + 1 + K])) * n * 2 * world
+    passes = 2 if iters == 1 else iters + 1       # likelihood passes per step
+    evals = float(np.sum(valid[W + 1:W + 1 + K])) * n * passes * world
     value = evals / (total_ms * 1e-3)
 
     # ---- e2e leg: public API, host buffers in, host estimate out ----------------------------
@@ -276,7 +289,10 @@ def run_native(args):
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        loc.step(poses[k], scans[k], angles=angles)
+        if iters == 1:
+            loc.step(poses[k], scans[k], angles=angles)
+        else:
+            loc.predict(poses[k]); loc.update_chain(scans[k], angles=angles, iters=iters); loc.estimate(); loc.resample()
         barrier()
         e2e_t += time.perf_counter() - t0
         h2d += int(valid[k]) * 16 + 0      # the per-scan beam table (fp64 pairs) is what crosses PCIe
@@ -289,7 +305,7 @@ def run_native(args):
 
     # ---- the same step with the reference's own resampling arithmetic (sequential-f32 sums, bit-exact) ---
     ref_mode_ms = None
-    if world == 1 and args.resample == "fixed" and not args.quick:
+    if world == 1 and args.resample == "fixed" and not args.quick and iters == 1:
         from mcmh_localization_b200 import RESAMPLE_REFERENCE_F32, RESAMPLE_FIXED_POINT
         loc.h.call("mcl_filter_configure", 1, RESAMPLE_REFERENCE_F32, loc.seed, 0, -1)
         ts = []
@@ -326,7 +342,7 @@ def run_native(args):
     achieved = (gather_bytes + stream_bytes) / (lik_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": 24084224,
-                "traffic_source": "profiles/r1c_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum per k_likelihood_g1 launch (ncu --set full)",
+                "traffic_source": "profiles/r1e_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum per k_likelihood_g1 launch (ncu --set full)",
                 "kernel": "k_likelihood_g1", "launch_ms": lik_launch_ms, "launches_timed": int(lik_n.value),
                 "algorithmic_bytes_per_launch": gather_bytes + stream_bytes,
                 "hbm_stream_only_gbs": stream_bytes / (lik_launch_ms * 1e-3) / 1e9,
@@ -353,7 +369,7 @@ def run_native(args):
 
     # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) -------------
     cpu = None
-    if world == 1 and not args.no_cpu and not args.quick:
+    if world == 1 and not args.no_cpu and not args.quick and iters == 1:
         ns = args.cpu_sample
         cv, cms, cdone, threads = cpu_filter_run(gm, free_space_particles(gm, ns, seed=1234), poses, scans, angles,
                                                  YAML_PARAMS, args.cpu_seconds, 3)
@@ -362,6 +378,9 @@ def run_native(args):
                          "host cores) + NumPy glue" % (ns, n, args.beams, cdone, cms * cdone / 1e3)}
 
     cfg = workload_config(args, gm)
+    cfg["likelihood_passes_per_step"] = passes
+    if iters > 1:
+        cfg["workload"] += "; %d MH iterations per scan (BASELINE configs[3])" % iters
     if world > 1:
         cfg["parallelism"] = "particles sharded over %d ranks (weak scaling), map replicated" % world
         cfg["resample_exchange"] = ("peer-push over NVLink symmetric memory (gather fused with the exchange)"
@@ -399,6 +418,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=262144)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mh-iters", type=int, default=1,
+                    help="MH iterations per scan (BASELINE config 4 uses 32); 1 = the reference's single accept")
     ap.add_argument("--quick", action="store_true", help="skip the gather microbenchmark and the CPU baseline (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
