@@ -42,19 +42,33 @@ struct mcl_handle {
     bool tab_dirty = true;
     int32_t *d_logtab = nullptr; // W*H
     int32_t c0 = 0;              // table value on dist == 0 cells (everything outside the window)
+    // The shared-memory copies of the table (d_win, d_lut) hold v - voff >= 0 (voff <= every table value), so
+    // the kernels can add up to MCL_ACC_TERMS of them in one unsigned 32-bit register before widening.
+    int32_t voff = 0;
+    bool acc_terms_ok = false;   // MCL_ACC_TERMS * (c0 - voff) < 2^32 (c0 is the table maximum: dist == 0)
     // free-space window [wx0, wx0+ww) x [wy0, wy0+wh): outside it every in-map cell holds c0.
-    // d_win is the packed window with a one-cell c0 border: (wh+2) x (ww+2) floats.
+    // d_win is the window with a one-cell c0 border, (wh+2) x (ww+2) cells, stored with a pitch of 256
+    // cells along its "minor" axis (x, or y when win_tpose) so that a cell index is one byte permute of
+    // the two clamped coordinates: index = minor | major << 8 (likelihood.cu).  win_ok = false when
+    // neither axis fits in 256 columns (the table is then gathered from global memory / L2).
     int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
+    bool win_ok = false, win_tpose = false;
+    int win_rows = 0;            // (major extent + 2) rows of 256 cells
     int32_t *d_win = nullptr;
     size_t win_bytes = 0;
     int lik_path = 0;            // 0 auto, 1 global, 2 smem window
     // coded window for maps whose int32 window exceeds shared memory: one byte per cell indexing a
     // table of the (<= 256) distinct values (the value depends only on dist, and an EDT on a grid takes
-    // few distinct values near walls: 85 on map_world, 242 on map_house)
+    // few distinct values near walls: 85 on map_world, 242 on map_house); same layout as d_win
     bool coded = false;
     uint8_t *d_win8 = nullptr;
     int32_t *d_lut = nullptr;
     size_t win8_bytes = 0;
+    // cell-index arithmetic (likelihood.cu): endpoints are evaluated relative to the window origin in the
+    // "magic" form cell_M + t, cell_M = 1.5 * 2^(20 - cell_S): the high word of the double then holds
+    // floor(t * 2^cell_S) + cell_K.  |t| must stay below cell_lim (particles further out see no map cell).
+    int cell_S = 8, cell_K = 0;
+    double cell_M = 0, cell_lim = 0;
 
     // scan (node:341-348): valid beams with r >= 0 first, then valid beams with r < 0
     bool scan_set = false;
@@ -228,5 +242,6 @@ __device__ __forceinline__ double cell_logp(float d, double sigma_hit, double z_
 }
 
 #define MCL_LOGP_SCALE 33554432.0   // 2^25
+#define MCL_ACC_TERMS 8
 __device__ __forceinline__ int32_t quantise_logp(double lp) { return __double2int_rn(lp * MCL_LOGP_SCALE); }
 #endif  // __CUDACC__

@@ -3,17 +3,26 @@
 // Per particle i and valid beam j the reference evaluates
 //     lx = x + r cos(theta + a_j),  mx = int((lx - ox) / res)   (fp64, trunc toward zero)
 //     log p(dist[my*W+mx])  accumulated in fp64, mean over valid_count, stored as fp32.
-// Here the per-cell value log p(dist[c]) is a precomputed fp32 table (mcl_core.cu), the beam
-// endpoints r (cos a_j, sin a_j) / res are a per-scan fp64 table, and a particle needs one
-// fp64 sincos; per (particle, beam) that leaves 4 DFMA + 2 F2I + one 4-byte table gather:
-//     tx = px + c bx - s by,   ty = py + s bx + c by      (cell units, fp64: cell-index parity
-//     with the fp64 reference needs ~1e-9 cell accuracy, SURVEY 7 hard part 1)
+// Here the per-cell value log p(dist[c]) is a precomputed fixed-point table (mcl_core.cu), the beam
+// endpoints r (cos a_j, sin a_j) / res are a per-scan fp64 table, and a particle needs one fp64 sincos.
+//
+// Cell index.  Per (particle, beam) the endpoint is  t = p + c bx - s by  in cell units; the cell index
+// must agree with the fp64 reference (SURVEY 7 hard part 1: fp32 flips 6e-5 of the cells), and only the
+// integer part of t is wanted.  The particle coordinate is taken relative to the window origin and
+// biased by the "magic" constant M = 1.5 * 2^(20-S) once per particle; the two FMAs of a coordinate then
+// produce M + t directly, a double whose HIGH WORD is  K + floor(t * 2^S)  (S = 8 for maps up to ~1800
+// cells).  No conversion instruction, no fp64 floor: the clamp onto the window is one VIADDMNMX on the
+// high word and the table index is one byte permute of the two clamped words.  The bias rounds t to
+// 2^-(32+S) (2^-40 cell for S = 8, ~1e-12 against the reference's own ~1e-14 endpoint rounding): every
+// kernel and path below uses exactly this arithmetic, so cell indices -- and, the table being fixed
+// point, scores -- are identical for any lanes-per-particle mapping, path or number of ranks.
+//
 // The table is staged in shared memory: the free-space window of the map (all cells outside
 // it hold one constant c0) plus a one-cell c0 border, so out-of-window lookups clamp onto the
 // border instead of branching.  Staging uses the bulk-copy engine (cp.async.bulk + mbarrier, "TMA"
 // 1-D form); CTAs are persistent and stage once.  If the window does not fit in shared memory the
 // table is gathered from global memory / L2.
-// Mapping: G lanes per particle (G = 1 for large N: beam constants are then warp-uniform shared
+// Mapping: G lanes per particle (G = 1 for large N: beam constants are then warp-uniform constant-bank
 // loads; G up to 32 for small N to fill the machine), beams strided over the G lanes and reduced
 // with __shfl_xor.
 #include <stdlib.h>
@@ -36,9 +45,13 @@ struct LikParams {
     const float *dist;
     const uint8_t *win8;       // coded window + table of distinct values (maps whose int32 window is too big)
     const int32_t *lut;
-    uint32_t win8_bytes;
-    int wx0, wy0, ww, wh;
-    uint32_t win_bytes;
+    uint32_t win8_bytes, win_bytes;
+    int32_t voff;              // shared-memory table values are v - voff (mcl_handle::voff)
+    int wofx, wofy;            // window origin incl. border: wx0 - 1, wy0 - 1
+    int cx, cy;                // largest window index per axis: ww + 1, wh + 1
+    int tpose;                 // window stored with y as the minor (pitch-256) axis
+    double M, lim;             // cell arithmetic: bias and validity limit (mcl_handle::cell_*)
+    int K, S;
     double sigma_hit, z_hit, z_rand, max_range;
     double margin;     // rmax_cells + 2: particles further than this from every map edge cannot
                        // produce an out-of-map endpoint
@@ -78,11 +91,54 @@ __device__ __forceinline__ void bulk_g2s_chunked(unsigned char *dst, const unsig
     for (uint32_t o = 0; o < bytes; o += CH) bulk_g2s(dst + o, src + o, min(CH, bytes - o), bar);
 }
 
+// ---------------------------------------------------------------------------------------------
+// the cell arithmetic shared by every path
+// ---------------------------------------------------------------------------------------------
+struct Pose {          // one particle, ready for the beam loop
+    double PX, PY;     // M + window-relative position (cells)
+    double s, c;
+    bool interior;     // no endpoint can leave the map (coordinates >= 1: trunc == floor, no bounds test)
+    bool far;          // outside the range of the arithmetic: no endpoint can be inside the map
+};
+
+__device__ __forceinline__ Pose load_pose(const LikParams &p, int64_t i) {
+    Pose q;
+    const double x = p.x[i], y = p.y[i], th = p.th[i];
+    sincos(th, &q.s, &q.c);
+    const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);          // pu:128: (lx - ox) / res, distributed
+    const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
+    const double wx = __dadd_rn(px, -(double)p.wofx), wy = __dadd_rn(py, -(double)p.wofy);   // exact
+    q.far = !(fabs(wx) < p.lim && fabs(wy) < p.lim);                   // also catches NaN poses
+    q.PX = __dadd_rn(q.far ? 0.0 : wx, p.M);
+    q.PY = __dadd_rn(q.far ? 0.0 : wy, p.M);
+    q.interior = (px >= p.margin) && (px <= (double)p.W - p.margin) && (py >= p.margin) && (py <= (double)p.H - p.margin);
+    return q;
+}
+
+__device__ __forceinline__ double end_x(const Pose &q, const double2 b) { return fma(q.c, b.x, fma(-q.s, b.y, q.PX)); }
+__device__ __forceinline__ double end_y(const Pose &q, const double2 b) { return fma(q.s, b.x, fma(q.c, b.y, q.PY)); }
+
+// clamped window coordinate scaled by 2^S (low S bits: fraction)
+__device__ __forceinline__ int win_coord(double T, int K, int cmax) {
+    return __viaddmin_s32_relu(__double2hiint(T), -K, cmax);
+}
+// map cell with the reference's int() (trunc toward zero) semantics; exact on the 2^-(32+S) grid
+__device__ __forceinline__ int map_coord(double T, int K, int S, int wof) {
+    const long long F = (long long)(__double2hiint(T) - K);
+    const long long q = (F << 32) + (long long)(unsigned)__double2loint(T) + ((long long)wof << (32 + S));
+    const int sh = 32 + S;
+    return (int)(q >= 0 ? (q >> sh) : -((-q) >> sh));
+}
+__device__ __forceinline__ int win_index(int rx, int ry, int S, int tpose) {   // generic (S != 8 or run-time layout)
+    const int ix = rx >> S, iy = ry >> S;
+    return tpose ? (ix << 8) | iy : (iy << 8) | ix;
+}
+
 template <int G, bool SMEM>
 __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    BeamTable *sb = reinterpret_cast<BeamTable *>(smem + 16);
+    double2 *sb = reinterpret_cast<double2 *>(smem + 16);
     const int nb = p.n_pos + p.n_neg;
     const uint32_t beam_bytes = (uint32_t)nb * (uint32_t)sizeof(BeamTable);
     int32_t *swin = reinterpret_cast<int32_t *>(smem + 16 + beam_bytes);
@@ -102,72 +158,46 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
     constexpr int GROUPS = LIK_THREADS / G;
     const int g = threadIdx.x & (G - 1);
     const int grp = threadIdx.x / G;
-    const int pw = p.ww + 2;
-    const int cx = p.ww + 1, cy = p.wh + 1;
-    const int ofx = 1 - p.wx0, ofy = 1 - p.wy0;
-    const double inv_count = 1.0;  // (division done in fp64 below, like the reference)
-    (void)inv_count;
-    const double lo = p.margin, hix = (double)p.W - p.margin, hiy = (double)p.H - p.margin;
+    const int cmx = (p.cx << p.S) | ((1 << p.S) - 1), cmy = (p.cy << p.S) | ((1 << p.S) - 1);
 
     // warp-uniform trip count: every lane iterates while the FIRST group of its warp is in range
     const int64_t stride = (int64_t)gridDim.x * GROUPS;
     const int warp_first_grp = (threadIdx.x & ~31) / G;
     for (int64_t base = (int64_t)blockIdx.x * GROUPS; base + warp_first_grp < p.n; base += stride) {
         const int64_t i = base + grp;
-        const int64_t il = i < p.n ? i : p.n - 1;
-        const double x = p.x[il], y = p.y[il], th = p.th[il];
-        double s, c;
-        sincos(th, &s, &c);
-        const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);
-        const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
-        const bool interior = (px >= lo) && (px <= hix) && (py >= lo) && (py <= hiy);
+        const Pose q = load_pose(p, i < p.n ? i : p.n - 1);
         long long acc = 0;
-        if (SMEM) {
-            if (__all_sync(0xffffffffu, interior)) {
-                // no endpoint can leave the map: coordinates are >= 1, trunc == floor, no bounds test
+        if (!q.far) {
+            if (SMEM && __all_sync(0xffffffffu, q.interior)) {
 #pragma unroll 4
                 for (int j = g; j < p.n_pos; j += G) {
-                    const BeamTable b = sb[j];
-                    const double tx = fma(c, b.bx, fma(-s, b.by, px));
-                    const double ty = fma(s, b.bx, fma(c, b.by, py));
-                    const int ix = min(max(__double2int_rz(tx) + ofx, 0), cx);
-                    const int iy = min(max(__double2int_rz(ty) + ofy, 0), cy);
-                    acc += swin[iy * pw + ix];
+                    const double2 b = sb[j];
+                    const int rx = win_coord(end_x(q, b), p.K, cmx), ry = win_coord(end_y(q, b), p.K, cmy);
+                    acc += swin[win_index(rx, ry, p.S, p.tpose)] + (long long)p.voff;
                 }
             } else {
 #pragma unroll 2
                 for (int j = g; j < p.n_pos; j += G) {
-                    const BeamTable b = sb[j];
-                    const double tx = fma(c, b.bx, fma(-s, b.by, px));
-                    const double ty = fma(s, b.bx, fma(c, b.by, py));
-                    const int mx = __double2int_rz(tx), my = __double2int_rz(ty);  // pu:128-129 int()
-                    const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
-                    const int ix = min(max(mx + ofx, 0), cx);
-                    const int iy = min(max(my + ofy, 0), cy);
-                    const int v = swin[iy * pw + ix];
-                    acc += inmap ? v : 0;                                           // pu:131-132
+                    const double2 b = sb[j];
+                    const int mx = map_coord(end_x(q, b), p.K, p.S, p.wofx), my = map_coord(end_y(q, b), p.K, p.S, p.wofy);  // pu:128-129
+                    if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H)) {                                  // pu:131-132
+                        if (SMEM) {
+                            const int ix = min(max(mx - p.wofx, 0), p.cx), iy = min(max(my - p.wofy, 0), p.cy);
+                            acc += swin[p.tpose ? (ix << 8) | iy : (iy << 8) | ix] + (long long)p.voff;
+                        } else {
+                            acc += __ldg(p.logtab + (size_t)my * p.W + mx);
+                        }
+                    }
                 }
             }
-        } else {
-#pragma unroll 4
-            for (int j = g; j < p.n_pos; j += G) {
-                const BeamTable b = sb[j];
-                const double tx = fma(c, b.bx, fma(-s, b.by, px));
-                const double ty = fma(s, b.bx, fma(c, b.by, py));
-                const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
-                const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
-                if (inmap) acc += __ldg(p.logtab + (size_t)my * p.W + mx);
+            // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
+            for (int j = p.n_pos + g; j < nb; j += G) {
+                const double2 b = sb[j];
+                const int mx = map_coord(end_x(q, b), p.K, p.S, p.wofx), my = map_coord(end_y(q, b), p.K, p.S, p.wofy);
+                if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
+                    acc += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
+                                                   p.z_rand, p.max_range, false));
             }
-        }
-        // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
-        for (int j = p.n_pos + g; j < nb; j += G) {
-            const BeamTable b = sb[j];
-            const double tx = fma(c, b.bx, fma(-s, b.by, px));
-            const double ty = fma(s, b.bx, fma(c, b.by, py));
-            const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
-            if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
-                acc += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
-                                               p.z_rand, p.max_range, false));
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -180,31 +210,124 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
 // G = 1 (one thread per particle, N large): every lane of a warp evaluates the SAME beam, so the
 // beam constants are warp-uniform and come from the constant bank (no LSU / shared-memory traffic:
 // ncu on the first version showed the shared-memory pipe at 78 % with 40 % of its wavefronts spent on
-// the beam table, and the XU pipe at 66 % on the two F2I.F64 per evaluation).  The cell index is
-// extracted with the round-down magic-number add (FP64 pipe, exact floor for |t| < 2^31) and the
-// window offset + clamp is one VIADDMNMX (__viaddmin_s32_relu).
+// the beam table).  Per evaluation: 4 DFMA, 2 VIADDMNMX, 1 PRMT, 1 LEA, 1 LDS, ~0.75 integer adds and,
+// shared by the two particles of a thread, the uniform loads of the beam.
+//
+// Work split: every CTA owns an equal contiguous share of the particles and walks it in rows of one
+// particle per thread; a warp takes its 32-particle slices two rows at a time and a last odd slice alone,
+// so all warps of the grid carry the same number of slices +-1 (no tail of half-empty SMs).
+// Table values in shared memory are v - voff >= 0, so MCL_ACC_TERMS of them are summed in one unsigned
+// 32-bit register before the 64-bit accumulator is touched.
 // ---------------------------------------------------------------------------------------------
 #define MAX_CBEAMS 2048
-__constant__ BeamTable c_beams[MAX_CBEAMS];
-#define MCL_FLOOR_MAGIC 6755399441055744.0   // 2^52 + 2^51
+__constant__ BeamTable c_beams_raw[MAX_CBEAMS];
+#define c_beams (reinterpret_cast<const double2 *>(c_beams_raw))
 
-__device__ __forceinline__ int floor_to_int(double t) {   // exact floor(t) for |t| < 2^31
-    return __double2loint(__dadd_rd(t, MCL_FLOOR_MAGIC));
+struct G1Ctx {
+    const int32_t *swin, *slut;
+    const uint8_t *swin8;
+    int lane, nb, cmx, cmy;
+};
+
+template <bool CODED>
+__device__ __forceinline__ uint32_t g1_fetch(const G1Ctx &k, int cell) {
+    return (uint32_t)(CODED ? k.slut[(int)k.swin8[cell] * 32 + k.lane] : k.swin[cell]);
 }
 
-// Tunables (chosen by measurement, see profiles/): threads per CTA, particles per thread (the uniform beam
-// loads and loop overhead are shared), minimum CTAs per SM, and MIXED = take the y index with F2I (XU pipe)
-// instead of the magic add (FP64 pipe) to spread the conversions over two pipes.
-template <bool SMEM, int G1_THREADS, int G1_P, int MINB, bool MIXED, bool CODED = false>
+// P slices (rows i0, i0 + row, ...) of one warp; lanes whose particle index is >= end idle on a copy of end - 1
+template <bool SMEM, bool CODED, bool TPOSE, int P>
+__device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, int64_t i0, int64_t row, int64_t end) {
+    int64_t idx[P];
+    Pose q[P];
+    bool interior = true, any_near = false;
+#pragma unroll
+    for (int u = 0; u < P; ++u) {
+        idx[u] = i0 + u * row;
+        q[u] = load_pose(p, idx[u] < end ? idx[u] : end - 1);
+        interior = interior && q[u].interior;
+        any_near = any_near || !q[u].far;
+    }
+    long long acc[P];
+#pragma unroll
+    for (int u = 0; u < P; ++u) acc[u] = 0;
+    if (SMEM && __all_sync(0xffffffffu, interior)) {
+        unsigned long long uacc[P];
+#pragma unroll
+        for (int u = 0; u < P; ++u) uacc[u] = 0;
+        // plain register arrays (not the Pose structs): ptxas then keeps the beam loop on the uniform datapath
+        double PX[P], PY[P], ss[P], cc[P];
+#pragma unroll
+        for (int u = 0; u < P; ++u) { PX[u] = q[u].PX; PY[u] = q[u].PY; ss[u] = q[u].s; cc[u] = q[u].c; }
+        const int negK = -p.K;
+        auto eval = [&](int u, const double2 b) -> uint32_t {
+            const double TX = fma(cc[u], b.x, fma(-ss[u], b.y, PX[u])), TY = fma(ss[u], b.x, fma(cc[u], b.y, PY[u]));
+            const int rx = __viaddmin_s32_relu(__double2hiint(TX), negK, k.cmx);
+            const int ry = __viaddmin_s32_relu(__double2hiint(TY), negK, k.cmy);
+            return g1_fetch<CODED>(k, (int)(TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651)));
+        };
+        int j = 0;
+        for (; j + MCL_ACC_TERMS <= p.n_pos; j += MCL_ACC_TERMS) {
+            uint32_t part[P];
+#pragma unroll
+            for (int u = 0; u < P; ++u) part[u] = 0;
+#pragma unroll
+            for (int t = 0; t < MCL_ACC_TERMS; ++t) {
+                const double2 b = c_beams[j + t];
+#pragma unroll
+                for (int u = 0; u < P; ++u) part[u] += eval(u, b);
+            }
+#pragma unroll
+            for (int u = 0; u < P; ++u) uacc[u] += part[u];
+        }
+        for (; j < p.n_pos; ++j) {
+            const double2 b = c_beams[j];
+#pragma unroll
+            for (int u = 0; u < P; ++u) uacc[u] += eval(u, b);
+        }
+#pragma unroll
+        for (int u = 0; u < P; ++u) acc[u] = (long long)uacc[u] + (long long)p.n_pos * p.voff;
+    } else if (__any_sync(0xffffffffu, any_near)) {
+        for (int j = 0; j < p.n_pos; ++j) {
+            const double2 b = c_beams[j];
+#pragma unroll
+            for (int u = 0; u < P; ++u) {
+                const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx), my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy);  // pu:128-129
+                const bool inmap = !q[u].far && ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
+                int v;
+                if (SMEM) {
+                    const int ix = min(max(mx - p.wofx, 0), p.cx), iy = min(max(my - p.wofy, 0), p.cy);
+                    v = (int)g1_fetch<CODED>(k, TPOSE ? (ix << 8) | iy : (iy << 8) | ix) + p.voff;
+                    v = inmap ? v : 0;                                             // pu:131-132
+                } else {
+                    v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
+                }
+                acc[u] += v;
+            }
+        }
+    }
+    // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
+    for (int j = p.n_pos; j < k.nb; ++j) {
+        const double2 b = c_beams[j];
+#pragma unroll
+        for (int u = 0; u < P; ++u) {
+            const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx), my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy);
+            if (!q[u].far && ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
+                acc[u] += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
+                                                  p.z_rand, p.max_range, false));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < P; ++u)
+        if (idx[u] < end) p.score[idx[u]] = (float)(((double)acc[u] / MCL_LOGP_SCALE) / (double)k.nb);   // pu:144-145
+}
+
+// Tunables (chosen by measurement, see profiles/): threads per CTA and minimum CTAs per SM.
+template <bool SMEM, int G1_THREADS, int MINB, bool CODED = false, bool TPOSE = false>
 __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    int32_t *swin = reinterpret_cast<int32_t *>(smem + 16);
+    // plain: [16 B barrier][int32 window]
     // CODED: [16 B barrier][table of distinct values replicated per lane: 256 x 32 int32][uint8 window]
-    int32_t *slut = reinterpret_cast<int32_t *>(smem + 16);
-    const uint8_t *swin8 = smem + 16 + 32768;
-    const int nb = p.n_pos + p.n_neg;
-    const int lane = threadIdx.x & 31;
     if (SMEM) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
@@ -214,106 +337,31 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
                 bulk_g2s_chunked(smem + 16 + 32768, p.win8, p.win8_bytes, bar);
             } else {
                 mbar_expect_tx(bar, p.win_bytes);
-                bulk_g2s_chunked(reinterpret_cast<unsigned char *>(swin), reinterpret_cast<const unsigned char *>(p.win),
-                                 p.win_bytes, bar);
+                bulk_g2s_chunked(smem + 16, reinterpret_cast<const unsigned char *>(p.win), p.win_bytes, bar);
             }
         }
         if (CODED) {   // lane-private copies of the value table: slut[code * 32 + lane] is always conflict-free
+            int32_t *slut = reinterpret_cast<int32_t *>(smem + 16);
             for (int e = threadIdx.x; e < 256 * 32; e += G1_THREADS) slut[e] = __ldg(p.lut + (e >> 5));
             __syncthreads();
         }
         mbar_wait(bar, 0);
     }
-    auto fetch = [&](int cell) -> int { return CODED ? slut[(int)swin8[cell] * 32 + lane] : swin[cell]; };
-    const int pw = p.ww + 2;
-    const int cx = p.ww + 1, cy = p.wh + 1;
-    const int ofx = 1 - p.wx0, ofy = 1 - p.wy0;
-    const double lo = p.margin, hix = (double)p.W - p.margin, hiy = (double)p.H - p.margin;
-    const double2 *cb = reinterpret_cast<const double2 *>(c_beams);
-    const int64_t stride = (int64_t)gridDim.x * (G1_THREADS * G1_P);
-    const int warp_first = threadIdx.x & ~31;
-    for (int64_t base = (int64_t)blockIdx.x * (G1_THREADS * G1_P); base + warp_first < p.n; base += stride) {
-        int64_t idx[G1_P];
-        double px[G1_P], py[G1_P], s[G1_P], c[G1_P];
-        bool interior = true;
-#pragma unroll
-        for (int q = 0; q < G1_P; ++q) {
-            idx[q] = base + q * G1_THREADS + threadIdx.x;
-            const int64_t il = idx[q] < p.n ? idx[q] : p.n - 1;
-            const double x = p.x[il], y = p.y[il], th = p.th[il];
-            sincos(th, &s[q], &c[q]);
-            px[q] = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);
-            py[q] = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
-            interior = interior && (px[q] >= lo) && (px[q] <= hix) && (py[q] >= lo) && (py[q] <= hiy);
-        }
-        long long acc[G1_P];
-#pragma unroll
-        for (int q = 0; q < G1_P; ++q) acc[q] = 0;
-        if (SMEM && __all_sync(0xffffffffu, interior)) {
-            // no endpoint can leave the map: coordinates >= 1, floor == trunc, no bounds test
-            int j = 0;
-#pragma unroll 2
-            for (; j + 1 < p.n_pos; j += 2) {
-                const double2 b0 = cb[j], b1 = cb[j + 1];
-#pragma unroll
-                for (int q = 0; q < G1_P; ++q) {
-                    const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
-                    const double tx1 = fma(c[q], b1.x, fma(-s[q], b1.y, px[q])), ty1 = fma(s[q], b1.x, fma(c[q], b1.y, py[q]));
-                    const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
-                    const int iy0 = __viaddmin_s32_relu(MIXED ? __double2int_rz(ty0) : floor_to_int(ty0), ofy, cy);
-                    const int ix1 = __viaddmin_s32_relu(floor_to_int(tx1), ofx, cx);
-                    const int iy1 = __viaddmin_s32_relu(MIXED ? __double2int_rz(ty1) : floor_to_int(ty1), ofy, cy);
-                    acc[q] += fetch(iy0 * pw + ix0) + fetch(iy1 * pw + ix1);      // two terms fit int32
-                }
-            }
-            if (j < p.n_pos) {
-                const double2 b0 = cb[j];
-#pragma unroll
-                for (int q = 0; q < G1_P; ++q) {
-                    const double tx0 = fma(c[q], b0.x, fma(-s[q], b0.y, px[q])), ty0 = fma(s[q], b0.x, fma(c[q], b0.y, py[q]));
-                    const int ix0 = __viaddmin_s32_relu(floor_to_int(tx0), ofx, cx);
-                    const int iy0 = __viaddmin_s32_relu(floor_to_int(ty0), ofy, cy);
-                    acc[q] += fetch(iy0 * pw + ix0);
-                }
-            }
-        } else {
-            for (int j = 0; j < p.n_pos; ++j) {
-                const double2 b = cb[j];
-#pragma unroll
-                for (int q = 0; q < G1_P; ++q) {
-                    const double tx = fma(c[q], b.x, fma(-s[q], b.y, px[q]));
-                    const double ty = fma(s[q], b.x, fma(c[q], b.y, py[q]));
-                    const int mx = __double2int_rz(tx), my = __double2int_rz(ty);      // pu:128-129 int()
-                    const bool inmap = ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
-                    int v;
-                    if (SMEM) {
-                        const int ix = min(max(mx + ofx, 0), cx), iy = min(max(my + ofy, 0), cy);
-                        v = fetch(iy * pw + ix);
-                        v = inmap ? v : 0;                                             // pu:131-132
-                    } else {
-                        v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
-                    }
-                    acc[q] += v;
-                }
-            }
-        }
-        // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
-        for (int j = p.n_pos; j < nb; ++j) {
-            const double2 b = cb[j];
-#pragma unroll
-            for (int q = 0; q < G1_P; ++q) {
-                const double tx = fma(c[q], b.x, fma(-s[q], b.y, px[q]));
-                const double ty = fma(s[q], b.x, fma(c[q], b.y, py[q]));
-                const int mx = __double2int_rz(tx), my = __double2int_rz(ty);
-                if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
-                    acc[q] += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
-                                                      p.z_rand, p.max_range, false));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < G1_P; ++q)
-            if (idx[q] < p.n) p.score[idx[q]] = (float)(((double)acc[q] / MCL_LOGP_SCALE) / (double)nb);   // pu:144-145
-    }
+    G1Ctx k;
+    k.swin = reinterpret_cast<const int32_t *>(smem + 16);
+    k.slut = reinterpret_cast<const int32_t *>(smem + 16);
+    k.swin8 = smem + 16 + 32768;
+    k.lane = threadIdx.x & 31;
+    k.nb = p.n_pos + p.n_neg;
+    k.cmx = (p.cx << 8) | 255; k.cmy = (p.cy << 8) | 255;
+
+    const int64_t per = p.n / gridDim.x, rem = p.n % gridDim.x;
+    const int64_t first = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+    const int64_t end = first + per + ((int64_t)blockIdx.x < rem ? 1 : 0);
+    int64_t i = first + (threadIdx.x & ~31);          // start of this warp's slice in row 0
+    for (; i + G1_THREADS < end; i += 2 * G1_THREADS)
+        g1_slices<SMEM, CODED, TPOSE, 2>(p, k, i + k.lane, G1_THREADS, end);
+    if (i < end) g1_slices<SMEM, CODED, TPOSE, 1>(p, k, i + k.lane, 0, end);
 }
 
 __global__ void k_fill_f32(float *out, int64_t n, float v) {
@@ -323,11 +371,11 @@ __global__ void k_fill_f32(float *out, int64_t n, float v) {
 
 template <typename K>
 static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t smem_bytes, int G,
-                             int threads = LIK_THREADS, int per_thread = 1) {
+                             int threads = LIK_THREADS, bool balanced = false) {
     // attribute + occupancy queries are cached per (kernel, smem size): they cost tens of microseconds
-    static thread_local const void *c_kern[16];
-    static thread_local size_t c_smem[16];
-    static thread_local int c_occ[16], c_dev[16], c_n = 0;
+    static thread_local const void *c_kern[32];
+    static thread_local size_t c_smem[32];
+    static thread_local int c_occ[32], c_dev[32], c_n = 0;
     int occ = 0;
     for (int k = 0; k < c_n; ++k)
         if (c_kern[k] == (const void *)kern && c_smem[k] == smem_bytes && c_dev[k] == h->device) occ = c_occ[k];
@@ -336,12 +384,14 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
         MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
         MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem_bytes));
         if (occ < 1) return mcl_fail(h, MCL_ERR_CAPACITY, "likelihood kernel does not fit on an SM");
-        const int k = c_n < 16 ? c_n++ : 15;
+        const int k = c_n < 32 ? c_n++ : 31;
         c_kern[k] = (const void *)kern; c_smem[k] = smem_bytes; c_occ[k] = occ; c_dev[k] = h->device;
     }
-    const int64_t groups = (int64_t)threads * per_thread / G;
+    const int64_t groups = (int64_t)threads / G;
     const int64_t need = (p.n + groups - 1) / groups;
-    const int blocks = (int)std::min<int64_t>(need, (int64_t)h->sm_count * occ);
+    int blocks = (int)std::min<int64_t>(need, (int64_t)h->sm_count * occ);
+    if (balanced)   // equal contiguous shares: the same number of CTAs on every SM
+        blocks = (int)std::min<int64_t>((p.n + 31) / 32, (int64_t)h->sm_count * occ);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         MCL_CUDA(h, cudaEventCreate(&e0));
@@ -360,6 +410,21 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
 template <int G, bool SMEM>
 static int launch_lik(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
     return launch_lik_kernel(h, k_likelihood<G, SMEM>, p, smem_bytes, G);
+}
+
+// G = 1: <threads, CTAs per SM> by variant (MCL_LIK_VARIANT, for tuning runs); layout by the handle
+template <bool SMEM, bool CODED, bool TPOSE>
+static int launch_g1(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("MCL_LIK_VARIANT"); variant = e ? atoi(e) : 0; }
+    // does a second CTA fit next to the first?
+    const bool two = 2 * (smem_bytes + 1024) <= (size_t)h->smem_optin;
+    switch (variant) {
+        case 1: if (two) return launch_lik_kernel(h, k_likelihood_g1<SMEM, 512, 2, CODED, TPOSE>, p, smem_bytes, 1, 512, true);
+        case 2: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 768, 1, CODED, TPOSE>, p, smem_bytes, 1, 768, true);
+        case 3: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 896, 1, CODED, TPOSE>, p, smem_bytes, 1, 896, true);
+        default: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 1024, 1, CODED, TPOSE>, p, smem_bytes, 1, 1024, true);
+    }
 }
 
 // the constant-bank beam table is module-global: re-upload when the active scan (or handle) changed
@@ -388,7 +453,10 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     p.ox = h->ox; p.oy = h->oy; p.res = h->res; p.W = h->W; p.H = h->H;
     p.logtab = h->d_logtab; p.dist = h->d_dist; p.win = h->d_win;
     p.win8 = h->d_win8; p.lut = h->d_lut; p.win8_bytes = (uint32_t)h->win8_bytes;
-    p.wx0 = h->wx0; p.wy0 = h->wy0; p.ww = h->ww; p.wh = h->wh; p.win_bytes = (uint32_t)h->win_bytes;
+    p.win_bytes = (uint32_t)h->win_bytes;
+    p.voff = h->voff;
+    p.wofx = h->wx0 - 1; p.wofy = h->wy0 - 1; p.cx = h->ww + 1; p.cy = h->wh + 1; p.tpose = h->win_tpose ? 1 : 0;
+    p.M = h->cell_M; p.lim = h->cell_lim; p.K = h->cell_K; p.S = h->cell_S;
     p.sigma_hit = h->sigma_hit; p.z_hit = h->z_hit; p.z_rand = h->z_rand; p.max_range = h->max_range;
     p.margin = h->rmax_cells + 2.0;
 
@@ -397,42 +465,33 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     const size_t smem_win = smem_glob + h->win_bytes;
     const size_t smem_limit = (size_t)h->smem_optin;
     if (smem_glob > smem_limit) return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: too many beams for shared memory");
-    bool use_smem = smem_win <= smem_limit;
+    bool use_smem = h->win_ok && smem_win <= smem_limit;
     if (h->lik_path == 1) use_smem = false;
-    if (h->lik_path == 2 && !use_smem && !h->coded)
+    const bool use_coded = !use_smem && h->coded && h->lik_path != 1 && h->cell_S == 8;
+    if (h->lik_path == 2 && !use_smem && !use_coded)
         return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: free-space window does not fit in shared memory");
 
     int G = 1;
     const int64_t target = (int64_t)h->sm_count * 2048;
     while (G < 32 && n * G < target) G *= 2;
-    if (G == 1 && nb <= MAX_CBEAMS) {
+    if (G == 1 && nb <= MAX_CBEAMS && h->acc_terms_ok) {
         if (g_cbeams_src != (const void *)h->d_beams_active || g_cbeams_gen != h->scan_gen) {
-            MCL_CUDA(h, cudaMemcpyToSymbolAsync(c_beams, h->d_beams_active, beam_bytes, 0, cudaMemcpyDeviceToDevice,
+            MCL_CUDA(h, cudaMemcpyToSymbolAsync(c_beams_raw, h->d_beams_active, beam_bytes, 0, cudaMemcpyDeviceToDevice,
                                                 h->stream));
             g_cbeams_src = (const void *)h->d_beams_active;
             g_cbeams_gen = h->scan_gen;
         }
-        if (!use_smem && h->coded && h->lik_path != 1)
-            return launch_lik_kernel(h, k_likelihood_g1<true, 512, 2, 1, false, true>, p, 16 + 32768 + h->win8_bytes, 1, 512, 2);
-        static int variant = -1;
-        if (variant < 0) { const char *e = getenv("MCL_LIK_VARIANT"); variant = e ? atoi(e) : 0; }
-#define G1_CASE(V, T, P, B, M)                                                                              \
-    case V:                                                                                                 \
-        if (use_smem) return launch_lik_kernel(h, k_likelihood_g1<true, T, P, B, M>, p, 16 + h->win_bytes, 1, T, P); \
-        return launch_lik_kernel(h, k_likelihood_g1<false, T, P, B, M>, p, 16, 1, T, P);
-        switch (variant) {
-            G1_CASE(1, 256, 2, 4, false)
-            G1_CASE(2, 512, 1, 2, false)
-            G1_CASE(3, 256, 1, 4, false)
-            G1_CASE(4, 256, 2, 3, true)
-            G1_CASE(5, 128, 2, 6, false)
-            G1_CASE(6, 256, 1, 4, true)
-            G1_CASE(7, 256, 4, 2, false)
-            default:
-            G1_CASE(0, 256, 2, 4, false)
+        if (use_coded) {
+            const size_t sm = 16 + 32768 + h->win8_bytes;
+            return h->win_tpose ? launch_g1<true, true, true>(h, p, sm) : launch_g1<true, true, false>(h, p, sm);
         }
-#undef G1_CASE
+        if (use_smem && h->cell_S == 8)
+            return h->win_tpose ? launch_g1<true, false, true>(h, p, 16 + h->win_bytes)
+                                : launch_g1<true, false, false>(h, p, 16 + h->win_bytes);
+        return launch_g1<false, false, false>(h, p, 16);
     }
+    if (use_coded && !use_smem && h->lik_path == 2)
+        return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: the coded window needs the one-thread-per-particle kernel (larger n)");
 #define LIK_CASE(GV)                                                                   \
     case GV:                                                                           \
         return use_smem ? launch_lik<GV, true>(h, p, smem_win) : launch_lik<GV, false>(h, p, smem_glob);

@@ -132,7 +132,7 @@ extern "C" int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_di
         MCL_CUDA(h, cudaMalloc((void **)&h->d_occ, cells));
         MCL_CUDA(h, cudaMemcpy(h->d_occ, h_occ, cells, cudaMemcpyHostToDevice));
     }
-    if (!h_dist) { h->wx0 = h->wy0 = h->ww = h->wh = 0; h->win_bytes = 0; return MCL_OK; }
+    if (!h_dist) { h->wx0 = h->wy0 = h->ww = h->wh = 0; h->win_bytes = 0; h->win_ok = false; return MCL_OK; }
     MCL_CUDA(h, cudaMalloc((void **)&h->d_dist, cells * sizeof(float)));
     MCL_CUDA(h, cudaMalloc((void **)&h->d_logtab, cells * sizeof(int32_t)));
     MCL_CUDA(h, cudaMemcpy(h->d_dist, h_dist, cells * sizeof(float), cudaMemcpyHostToDevice));
@@ -149,8 +149,13 @@ extern "C" int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_di
     }
     if (x1 < 0) { h->wx0 = 0; h->wy0 = 0; h->ww = 0; h->wh = 0; }
     else { h->wx0 = x0; h->wy0 = y0; h->ww = x1 - x0 + 1; h->wh = y1 - y0 + 1; }
-    h->win_bytes = (((size_t)(h->ww + 2) * (h->wh + 2) * sizeof(int32_t)) + 15) & ~(size_t)15;
-    MCL_CUDA(h, cudaMalloc((void **)&h->d_win, h->win_bytes));
+    // pitch-256 layout: the minor axis is the larger extent that still fits in 256 columns (fewest rows)
+    const int ex = h->ww + 2, ey = h->wh + 2;
+    h->win_ok = std::min(ex, ey) <= 256;
+    h->win_tpose = h->win_ok && (ex > 256 || (ey <= 256 && ey > ex));
+    h->win_rows = h->win_tpose ? ex : ey;
+    h->win_bytes = h->win_ok ? (size_t)h->win_rows * 256 * sizeof(int32_t) : 0;
+    if (h->win_ok) MCL_CUDA(h, cudaMalloc((void **)&h->d_win, h->win_bytes));
     h->tab_dirty = true;
     return MCL_OK;
 }
@@ -189,14 +194,14 @@ __global__ void k_build_logtab(const float *__restrict__ dist, int32_t *__restri
 }
 
 __global__ void k_pack_window(const int32_t *__restrict__ logtab, int32_t *__restrict__ win, int W, int wx0,
-                              int wy0, int ww, int wh, int32_t c0) {
-    const int pw = ww + 2, ph = wh + 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pw * ph; i += gridDim.x * blockDim.x) {
-        const int iy = i / pw, ix = i - iy * pw;
+                              int wy0, int ww, int wh, int rows, int tpose, int32_t c0, int32_t voff) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * 256; i += gridDim.x * blockDim.x) {
+        const int major = i >> 8, minor = i & 255;
+        const int ix = tpose ? major : minor, iy = tpose ? minor : major;
         int32_t v = c0;
         if (ix >= 1 && ix <= ww && iy >= 1 && iy <= wh)
             v = logtab[(size_t)(wy0 + iy - 1) * W + (wx0 + ix - 1)];
-        win[i] = v;
+        win[i] = v - voff;     // >= 0: see mcl_handle::voff
     }
 }
 
@@ -220,32 +225,49 @@ int mcl_prepare_table(mcl_handle *h) {
     MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scratch, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     MCL_CUDA(h, cudaStreamSynchronize(h->stream));
     memcpy(&h->c0, h->h_pinned, sizeof(int32_t));
-    const int n = (h->ww + 2) * (h->wh + 2);
-    k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
-        h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->c0);
-    MCL_LAUNCH_CHECK(h);
-    // coded window (uint8 + table of distinct values) when the int32 window does not fit in shared memory
+    // every table value is >= quantise(log 1e-6) (pu:141 clamps p at 1e-6); 4 units of slack for libm differences
+    h->voff = (int32_t)llrint(log(1e-6) * MCL_LOGP_SCALE) - 4;
+    h->acc_terms_ok = (uint64_t)((int64_t)h->c0 - h->voff) * MCL_ACC_TERMS < ((uint64_t)1 << 32);
+    // cell arithmetic: 2^(E-1) must cover the map, the window offset and two beam lengths
+    {
+        const double rmax = ceil(h->max_range / h->res);
+        const double need = (double)std::max(h->W, h->H) + 2.0 * rmax + 8.0;
+        int E = 12;
+        while (E < 40 && ldexp(1.0, E - 1) < need) ++E;
+        if (E > 20) return mcl_fail(h, MCL_ERR_CAPACITY, "map extent + max_range/res exceeds 2^19 cells");
+        h->cell_S = 20 - E;
+        h->cell_M = ldexp(1.5, E);
+        h->cell_K = (int)(((uint32_t)(1023 + E) << 20) + (1u << 19));
+        h->cell_lim = ldexp(1.0, E - 1) - rmax - 4.0;
+    }
     cudaFree(h->d_win8); cudaFree(h->d_lut);
     h->d_win8 = nullptr; h->d_lut = nullptr; h->coded = false; h->win8_bytes = 0;
-    const size_t limit = (size_t)h->smem_optin;
-    if (16 + h->win_bytes > limit && (size_t)n + 16 + 32768 + 64 <= limit) {
-        std::vector<int32_t> win((size_t)n);
-        MCL_CUDA(h, cudaMemcpyAsync(win.data(), h->d_win, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
-        std::vector<int32_t> uniq(win);
-        std::sort(uniq.begin(), uniq.end());
-        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-        if (uniq.size() <= 256) {
-            std::vector<uint8_t> codes((((size_t)n + 15) / 16) * 16, 0);
-            for (int i = 0; i < n; ++i)
-                codes[i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), win[i]) - uniq.begin());
-            uniq.resize(256, 0);
-            MCL_CUDA(h, cudaMalloc((void **)&h->d_win8, codes.size()));
-            MCL_CUDA(h, cudaMalloc((void **)&h->d_lut, 256 * sizeof(int32_t)));
-            MCL_CUDA(h, cudaMemcpy(h->d_win8, codes.data(), codes.size(), cudaMemcpyHostToDevice));
-            MCL_CUDA(h, cudaMemcpy(h->d_lut, uniq.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
-            h->win8_bytes = codes.size();
-            h->coded = true;
+    if (h->win_ok) {
+        const int n = h->win_rows * 256;
+        k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
+            h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->win_rows, h->win_tpose ? 1 : 0, h->c0, h->voff);
+        MCL_LAUNCH_CHECK(h);
+        // coded window (uint8 + table of distinct values) when the int32 window does not fit in shared memory
+        const size_t limit = (size_t)h->smem_optin;
+        if (16 + h->win_bytes > limit && (size_t)n + 16 + 32768 + 64 <= limit) {
+            std::vector<int32_t> win((size_t)n);
+            MCL_CUDA(h, cudaMemcpyAsync(win.data(), h->d_win, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            std::vector<int32_t> uniq(win);
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            if (uniq.size() <= 256) {
+                std::vector<uint8_t> codes((size_t)n, 0);
+                for (int i = 0; i < n; ++i)
+                    codes[i] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), win[i]) - uniq.begin());
+                uniq.resize(256, 0);
+                MCL_CUDA(h, cudaMalloc((void **)&h->d_win8, codes.size()));
+                MCL_CUDA(h, cudaMalloc((void **)&h->d_lut, 256 * sizeof(int32_t)));
+                MCL_CUDA(h, cudaMemcpy(h->d_win8, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+                MCL_CUDA(h, cudaMemcpy(h->d_lut, uniq.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
+                h->win8_bytes = codes.size();
+                h->coded = true;
+            }
         }
     }
     h->tab_dirty = false;
