@@ -267,6 +267,7 @@ def run_native(args):
     import ctypes as C
     lik_ms, lik_n = C.c_double(0), C.c_int64(0)
     lib.mcl_timing_stop(h, C.byref(lik_ms), C.byref(lik_n))
+    lik_sets = int(lib.mcl_timing_sets(h)) or int(lik_n.value)      # particle sets scored by those launches
     launches = lib.mcl_launch_count(h) - launches0
     clocks = sampler.stop() if rank == 0 else None
     step_ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
@@ -337,13 +338,15 @@ def run_native(args):
     # evaluation + (pose read + score write) per particle (here fp64 SoA poses: 24 B + 4 B), times the units
     # one launch processes.  The gathered bytes are served from the shared-memory copy of the table, so the
     # DRAM traffic ncu sees (`traffic`) is only the pose stream.
-    gather_bytes = 4.0 * n * mv
-    stream_bytes = n * (24 + 4)
+    sets_per_launch = lik_sets / max(1, lik_n.value)      # 2: particles and particles_prev scored by one launch
+    gather_bytes = 4.0 * n * mv * sets_per_launch
+    stream_bytes = n * (24 + 4) * sets_per_launch
     achieved = (gather_bytes + stream_bytes) / (lik_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": 24084224,
                 "traffic_source": "profiles/r1e_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum per k_likelihood_g1 launch (ncu --set full)",
                 "kernel": "k_likelihood_g1", "launch_ms": lik_launch_ms, "launches_timed": int(lik_n.value),
+                "particle_sets_per_launch": sets_per_launch,
                 "algorithmic_bytes_per_launch": gather_bytes + stream_bytes,
                 "hbm_stream_only_gbs": stream_bytes / (lik_launch_ms * 1e-3) / 1e9,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
@@ -358,7 +361,7 @@ def run_native(args):
         s_rate, g_rate = C.c_double(0), C.c_double(0)
         loc.h.call("mcl_bench_gather", 0, win_bytes, 1 << 32, 3, C.byref(s_rate))
         loc.h.call("mcl_bench_gather", 1, gm.width * gm.height * 4, 1 << 31, 3, C.byref(g_rate))
-        lik_rate = n * mv / (lik_launch_ms * 1e-3)
+        lik_rate = n * mv * sets_per_launch / (lik_launch_ms * 1e-3)
         gl = {"bound": "smem_gather", "achieved": lik_rate, "peak": s_rate.value, "unit": "lookups/s",
               "frac": lik_rate / s_rate.value, "l2_gather_peak": g_rate.value,
               "frac_of_l2_gather": lik_rate / g_rate.value,
@@ -394,7 +397,7 @@ def run_native(args):
         "step_ms_median": float(np.median(step_ms)), "step_ms_min": float(step_ms.min()),
         "host_wall_ms_per_step": 1e3 * t_wall / K,
         "step_ms_reference_resampling": ref_mode_ms,
-        "valid_beams_mean": mv, "likelihood_kernel_evals_per_s": n * mv / (lik_launch_ms * 1e-3),
+        "valid_beams_mean": mv, "likelihood_kernel_evals_per_s": n * mv * sets_per_launch / (lik_launch_ms * 1e-3),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_t / K,
                 "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,

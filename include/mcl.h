@@ -318,6 +318,8 @@ int64_t mcl_launch_count(const mcl_handle *h);
  * mcl_likelihood launch between start and stop (events on the handle's stream). */
 int mcl_timing_start(mcl_handle *h);
 int mcl_timing_stop(mcl_handle *h, double *likelihood_ms, int64_t *likelihood_launches);
+/* particle sets evaluated by those launches (the fused step scores particles and particles_prev in one launch) */
+int64_t mcl_timing_sets(const mcl_handle *h);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,7 @@ SIGNATURES = {
     "mcl_launch_count": (_i64, [_vp]),
     "mcl_timing_start": (_i, [_vp]),
     "mcl_timing_stop": (_i, [_vp, _pd, C.POINTER(_i64)]),
+    "mcl_timing_sets": (_i64, [_vp]),
 }
 
 

@@ -94,12 +94,15 @@ struct mcl_handle {
     size_t seq_bytes = 0;
     void *d_kld = nullptr;       // KLD-sampling work buffers (kld.cu)
     size_t kld_bytes = 0;
+    void *d_fused = nullptr;     // work area of the fused step tail (fused.cu)
+    size_t fused_bytes = 0;
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;
 
     // timing of likelihood launches
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> lik_events;
+    int64_t lik_sets_timed = 0;  // particle sets evaluated by the timed launches (a pair launch evaluates two)
 };
 
 extern thread_local std::string g_create_err;
@@ -110,6 +113,18 @@ int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
 void mcl_filter_forget(const mcl_handle *h);
 int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c);
 int mcl_softmax_pair(mcl_handle *h, const float *s0, float *w0, const float *s1, float *w1, int64_t n);
+// fused.cu: softmax -> MH -> estimate sums -> cumulative sums, then search + gather (single-GPU step tail)
+int mcl_fused_prepare(mcl_handle *h, int64_t n);
+unsigned *mcl_fused_keymax(mcl_handle *h);
+int mcl_fused_update_estimate(mcl_handle *h, int64_t n, int use_mh, const float *s_post, const float *s_pre, float *w_post,
+                              float *w_pre, float *w_out, const double *px, const double *py, const double *pt,
+                              const double *ox, const double *oy, const double *ot, double *nx, double *ny, double *nth,
+                              uint64_t seed, uint64_t step, uint64_t first_index, double *est18);
+int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, const double *ny, const double *nth,
+                       int32_t *idx, double *gx, double *gy, double *gt);
+int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
+                        const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
+                        unsigned *d_keymax, bool *g1_used);
 
 #define MCL_CUDA(h, expr)                                                                   \
     do {                                                                                    \
@@ -241,6 +256,14 @@ __device__ __forceinline__ double cell_logp(float d, double sigma_hit, double z_
     return log(p);
 }
 
+// order-preserving map float -> unsigned (atomicMax on the key == max on the float; key 0 is below every float)
+__device__ __forceinline__ unsigned mcl_key_of_float(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float mcl_float_of_key(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 #define MCL_LOGP_SCALE 33554432.0   // 2^25
 #define MCL_ACC_TERMS 8
 __device__ __forceinline__ int32_t quantise_logp(double lp) { return __double2int_rn(lp * MCL_LOGP_SCALE); }

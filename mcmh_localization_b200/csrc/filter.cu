@@ -4,6 +4,7 @@
 // pays one ctypes call per step instead of ~15; buffer roles (particles / particles_prev / spare)
 // rotate inside the handle exactly like the node's copies at node:404-405, node:370 and node:490.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -539,6 +540,68 @@ extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
     return MCL_OK;
 }
 
+// update -> estimate -> resample through the fused kernels (fused.cu) when the configuration allows it:
+// one GPU, symmetric MH or plain MCL, fixed-point resampling, enough particles for the one-thread-per-particle
+// likelihood kernel.  *done = false: nothing was enqueued, the caller runs the stand-alone sequence.
+// MCL_NO_FUSE=1 in the environment disables it (A/B checks).
+static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_out16[16], bool *done) {
+    *done = false;
+    static int off = -1;
+    if (off < 0) { const char *e = getenv("MCL_NO_FUSE"); off = (e && atoi(e)) ? 1 : 0; }
+    if (off || f->comm || f->assym || f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
+    DeviceGuard guard(h->device);
+    int rc = mcl_fused_prepare(h, f->n);
+    if (rc) return rc;
+    bool g1 = false;
+    const int cur = f->cur, prev = f->prev, spare = f->spare;
+    if (f->use_mh)
+        rc = mcl_likelihood_pair(h, f->x[cur], f->y[cur], f->th[cur], f->score_post, f->x[prev], f->y[prev], f->th[prev],
+                                 f->score_pre, f->n, mcl_fused_keymax(h), &g1);
+    else
+        rc = mcl_likelihood_pair(h, f->x[cur], f->y[cur], f->th[cur], f->score_post, nullptr, nullptr, nullptr, nullptr,
+                                 f->n, mcl_fused_keymax(h), &g1);
+    if (rc || !g1) return rc;
+    *done = true;
+    double *est = h->d_est18;
+    int res;                                   // the set that holds the particles after the MH step
+    if (f->use_mh) {
+        f->tick++;
+        // mh_resampling(particles_prev, particles, weights_post, weights_pre)  (node:363) -> spare set
+        rc = mcl_fused_update_estimate(h, f->n, 1, f->score_post, f->score_pre, f->w_post, f->w_pre, f->w[f->wslot],
+                                       f->x[cur], f->y[cur], f->th[cur], f->x[prev], f->y[prev], f->th[prev],
+                                       f->x[spare], f->y[spare], f->th[spare], f->seed, f->tick, f->first_index, est);
+        if (rc) return rc;
+        f->cur = spare; f->spare = cur;        // self.particles = mh_particles (node:370)
+        res = spare;
+    } else {
+        rc = mcl_fused_update_estimate(h, f->n, 0, f->score_post, nullptr, nullptr, nullptr, f->w[f->wslot], f->x[cur],
+                                       f->y[cur], f->th[cur], nullptr, nullptr, nullptr, f->x[cur], f->y[cur], f->th[cur],
+                                       f->seed, f->tick, f->first_index, est);
+        if (rc) return rc;
+        res = cur;
+    }
+    if (h_out16) {
+        MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, est, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MCL_CUDA(h, cudaEventRecord(h->ev_est, h->stream));
+    }
+    if (d_out18) MCL_CUDA(h, cudaMemcpyAsync(d_out18, est, 18 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    // node:488-492 resample_lvr: gather from the MH result into the free set
+    f->tick++;
+    const double r = mcl_resample_offset(f->seed, f->tick, f->n);
+    const int dst = f->spare;
+    rc = mcl_fused_resample(h, f->n, r, f->x[res], f->y[res], f->th[res], f->idx, f->x[dst], f->y[dst], f->th[dst]);
+    if (rc) return rc;
+    f->cur = dst; f->spare = res;
+    if (h_out16) {
+        MCL_CUDA(h, cudaEventSynchronize(h->ev_est));
+        const double *o = h->h_pinned;
+        h_out16[0] = o[0]; h_out16[1] = o[1]; h_out16[2] = o[6]; h_out16[3] = o[7]; h_out16[4] = o[8];
+        for (int k = 0; k < 9; ++k) h_out16[5 + k] = o[9 + k];
+        h_out16[14] = 0; h_out16[15] = 0;
+    }
+    return MCL_OK;
+}
+
 // one odom message followed by one scan: predict -> update -> estimate -> resample
 extern "C" int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
                                double h_out16[16]) {
@@ -546,6 +609,11 @@ extern "C" int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_sl
     int rc;
     if (delta) { rc = mcl_filter_predict(h, delta, nullptr, 0); if (rc) return rc; }
     if (scan_slot >= 0) { rc = mcl_use_scan(h, scan_slot); if (rc) return rc; }
+    {
+        bool done = false;
+        rc = fused_tail(h, f, d_out18, h_out16, &done);
+        if (rc || done) return rc;
+    }
     rc = mcl_filter_update(h, nullptr);
     if (rc) return rc;
     if (!h_out16) {

@@ -25,6 +25,7 @@
 // Mapping: G lanes per particle (G = 1 for large N: beam constants are then warp-uniform constant-bank
 // loads; G up to 32 for small N to fill the machine), beams strided over the G lanes and reduced
 // with __shfl_xor.
+#include <float.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -37,6 +38,12 @@ struct LikParams {
     const double *x, *y, *th;
     int64_t n;
     float *score;
+    // G = 1 kernels only: an optional second particle set of the same length evaluated by the same launch
+    // (the MH update scores particles and particles_prev, node:254-268), and an optional pair of cells that
+    // receive the maximum score of each set as an order-preserving unsigned key (mcl_key_of_float)
+    const double *x2, *y2, *th2;
+    float *score2;
+    unsigned *keymax;
     const BeamTable *beams;
     int n_pos, n_neg;
     double ox, oy, res;
@@ -101,9 +108,10 @@ struct Pose {          // one particle, ready for the beam loop
     bool far;          // outside the range of the arithmetic: no endpoint can be inside the map
 };
 
-__device__ __forceinline__ Pose load_pose(const LikParams &p, int64_t i) {
+__device__ __forceinline__ Pose load_pose(const LikParams &p, const double *__restrict__ xs, const double *__restrict__ ys,
+                                          const double *__restrict__ ts, int64_t i) {
     Pose q;
-    const double x = p.x[i], y = p.y[i], th = p.th[i];
+    const double x = xs[i], y = ys[i], th = ts[i];
     sincos(th, &q.s, &q.c);
     const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);          // pu:128: (lx - ox) / res, distributed
     const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
     const int warp_first_grp = (threadIdx.x & ~31) / G;
     for (int64_t base = (int64_t)blockIdx.x * GROUPS; base + warp_first_grp < p.n; base += stride) {
         const int64_t i = base + grp;
-        const Pose q = load_pose(p, i < p.n ? i : p.n - 1);
+        const Pose q = load_pose(p, p.x, p.y, p.th, i < p.n ? i : p.n - 1);
         long long acc = 0;
         if (!q.far) {
             if (SMEM && __all_sync(0xffffffffu, q.interior)) {
@@ -236,21 +244,23 @@ __device__ __forceinline__ uint32_t g1_fetch(const G1Ctx &k, int cell) {
 
 // P slices (rows i0, i0 + row, ...) of one warp; lanes whose particle index is >= end idle on a copy of end - 1
 template <bool SMEM, bool CODED, bool TPOSE, int P>
-__device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, int64_t i0, int64_t row, int64_t end) {
+__device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, const double *__restrict__ xs,
+                                          const double *__restrict__ ys, const double *__restrict__ ts,
+                                          float *__restrict__ score, int64_t i0, int64_t row, int64_t end, float &smax) {
     int64_t idx[P];
     Pose q[P];
     bool interior = true, any_near = false;
 #pragma unroll
     for (int u = 0; u < P; ++u) {
         idx[u] = i0 + u * row;
-        q[u] = load_pose(p, idx[u] < end ? idx[u] : end - 1);
+        q[u] = load_pose(p, xs, ys, ts, idx[u] < end ? idx[u] : end - 1);
         interior = interior && q[u].interior;
         any_near = any_near || !q[u].far;
     }
     long long acc[P];
 #pragma unroll
     for (int u = 0; u < P; ++u) acc[u] = 0;
-    if (SMEM && __all_sync(0xffffffffu, interior)) {
+    if (SMEM && __reduce_and_sync(0xffffffffu, interior ? 1u : 0u)) {   // REDUX: the result is a uniform register, the branch stays uniform
         unsigned long long uacc[P];
 #pragma unroll
         for (int u = 0; u < P; ++u) uacc[u] = 0;
@@ -318,7 +328,11 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, in
     }
 #pragma unroll
     for (int u = 0; u < P; ++u)
-        if (idx[u] < end) p.score[idx[u]] = (float)(((double)acc[u] / MCL_LOGP_SCALE) / (double)k.nb);   // pu:144-145
+        if (idx[u] < end) {
+            const float sc = (float)(((double)acc[u] / MCL_LOGP_SCALE) / (double)k.nb);   // pu:144-145
+            score[idx[u]] = sc;
+            smax = fmaxf(smax, sc);
+        }
 }
 
 // Tunables (chosen by measurement, see profiles/): threads per CTA and minimum CTAs per SM.
@@ -358,10 +372,34 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
     const int64_t per = p.n / gridDim.x, rem = p.n % gridDim.x;
     const int64_t first = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
     const int64_t end = first + per + ((int64_t)blockIdx.x < rem ? 1 : 0);
-    int64_t i = first + (threadIdx.x & ~31);          // start of this warp's slice in row 0
-    for (; i + G1_THREADS < end; i += 2 * G1_THREADS)
-        g1_slices<SMEM, CODED, TPOSE, 2>(p, k, i + k.lane, G1_THREADS, end);
-    if (i < end) g1_slices<SMEM, CODED, TPOSE, 1>(p, k, i + k.lane, 0, end);
+    // The CTA's share is cut into pairs of adjacent 32-particle slices, dealt round-robin to the warps.  With
+    // a second particle set, blockIdx.y selects the set (the second wave of CTAs follows the first without a
+    // launch gap).  ONE instance of the beam loop in the code, reached through uniform control flow only:
+    // otherwise ptxas moves the beam constants from the uniform datapath (LDCU + UR operands) to per-thread
+    // LDC, which costs 15 % (ncu: idc pipe 46 % busy, dispatch stalls).
+    const bool second = blockIdx.y != 0;
+    const double *__restrict__ xs = second ? p.x2 : p.x, *__restrict__ ys = second ? p.y2 : p.y,
+                 *__restrict__ ts = second ? p.th2 : p.th;
+    float *__restrict__ score = second ? p.score2 : p.score;
+    float smax0 = -FLT_MAX;
+    int64_t i = first + 2 * (threadIdx.x & ~31);
+    for (; i < end; i += 2 * G1_THREADS)
+        g1_slices<SMEM, CODED, TPOSE, 2>(p, k, xs, ys, ts, score, i + k.lane, 32, end, smax0);
+    // Never taken (the host rejects n < 0).  With this second, cold copy of the slice code in the kernel
+    // ptxas keeps the hot copy above on the uniform datapath; without it the beam constants are fetched with
+    // per-thread LDC (found by bisection on the SASS, CUDA 12.9).
+    if (p.n < 0) g1_slices<SMEM, CODED, TPOSE, 1>(p, k, xs, ys, ts, score, i + k.lane, 0, end, smax0);
+    if (p.keymax) {                                        // maximum score of the set (first softmax pass, node:353)
+        __shared__ float smx[32];
+        smax0 = warp_max(smax0);
+        if (k.lane == 0) smx[threadIdx.x >> 5] = smax0;
+        __syncthreads();
+        if (threadIdx.x < 32 && end > first) {
+            float t = k.lane < (G1_THREADS >> 5) ? smx[k.lane] : -FLT_MAX;
+            t = warp_max(t);
+            if (k.lane == 0) atomicMax(p.keymax + (second ? 1 : 0), mcl_key_of_float(t));
+        }
+    }
 }
 
 __global__ void k_fill_f32(float *out, int64_t n, float v) {
@@ -381,7 +419,10 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
         if (c_kern[k] == (const void *)kern && c_smem[k] == smem_bytes && c_dev[k] == h->device) occ = c_occ[k];
     if (occ == 0) {
         // opt in to the device maximum once (a later, smaller request must not lower the limit)
-        MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+        cudaFuncAttributes fa;
+        MCL_CUDA(h, cudaFuncGetAttributes(&fa, kern));
+        MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->smem_optin - (int)fa.sharedSizeBytes));     // static + dynamic <= opt-in limit
         MCL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem_bytes));
         if (occ < 1) return mcl_fail(h, MCL_ERR_CAPACITY, "likelihood kernel does not fit on an SM");
         const int k = c_n < 32 ? c_n++ : 31;
@@ -398,11 +439,12 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
         MCL_CUDA(h, cudaEventCreate(&e1));
         MCL_CUDA(h, cudaEventRecord(e0, h->stream));
     }
-    kern<<<blocks, threads, smem_bytes, h->stream>>>(p);
+    kern<<<dim3(blocks, balanced && p.x2 ? 2 : 1), threads, smem_bytes, h->stream>>>(p);
     MCL_LAUNCH_CHECK(h);
     if (h->timing) {
         MCL_CUDA(h, cudaEventRecord(e1, h->stream));
         h->lik_events.emplace_back(e0, e1);
+        h->lik_sets_timed += (balanced && p.x2) ? 2 : 1;
     }
     return MCL_OK;
 }
@@ -431,8 +473,27 @@ static int launch_g1(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
 static const void *g_cbeams_src = nullptr;
 static uint64_t g_cbeams_gen = 0;
 
+static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
+                           float *d_score, const double *d_x2, const double *d_y2, const double *d_theta2,
+                           float *d_score2, unsigned *d_keymax, bool *g1_used);
+
 extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                               int64_t n, float *d_score) {
+    return likelihood_impl(h, d_x, d_y, d_theta, n, d_score, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// internal (filter.cu): both score sets of an MH update in one launch + their maxima as keys.  Only the
+// one-thread-per-particle kernels implement it: *g1_used = false and NOTHING is launched otherwise.
+int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
+                        const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
+                        unsigned *d_keymax, bool *g1_used) {
+    return likelihood_impl(h, d_x, d_y, d_theta, n, d_score, d_x2, d_y2, d_theta2, d_score2, d_keymax, g1_used);
+}
+
+static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
+                           float *d_score, const double *d_x2, const double *d_y2, const double *d_theta2,
+                           float *d_score2, unsigned *d_keymax, bool *g1_used) {
+    if (g1_used) *g1_used = false;
     if (!h) return MCL_ERR_ARG;
     if (n < 0 || (n > 0 && (!d_x || !d_y || !d_theta || !d_score)))
         return mcl_fail(h, MCL_ERR_ARG, "mcl_likelihood: bad argument");
@@ -442,6 +503,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     int rc = mcl_prepare_table(h);
     if (rc) return rc;
     const int nb = h->n_pos + h->n_neg;
+    if (g1_used && nb == 0) return MCL_OK;
     if (nb == 0) {   // pu:146-147: no valid beam -> -50 for every particle
         k_fill_f32<<<(int)std::min<int64_t>((n + 255) / 256, h->sm_count * 8), 256, 0, h->stream>>>(d_score, n, -50.0f);
         MCL_LAUNCH_CHECK(h);
@@ -449,6 +511,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     }
     LikParams p;
     p.x = d_x; p.y = d_y; p.th = d_theta; p.n = n; p.score = d_score;
+    p.x2 = d_x2; p.y2 = d_y2; p.th2 = d_theta2; p.score2 = d_score2; p.keymax = d_keymax;
     p.beams = h->d_beams_active; p.n_pos = h->n_pos; p.n_neg = h->n_neg;
     p.ox = h->ox; p.oy = h->oy; p.res = h->res; p.W = h->W; p.H = h->H;
     p.logtab = h->d_logtab; p.dist = h->d_dist; p.win = h->d_win;
@@ -463,7 +526,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     const size_t beam_bytes = (size_t)nb * sizeof(BeamTable);
     const size_t smem_glob = 16 + beam_bytes;
     const size_t smem_win = smem_glob + h->win_bytes;
-    const size_t smem_limit = (size_t)h->smem_optin;
+    const size_t smem_limit = (size_t)h->smem_optin - 512;      // room for the kernels' static shared memory
     if (smem_glob > smem_limit) return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: too many beams for shared memory");
     bool use_smem = h->win_ok && smem_win <= smem_limit;
     if (h->lik_path == 1) use_smem = false;
@@ -475,6 +538,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
     const int64_t target = (int64_t)h->sm_count * 2048;
     while (G < 32 && n * G < target) G *= 2;
     if (G == 1 && nb <= MAX_CBEAMS && h->acc_terms_ok) {
+        if (g1_used) *g1_used = true;
         if (g_cbeams_src != (const void *)h->d_beams_active || g_cbeams_gen != h->scan_gen) {
             MCL_CUDA(h, cudaMemcpyToSymbolAsync(c_beams_raw, h->d_beams_active, beam_bytes, 0, cudaMemcpyDeviceToDevice,
                                                 h->stream));
@@ -490,6 +554,7 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
                                 : launch_g1<true, false, false>(h, p, 16 + h->win_bytes);
         return launch_g1<false, false, false>(h, p, 16);
     }
+    if (g1_used) return MCL_OK;     // pair / key form not available: the caller falls back to separate launches
     if (use_coded && !use_smem && h->lik_path == 2)
         return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: the coded window needs the one-thread-per-particle kernel (larger n)");
 #define LIK_CASE(GV)                                                                   \

@@ -63,7 +63,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
     mcl_filter_forget(h);
-    cudaFree(h->d_est18);
+    cudaFree(h->d_est18); cudaFree(h->d_fused);
     cudaFree(h->d_kld);
     cudaFree(h->d_seq);
     if (h->ev_est) cudaEventDestroy(h->ev_est);
@@ -248,7 +248,7 @@ int mcl_prepare_table(mcl_handle *h) {
             h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->win_rows, h->win_tpose ? 1 : 0, h->c0, h->voff);
         MCL_LAUNCH_CHECK(h);
         // coded window (uint8 + table of distinct values) when the int32 window does not fit in shared memory
-        const size_t limit = (size_t)h->smem_optin;
+        const size_t limit = (size_t)h->smem_optin - 512;
         if (16 + h->win_bytes > limit && (size_t)n + 16 + 32768 + 64 <= limit) {
             std::vector<int32_t> win((size_t)n);
             MCL_CUDA(h, cudaMemcpyAsync(win.data(), h->d_win, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -385,9 +385,13 @@ extern "C" int mcl_timing_start(mcl_handle *h) {
     if (!h) return MCL_ERR_ARG;
     for (auto &p : h->lik_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     h->lik_events.clear();
+    h->lik_sets_timed = 0;
     h->timing = true;
     return MCL_OK;
 }
+
+// particle sets evaluated by the likelihood launches of the last timing window (a pair launch counts two)
+extern "C" int64_t mcl_timing_sets(const mcl_handle *h) { return h ? h->lik_sets_timed : 0; }
 
 extern "C" int mcl_timing_stop(mcl_handle *h, double *ms, int64_t *launches) {
     if (!h) return MCL_ERR_ARG;

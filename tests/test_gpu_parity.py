@@ -742,6 +742,49 @@ def test_localizer_production_step_runs_and_is_deterministic():
     assert np.isfinite(outs[0][1][3]).all()
 
 
+@pytest.mark.parametrize("mode", ["MHMCL", "MCL"])
+def test_fused_step_equals_standalone_sequence(mode):
+    """Localizer.step() runs the step tail through the fused kernels (fused.cu: likelihood pair with max keys,
+    sum-exp, weights + MH + raw estimate sums, central sums + look-back scan, search + gather).  It must leave
+    the SAME particles, weights and resampled indices, bit for bit, as predict/update/estimate/resample issued
+    one by one through the stand-alone kernels (which the other tests pin to the oracle); the estimate differs
+    only by the order of the fp64 partial sums."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan, free_space_particles
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    n = 400_003                                   # one-thread-per-particle likelihood kernel, ragged last tile
+    p0 = free_space_particles(gm, n, seed=5)
+    locs = []
+    for _ in range(2):
+        loc = Localizer(params=P, mode=mode, seed=21, resample_mode="fixed")
+        loc.load_map(gm)
+        loc.set_particles(p0)
+        locs.append(loc)
+    fused, plain = locs
+    pose = np.array([-2.0, -0.5, 0.0])
+    for k in range(6):
+        scan, angles = raycast_scan(gm, pose, noise_sigma=0.01, seed=77 + k)
+        e_f = fused.step(pose, scan, angles=angles)
+        plain.predict(pose)
+        plain.update(scan, angles=angles)
+        e_p = plain.estimate()
+        plain.resample()
+        assert fused.tick == plain.tick
+        assert np.array_equal(fused.particles(), plain.particles()), k
+        assert np.array_equal(fused.particles_prev(), plain.particles_prev()), k
+        assert np.array_equal(fused.weights(), plain.weights()), k
+        assert np.array_equal(fused.idx.cpu().numpy(), plain.idx.cpu().numpy()), k
+        sf, sp = fused.scores(), plain.scores()
+        assert np.array_equal(sf[1], sp[1]) and (mode == "MCL" or np.array_equal(sf[0], sp[0]))
+        np.testing.assert_allclose(e_f[:3], e_p[:3], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(e_f[3], e_p[3], rtol=1e-9, atol=1e-15)
+        pose = pose + np.array([0.02 * np.cos(pose[2]), 0.02 * np.sin(pose[2]), 0.01])
+
+
 def test_sharded_two_gpus_equals_single_gpu():
     """ShardedLocalizer over 2 ranks == single-GPU Localizer (needs >= 2 GPUs; skipped otherwise)."""
     _need_gpu()
