@@ -188,6 +188,8 @@ def workload_config(args, gm, n_cpu=None):
 
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
+    # NCCL announces its version on stdout at INFO/VERSION level: keep stdout to the one JSON line
+    os.environ["NCCL_DEBUG"] = os.environ.get("MCL_NCCL_DEBUG", "WARN")
     import torch
     import torch.distributed as dist
     from mcmh_localization_b200 import Localizer

@@ -113,18 +113,34 @@ int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
 void mcl_filter_forget(const mcl_handle *h);
 int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c);
 int mcl_softmax_pair(mcl_handle *h, const float *s0, float *w0, const float *s1, float *w1, int64_t n);
-// fused.cu: softmax -> MH -> estimate sums -> cumulative sums, then search + gather (single-GPU step tail)
+// fused.cu: the step tail in four kernels (softmax sums -> weights + MH + raw estimate sums -> central sums +
+// cumulative weights -> search + gather); a sharded run exchanges the quantities of FusedPtrs between stages
+struct FusedStep {
+    int64_t n, n_global;
+    int use_mh;
+    const float *s_post, *s_pre;
+    float *w_post, *w_pre, *w_out;
+    const double *px, *py, *pt, *ox, *oy, *ot;
+    double *nx, *ny, *nth;
+    uint64_t seed, step, first_index;
+    double *est18;
+};
+struct FusedPtrs { unsigned long long *keymax, *sumq, *total; double *msum, *csum; };
 int mcl_fused_prepare(mcl_handle *h, int64_t n);
-unsigned *mcl_fused_keymax(mcl_handle *h);
-int mcl_fused_update_estimate(mcl_handle *h, int64_t n, int use_mh, const float *s_post, const float *s_pre, float *w_post,
-                              float *w_pre, float *w_out, const double *px, const double *py, const double *pt,
-                              const double *ox, const double *oy, const double *ot, double *nx, double *ny, double *nth,
-                              uint64_t seed, uint64_t step, uint64_t first_index, double *est18);
+unsigned long long *mcl_fused_keymax(mcl_handle *h);
+void mcl_fused_exchange_ptrs(mcl_handle *h, FusedPtrs *out);
+const unsigned long long *mcl_fused_cumsum(mcl_handle *h, int64_t n);
+int mcl_fused_sumexp(mcl_handle *h, const FusedStep &u);
+int mcl_fused_weights(mcl_handle *h, const FusedStep &u);
+int mcl_fused_scan(mcl_handle *h, const FusedStep &u);
 int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, const double *ny, const double *nth,
                        int32_t *idx, double *gx, double *gy, double *gt);
+int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, int64_t n_in, const uint64_t *d_totals_all,
+                           int rank, int world, double r, int64_t n_global, int64_t n_per_rank, const double *d_x,
+                           const double *d_y, const double *d_theta, const uint64_t *d_peer_ptrs);
 int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
                         const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
-                        unsigned *d_keymax, bool *g1_used);
+                        unsigned long long *d_keymax, bool *g1_used);
 
 #define MCL_CUDA(h, expr)                                                                   \
     do {                                                                                    \

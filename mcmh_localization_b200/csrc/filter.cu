@@ -165,7 +165,8 @@ extern "C" int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode
 // cannot overwrite what a slow rank is still reading from exchange k (a rank cannot finish k+1 before every
 // peer has entered k+1, i.e. finished k).
 // ---------------------------------------------------------------------------------------------
-enum { XCH_SUM_F64 = 0, XCH_MAX_F64 = 1, XCH_SUM_U64 = 2, XCH_GATHER = 3 };
+enum { XCH_SUM_F64 = 0, XCH_MAX_F64 = 1, XCH_SUM_U64 = 2, XCH_GATHER = 3, XCH_MAX_U64 = 4,
+       XCH_SUM_F64_MAXLAST = 5 /* sums, except the last value: maximum */ };
 #define XCH_MAXV 16
 
 struct XchArgs {
@@ -209,15 +210,19 @@ __global__ void __launch_bounds__(32) k_exchange(const XchArgs a, const unsigned
         const unsigned long long *slots = a.mailbox + 32 + (size_t)par * 16 * XCH_MAXV;
         if (op == XCH_GATHER) {
             for (int d = 0; d < a.world; ++d) out[d * nvals + t] = ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
-        } else if (op == XCH_SUM_U64) {
+        } else if (op == XCH_SUM_U64 || op == XCH_MAX_U64) {
             unsigned long long acc = 0;
-            for (int d = 0; d < a.world; ++d) acc += ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
+            for (int d = 0; d < a.world; ++d) {
+                const unsigned long long v = ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
+                acc = op == XCH_MAX_U64 ? (v > acc ? v : acc) : acc + v;
+            }
             out[t] = acc;
         } else {
             double acc = __longlong_as_double((long long)((volatile const unsigned long long *)slots)[t]);
             for (int d = 1; d < a.world; ++d) {
                 const double v = __longlong_as_double((long long)((volatile const unsigned long long *)slots)[d * XCH_MAXV + t]);
-                acc = op == XCH_MAX_F64 ? fmax(acc, v) : acc + v;            // rank order: deterministic
+                const bool mx = op == XCH_MAX_F64 || (op == XCH_SUM_F64_MAXLAST && t == nvals - 1);
+                acc = mx ? fmax(acc, v) : acc + v;                           // rank order: deterministic
             }
             out[t] = (unsigned long long)__double_as_longlong(acc);
         }
@@ -541,14 +546,15 @@ extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
 }
 
 // update -> estimate -> resample through the fused kernels (fused.cu) when the configuration allows it:
-// one GPU, symmetric MH or plain MCL, fixed-point resampling, enough particles for the one-thread-per-particle
-// likelihood kernel.  *done = false: nothing was enqueued, the caller runs the stand-alone sequence.
-// MCL_NO_FUSE=1 in the environment disables it (A/B checks).
+// symmetric MH or plain MCL, fixed-point resampling, enough particles for the one-thread-per-particle likelihood
+// kernel.  Sharded (f->comm): the same four kernels with the peer-memory exchanges between them (score maxima,
+// softmax sums, raw estimate sums + weight maximum, central sums, totals) and the peer-push gather.
+// *done = false: nothing was enqueued, the caller runs the stand-alone sequence.  MCL_NO_FUSE=1 disables it (A/B).
 static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_out16[16], bool *done) {
     *done = false;
     static int off = -1;
     if (off < 0) { const char *e = getenv("MCL_NO_FUSE"); off = (e && atoi(e)) ? 1 : 0; }
-    if (off || f->comm || f->assym || f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
+    if (off || f->assym || f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
     DeviceGuard guard(h->device);
     int rc = mcl_fused_prepare(h, f->n);
     if (rc) return rc;
@@ -562,24 +568,39 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
                                  f->n, mcl_fused_keymax(h), &g1);
     if (rc || !g1) return rc;
     *done = true;
+    FusedPtrs xp;
+    mcl_fused_exchange_ptrs(h, &xp);
     double *est = h->d_est18;
+    FusedStep u;
+    memset(&u, 0, sizeof(u));
+    u.n = f->n; u.n_global = f->comm ? f->n_global : f->n; u.use_mh = f->use_mh;
+    u.s_post = f->score_post; u.w_out = f->w[f->wslot];
+    u.px = f->x[cur]; u.py = f->y[cur]; u.pt = f->th[cur];
+    u.seed = f->seed; u.first_index = f->first_index; u.est18 = est;
     int res;                                   // the set that holds the particles after the MH step
     if (f->use_mh) {
         f->tick++;
         // mh_resampling(particles_prev, particles, weights_post, weights_pre)  (node:363) -> spare set
-        rc = mcl_fused_update_estimate(h, f->n, 1, f->score_post, f->score_pre, f->w_post, f->w_pre, f->w[f->wslot],
-                                       f->x[cur], f->y[cur], f->th[cur], f->x[prev], f->y[prev], f->th[prev],
-                                       f->x[spare], f->y[spare], f->th[spare], f->seed, f->tick, f->first_index, est);
-        if (rc) return rc;
-        f->cur = spare; f->spare = cur;        // self.particles = mh_particles (node:370)
+        u.s_pre = f->score_pre; u.w_post = f->w_post; u.w_pre = f->w_pre;
+        u.ox = f->x[prev]; u.oy = f->y[prev]; u.ot = f->th[prev];
+        u.nx = f->x[spare]; u.ny = f->y[spare]; u.nth = f->th[spare];
         res = spare;
     } else {
-        rc = mcl_fused_update_estimate(h, f->n, 0, f->score_post, nullptr, nullptr, nullptr, f->w[f->wslot], f->x[cur],
-                                       f->y[cur], f->th[cur], nullptr, nullptr, nullptr, f->x[cur], f->y[cur], f->th[cur],
-                                       f->seed, f->tick, f->first_index, est);
-        if (rc) return rc;
+        u.nx = f->x[cur]; u.ny = f->y[cur]; u.nth = f->th[cur];
         res = cur;
     }
+    u.step = f->tick;
+    if (f->comm) { rc = comm_exchange(h, f, xp.keymax, 2, XCH_MAX_U64, xp.keymax); if (rc) return rc; }
+    rc = mcl_fused_sumexp(h, u);
+    if (rc) return rc;
+    if (f->comm) { rc = comm_exchange(h, f, xp.sumq, 2, XCH_SUM_U64, xp.sumq); if (rc) return rc; }
+    rc = mcl_fused_weights(h, u);
+    if (rc) return rc;
+    if (f->use_mh) { f->cur = spare; f->spare = cur; }      // self.particles = mh_particles (node:370)
+    if (f->comm) { rc = comm_exchange(h, f, xp.msum, 7, XCH_SUM_F64_MAXLAST, xp.msum); if (rc) return rc; }
+    rc = mcl_fused_scan(h, u);
+    if (rc) return rc;
+    if (f->comm) { rc = comm_exchange(h, f, xp.csum, 9, XCH_SUM_F64, est + 9); if (rc) return rc; }
     if (h_out16) {
         MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, est, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         MCL_CUDA(h, cudaEventRecord(h->ev_est, h->stream));
@@ -587,10 +608,22 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     if (d_out18) MCL_CUDA(h, cudaMemcpyAsync(d_out18, est, 18 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     // node:488-492 resample_lvr: gather from the MH result into the free set
     f->tick++;
-    const double r = mcl_resample_offset(f->seed, f->tick, f->n);
     const int dst = f->spare;
-    rc = mcl_fused_resample(h, f->n, r, f->x[res], f->y[res], f->th[res], f->idx, f->x[dst], f->y[dst], f->th[dst]);
-    if (rc) return rc;
+    if (f->comm) {
+        const double r = mcl_resample_offset(f->seed, f->tick, f->n_global);
+        rc = comm_exchange(h, f, xp.total, 1, XCH_GATHER, f->d_x8 + 16);          // totals of every rank
+        if (rc) return rc;
+        rc = mcl_resample_push_from(h, mcl_fused_cumsum(h, f->n), f->n, (const uint64_t *)(f->d_x8 + 16), f->rank, f->world,
+                                    r, f->n_global, f->n, f->x[res], f->y[res], f->th[res],
+                                    f->d_peer_pose + (size_t)dst * 3 * f->world);
+        if (rc) return rc;
+        rc = comm_exchange(h, f, f->d_x8, 0, XCH_GATHER, f->d_x8 + 16);          // barrier: all pushes have landed
+        if (rc) return rc;
+    } else {
+        const double r = mcl_resample_offset(f->seed, f->tick, f->n);
+        rc = mcl_fused_resample(h, f->n, r, f->x[res], f->y[res], f->th[res], f->idx, f->x[dst], f->y[dst], f->th[dst]);
+        if (rc) return rc;
+    }
     f->cur = dst; f->spare = res;
     if (h_out16) {
         MCL_CUDA(h, cudaEventSynchronize(h->ev_est));

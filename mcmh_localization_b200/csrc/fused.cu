@@ -30,17 +30,20 @@
 #define SOFTMAX_FIX 1099511627776.0   // 2^40 (mh_softmax.cu)
 
 struct FzHeader {               // device, zero-initialised once; every counter is reset by its last user
-    unsigned keymax[2];         // written by the likelihood kernel, cleared by k_fz_sumexp
+    unsigned long long keymax[2];   // max score per set as order-preserving keys: written by the likelihood kernel
+                                    // (sharded: then MAX-exchanged in place), cleared by k_fz_sumexp
+    unsigned long long sumq[2];     // sums of the softmax numerators, raw 2^-40 integers (sharded: SUM-exchanged)
+    double smax[2];                 // the maxima as floats (copied from the keys before they are cleared)
+    double msum[8];                 // six raw estimate sums, weight maximum (sharded: SUM / MAX-exchanged)
+    double csum[10];                // nine central estimate sums of this rank
+    unsigned long long total;       // total of this rank's quantised weights
     unsigned cnt_sumexp[2];
     unsigned cnt_moments, cnt_central, ticket, pad;
-    double stats[2][4];         // per set: max, sum, sum as raw 2^-40 integer
-    double scale[2];            // resampling scale 2^(62 - ceil(log2 n) - e), weight maximum
-    unsigned long long total;   // grand total of the quantised weights
 };
 
 struct FzArgs {
     FzHeader *hd;
-    int64_t n;
+    int64_t n, n_global;                       // particles on this rank / in the whole population
     int nt;                                    // tiles of FZ_TILE particles
     const float *s_post, *s_pre;
     float *w_post, *w_pre, *w_out;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_sumexp(const FzArgs a) {
     __shared__ bool last;
     const int y = blockIdx.y;
     const float *__restrict__ s = y ? a.s_pre : a.s_post;
-    const unsigned key = ((volatile unsigned *)a.hd->keymax)[y];
+    const unsigned key = (unsigned)((volatile unsigned long long *)a.hd->keymax)[y];
     const float m = key ? mcl_float_of_key(key) : -FLT_MAX;
     unsigned long long acc = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x)
@@ -108,11 +111,10 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_sumexp(const FzArgs a) {
         if (threadIdx.x == 0) {
             unsigned long long tot = 0;
             for (int k = 0; k < FZ_THREADS / 32; ++k) tot += shq[k];
-            a.hd->stats[y][0] = (double)m;
-            a.hd->stats[y][1] = (double)tot / SOFTMAX_FIX;
-            ((unsigned long long *)a.hd->stats[y])[2] = tot;
+            a.hd->smax[y] = (double)m;
+            a.hd->sumq[y] = tot;
             a.hd->cnt_sumexp[y] = 0;
-            a.hd->keymax[y] = 0;        // every block of this set has read it
+            a.hd->keymax[y] = 0ull;     // every block of this set has read it
         }
     }
 }
@@ -144,8 +146,9 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_weights_mh_moments(const FzAr
     __shared__ double sh[6 * 8];
     __shared__ float shm[FZ_THREADS / 32];
     __shared__ bool last;
-    const float m_post = (float)a.hd->stats[0][0], sum_post = (float)a.hd->stats[0][1];
-    const float m_pre = MH ? (float)a.hd->stats[1][0] : 0.f, sum_pre = MH ? (float)a.hd->stats[1][1] : 1.f;
+    // sum as f32 of the exact integer (node:356-357: f32 divide by the f32-rounded sum)
+    const float m_post = (float)a.hd->smax[0], sum_post = (float)((double)a.hd->sumq[0] / SOFTMAX_FIX);
+    const float m_pre = MH ? (float)a.hd->smax[1] : 0.f, sum_pre = MH ? (float)((double)a.hd->sumq[1] / SOFTMAX_FIX) : 1.f;
     double v[6] = {0, 0, 0, 0, 0, 0};
     float wmax = 0.0f;
     const int64_t base = (int64_t)blockIdx.x * FZ_TILE + threadIdx.x;
@@ -215,20 +218,8 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_weights_mh_moments(const FzAr
         for (int b = threadIdx.x; b < a.nt; b += blockDim.x) a.status[b] = 0ull;     // look-back descriptors of the scan
         __syncthreads();
         if (threadIdx.x == 0) {
-            double *o = a.est18;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) o[k] = sh[k];
-            o[6] = sh[2] / sh[0];                     // np.average: sum(w x) / sum(w)
-            o[7] = sh[3] / sh[0];
-            o[8] = atan2(sh[5], sh[4]);               // node:589
-            // scale = 2^(62 - ceil(log2 n) - e), 2^e > wmax   (resample.cu k_wmax, oracle orc_resample_scale)
-            const float wm = (float)sh[6];
-            int e = 0;
-            if (wm > 0.0f) frexp((double)wm, &e);
-            int lg = 0;
-            while (((int64_t)1 << lg) < a.n) ++lg;
-            a.hd->scale[0] = ldexp(1.0, 62 - lg - e);
-            a.hd->scale[1] = (double)wm;
+            for (int k = 0; k < 7; ++k) a.hd->msum[k] = sh[k];      // this rank's sums; means and scale: k_fz_central_scan
             a.hd->cnt_moments = 0;
             a.hd->ticket = 0;
         }
@@ -250,11 +241,30 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_central_scan(const FzArgs a) 
     __shared__ unsigned long long sh_excl;
     __shared__ int sh_tile;
     __shared__ bool last;
-    if (threadIdx.x == 0) sh_tile = (int)atomicAdd(&a.hd->ticket, 1u);
+    __shared__ double sh_par[4];
+    if (threadIdx.x == 0) {
+        const int tk = (int)atomicAdd(&a.hd->ticket, 1u);
+        sh_tile = tk;
+        // means (node:586-589) and resampling scale from the population's raw sums and weight maximum
+        const double *ms = a.hd->msum;
+        const double pmx = ms[2] / ms[0], pmy = ms[3] / ms[0], pmt = atan2(ms[5], ms[4]);   // np.average; arctan2(sin, cos)
+        const float wm = (float)ms[6];
+        int e = 0;
+        if (wm > 0.0f) frexp((double)wm, &e);
+        int lg = 0;
+        while (((int64_t)1 << lg) < a.n_global) ++lg;
+        // scale = 2^(62 - ceil(log2 n) - e), 2^e > wmax   (resample.cu k_wmax, oracle orc_resample_scale)
+        sh_par[0] = pmx; sh_par[1] = pmy; sh_par[2] = pmt; sh_par[3] = ldexp(1.0, 62 - lg - e);
+        if (tk == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.est18[k] = ms[k];
+            a.est18[6] = pmx; a.est18[7] = pmy; a.est18[8] = pmt;
+        }
+    }
     __syncthreads();
     const int tile = sh_tile;
-    const double scale = a.hd->scale[0];
-    const double mx = a.est18[6], my = a.est18[7], mt = a.est18[8];
+    const double scale = sh_par[3];
+    const double mx = sh_par[0], my = sh_par[1], mt = sh_par[2];
     const int64_t base = (int64_t)tile * FZ_TILE + threadIdx.x;     // rows of 256 consecutive particles
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long inc[FZ_ITEMS];           // inclusive scan of the row inside this warp
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_central_scan(const FzArgs a) 
         fz_block_sum<9>(t, sh);
         if (threadIdx.x == 0)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a.est18[9 + k] = t[k];
+            for (int k = 0; k < 9; ++k) { a.est18[9 + k] = t[k]; a.hd->csum[k] = t[k]; }   // sharded: csum is SUM-exchanged into est18
         if (threadIdx.x == 0) a.hd->cnt_central = 0;
     }
 }
@@ -424,36 +434,58 @@ int mcl_fused_prepare(mcl_handle *h, int64_t n) {
     return MCL_OK;
 }
 
-unsigned *mcl_fused_keymax(mcl_handle *h) { return reinterpret_cast<FzHeader *>(h->d_fused)->keymax; }
+unsigned long long *mcl_fused_keymax(mcl_handle *h) { return reinterpret_cast<FzHeader *>(h->d_fused)->keymax; }
 
-// softmax (both sets when use_mh) -> MH accept into (nx, ny, nth) -> estimate sums in est18 -> cumulative sums.
-// Without MH the weights of the post set go to w_out and (nx, ny, nth) must be the particles themselves.
-int mcl_fused_update_estimate(mcl_handle *h, int64_t n, int use_mh, const float *s_post, const float *s_pre, float *w_post,
-                              float *w_pre, float *w_out, const double *px, const double *py, const double *pt,
-                              const double *ox, const double *oy, const double *ot, double *nx, double *ny, double *nth,
-                              uint64_t seed, uint64_t step, uint64_t first_index, double *est18) {
-    const FzPlan p = fz_plan(h, n);
+// device addresses of the quantities a sharded run exchanges between the stages (payload == result, in place)
+void mcl_fused_exchange_ptrs(mcl_handle *h, FusedPtrs *out) {
+    FzHeader *hd = reinterpret_cast<FzHeader *>(h->d_fused);
+    out->keymax = hd->keymax; out->sumq = hd->sumq; out->msum = hd->msum; out->csum = hd->csum; out->total = &hd->total;
+}
+const unsigned long long *mcl_fused_cumsum(mcl_handle *h, int64_t n) {
+    return reinterpret_cast<const unsigned long long *>((char *)h->d_fused + fz_plan(h, n).o_C);
+}
+
+static void fz_fill(mcl_handle *h, const FusedStep &u, FzArgs &a) {
+    const FzPlan p = fz_plan(h, u.n);
     char *b = (char *)h->d_fused;
-    FzArgs a;
     memset(&a, 0, sizeof(a));
-    a.hd = (FzHeader *)b; a.n = n; a.nt = p.nt;
-    a.s_post = s_post; a.s_pre = s_pre; a.w_post = w_post; a.w_pre = w_pre; a.w_out = w_out;
-    a.px = px; a.py = py; a.pt = pt; a.ox = ox; a.oy = oy; a.ot = ot; a.nx = nx; a.ny = ny; a.nth = nth;
-    a.use_mh = use_mh; a.seed = seed; a.step = step; a.first_index = first_index;
+    a.hd = (FzHeader *)b; a.n = u.n; a.n_global = u.n_global; a.nt = p.nt;
+    a.s_post = u.s_post; a.s_pre = u.s_pre; a.w_post = u.w_post; a.w_pre = u.w_pre; a.w_out = u.w_out;
+    a.px = u.px; a.py = u.py; a.pt = u.pt; a.ox = u.ox; a.oy = u.oy; a.ot = u.ot; a.nx = u.nx; a.ny = u.ny; a.nth = u.nth;
+    a.use_mh = u.use_mh; a.seed = u.seed; a.step = u.step; a.first_index = u.first_index;
     a.part_q = (unsigned long long *)(b + p.o_q); a.part_m = (double *)(b + p.o_m); a.part_c = (double *)(b + p.o_c);
     a.status = (unsigned long long *)(b + p.o_st); a.C = (unsigned long long *)(b + p.o_C);
-    a.est18 = est18;
-    k_fz_sumexp<<<dim3(p.nb2, use_mh ? 2 : 1), FZ_THREADS, 0, h->stream>>>(a);
+    a.est18 = u.est18;
+}
+
+// stage 1: sums of the softmax numerators (needs the population's score maxima in keymax)
+int mcl_fused_sumexp(mcl_handle *h, const FusedStep &u) {
+    FzArgs a;
+    fz_fill(h, u, a);
+    k_fz_sumexp<<<dim3(fz_plan(h, u.n).nb2, u.use_mh ? 2 : 1), FZ_THREADS, 0, h->stream>>>(a);
     MCL_LAUNCH_CHECK(h);
-    if (use_mh) k_fz_weights_mh_moments<true><<<p.nt, FZ_THREADS, 0, h->stream>>>(a);
-    else k_fz_weights_mh_moments<false><<<p.nt, FZ_THREADS, 0, h->stream>>>(a);
+    return MCL_OK;
+}
+// stage 2: weights, MH accept into (nx, ny, nth), raw estimate sums + weight maximum of this rank (needs the
+// population's sums in sumq).  Without MH the post weights go to w_out and (nx, ny, nth) are the particles.
+int mcl_fused_weights(mcl_handle *h, const FusedStep &u) {
+    FzArgs a;
+    fz_fill(h, u, a);
+    if (u.use_mh) k_fz_weights_mh_moments<true><<<a.nt, FZ_THREADS, 0, h->stream>>>(a);
+    else k_fz_weights_mh_moments<false><<<a.nt, FZ_THREADS, 0, h->stream>>>(a);
     MCL_LAUNCH_CHECK(h);
-    k_fz_central_scan<<<p.nt, FZ_THREADS, 0, h->stream>>>(a);
+    return MCL_OK;
+}
+// stage 3: means + scale from the population's msum, central sums and cumulative quantised weights of this rank
+int mcl_fused_scan(mcl_handle *h, const FusedStep &u) {
+    FzArgs a;
+    fz_fill(h, u, a);
+    k_fz_central_scan<<<a.nt, FZ_THREADS, 0, h->stream>>>(a);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }
 
-// systematic resampling from the cumulative sums left by mcl_fused_update_estimate: (nx, ny, nth) -> (gx, gy, gt)
+// systematic resampling from the cumulative sums left by mcl_fused_scan: (nx, ny, nth) -> (gx, gy, gt)
 int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, const double *ny, const double *nth,
                        int32_t *idx, double *gx, double *gy, double *gt) {
     const FzPlan p = fz_plan(h, n);

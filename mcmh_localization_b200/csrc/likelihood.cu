@@ -43,7 +43,7 @@ struct LikParams {
     // receive the maximum score of each set as an order-preserving unsigned key (mcl_key_of_float)
     const double *x2, *y2, *th2;
     float *score2;
-    unsigned *keymax;
+    unsigned long long *keymax;
     const BeamTable *beams;
     int n_pos, n_neg;
     double ox, oy, res;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
         if (threadIdx.x < 32 && end > first) {
             float t = k.lane < (G1_THREADS >> 5) ? smx[k.lane] : -FLT_MAX;
             t = warp_max(t);
-            if (k.lane == 0) atomicMax(p.keymax + (second ? 1 : 0), mcl_key_of_float(t));
+            if (k.lane == 0) atomicMax(p.keymax + (second ? 1 : 0), (unsigned long long)mcl_key_of_float(t));
         }
     }
 }
@@ -475,7 +475,7 @@ static uint64_t g_cbeams_gen = 0;
 
 static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
                            float *d_score, const double *d_x2, const double *d_y2, const double *d_theta2,
-                           float *d_score2, unsigned *d_keymax, bool *g1_used);
+                           float *d_score2, unsigned long long *d_keymax, bool *g1_used);
 
 extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
                               int64_t n, float *d_score) {
@@ -486,13 +486,13 @@ extern "C" int mcl_likelihood(mcl_handle *h, const double *d_x, const double *d_
 // one-thread-per-particle kernels implement it: *g1_used = false and NOTHING is launched otherwise.
 int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
                         const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
-                        unsigned *d_keymax, bool *g1_used) {
+                        unsigned long long *d_keymax, bool *g1_used) {
     return likelihood_impl(h, d_x, d_y, d_theta, n, d_score, d_x2, d_y2, d_theta2, d_score2, d_keymax, g1_used);
 }
 
 static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
                            float *d_score, const double *d_x2, const double *d_y2, const double *d_theta2,
-                           float *d_score2, unsigned *d_keymax, bool *g1_used) {
+                           float *d_score2, unsigned long long *d_keymax, bool *g1_used) {
     if (g1_used) *g1_used = false;
     if (!h) return MCL_ERR_ARG;
     if (n < 0 || (n > 0 && (!d_x || !d_y || !d_theta || !d_score)))

@@ -934,6 +934,22 @@ extern "C" int mcl_resample_push(mcl_handle *h, int64_t n_in, const uint64_t *d_
     return MCL_OK;
 }
 
+// the same push reading the cumulative sums from d_C (fused.cu's scan) instead of the scratch of mcl_resample_scan
+int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, int64_t n_in, const uint64_t *d_totals_all,
+                           int rank, int world, double r, int64_t n_global, int64_t n_per_rank, const double *d_x,
+                           const double *d_y, const double *d_theta, const uint64_t *d_peer_ptrs) {
+    int rc = mcl_ensure_scratch(h, 256);
+    if (rc) return rc;
+    PushPlan *plan = (PushPlan *)((char *)h->d_scratch + 64 + 32);
+    k_push_plan<<<1, 1, 0, h->stream>>>(d_totals_all, rank, world, r, (long long)n_global, plan);
+    MCL_LAUNCH_CHECK(h);
+    k_push<<<h->sm_count * 8, 256, 0, h->stream>>>((const uint64_t *)d_C, n_in - 1, plan, r, (long long)n_global,
+                                                   (long long)n_per_rank, world, d_x, d_y, d_theta,
+                                                   (const unsigned long long *)d_peer_ptrs);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
 // test hook: the running f32 sums themselves (normalise != 0: of w / seq_sum(w), else of w as given);
 // serial != 0 uses the one-warp replay instead of the parallel scan
 extern "C" int mcl_debug_seq_cumsum(mcl_handle *h, const float *d_w, int64_t n, int normalise, int serial, float *d_c) {

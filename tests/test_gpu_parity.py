@@ -803,6 +803,13 @@ def test_sharded_two_gpus_equals_single_gpu():
                             os.path.join(ROOT, "scripts", "dist_check.py"), "20000"],
                            capture_output=True, text=True, timeout=600, env=dict(os.environ, MCL_EXCHANGE=mode))
         assert "DIST_CHECK OK" in r.stdout, (mode, r.stdout[-2000:] + r.stderr[-2000:])
+    # enough particles per rank for the one-thread-per-particle likelihood kernel: the step then runs through
+    # the fused kernels (fused.cu) with the peer-memory exchanges between their stages
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29539",
+                        os.path.join(ROOT, "scripts", "dist_check.py"), "320000"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, MCL_EXCHANGE="native"))
+    assert "DIST_CHECK OK" in r.stdout, ("native/fused", r.stdout[-2000:] + r.stderr[-2000:])
 
 
 def test_c_abi_error_behaviour():
