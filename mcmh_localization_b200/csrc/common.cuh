@@ -187,8 +187,16 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // pu:62-67 normalize_angle with Python modulo semantics; fmod is exact.
+// fmod(a, 2 pi), bit for bit, without libdevice's division loop in the common range: for |a| < 2 pi the result
+// is a itself; for 2 pi <= |a| < 4 pi it is |a| - 2 pi with a's sign, which is exact (Sterbenz: y <= x <= 2y)
+__device__ __forceinline__ double fmod_two_pi(double a) {
+    const double aa = fabs(a);
+    if (aa < MCL_TWO_PI) return a;
+    if (aa < 2.0 * MCL_TWO_PI) return copysign(__dadd_rn(aa, -MCL_TWO_PI), a);
+    return fmod(a, MCL_TWO_PI);
+}
 __device__ __forceinline__ double normalize_angle_dev(double theta) {
-    double r = fmod(__dadd_rn(theta, MCL_PI), MCL_TWO_PI);
+    double r = fmod_two_pi(__dadd_rn(theta, MCL_PI));
     if (r != 0.0 && r < 0.0) r = __dadd_rn(r, MCL_TWO_PI);
     return __dadd_rn(r, -MCL_PI);
 }

@@ -25,7 +25,7 @@
 #include "common.cuh"
 
 #define FZ_THREADS 256
-#define FZ_ITEMS 8
+#define FZ_ITEMS 4
 #define FZ_TILE (FZ_THREADS * FZ_ITEMS)
 #define SOFTMAX_FIX 1099511627776.0   // 2^40 (mh_softmax.cu)
 
@@ -142,7 +142,7 @@ __device__ __forceinline__ void fz_block_sum(double (&v)[K], double *sh /* K * 8
 // weights (node:356-357), MH accept (pu:229-233), raw estimate sums (node:586-589), weight maximum
 // ---------------------------------------------------------------------------------------------
 template <bool MH>
-__global__ void __launch_bounds__(FZ_THREADS) k_fz_weights_mh_moments(const FzArgs a) {
+__global__ void __launch_bounds__(FZ_THREADS, 4) k_fz_weights_mh_moments(const FzArgs a) {
     __shared__ double sh[6 * 8];
     __shared__ float shm[FZ_THREADS / 32];
     __shared__ bool last;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_weights_mh_moments(const FzAr
 #define FZ_FLAG_INC (2ull << 62)
 #define FZ_VALUE_MASK ((1ull << 62) - 1)
 
-__global__ void __launch_bounds__(FZ_THREADS) k_fz_central_scan(const FzArgs a) {
+__global__ void __launch_bounds__(FZ_THREADS, 4) k_fz_central_scan(const FzArgs a) {
     __shared__ double sh[9 * 8];
     __shared__ unsigned long long shw[FZ_ITEMS][FZ_THREADS / 32];
     __shared__ unsigned long long sh_excl;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_central_scan(const FzArgs a) 
             agg += t;
         }
     }
-    // publish + look back (warp 0)
+    // publish + look back (warp 0; a block-wide look-back, 256 descriptors per round, measured slower)
     if (warp == 0) {
         volatile unsigned long long *st = a.status;
         if (lane == 0) st[tile] = (tile == 0 ? FZ_FLAG_INC : FZ_FLAG_AGG) | agg;
@@ -362,11 +362,11 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fz_central_scan(const FzArgs a) 
 // ---------------------------------------------------------------------------------------------
 // idx[m] = min(first i with C_i >= T_m, n - 1), T_m = ceil((r + m step) total)  (k_search_fixed) + pu:445 gather
 // ---------------------------------------------------------------------------------------------
-#define FZ_SEARCH_SMEM_TILES 4096
+#define FZ_SEARCH_SMEM_TILES 6144      // 48 KB of tile prefixes
 __global__ void __launch_bounds__(256) k_fz_search_gather(const FzArgs a) {
     // two levels: the tiles' inclusive prefixes (left in the look-back descriptors) are searched in shared
     // memory, then 11 steps inside one tile of C -- half the dependent L2 round trips of a flat search
-    __shared__ unsigned long long tp[FZ_SEARCH_SMEM_TILES];
+    extern __shared__ unsigned long long tp[];
     const bool coarse = a.nt <= FZ_SEARCH_SMEM_TILES;
     if (coarse) {
         for (int t = threadIdx.x; t < a.nt; t += blockDim.x) tp[t] = __ldcg(a.status + t) & FZ_VALUE_MASK;
@@ -498,7 +498,7 @@ int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, con
     a.r = r; a.rstep = 1.0 / (double)n;                       // pu:434
     a.idx = idx; a.gx = gx; a.gy = gy; a.gt = gt;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
-    k_fz_search_gather<<<blocks, 256, 0, h->stream>>>(a);
+    k_fz_search_gather<<<blocks, 256, p.nt <= FZ_SEARCH_SMEM_TILES ? (size_t)p.nt * 8 : 0, h->stream>>>(a);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }

@@ -465,7 +465,8 @@ static int launch_g1(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
         case 1: if (two) return launch_lik_kernel(h, k_likelihood_g1<SMEM, 512, 2, CODED, TPOSE>, p, smem_bytes, 1, 512, true);
         case 2: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 768, 1, CODED, TPOSE>, p, smem_bytes, 1, 768, true);
         case 3: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 896, 1, CODED, TPOSE>, p, smem_bytes, 1, 896, true);
-        default: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 1024, 1, CODED, TPOSE>, p, smem_bytes, 1, 1024, true);
+        case 4: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 1024, 1, CODED, TPOSE>, p, smem_bytes, 1, 1024, true);
+        default: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 896, 1, CODED, TPOSE>, p, smem_bytes, 1, 896, true);   // 72 registers: fastest measured
     }
 }
 

@@ -141,3 +141,41 @@ def test_gaussian_init_matches_reference():
         p = gaussian_particles(g["mean_%d" % k], g["cov_%d" % k], 500, gm, int(g["seed_%d" % k]))
         assert np.array_equal(p, g["out_%d" % k])
     assert (g["out_1"] == 0).all(axis=1).sum() > 0
+
+
+def test_likelihood_hot_loop_stays_on_the_uniform_datapath():
+    """The one-thread-per-particle likelihood kernel reads the beam constants warp-uniformly from the constant
+    bank (LDCU into uniform registers, used as DFMA operands).  ptxas silently falls back to per-thread LDC when
+    the control flow around the beam loop changes shape (likelihood.cu documents the workaround), which costs
+    ~15 % of the kernel: check the SASS of every shared-memory variant after each build.  Also pins the
+    instruction mix the design relies on: no fp64 convert / floor in the loop (cell index = high word of the
+    biased FMA chain), byte-permute table index."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from mcmh_localization_b200 import _lib
+    lib = _lib.LIB_PATH if hasattr(_lib, "LIB_PATH") else os.path.join(ROOT, "mcmh_localization_b200", "libmcl.so")
+    _lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)
+    checked = 0
+    for f in funcs:
+        name = f.split("\n", 1)[0]
+        if not name.startswith("_Z15k_likelihood_g1ILb1E"):      # SMEM = true variants
+            continue
+        checked += 1
+        body = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", l)]
+        first = next(i for i, l in enumerate(body) if re.search(r"\bPRMT R", l))
+        # the unrolled beam loop: from the last branch before the first PRMT to the next backward branch
+        start = max(i for i in range(first) if " BRA" in body[i])
+        end = next(i for i in range(first, len(body)) if " BRA" in body[i])
+        loop = body[start + 1:end]
+        ops = [re.search(r"\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", l).group(1).split(".")[0] for l in loop]
+        n_ev = ops.count("PRMT")                    # evaluations in the loop body (coded windows: 2 LDS each)
+        assert n_ev >= 8 and ops.count("LDS") >= n_ev, (name, n_ev)
+        assert ops.count("LDCU") >= n_ev // 2 and ops.count("LDC") <= 1, (name, ops.count("LDCU"), ops.count("LDC"))
+        assert ops.count("DFMA") == 4 * n_ev, name
+        assert "F2I" not in ops and "DADD" not in ops, name
+    assert checked >= 4
