@@ -546,8 +546,7 @@ extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
 }
 
 // update -> estimate -> resample through the fused kernels (fused.cu) when the configuration allows it:
-// symmetric MH or plain MCL, fixed-point resampling, enough particles for the one-thread-per-particle likelihood
-// kernel.  Sharded (f->comm): the same four kernels with the peer-memory exchanges between them (score maxima,
+// symmetric MH or plain MCL, fixed-point resampling.  Sharded (f->comm): the same four kernels with the peer-memory exchanges between them (score maxima,
 // softmax sums, raw estimate sums + weight maximum, central sums, totals) and the peer-push gather.
 // *done = false: nothing was enqueued, the caller runs the stand-alone sequence.  MCL_NO_FUSE=1 disables it (A/B).
 static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_out16[16], bool *done) {

@@ -168,12 +168,18 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
     const int grp = threadIdx.x / G;
     const int cmx = (p.cx << p.S) | ((1 << p.S) - 1), cmy = (p.cy << p.S) | ((1 << p.S) - 1);
 
+    // blockIdx.y selects the particle set (pair launches of the fused step)
+    const bool second = blockIdx.y != 0;
+    const double *__restrict__ xs = second ? p.x2 : p.x, *__restrict__ ys = second ? p.y2 : p.y,
+                 *__restrict__ ts = second ? p.th2 : p.th;
+    float *__restrict__ score = second ? p.score2 : p.score;
+    float smax = -FLT_MAX;
     // warp-uniform trip count: every lane iterates while the FIRST group of its warp is in range
     const int64_t stride = (int64_t)gridDim.x * GROUPS;
     const int warp_first_grp = (threadIdx.x & ~31) / G;
     for (int64_t base = (int64_t)blockIdx.x * GROUPS; base + warp_first_grp < p.n; base += stride) {
         const int64_t i = base + grp;
-        const Pose q = load_pose(p, p.x, p.y, p.th, i < p.n ? i : p.n - 1);
+        const Pose q = load_pose(p, xs, ys, ts, i < p.n ? i : p.n - 1);
         long long acc = 0;
         if (!q.far) {
             if (SMEM && __all_sync(0xffffffffu, q.interior)) {
@@ -209,7 +215,23 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (g == 0 && i < p.n) p.score[i] = (float)(((double)acc / MCL_LOGP_SCALE) / (double)nb);   // pu:144-145
+        if (g == 0 && i < p.n) {
+            const float sc = (float)(((double)acc / MCL_LOGP_SCALE) / (double)nb);   // pu:144-145
+            score[i] = sc;
+            smax = fmaxf(smax, sc);
+        }
+    }
+    if (p.keymax) {                                        // maximum score of the set (first softmax pass, node:353)
+        __shared__ float smx[LIK_THREADS / 32];
+        smax = warp_max(smax);
+        if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = smax;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float t = threadIdx.x < LIK_THREADS / 32 ? smx[threadIdx.x] : -FLT_MAX;
+            t = warp_max(t);
+            if (threadIdx.x == 0 && (int64_t)blockIdx.x * GROUPS < p.n)
+                atomicMax(p.keymax + (second ? 1 : 0), (unsigned long long)mcl_key_of_float(t));
+        }
     }
 }
 
@@ -439,12 +461,12 @@ static int launch_lik_kernel(mcl_handle *h, K kern, const LikParams &p, size_t s
         MCL_CUDA(h, cudaEventCreate(&e1));
         MCL_CUDA(h, cudaEventRecord(e0, h->stream));
     }
-    kern<<<dim3(blocks, balanced && p.x2 ? 2 : 1), threads, smem_bytes, h->stream>>>(p);
+    kern<<<dim3(blocks, p.x2 ? 2 : 1), threads, smem_bytes, h->stream>>>(p);
     MCL_LAUNCH_CHECK(h);
     if (h->timing) {
         MCL_CUDA(h, cudaEventRecord(e1, h->stream));
         h->lik_events.emplace_back(e0, e1);
-        h->lik_sets_timed += (balanced && p.x2) ? 2 : 1;
+        h->lik_sets_timed += p.x2 ? 2 : 1;
     }
     return MCL_OK;
 }
@@ -555,7 +577,7 @@ static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, 
                                 : launch_g1<true, false, false>(h, p, 16 + h->win_bytes);
         return launch_g1<false, false, false>(h, p, 16);
     }
-    if (g1_used) return MCL_OK;     // pair / key form not available: the caller falls back to separate launches
+    if (g1_used) *g1_used = true;   // the lanes-per-particle kernels implement the pair / key form as well
     if (use_coded && !use_smem && h->lik_path == 2)
         return mcl_fail(h, MCL_ERR_CAPACITY, "mcl_likelihood: the coded window needs the one-thread-per-particle kernel (larger n)");
 #define LIK_CASE(GV)                                                                   \

@@ -742,8 +742,9 @@ def test_localizer_production_step_runs_and_is_deterministic():
     assert np.isfinite(outs[0][1][3]).all()
 
 
+@pytest.mark.parametrize("n", [1000, 33333, 400_003])
 @pytest.mark.parametrize("mode", ["MHMCL", "MCL"])
-def test_fused_step_equals_standalone_sequence(mode):
+def test_fused_step_equals_standalone_sequence(mode, n):
     """Localizer.step() runs the step tail through the fused kernels (fused.cu: likelihood pair with max keys,
     sum-exp, weights + MH + raw estimate sums, central sums + look-back scan, search + gather).  It must leave
     the SAME particles, weights and resampled indices, bit for bit, as predict/update/estimate/resample issued
@@ -756,7 +757,7 @@ def test_fused_step_equals_standalone_sequence(mode):
     from mcmh_localization_b200.maps import load_npz
     from mcmh_localization_b200.synth import raycast_scan, free_space_particles
     gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
-    n = 400_003                                   # one-thread-per-particle likelihood kernel, ragged last tile
+    # 1000 / 33333: lanes-per-particle likelihood kernels; 400003: one thread per particle, ragged last tile
     p0 = free_space_particles(gm, n, seed=5)
     locs = []
     for _ in range(2):
