@@ -135,9 +135,11 @@ int mcl_fused_weights(mcl_handle *h, const FusedStep &u);
 int mcl_fused_scan(mcl_handle *h, const FusedStep &u);
 int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, const double *ny, const double *nth,
                        int32_t *idx, double *gx, double *gy, double *gt);
-int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, int64_t n_in, const uint64_t *d_totals_all,
-                           int rank, int world, double r, int64_t n_global, int64_t n_per_rank, const double *d_x,
-                           const double *d_y, const double *d_theta, const uint64_t *d_peer_ptrs);
+const unsigned long long *mcl_fused_tile_prefix(mcl_handle *h, int64_t n, int *nt, int *tile);
+int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, const unsigned long long *d_tile_prefix, int nt,
+                           int tile, int64_t n_in, const uint64_t *d_totals_all, int rank, int world, double r,
+                           int64_t n_global, int64_t n_per_rank, const double *d_x, const double *d_y,
+                           const double *d_theta, const uint64_t *d_peer_ptrs);
 int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
                         const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
                         unsigned long long *d_keymax, bool *g1_used);

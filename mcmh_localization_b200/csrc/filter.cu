@@ -166,7 +166,8 @@ extern "C" int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode
 // peer has entered k+1, i.e. finished k).
 // ---------------------------------------------------------------------------------------------
 enum { XCH_SUM_F64 = 0, XCH_MAX_F64 = 1, XCH_SUM_U64 = 2, XCH_GATHER = 3, XCH_MAX_U64 = 4,
-       XCH_SUM_F64_MAXLAST = 5 /* sums, except the last value: maximum */ };
+       XCH_SUM_F64_MAXLAST = 5 /* sums, except the last value: maximum */,
+       XCH_SUM_F64_GATHERLAST = 6 /* sums, except the last value: gathered (raw 64 bits) into out2[rank] */ };
 #define XCH_MAXV 16
 
 struct XchArgs {
@@ -187,7 +188,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 __global__ void __launch_bounds__(32) k_exchange(const XchArgs a, const unsigned long long *payload, int nvals, int op,
-                                                 unsigned long long *out) {
+                                                 unsigned long long *out, unsigned long long *out2) {
     const int t = threadIdx.x;
     const int par = (int)(a.epoch & 1ull);
     if (t < a.world) {
@@ -208,7 +209,9 @@ __global__ void __launch_bounds__(32) k_exchange(const XchArgs a, const unsigned
     if (!__all_sync(0xffffffffu, ok)) { if (t == 0) *a.err = 1; return; }
     if (t < nvals) {
         const unsigned long long *slots = a.mailbox + 32 + (size_t)par * 16 * XCH_MAXV;
-        if (op == XCH_GATHER) {
+        if (op == XCH_SUM_F64_GATHERLAST && t == nvals - 1) {
+            for (int d = 0; d < a.world; ++d) out2[d] = ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
+        } else if (op == XCH_GATHER) {
             for (int d = 0; d < a.world; ++d) out[d * nvals + t] = ((volatile const unsigned long long *)slots)[d * XCH_MAXV + t];
         } else if (op == XCH_SUM_U64 || op == XCH_MAX_U64) {
             unsigned long long acc = 0;
@@ -229,13 +232,15 @@ __global__ void __launch_bounds__(32) k_exchange(const XchArgs a, const unsigned
     }
 }
 
-static int comm_exchange(mcl_handle *h, FilterState *f, const void *d_payload, int nvals, int op, void *d_out) {
+static int comm_exchange(mcl_handle *h, FilterState *f, const void *d_payload, int nvals, int op, void *d_out,
+                         void *d_out2 = nullptr) {
     if (nvals > XCH_MAXV) return mcl_fail(h, MCL_ERR_ARG, "comm_exchange: payload too large");
     XchArgs a;
     a.mailbox = f->mailbox;
     for (int d = 0; d < 16; ++d) a.peers[d] = f->peer_mailbox[d];
     a.rank = f->rank; a.world = f->world; a.epoch = ++f->epoch; a.err = f->d_comm_err;
-    k_exchange<<<1, 32, 0, h->stream>>>(a, (const unsigned long long *)d_payload, nvals, op, (unsigned long long *)d_out);
+    k_exchange<<<1, 32, 0, h->stream>>>(a, (const unsigned long long *)d_payload, nvals, op, (unsigned long long *)d_out,
+                                        (unsigned long long *)d_out2);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }
@@ -599,7 +604,8 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     if (f->comm) { rc = comm_exchange(h, f, xp.msum, 7, XCH_SUM_F64_MAXLAST, xp.msum); if (rc) return rc; }
     rc = mcl_fused_scan(h, u);
     if (rc) return rc;
-    if (f->comm) { rc = comm_exchange(h, f, xp.csum, 9, XCH_SUM_F64, est + 9); if (rc) return rc; }
+    // central sums -> est[9..17]; the tenth value is this rank's total of quantised weights -> totals of every rank
+    if (f->comm) { rc = comm_exchange(h, f, xp.csum, 10, XCH_SUM_F64_GATHERLAST, est + 9, f->d_x8 + 16); if (rc) return rc; }
     if (h_out16) {
         MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, est, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         MCL_CUDA(h, cudaEventRecord(h->ev_est, h->stream));
@@ -610,9 +616,9 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     const int dst = f->spare;
     if (f->comm) {
         const double r = mcl_resample_offset(f->seed, f->tick, f->n_global);
-        rc = comm_exchange(h, f, xp.total, 1, XCH_GATHER, f->d_x8 + 16);          // totals of every rank
-        if (rc) return rc;
-        rc = mcl_resample_push_from(h, mcl_fused_cumsum(h, f->n), f->n, (const uint64_t *)(f->d_x8 + 16), f->rank, f->world,
+        int pnt = 0, ptile = 0;
+        const unsigned long long *tprefix = mcl_fused_tile_prefix(h, f->n, &pnt, &ptile);
+        rc = mcl_resample_push_from(h, mcl_fused_cumsum(h, f->n), tprefix, pnt, ptile, f->n, (const uint64_t *)(f->d_x8 + 16), f->rank, f->world,
                                     r, f->n_global, f->n, f->x[res], f->y[res], f->th[res],
                                     f->d_peer_pose + (size_t)dst * 3 * f->world);
         if (rc) return rc;

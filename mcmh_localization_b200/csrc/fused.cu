@@ -35,7 +35,7 @@ struct FzHeader {               // device, zero-initialised once; every counter 
     unsigned long long sumq[2];     // sums of the softmax numerators, raw 2^-40 integers (sharded: SUM-exchanged)
     double smax[2];                 // the maxima as floats (copied from the keys before they are cleared)
     double msum[8];                 // six raw estimate sums, weight maximum (sharded: SUM / MAX-exchanged)
-    double csum[10];                // nine central estimate sums of this rank
+    double csum[10];                // nine central estimate sums of this rank; [9]: `total` again (one exchange)
     unsigned long long total;       // total of this rank's quantised weights
     unsigned cnt_sumexp[2];
     unsigned cnt_moments, cnt_central, ticket, pad;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 4) k_fz_central_scan(const FzArgs 
         if (lane == 0) {
             if (tile > 0) st[tile] = FZ_FLAG_INC | (excl + agg);
             sh_excl = excl;
-            if (tile == a.nt - 1) a.hd->total = excl + agg;
+            if (tile == a.nt - 1) { a.hd->total = excl + agg; ((unsigned long long *)a.hd->csum)[9] = excl + agg; }
         }
     }
     fz_block_sum<9>(v, sh);                     // (contains the barriers that publish sh_excl)
@@ -443,6 +443,13 @@ void mcl_fused_exchange_ptrs(mcl_handle *h, FusedPtrs *out) {
 }
 const unsigned long long *mcl_fused_cumsum(mcl_handle *h, int64_t n) {
     return reinterpret_cast<const unsigned long long *>((char *)h->d_fused + fz_plan(h, n).o_C);
+}
+
+// the look-back descriptors hold every tile's inclusive prefix after mcl_fused_scan (flag bits in the top two)
+const unsigned long long *mcl_fused_tile_prefix(mcl_handle *h, int64_t n, int *nt, int *tile) {
+    const FzPlan p = fz_plan(h, n);
+    *nt = p.nt; *tile = FZ_TILE;
+    return reinterpret_cast<const unsigned long long *>((char *)h->d_fused + p.o_st);
 }
 
 static void fz_fill(mcl_handle *h, const FusedStep &u, FzArgs &a) {

@@ -130,12 +130,19 @@ __device__ __forceinline__ double end_y(const Pose &q, const double2 b) { return
 __device__ __forceinline__ int win_coord(double T, int K, int cmax) {
     return __viaddmin_s32_relu(__double2hiint(T), -K, cmax);
 }
-// map cell with the reference's int() (trunc toward zero) semantics; exact on the 2^-(32+S) grid
-__device__ __forceinline__ int map_coord(double T, int K, int S, int wof) {
-    const long long F = (long long)(__double2hiint(T) - K);
-    const long long q = (F << 32) + (long long)(unsigned)__double2loint(T) + ((long long)wof << (32 + S));
-    const int sh = 32 + S;
-    return (int)(q >= 0 ? (q >> sh) : -((-q) >> sh));
+// In-map test and map cell with the reference's int() (trunc toward zero) semantics, exact on the 2^-(32+S) grid.
+// Fm = floor(map coordinate * 2^S) = high word - Km, Km = K - (window origin << S).  int() sends (-1, 0) to cell
+// 0 (SURVEY 7 hard part 2), so a coordinate is inside iff it lies in (-1, dim): Fm in [-2^S, dim * 2^S), minus
+// the single point -1.0 (Fm == -2^S with a zero low word).  The cell is then max(Fm >> S, 0).
+__device__ __forceinline__ bool coord_in_map(double T, int Fm, int S, unsigned lim /* (dim + 1) << S */) {
+    bool in = (unsigned)(Fm + (1 << S)) < lim;
+    if (Fm == -(1 << S)) in = __double2loint(T) != 0;
+    return in;
+}
+__device__ __forceinline__ int map_coord(double T, int K, int S, int wof, int dim, bool &in) {
+    const int Fm = (__double2hiint(T) - K) + (wof << S);
+    in = coord_in_map(T, Fm, S, (unsigned)(dim + 1) << S);
+    return max(Fm >> S, 0);
 }
 __device__ __forceinline__ int win_index(int rx, int ry, int S, int tpose) {   // generic (S != 8 or run-time layout)
     const int ix = rx >> S, iy = ry >> S;
@@ -193,8 +200,10 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
 #pragma unroll 2
                 for (int j = g; j < p.n_pos; j += G) {
                     const double2 b = sb[j];
-                    const int mx = map_coord(end_x(q, b), p.K, p.S, p.wofx), my = map_coord(end_y(q, b), p.K, p.S, p.wofy);  // pu:128-129
-                    if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H)) {                                  // pu:131-132
+                    bool inx, iny;
+                    const int mx = map_coord(end_x(q, b), p.K, p.S, p.wofx, p.W, inx);      // pu:128-129
+                    const int my = map_coord(end_y(q, b), p.K, p.S, p.wofy, p.H, iny);
+                    if (inx && iny) {                                                       // pu:131-132
                         if (SMEM) {
                             const int ix = min(max(mx - p.wofx, 0), p.cx), iy = min(max(my - p.wofy, 0), p.cy);
                             acc += swin[p.tpose ? (ix << 8) | iy : (iy << 8) | ix] + (long long)p.voff;
@@ -207,8 +216,10 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
             // valid beams with a negative range: p_rand = 0 (pu:139); evaluated from the distance map
             for (int j = p.n_pos + g; j < nb; j += G) {
                 const double2 b = sb[j];
-                const int mx = map_coord(end_x(q, b), p.K, p.S, p.wofx), my = map_coord(end_y(q, b), p.K, p.S, p.wofy);
-                if (((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
+                bool inx, iny;
+                const int mx = map_coord(end_x(q, b), p.K, p.S, p.wofx, p.W, inx);
+                const int my = map_coord(end_y(q, b), p.K, p.S, p.wofy, p.H, iny);
+                if (inx && iny)
                     acc += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
                                                    p.z_rand, p.max_range, false));
             }
@@ -319,21 +330,55 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
 #pragma unroll
         for (int u = 0; u < P; ++u) acc[u] = (long long)uacc[u] + (long long)p.n_pos * p.voff;
     } else if (__any_sync(0xffffffffu, any_near)) {
-        for (int j = 0; j < p.n_pos; ++j) {
-            const double2 b = c_beams[j];
+        // an endpoint may leave the map: same loop with the in-map test of pu:131-132 (out-of-map beams add 0)
+        if (SMEM) {
+            unsigned long long uacc[P];
+            double PX[P], PY[P], ss[P], cc[P];
 #pragma unroll
-            for (int u = 0; u < P; ++u) {
-                const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx), my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy);  // pu:128-129
-                const bool inmap = !q[u].far && ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H);
-                int v;
-                if (SMEM) {
-                    const int ix = min(max(mx - p.wofx, 0), p.cx), iy = min(max(my - p.wofy, 0), p.cy);
-                    v = (int)g1_fetch<CODED>(k, TPOSE ? (ix << 8) | iy : (iy << 8) | ix) + p.voff;
-                    v = inmap ? v : 0;                                             // pu:131-132
-                } else {
-                    v = inmap ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
+            for (int u = 0; u < P; ++u) { uacc[u] = 0; PX[u] = q[u].PX; PY[u] = q[u].PY; ss[u] = q[u].s; cc[u] = q[u].c; }
+            const int negK = -p.K, Kmx = p.K - (p.wofx << 8), Kmy = p.K - (p.wofy << 8);
+            const unsigned limx = (unsigned)(p.W + 1) << 8, limy = (unsigned)(p.H + 1) << 8;
+            const uint32_t zero_off = (uint32_t)(-p.voff);
+            auto eval = [&](int u, const double2 b) -> uint32_t {
+                const double TX = fma(cc[u], b.x, fma(-ss[u], b.y, PX[u])), TY = fma(ss[u], b.x, fma(cc[u], b.y, PY[u]));
+                const int hx = __double2hiint(TX), hy = __double2hiint(TY);
+                const int rx = __viaddmin_s32_relu(hx, negK, k.cmx), ry = __viaddmin_s32_relu(hy, negK, k.cmy);
+                const uint32_t v = g1_fetch<CODED>(k, (int)(TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651)));
+                const bool in = coord_in_map(TX, hx - Kmx, 8, limx) && coord_in_map(TY, hy - Kmy, 8, limy);
+                return in ? v : zero_off;
+            };
+            int j = 0;
+            for (; j + MCL_ACC_TERMS <= p.n_pos; j += MCL_ACC_TERMS) {
+                uint32_t part[P];
+#pragma unroll
+                for (int u = 0; u < P; ++u) part[u] = 0;
+#pragma unroll
+                for (int t = 0; t < MCL_ACC_TERMS; ++t) {
+                    const double2 b = c_beams[j + t];
+#pragma unroll
+                    for (int u = 0; u < P; ++u) part[u] += eval(u, b);
                 }
-                acc[u] += v;
+#pragma unroll
+                for (int u = 0; u < P; ++u) uacc[u] += part[u];
+            }
+            for (; j < p.n_pos; ++j) {
+                const double2 b = c_beams[j];
+#pragma unroll
+                for (int u = 0; u < P; ++u) uacc[u] += eval(u, b);
+            }
+#pragma unroll
+            for (int u = 0; u < P; ++u) acc[u] = q[u].far ? 0 : (long long)uacc[u] + (long long)p.n_pos * p.voff;
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < p.n_pos; ++j) {
+                const double2 b = c_beams[j];
+#pragma unroll
+                for (int u = 0; u < P; ++u) {
+                    bool inx, iny;
+                    const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx, p.W, inx);      // pu:128-129
+                    const int my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy, p.H, iny);
+                    acc[u] += (!q[u].far && inx && iny) ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
+                }
             }
         }
     }
@@ -342,8 +387,10 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
         const double2 b = c_beams[j];
 #pragma unroll
         for (int u = 0; u < P; ++u) {
-            const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx), my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy);
-            if (!q[u].far && ((unsigned)mx < (unsigned)p.W) && ((unsigned)my < (unsigned)p.H))
+            bool inx, iny;
+            const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx, p.W, inx);
+            const int my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy, p.H, iny);
+            if (!q[u].far && inx && iny)
                 acc[u] += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
                                                   p.z_rand, p.max_range, false));
         }

@@ -872,34 +872,62 @@ __device__ long long count_thresholds_le_dev(uint64_t x, double r, double step, 
 }
 // same partition as sharded.plan_resample (host): ranks without weight emit nothing, rank 0 starts at 0,
 // the last rank ends at n_out
-__global__ void k_push_plan(const uint64_t *totals, int rank, int world, double r, long long n_out, PushPlan *plan) {
-    uint64_t off[17];
-    uint64_t acc = 0;
-    for (int k = 0; k < world; ++k) { off[k] = acc; acc += totals[k]; }
-    off[world] = acc;
-    const double step = 1.0 / (double)n_out, totd = (double)acc;
-    long long prev_hi = 0, my_lo = 0, my_hi = 0;
-    for (int k = 0; k < world; ++k) {
-        long long lo = k == 0 ? 0 : count_thresholds_le_dev(off[k], r, step, totd, n_out);
-        long long hi = k == world - 1 ? n_out : count_thresholds_le_dev(off[k + 1], r, step, totd, n_out);
-        if (hi < lo) hi = lo;
-        if (k > 0) { if (lo < prev_hi) lo = prev_hi; if (hi < lo) hi = lo; }
-        if (k == world - 1) hi = n_out;
-        if (k == rank) { my_lo = lo; my_hi = hi; }
-        prev_hi = hi;
+__global__ void __launch_bounds__(32) k_push_plan(const uint64_t *totals, int rank, int world, double r, long long n_out,
+                                                  PushPlan *plan) {
+    // one lane per rank boundary (the 2 x world binary searches of ~25 fp64 steps each took ~40 us on one thread)
+    __shared__ uint64_t off[17];
+    __shared__ long long cnt[17];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        uint64_t acc = 0;
+        for (int k = 0; k < world; ++k) { off[k] = acc; acc += totals[k]; }
+        off[world] = acc;
     }
-    plan->offset = off[rank]; plan->grand = acc; plan->m_lo = my_lo; plan->m_hi = my_hi;
+    __syncwarp();
+    const double step = 1.0 / (double)n_out, totd = (double)off[world];
+    if (t <= world) cnt[t] = count_thresholds_le_dev(off[t], r, step, totd, n_out);
+    __syncwarp();
+    if (t == 0) {
+        long long prev_hi = 0, my_lo = 0, my_hi = 0;
+        for (int k = 0; k < world; ++k) {
+            long long lo = k == 0 ? 0 : cnt[k];
+            long long hi = k == world - 1 ? n_out : cnt[k + 1];
+            if (hi < lo) hi = lo;
+            if (k > 0) { if (lo < prev_hi) lo = prev_hi; if (hi < lo) hi = lo; }
+            if (k == world - 1) hi = n_out;
+            if (k == rank) { my_lo = lo; my_hi = hi; }
+            prev_hi = hi;
+        }
+        plan->offset = off[rank]; plan->grand = off[world]; plan->m_lo = my_lo; plan->m_hi = my_hi;
+    }
 }
 
+// tile_prefix (optional): inclusive cumulative sum at the end of every `tile` inputs (low 62 bits), searched in
+// shared memory before the 10-11 steps inside one tile of C
 __global__ void k_push(const uint64_t *__restrict__ C, int64_t limit, const PushPlan *plan, double r, long long n_out,
                        long long n_per_rank, int world, const double *__restrict__ x, const double *__restrict__ y,
-                       const double *__restrict__ th, const unsigned long long *peers /* [3][world] */) {
+                       const double *__restrict__ th, const unsigned long long *peers /* [3][world] */,
+                       const unsigned long long *__restrict__ tile_prefix, int nt, int tile) {
+    extern __shared__ unsigned long long tp[];
+    if (tile_prefix) {
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) tp[t] = __ldcg(tile_prefix + t) & ((1ull << 62) - 1);
+        __syncthreads();
+    }
     const PushPlan pl = *plan;
     const double step = 1.0 / (double)n_out, totd = (double)pl.grand;
     for (long long m = pl.m_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; m < pl.m_hi;
          m += (long long)gridDim.x * blockDim.x) {
         const uint64_t T = push_threshold(m, r, step, totd);
         int64_t lo = 0, hi = limit;
+        if (tile_prefix) {
+            int tl = 0, th2 = nt - 1;
+            while (tl < th2) {
+                const int mid = (tl + th2) >> 1;
+                if (T > tp[mid] + pl.offset) tl = mid + 1; else th2 = mid;
+            }
+            lo = (int64_t)tl * tile;
+            hi = min(lo + tile - 1, limit);
+        }
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
             if (T > C[mid] + pl.offset) lo = mid + 1; else hi = mid;
@@ -926,26 +954,28 @@ extern "C" int mcl_resample_push(mcl_handle *h, int64_t n_in, const uint64_t *d_
     if (L.total > h->scratch_bytes) return mcl_fail(h, MCL_ERR_STATE, "mcl_resample_push: call mcl_resample_scan first");
     const uint64_t *C = (const uint64_t *)((char *)h->d_scratch + L.o_c);
     PushPlan *plan = (PushPlan *)((char *)h->d_scratch + 64 + 32);      // after the scale slot
-    k_push_plan<<<1, 1, 0, h->stream>>>(d_totals_all, rank, world, r, (long long)n_global, plan);
+    k_push_plan<<<1, 32, 0, h->stream>>>(d_totals_all, rank, world, r, (long long)n_global, plan);
     MCL_LAUNCH_CHECK(h);
     k_push<<<h->sm_count * 8, 256, 0, h->stream>>>(C, n_in - 1, plan, r, (long long)n_global, (long long)n_per_rank, world,
-                                                   d_x, d_y, d_theta, (const unsigned long long *)d_peer_ptrs);
+                                                   d_x, d_y, d_theta, (const unsigned long long *)d_peer_ptrs, nullptr, 0, 0);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }
 
 // the same push reading the cumulative sums from d_C (fused.cu's scan) instead of the scratch of mcl_resample_scan
-int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, int64_t n_in, const uint64_t *d_totals_all,
-                           int rank, int world, double r, int64_t n_global, int64_t n_per_rank, const double *d_x,
-                           const double *d_y, const double *d_theta, const uint64_t *d_peer_ptrs) {
+int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, const unsigned long long *d_tile_prefix, int nt,
+                           int tile, int64_t n_in, const uint64_t *d_totals_all, int rank, int world, double r,
+                           int64_t n_global, int64_t n_per_rank, const double *d_x, const double *d_y,
+                           const double *d_theta, const uint64_t *d_peer_ptrs) {
     int rc = mcl_ensure_scratch(h, 256);
     if (rc) return rc;
     PushPlan *plan = (PushPlan *)((char *)h->d_scratch + 64 + 32);
-    k_push_plan<<<1, 1, 0, h->stream>>>(d_totals_all, rank, world, r, (long long)n_global, plan);
+    k_push_plan<<<1, 32, 0, h->stream>>>(d_totals_all, rank, world, r, (long long)n_global, plan);
     MCL_LAUNCH_CHECK(h);
-    k_push<<<h->sm_count * 8, 256, 0, h->stream>>>((const uint64_t *)d_C, n_in - 1, plan, r, (long long)n_global,
-                                                   (long long)n_per_rank, world, d_x, d_y, d_theta,
-                                                   (const unsigned long long *)d_peer_ptrs);
+    const bool coarse = d_tile_prefix && nt > 0 && (size_t)nt * 8 <= 48 * 1024;
+    k_push<<<h->sm_count * 8, 256, coarse ? (size_t)nt * 8 : 0, h->stream>>>(
+        (const uint64_t *)d_C, n_in - 1, plan, r, (long long)n_global, (long long)n_per_rank, world, d_x, d_y, d_theta,
+        (const unsigned long long *)d_peer_ptrs, coarse ? d_tile_prefix : nullptr, nt, tile);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }
