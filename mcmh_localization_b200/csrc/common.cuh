@@ -64,6 +64,14 @@ struct mcl_handle {
     uint8_t *d_win8 = nullptr;
     int32_t *d_lut = nullptr;
     size_t win8_bytes = 0;
+    // Large maps (no window fits in shared memory): the whole table as one byte per cell (codes into d_lut, code
+    // 255 = "outside the map", contributing 0) so that the tiled likelihood kernel can stage the neighbourhood of
+    // one map tile at a time; particles are binned by tile first (likelihood.cu, k_likelihood_tiled).
+    bool tiled_ok = false;
+    uint8_t *d_code8 = nullptr;      // W * H
+    int tile_w = 0, tile_h = 0, tile_margin = 0, tiles_x = 0, tiles_y = 0;
+    void *d_tiled = nullptr;         // per-call binning buffers
+    size_t tiled_bytes = 0;
     // cell-index arithmetic (likelihood.cu): endpoints are evaluated relative to the window origin in the
     // "magic" form cell_M + t, cell_M = 1.5 * 2^(20 - cell_S): the high word of the double then holds
     // floor(t * 2^cell_S) + cell_K.  |t| must stay below cell_lim (particles further out see no map cell).

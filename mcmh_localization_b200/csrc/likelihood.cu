@@ -109,13 +109,13 @@ struct Pose {          // one particle, ready for the beam loop
 };
 
 __device__ __forceinline__ Pose load_pose(const LikParams &p, const double *__restrict__ xs, const double *__restrict__ ys,
-                                          const double *__restrict__ ts, int64_t i) {
+                                          const double *__restrict__ ts, int64_t i, int wofx, int wofy) {
     Pose q;
     const double x = xs[i], y = ys[i], th = ts[i];
     sincos(th, &q.s, &q.c);
     const double px = __ddiv_rn(__dadd_rn(x, -p.ox), p.res);          // pu:128: (lx - ox) / res, distributed
     const double py = __ddiv_rn(__dadd_rn(y, -p.oy), p.res);
-    const double wx = __dadd_rn(px, -(double)p.wofx), wy = __dadd_rn(py, -(double)p.wofy);   // exact
+    const double wx = __dadd_rn(px, -(double)wofx), wy = __dadd_rn(py, -(double)wofy);       // exact
     q.far = !(fabs(wx) < p.lim && fabs(wy) < p.lim);                   // also catches NaN poses
     q.PX = __dadd_rn(q.far ? 0.0 : wx, p.M);
     q.PY = __dadd_rn(q.far ? 0.0 : wy, p.M);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
     const int warp_first_grp = (threadIdx.x & ~31) / G;
     for (int64_t base = (int64_t)blockIdx.x * GROUPS; base + warp_first_grp < p.n; base += stride) {
         const int64_t i = base + grp;
-        const Pose q = load_pose(p, xs, ys, ts, i < p.n ? i : p.n - 1);
+        const Pose q = load_pose(p, xs, ys, ts, i < p.n ? i : p.n - 1, p.wofx, p.wofy);
         long long acc = 0;
         if (!q.far) {
             if (SMEM && __all_sync(0xffffffffu, q.interior)) {
@@ -268,6 +268,7 @@ struct G1Ctx {
     const int32_t *swin, *slut;
     const uint8_t *swin8;
     int lane, nb, cmx, cmy;
+    int wofx, wofy;            // tiled kernel only: origin of the staged sub-window (map cells)
 };
 
 template <bool CODED>
@@ -276,17 +277,23 @@ __device__ __forceinline__ uint32_t g1_fetch(const G1Ctx &k, int cell) {
 }
 
 // P slices (rows i0, i0 + row, ...) of one warp; lanes whose particle index is >= end idle on a copy of end - 1
-template <bool SMEM, bool CODED, bool TPOSE, int P>
+// PERM: i0 / end are positions in a tile-sorted order and perm[] maps them to particle indices (tiled kernel)
+template <bool SMEM, bool CODED, bool TPOSE, int P, bool PERM = false>
 __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, const double *__restrict__ xs,
                                           const double *__restrict__ ys, const double *__restrict__ ts,
-                                          float *__restrict__ score, int64_t i0, int64_t row, int64_t end, float &smax) {
+                                          float *__restrict__ score, int64_t i0, int64_t row, int64_t end, float &smax,
+                                          const int32_t *__restrict__ perm = nullptr) {
+    const int wofx = PERM ? k.wofx : p.wofx, wofy = PERM ? k.wofy : p.wofy;     // tiled: origin of the staged tile
     int64_t idx[P];
+    int64_t pidx[P];
     Pose q[P];
     bool interior = true, any_near = false;
 #pragma unroll
     for (int u = 0; u < P; ++u) {
         idx[u] = i0 + u * row;
-        q[u] = load_pose(p, xs, ys, ts, idx[u] < end ? idx[u] : end - 1);
+        const int64_t il = idx[u] < end ? idx[u] : end - 1;
+        pidx[u] = PERM ? (int64_t)perm[il] : il;
+        q[u] = load_pose(p, xs, ys, ts, pidx[u], wofx, wofy);
         interior = interior && q[u].interior;
         any_near = any_near || !q[u].far;
     }
@@ -306,7 +313,9 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
             const double TX = fma(cc[u], b.x, fma(-ss[u], b.y, PX[u])), TY = fma(ss[u], b.x, fma(cc[u], b.y, PY[u]));
             const int rx = __viaddmin_s32_relu(__double2hiint(TX), negK, k.cmx);
             const int ry = __viaddmin_s32_relu(__double2hiint(TY), negK, k.cmy);
-            return g1_fetch<CODED>(k, (int)(TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651)));
+            unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
+            if (PERM) cell += (cell >> 8) << 2;     // tiled kernel: rows of 260 bytes (see k_likelihood_tiled)
+            return g1_fetch<CODED>(k, (int)cell);
         };
         int j = 0;
         for (; j + MCL_ACC_TERMS <= p.n_pos; j += MCL_ACC_TERMS) {
@@ -336,15 +345,20 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
             double PX[P], PY[P], ss[P], cc[P];
 #pragma unroll
             for (int u = 0; u < P; ++u) { uacc[u] = 0; PX[u] = q[u].PX; PY[u] = q[u].PY; ss[u] = q[u].s; cc[u] = q[u].c; }
-            const int negK = -p.K, Kmx = p.K - (p.wofx << 8), Kmy = p.K - (p.wofy << 8);
+            const int negK = -p.K, Kmx = p.K - (wofx << 8), Kmy = p.K - (wofy << 8);
             const unsigned limx = (unsigned)(p.W + 1) << 8, limy = (unsigned)(p.H + 1) << 8;
             const uint32_t zero_off = (uint32_t)(-p.voff);
             auto eval = [&](int u, const double2 b) -> uint32_t {
                 const double TX = fma(cc[u], b.x, fma(-ss[u], b.y, PX[u])), TY = fma(ss[u], b.x, fma(cc[u], b.y, PY[u]));
                 const int hx = __double2hiint(TX), hy = __double2hiint(TY);
-                const int rx = __viaddmin_s32_relu(hx, negK, k.cmx), ry = __viaddmin_s32_relu(hy, negK, k.cmy);
-                const uint32_t v = g1_fetch<CODED>(k, (int)(TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651)));
-                const bool in = coord_in_map(TX, hx - Kmx, 8, limx) && coord_in_map(TY, hy - Kmy, 8, limy);
+                const int fx = hx - Kmx, fy = hy - Kmy;               // floor(map coordinate * 256)
+                // int() sends a coordinate in (-1, 0) to map cell 0: read that cell, not the one left of it
+                const int rx = __viaddmin_s32_relu(hx - min(fx, 0), negK, k.cmx);
+                const int ry = __viaddmin_s32_relu(hy - min(fy, 0), negK, k.cmy);
+                unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
+                if (PERM) cell += (cell >> 8) << 2;
+                const uint32_t v = g1_fetch<CODED>(k, (int)cell);
+                const bool in = coord_in_map(TX, fx, 8, limx) && coord_in_map(TY, fy, 8, limy);
                 return in ? v : zero_off;
             };
             int j = 0;
@@ -375,8 +389,8 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
 #pragma unroll
                 for (int u = 0; u < P; ++u) {
                     bool inx, iny;
-                    const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx, p.W, inx);      // pu:128-129
-                    const int my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy, p.H, iny);
+                    const int mx = map_coord(end_x(q[u], b), p.K, p.S, wofx, p.W, inx);      // pu:128-129
+                    const int my = map_coord(end_y(q[u], b), p.K, p.S, wofy, p.H, iny);
                     acc[u] += (!q[u].far && inx && iny) ? __ldg(p.logtab + (size_t)my * p.W + mx) : 0;
                 }
             }
@@ -388,8 +402,8 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
 #pragma unroll
         for (int u = 0; u < P; ++u) {
             bool inx, iny;
-            const int mx = map_coord(end_x(q[u], b), p.K, p.S, p.wofx, p.W, inx);
-            const int my = map_coord(end_y(q[u], b), p.K, p.S, p.wofy, p.H, iny);
+            const int mx = map_coord(end_x(q[u], b), p.K, p.S, wofx, p.W, inx);
+            const int my = map_coord(end_y(q[u], b), p.K, p.S, wofy, p.H, iny);
             if (!q[u].far && inx && iny)
                 acc[u] += quantise_logp(cell_logp(__ldg(p.dist + (size_t)my * p.W + mx), p.sigma_hit, p.z_hit,
                                                   p.z_rand, p.max_range, false));
@@ -399,7 +413,7 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
     for (int u = 0; u < P; ++u)
         if (idx[u] < end) {
             const float sc = (float)(((double)acc[u] / MCL_LOGP_SCALE) / (double)k.nb);   // pu:144-145
-            score[idx[u]] = sc;
+            score[PERM ? pidx[u] : idx[u]] = sc;
             smax = fmaxf(smax, sc);
         }
 }
@@ -471,6 +485,212 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Large maps (BASELINE config 5: 4096 x 4096, 64 MB of table): no window fits in shared memory and a gather
+// through L1/L2 runs at a quarter of the shared-memory rate.  The particles are binned by map tile (counting
+// sort: histogram, offsets, scatter of indices), and persistent CTAs walk the sorted order in chunks, staging
+// for every tile they meet the byte-coded neighbourhood of that tile -- tile + the beam reach on every side,
+// 256 columns wide so that the byte-permuted index of the coded kernel applies unchanged -- and then running
+// the same beam loop.  Coordinates are taken relative to the staged sub-window with S = 8.
+// ---------------------------------------------------------------------------------------------
+struct TiledArgs {
+    const uint8_t *code8;
+    const int32_t *lut;
+    const int32_t *perm, *offsets;        // particle index by sorted position; first sorted position of every tile
+    const int32_t *items;                 // work items (tile, first position, end position): one tile, <= piece particles
+    int *counters;                        // [0] number of items, [1] next item to hand out
+    int tile_w, tile_h, margin, tiles_x, tiles_y, ntiles, sub_rows, piece;
+};
+
+__device__ __forceinline__ int tile_index_1d(double pc, int tile, int ntile) {
+    if (!(pc >= 0.0)) return 0;                                   // negative or NaN
+    const double q = floor(pc / (double)tile);
+    return q < (double)ntile ? (int)q : ntile - 1;
+}
+// Histogram of the tiles.  SH: per-block histogram in shared memory, flushed once (a few thousand counters hit by
+// millions of global atomics cost 260 us at 6 M particles); the block walks a CONTIGUOUS share so that the scatter
+// kernel sees the same particles.
+template <bool SH>
+__global__ void __launch_bounds__(512) k_tile_count(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
+                                                    double ox, double oy, double res, int tile_w, int tile_h, int tiles_x,
+                                                    int tiles_y, int ntiles, int32_t *__restrict__ tile_of, int *hist) {
+    extern __shared__ int sh_hist[];
+    if (SH) {
+        for (int t = threadIdx.x; t < ntiles; t += blockDim.x) sh_hist[t] = 0;
+        __syncthreads();
+    }
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = min(n, lo + per);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double px = __ddiv_rn(__dadd_rn(x[i], -ox), res), py = __ddiv_rn(__dadd_rn(y[i], -oy), res);
+        const int t = tile_index_1d(py, tile_h, tiles_y) * tiles_x + tile_index_1d(px, tile_w, tiles_x);
+        tile_of[i] = t;
+        atomicAdd(SH ? sh_hist + t : hist + t, 1);
+    }
+    if (SH) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { const int c = sh_hist[t]; if (c) atomicAdd(hist + t, c); }
+    }
+}
+// exclusive offsets of the tiles (single block); hist is zeroed to serve as the scatter cursors.  Also cuts the
+// sorted order into work items for the tiled kernel: every non-empty tile in pieces of at most `piece` particles.
+__global__ void __launch_bounds__(1024) k_tile_offsets(int *hist, int ntiles, int32_t *offsets, int piece, int32_t *items,
+                                                       int *counters) {
+    __shared__ int sh[32], sh2[32];
+    __shared__ int carry, carry2;
+    if (threadIdx.x == 0) { carry = 0; carry2 = 0; }
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < ntiles ? hist[i] : 0;
+        const int np = (v + piece - 1) / piece;                 // pieces of this tile
+        int inc = v, inc2 = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o), t2 = __shfl_up_sync(0xffffffffu, inc2, o);
+            if ((threadIdx.x & 31) >= o) { inc += t; inc2 += t2; }
+        }
+        if ((threadIdx.x & 31) == 31) { sh[threadIdx.x >> 5] = inc; sh2[threadIdx.x >> 5] = inc2; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int t = sh[threadIdx.x], t2 = sh2[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, o), u2 = __shfl_up_sync(0xffffffffu, t2, o);
+                if (threadIdx.x >= o) { t += u; t2 += u2; }
+            }
+            sh[threadIdx.x] = t; sh2[threadIdx.x] = t2;
+        }
+        __syncthreads();
+        const int woff = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+        const int woff2 = (threadIdx.x >> 5) ? sh2[(threadIdx.x >> 5) - 1] : 0;
+        const int c0 = carry, c2 = carry2;
+        if (i < ntiles) {
+            const int first = c0 + woff + inc - v;
+            offsets[i] = first;
+            hist[i] = 0;
+            int it = c2 + woff2 + inc2 - np;
+            for (int j = 0; j < np; ++j, ++it) {
+                items[3 * it] = i;
+                items[3 * it + 1] = first + j * piece;
+                items[3 * it + 2] = min(first + v, first + (j + 1) * piece);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry = c0 + woff + inc; carry2 = c2 + woff2 + inc2; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { offsets[ntiles] = carry; counters[0] = carry2; counters[1] = 0; }
+}
+// perm[first position of the tile + rank inside the tile] = particle.  SH: the block counts its share per tile in
+// shared memory, reserves one range per tile with a single global atomic, then ranks its particles locally.
+template <bool SH>
+__global__ void __launch_bounds__(512) k_tile_scatter(const int32_t *__restrict__ tile_of, int64_t n, int ntiles,
+                                                      const int32_t *__restrict__ offsets, int *cursor,
+                                                      int32_t *__restrict__ perm) {
+    extern __shared__ int sh_cnt[];          // [ntiles] counts, then local cursors; [ntiles] base of this block in the tile
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = min(n, lo + per);
+    if (!SH) {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const int t = tile_of[i];
+            perm[offsets[t] + atomicAdd(cursor + t, 1)] = (int32_t)i;     // order inside a tile is irrelevant to the results
+        }
+        return;
+    }
+    int *sh_base = sh_cnt + ntiles;
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) sh_cnt[t] = 0;
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(sh_cnt + tile_of[i], 1);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+        const int c = sh_cnt[t];
+        sh_base[t] = c ? offsets[t] + atomicAdd(cursor + t, c) : 0;
+        sh_cnt[t] = 0;
+    }
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int t = tile_of[i];
+        perm[sh_base[t] + atomicAdd(sh_cnt + t, 1)] = (int32_t)i;
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k_likelihood_tiled(const LikParams p, const TiledArgs t) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [16 B][table of distinct values replicated per lane: 256 x 32 int32][uint8 sub-window: sub_rows x 260]
+    // Rows of 260 bytes, index = v + 4 (v >> 8): with 256-byte rows the bank would depend on the column only, and the
+    // 32 particles of a warp share a 48-column tile -- a dozen banks for 32 lanes (measured: the kernel ran at half rate)
+    int32_t *slut = reinterpret_cast<int32_t *>(smem + 16);
+    uint8_t *swin8 = smem + 16 + 32768;
+    for (int e = threadIdx.x; e < 256 * 32; e += THREADS) slut[e] = __ldg(t.lut + (e >> 5));
+    G1Ctx k;
+    k.swin = nullptr; k.slut = slut; k.swin8 = swin8;
+    k.lane = threadIdx.x & 31;
+    k.nb = p.n_pos + p.n_neg;
+    k.cmx = (255 << 8) | 255; k.cmy = ((t.sub_rows - 1) << 8) | 255;
+    k.wofx = 0; k.wofy = 0;
+    const int warp = threadIdx.x >> 5;
+    float smax = -FLT_MAX;
+    int staged = -1;
+    __shared__ int s_item;
+    const int nitems = t.counters[0];
+    for (;;) {                                                 // work items are handed out dynamically: their sizes vary
+        __syncthreads();                                       // previous item done (sub-window, s_item free)
+        if (threadIdx.x == 0) s_item = atomicAdd(t.counters + 1, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= nitems) break;
+        const int tile = __ldg(t.items + 3 * item);
+        const int64_t seg_lo = __ldg(t.items + 3 * item + 1), seg_hi = __ldg(t.items + 3 * item + 2);
+        const int sub_x0 = (tile % t.tiles_x) * t.tile_w - t.margin, sub_y0 = (tile / t.tiles_x) * t.tile_h - t.margin;
+        if (tile != staged) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(swin8);
+            const bool aligned = (p.W & 3) == 0;
+            for (int e = threadIdx.x; e < t.sub_rows * 64; e += THREADS) {
+                const int my = sub_y0 + (e >> 6), mx = sub_x0 + ((e & 63) << 2);
+                uint32_t *d = dst + (e >> 6) * 65 + (e & 63);          // rows of 65 words
+                if ((unsigned)my < (unsigned)p.H && aligned && mx >= 0 && mx < p.W) {
+                    // asynchronous 4-byte copies: all of a thread's ~40 loads in flight at once
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(d)),
+                                 "l"(t.code8 + (size_t)my * p.W + mx) : "memory");
+                } else {
+                    uint32_t v = 0xffffffffu;                          // code 255: outside the map
+                    if ((unsigned)my < (unsigned)p.H && !aligned) {
+                        const uint8_t *row = t.code8 + (size_t)my * p.W;
+                        v = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            v |= (uint32_t)((unsigned)(mx + b) < (unsigned)p.W ? row[mx + b] : 255) << (8 * b);
+                    }
+                    *d = v;
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            staged = tile;
+            __syncthreads();
+        }
+        k.wofx = sub_x0; k.wofy = sub_y0;
+        // one 32-particle slice per warp and round: twice the work units of the two-particle form, so that the
+        // warps of a CTA stay busy on tiles with few particles (the uniform beam loads are no longer shared)
+        int64_t pos = seg_lo + 32 * warp;
+        for (; pos < seg_hi; pos += 32 * (THREADS / 32))
+            g1_slices<true, true, false, 1, true>(p, k, p.x, p.y, p.th, p.score, pos + k.lane, 0, seg_hi, smax, t.perm);
+        // never taken: keeps the hot copy of the slice code on the uniform datapath (see k_likelihood_g1)
+        if (p.n < 0) g1_slices<true, true, false, 2, true>(p, k, p.x, p.y, p.th, p.score, pos + k.lane, 32, seg_hi, smax, t.perm);
+    }
+    if (p.keymax) {
+        __shared__ float smx[32];
+        smax = warp_max(smax);
+        if (k.lane == 0) smx[warp] = smax;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = k.lane < (THREADS >> 5) ? smx[k.lane] : -FLT_MAX;
+            v = warp_max(v);
+            if (k.lane == 0 && v > -FLT_MAX) atomicMax(p.keymax, (unsigned long long)mcl_key_of_float(v));
+        }
+    }
+}
+
 __global__ void k_fill_f32(float *out, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = v;
@@ -537,6 +757,90 @@ static int launch_g1(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
         case 4: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 1024, 1, CODED, TPOSE>, p, smem_bytes, 1, 1024, true);
         default: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 896, 1, CODED, TPOSE>, p, smem_bytes, 1, 896, true);   // 72 registers: fastest measured
     }
+}
+
+// tiled path: bin the particles of one set by map tile, then the tiled kernel (timed together)
+static int launch_tiled(mcl_handle *h, LikParams p, unsigned long long *keymax) {
+    const int ntiles = h->tiles_x * h->tiles_y;
+    const size_t o_tile = 0, o_perm = o_tile + (((size_t)p.n * 4 + 255) & ~(size_t)255);
+    const size_t o_hist = o_perm + (((size_t)p.n * 4 + 255) & ~(size_t)255);
+    const size_t o_off = o_hist + (((size_t)(ntiles + 1) * 4 + 255) & ~(size_t)255);
+    constexpr int PIECE = 16 * 448;                                   // particles per work item at most
+    const size_t max_items = (size_t)ntiles + (size_t)(p.n / PIECE) + 2;
+    const size_t o_items = o_off + (((size_t)(ntiles + 1) * 4 + 255) & ~(size_t)255);
+    const size_t o_cnt = o_items + ((max_items * 12 + 255) & ~(size_t)255);
+    const size_t bytes = o_cnt + 256;
+    if (bytes > h->tiled_bytes) {
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_tiled);
+        h->d_tiled = nullptr; h->tiled_bytes = 0;
+        MCL_CUDA(h, cudaMalloc(&h->d_tiled, bytes));
+        h->tiled_bytes = bytes;
+    }
+    char *b = (char *)h->d_tiled;
+    int32_t *tile_of = (int32_t *)(b + o_tile), *perm = (int32_t *)(b + o_perm), *offsets = (int32_t *)(b + o_off);
+    int *hist = (int *)(b + o_hist);
+    int32_t *items = (int32_t *)(b + o_items);
+    int *counters = (int *)(b + o_cnt);
+    // 14 warps per CTA, two CTAs per SM: a tile's ~1700 particles (27 slice pairs) fill two rounds of the warps;
+    // with one 28-warp CTA most tiles left a third of the warps idle
+    constexpr int THREADS = 448;
+    auto kern = k_likelihood_tiled<THREADS>;
+    const int sub_rows = h->tile_h + 2 * h->tile_margin;
+    const size_t smem_bytes = 16 + 32768 + (size_t)sub_rows * 260;
+    static thread_local int attr_dev = -1;
+    if (attr_dev != h->device) {
+        cudaFuncAttributes fa;
+        MCL_CUDA(h, cudaFuncGetAttributes(&fa, kern));
+        MCL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         h->smem_optin - (int)fa.sharedSizeBytes));
+        attr_dev = h->device;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        MCL_CUDA(h, cudaEventCreate(&e0));
+        MCL_CUDA(h, cudaEventCreate(&e1));
+        MCL_CUDA(h, cudaEventRecord(e0, h->stream));
+    }
+    MCL_CUDA(h, cudaMemsetAsync(hist, 0, (size_t)(ntiles + 1) * 4, h->stream));
+    const int gb = (int)std::max<int64_t>(1, std::min<int64_t>((p.n + 4095) / 4096, (int64_t)h->sm_count * 2));
+    const bool shist = (size_t)ntiles * 8 <= 96 * 1024;
+    if (shist) {
+        static thread_local int bin_dev = -1;
+        if (bin_dev != h->device) {
+            MCL_CUDA(h, cudaFuncSetAttribute(k_tile_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            MCL_CUDA(h, cudaFuncSetAttribute(k_tile_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            bin_dev = h->device;
+        }
+        k_tile_count<true><<<gb, 512, (size_t)ntiles * 4, h->stream>>>(p.x, p.y, p.n, p.ox, p.oy, p.res, h->tile_w, h->tile_h,
+                                                                      h->tiles_x, h->tiles_y, ntiles, tile_of, hist);
+    } else {
+        k_tile_count<false><<<gb, 512, 0, h->stream>>>(p.x, p.y, p.n, p.ox, p.oy, p.res, h->tile_w, h->tile_h, h->tiles_x,
+                                                      h->tiles_y, ntiles, tile_of, hist);
+    }
+    MCL_LAUNCH_CHECK(h);
+    k_tile_offsets<<<1, 1024, 0, h->stream>>>(hist, ntiles, offsets, PIECE, items, counters);
+    MCL_LAUNCH_CHECK(h);
+    if (shist) k_tile_scatter<true><<<gb, 512, (size_t)ntiles * 8, h->stream>>>(tile_of, p.n, ntiles, offsets, hist, perm);
+    else k_tile_scatter<false><<<gb, 512, 0, h->stream>>>(tile_of, p.n, ntiles, offsets, hist, perm);
+    MCL_LAUNCH_CHECK(h);
+    // coordinates relative to the staged sub-window: S = 8 whatever the map size
+    p.M = ldexp(1.5, 12); p.K = (int)(((uint32_t)(1023 + 12) << 20) + (1u << 19)); p.S = 8;
+    p.lim = 2048.0 - (double)h->tile_margin - 4.0;
+    p.x2 = nullptr; p.y2 = nullptr; p.th2 = nullptr; p.score2 = nullptr; p.keymax = keymax;
+    TiledArgs t;
+    t.code8 = h->d_code8; t.lut = h->d_lut; t.perm = perm; t.offsets = offsets;
+    t.tile_w = h->tile_w; t.tile_h = h->tile_h; t.margin = h->tile_margin; t.tiles_x = h->tiles_x; t.tiles_y = h->tiles_y;
+    t.ntiles = ntiles; t.sub_rows = sub_rows; t.piece = PIECE; t.items = items; t.counters = counters;
+    const int blocks = h->sm_count * 2;
+    kern<<<blocks, THREADS, smem_bytes, h->stream>>>(p, t);
+    MCL_LAUNCH_CHECK(h);
+    if (h->timing) {
+        MCL_CUDA(h, cudaEventRecord(e1, h->stream));
+        h->lik_events.emplace_back(e0, e1);
+        h->lik_sets_timed += 1;
+    }
+    return MCL_OK;
 }
 
 // the constant-bank beam table is module-global: re-upload when the active scan (or handle) changed
@@ -614,6 +918,16 @@ static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, 
                                                 h->stream));
             g_cbeams_src = (const void *)h->d_beams_active;
             g_cbeams_gen = h->scan_gen;
+        }
+        static int notile = -1;
+        if (notile < 0) { const char *e = getenv("MCL_NO_TILED"); notile = (e && atoi(e)) ? 1 : 0; }
+        if (!use_smem && !use_coded && h->tiled_ok && !notile && h->lik_path != 1 &&
+            n >= 64 * (int64_t)h->tiles_x * h->tiles_y && h->rmax_cells + 2.0 <= (double)h->tile_margin) {
+            rc = launch_tiled(h, p, d_keymax);
+            if (rc || !d_x2) return rc;
+            LikParams p2 = p;
+            p2.x = d_x2; p2.y = d_y2; p2.th = d_theta2; p2.score = d_score2;
+            return launch_tiled(h, p2, d_keymax ? d_keymax + 1 : nullptr);
         }
         if (use_coded) {
             const size_t sm = 16 + 32768 + h->win8_bytes;

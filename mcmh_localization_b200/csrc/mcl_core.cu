@@ -63,7 +63,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
     mcl_filter_forget(h);
-    cudaFree(h->d_est18); cudaFree(h->d_fused);
+    cudaFree(h->d_est18); cudaFree(h->d_fused); cudaFree(h->d_code8); cudaFree(h->d_tiled);
     cudaFree(h->d_kld);
     cudaFree(h->d_seq);
     if (h->ev_est) cudaEventDestroy(h->ev_est);
@@ -267,6 +267,50 @@ int mcl_prepare_table(mcl_handle *h) {
                 MCL_CUDA(h, cudaMemcpy(h->d_lut, uniq.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
                 h->win8_bytes = codes.size();
                 h->coded = true;
+            }
+        }
+    }
+    // large maps: byte-coded copy of the whole table for the tiled kernel
+    cudaFree(h->d_code8);
+    h->d_code8 = nullptr; h->tiled_ok = false;
+    const bool window_in_smem = h->win_ok && (16 + h->win_bytes <= (size_t)h->smem_optin - 512 || h->coded);
+    if (!window_in_smem && h->cell_S >= 0) {
+        const int margin = (((int)ceil(h->max_range / h->res) + 2) + 3) & ~3;       // multiple of 4: word-aligned staging
+        // tile height: the largest multiple of 32 (at most 96) whose sub-window lets two CTAs share an SM
+        const int tw = (256 - 2 * margin) & ~3;
+        int th = 96;
+        while (th > 32 && 2 * (16 + 32768 + (size_t)(th + 2 * margin) * 260 + 1536) > (size_t)h->smem_optin) th -= 32;
+        const int tx = tw > 0 ? (h->W + tw - 1) / tw : 0, ty = (h->H + th - 1) / th;
+        const size_t sub_bytes = (size_t)(th + 2 * margin) * 260;
+        if (tw >= 16 && (int64_t)tx * ty <= 65536 && 16 + 32768 + sub_bytes + 64 <= (size_t)h->smem_optin - 512) {
+            std::vector<int32_t> tab((size_t)cells);
+            MCL_CUDA(h, cudaMemcpyAsync(tab.data(), h->d_logtab, (size_t)cells * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            // distinct values (few: the value depends only on dist) through a small open-addressing table
+            const int HS = 2048;
+            std::vector<int32_t> hkey(HS, 0), hcode(HS, -1);
+            std::vector<char> hused(HS, 0);
+            std::vector<int32_t> uniq;
+            auto slot_of = [&](int32_t v) { unsigned s0 = ((unsigned)v * 2654435761u) >> 21; while (hused[s0] && hkey[s0] != v) s0 = (s0 + 1) & (HS - 1); return (int)s0; };
+            for (int64_t c = 0; c < cells && uniq.size() <= 255; ++c) {
+                const int sl = slot_of(tab[c]);
+                if (!hused[sl]) { hused[sl] = 1; hkey[sl] = tab[c]; uniq.push_back(tab[c]); }
+            }
+            if (uniq.size() <= 255) {
+                std::sort(uniq.begin(), uniq.end());
+                for (size_t k = 0; k < uniq.size(); ++k) hcode[slot_of(uniq[k])] = (int)k;
+                std::vector<uint8_t> codes((size_t)cells);
+                for (int64_t c = 0; c < cells; ++c) codes[c] = (uint8_t)hcode[slot_of(tab[c])];
+                std::vector<int32_t> lut(256, -h->voff);                  // code 255: outside the map, adds 0
+                for (size_t k = 0; k < uniq.size(); ++k) lut[k] = uniq[k] - h->voff;
+                MCL_CUDA(h, cudaMalloc((void **)&h->d_code8, (size_t)cells));
+                MCL_CUDA(h, cudaMemcpy(h->d_code8, codes.data(), (size_t)cells, cudaMemcpyHostToDevice));
+                cudaFree(h->d_lut);
+                h->d_lut = nullptr;
+                MCL_CUDA(h, cudaMalloc((void **)&h->d_lut, 256 * sizeof(int32_t)));
+                MCL_CUDA(h, cudaMemcpy(h->d_lut, lut.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice));
+                h->tile_w = tw; h->tile_h = th; h->tile_margin = margin; h->tiles_x = tx; h->tiles_y = ty;
+                h->tiled_ok = true;
             }
         }
     }

@@ -209,6 +209,10 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
                             cnt += pass[k];
                         }
                     }
+                    if (__ballot_sync(0xffffffffu, cnt > 0) == 0u) {  // nothing passed (the usual outcome for a particle
+                        g0 += 32;                                    // facing a wall): skip the queue bookkeeping
+                        continue;
+                    }
                     int pre = cnt;                                   // exclusive prefix over lanes -> queue order = attempt order
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }

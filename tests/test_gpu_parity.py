@@ -190,6 +190,44 @@ def test_likelihood_large_tiled_map_vs_oracle(pu):
     assert clib.compute_valid_mask(p0, gm.occ.ravel(), gm.width, gm.height, gm.resolution, gm.origin_x, gm.origin_y).all()
 
 
+def test_likelihood_tiled_kernel_equals_global_path(pu):
+    """Maps whose table does not fit in shared memory: particles binned by map tile + per-tile staged coded
+    sub-window (k_likelihood_tiled) against the global / L2 gather path and the oracle.  Includes particles on
+    the map border, outside the map and far away (tile index clamped, in-map test per beam)."""
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200.maps import load_npz, tiled_map
+    from mcmh_localization_b200.synth import free_space_particles, raycast_scan
+    from oracle import clib, node_glue as ng
+    gm = tiled_map(load_npz(os.path.join(GOLDEN, "map_house.npz")), 6, 6, 2048, 2048)
+    n = 400_000                                   # one thread per particle -> the tiled kernel is eligible
+    parts = free_space_particles(gm, n, seed=18)
+    rs = np.random.RandomState(3)
+    x0, y0 = gm.origin_x, gm.origin_y
+    ext = 2048 * gm.resolution
+    odd = np.column_stack((rs.uniform(x0 - 0.1 * ext, x0 + 1.1 * ext, 3000), rs.uniform(y0 - 0.1 * ext, y0 + 1.1 * ext, 3000),
+                           rs.uniform(-np.pi, np.pi, 3000)))
+    odd[:200, 0] = x0 + rs.uniform(-0.06, 0.06, 200)          # straddling the left edge (int() truncation zone)
+    odd[200:400, 1] = y0 + ext + rs.uniform(-0.06, 0.06, 200)  # straddling the top edge
+    odd[400, :2] = (1e7, -1e7)
+    parts[-3000:] = odd
+    scan, angles = raycast_scan(gm, parts[0])
+    mp = dict(distance_map=gm.dist.ravel(), resolution=gm.resolution, origin_np=np.array([x0, y0]), width=gm.width, height=gm.height)
+    gg = dict(scan=scan, angles=angles, particles=parts)
+    sensor = (P["sigma_hit"], P["z_hit"], P["z_rand"], P["max_range"], 1)
+    s_tiled = _lik(pu, gg, mp, *sensor, path=0)
+    s_glob = _lik(pu, gg, mp, *sensor, path=1)
+    # same fixed-point table, same cell semantics; the two paths round the endpoint on grids of 2^-40 and 2^-38
+    # cell, so a handful of beams in 1e8 may land in the neighbouring cell
+    differ = s_tiled != s_glob
+    assert differ.sum() <= 3, int(differ.sum())
+    assert lik_close(s_tiled, s_glob).all()
+    sl = np.r_[0:20_000, n - 3000:n]
+    ref = clib.compute_likelihoods(scan, angles, parts[sl], mp["distance_map"], gm.resolution, mp["origin_np"], gm.width,
+                                   gm.height, *sensor)
+    assert lik_close(s_tiled[sl], ref, rel=2e-6).all()
+
+
 @pytest.mark.parametrize("name", ["map_world", "map_house"])
 def test_raycast_likelihood_golden(pu, orc, name):
     """pu:151-201 compute_likelihoods_raycast (ray-marching beam model) against the reference's outputs."""
