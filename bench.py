@@ -348,7 +348,7 @@ def run_native(args):
     achieved = stream_bytes / (lik_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": int(24107776 * sets_per_launch),
-                "traffic_source": "profiles/r1f_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum per k_likelihood_g1 "
+                "traffic_source": "profiles/r1g_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum per k_likelihood_g1 "
                                   "launch (ncu --set full): 48.2 MB for a launch that scores both particle sets",
                 "kernel": "k_likelihood_g1", "launch_ms": lik_launch_ms, "launches_timed": int(lik_n.value),
                 "particle_sets_per_launch": sets_per_launch,
