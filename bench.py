@@ -188,8 +188,12 @@ def workload_config(args, gm, n_cpu=None):
 
 # ------------------------------------------------------------------------------------------------
 def run_native(args):
-    # NCCL announces its version on stdout at INFO/VERSION level: keep stdout to the one JSON line
+    # Libraries chat on stdout (NCCL announces its version there): keep the real stdout for the one JSON line and
+    # send everything else written to fd 1 to stderr.
     os.environ["NCCL_DEBUG"] = os.environ.get("MCL_NCCL_DEBUG", "WARN")
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from mcmh_localization_b200 import Localizer
@@ -413,7 +417,8 @@ def run_native(args):
                 "api": "Localizer.step(odom, ranges, angles): host scan + odom in, host estimate out, wall clock"},
         "gpu_launches": int(launches), "roofline": roofline, "gather_roofline": gl, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -120,6 +120,10 @@ int mcl_ensure_scratch(mcl_handle *h, size_t bytes);
 int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
 void mcl_filter_forget(const mcl_handle *h);
 int mcl_cumsum_f32_seq(mcl_handle *h, const float *d_w, int64_t n, float *d_c);
+int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
+                       const double delta[3], uint64_t seed, uint64_t step, uint64_t first_index,
+                       const double *d_normals, int A, int max_attempts, double *d_xo, double *d_yo, double *d_thetao,
+                       int32_t *d_attempts, unsigned long long *d_thr_cache);
 int mcl_softmax_pair(mcl_handle *h, const float *s0, float *w0, const float *s1, float *w1, int64_t n);
 // fused.cu: the step tail in four kernels (softmax sums -> weights + MH + raw estimate sums -> central sums +
 // cumulative weights -> search + gather); a sharded run exchanges the quantities of FusedPtrs between stages
@@ -141,6 +145,7 @@ const unsigned long long *mcl_fused_cumsum(mcl_handle *h, int64_t n);
 int mcl_fused_sumexp(mcl_handle *h, const FusedStep &u);
 int mcl_fused_weights(mcl_handle *h, const FusedStep &u);
 int mcl_fused_scan(mcl_handle *h, const FusedStep &u);
+int mcl_fused_chain_accept(mcl_handle *h, const FusedStep &u, float *score_chain);
 int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, const double *ny, const double *nth,
                        int32_t *idx, double *gx, double *gy, double *gt);
 const unsigned long long *mcl_fused_tile_prefix(mcl_handle *h, int64_t n, int *nt, int *tile);

@@ -26,6 +26,8 @@ struct FilterState {
     double delta[3] = {0, 0, 0}, delta_b[3] = {0, 0, 0};
     double *tf = nullptr, *tb = nullptr;
     int64_t t_cap = 0;
+    unsigned long long *thr = nullptr;      // screening thresholds of particles_prev during an MH chain (motion.cu)
+    int64_t thr_cap = 0;
     // sharded operation (one process per GPU): peer-memory mailboxes for the small exchanges and peer
     // pointers of every rank's pose buffers for the resampling push
     bool comm = false;
@@ -59,7 +61,7 @@ void mcl_filter_forget(const mcl_handle *h) {
     std::lock_guard<std::mutex> lk(g_filters_mu);
     auto it = g_filters.find(h);
     if (it != g_filters.end()) {
-        cudaFree(it->second.tf); cudaFree(it->second.tb); cudaFree(it->second.d_peer_pose);
+        cudaFree(it->second.tf); cudaFree(it->second.tb); cudaFree(it->second.d_peer_pose); cudaFree(it->second.thr);
         cudaFree(it->second.d_x8); cudaFree(it->second.d_comm_err);
     }
     g_filters.erase(h);
@@ -453,14 +455,64 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
     // roles during the chain: prev = particles_prev (fixed), prop = cur buffer, chain = spare buffer
     const int prev = f->prev, prop = f->cur, chain = f->spare;
     float *score_chain = f->score_pre, *score_prop = f->score_post;
-    int rc = mcl_likelihood(h, f->x[prev], f->y[prev], f->th[prev], f->n, score_chain);       // chain_0 = particles_prev
-    if (rc) return rc;
+    // single GPU: the likelihood launches leave the score maxima as keys and the iteration is two fused kernels
+    // (sum-exp of both sets; weights + accept + max of the carried scores) instead of five launches and a memset
+    static int nofuse = -1;
+    if (nofuse < 0) { const char *e = getenv("MCL_NO_FUSE"); nofuse = (e && atoi(e)) ? 1 : 0; }
+    bool fused = !f->comm && !nofuse;
+    int rc;
+    if (fused) {
+        rc = mcl_fused_prepare(h, f->n);
+        if (rc) return rc;
+        bool ok = false;
+        rc = mcl_likelihood_pair(h, f->x[prev], f->y[prev], f->th[prev], score_chain, nullptr, nullptr, nullptr, nullptr, f->n,
+                                 mcl_fused_keymax(h) + 1, &ok);                                // chain_0 = particles_prev
+        if (rc) return rc;
+        if (!ok) fused = false;      // no valid beam in the scan: nothing was launched
+    }
+    if (!fused) {
+        rc = mcl_likelihood(h, f->x[prev], f->y[prev], f->th[prev], f->n, score_chain);       // chain_0 = particles_prev
+        if (rc) return rc;
+    }
+    // every further proposal starts from particles_prev with the same increment: the geometric screening
+    // threshold of a particle (motion.cu) is computed once per scan and reused by the other iterations
+    if (iters > 1) {
+        if (f->thr_cap < f->n) {
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            cudaFree(f->thr); f->thr = nullptr; f->thr_cap = 0;
+            MCL_CUDA(h, cudaMalloc((void **)&f->thr, (size_t)f->n * sizeof(unsigned long long)));
+            f->thr_cap = f->n;
+        }
+        MCL_CUDA(h, cudaMemsetAsync(f->thr, 0xff, (size_t)f->n * sizeof(unsigned long long), h->stream));
+    }
     for (int it = 0; it < iters; ++it) {
         if (it > 0) {   // fresh proposal from particles_prev
             f->tick++;
-            rc = mcl_predict(h, f->x[prev], f->y[prev], f->th[prev], f->n, f->delta, f->seed, f->tick, f->first_index,
-                             nullptr, 0, f->max_attempts, f->x[prop], f->y[prop], f->th[prop], nullptr);
+            rc = mcl_predict_cached(h, f->x[prev], f->y[prev], f->th[prev], f->n, f->delta, f->seed, f->tick,
+                                    f->first_index, nullptr, 0, f->max_attempts, f->x[prop], f->y[prop], f->th[prop],
+                                    nullptr, f->thr);
             if (rc) return rc;
+        }
+        const int src = it == 0 ? prev : chain;       // iteration 1 reads particles_prev and writes the chain buffer
+        if (fused) {
+            bool ok = false;
+            rc = mcl_likelihood_pair(h, f->x[prop], f->y[prop], f->th[prop], score_prop, nullptr, nullptr, nullptr, nullptr,
+                                     f->n, mcl_fused_keymax(h), &ok);
+            if (rc) return rc;
+            f->tick++;
+            FusedStep u;
+            memset(&u, 0, sizeof(u));
+            u.n = f->n; u.n_global = f->n; u.use_mh = 1;
+            u.s_post = score_prop; u.s_pre = score_chain; u.w_post = f->w_post; u.w_pre = f->w_pre; u.w_out = f->w[f->wslot];
+            u.px = f->x[prop]; u.py = f->y[prop]; u.pt = f->th[prop];
+            u.ox = f->x[src]; u.oy = f->y[src]; u.ot = f->th[src];
+            u.nx = f->x[chain]; u.ny = f->y[chain]; u.nth = f->th[chain];
+            u.seed = f->seed; u.step = f->tick; u.first_index = f->first_index; u.est18 = h->d_est18;
+            rc = mcl_fused_sumexp(h, u);
+            if (rc) return rc;
+            rc = mcl_fused_chain_accept(h, u, score_chain);
+            if (rc) return rc;
+            continue;
         }
         rc = mcl_likelihood(h, f->x[prop], f->y[prop], f->th[prop], f->n, score_prop);
         if (rc) return rc;
@@ -468,12 +520,13 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
                      : mcl_softmax_pair(h, score_prop, f->w_post, score_chain, f->w_pre, f->n);
         if (rc) return rc;
         f->tick++;
-        const int src = it == 0 ? prev : chain;       // iteration 1 reads particles_prev and writes the chain buffer
         k_chain_accept<<<blocks, 256, 0, h->stream>>>(f->x[src], f->y[src], f->th[src], f->x[prop], f->y[prop], f->th[prop],
                                                       f->w_post, f->w_pre, score_chain, score_prop, f->n, f->seed, f->tick,
                                                       f->first_index, f->x[chain], f->y[chain], f->th[chain], f->w[f->wslot]);
         MCL_LAUNCH_CHECK(h);
     }
+    // the last iteration left the key of the carried scores behind: the next user of the keys starts from zero
+    if (fused) MCL_CUDA(h, cudaMemsetAsync(mcl_fused_keymax(h), 0, 2 * sizeof(unsigned long long), h->stream));
     f->cur = chain; f->spare = prop;                  // self.particles = chain
     return MCL_OK;
 }

@@ -227,6 +227,46 @@ __global__ void __launch_bounds__(FZ_THREADS, 4) k_fz_weights_mh_moments(const F
 }
 
 // ---------------------------------------------------------------------------------------------
+// One iteration of the MH refinement chain (filter.cu, BASELINE config 4): weights of proposal and chain from the
+// two softmax statistics, accept (pu:229-233), carried score; leaves max(score_chain) as the key of set 1 for the
+// next iteration's k_fz_sumexp (the proposal's key comes from the next likelihood launch).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FZ_THREADS) k_fz_chain_accept(const FzArgs a, float *score_chain) {
+    __shared__ float shm[FZ_THREADS / 32];
+    const float m_prop = (float)a.hd->smax[0], sum_prop = (float)((double)a.hd->sumq[0] / SOFTMAX_FIX);
+    const float m_chain = (float)a.hd->smax[1], sum_chain = (float)((double)a.hd->sumq[1] / SOFTMAX_FIX);
+    float smax = -FLT_MAX;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float s_prop = a.s_post[i], s_chain = score_chain[i];
+        const float p_new = __fdiv_rn(fz_softmax_num(s_prop, m_prop), sum_prop);
+        const float p_old = __fdiv_rn(fz_softmax_num(s_chain, m_chain), sum_chain);
+        a.w_post[i] = p_new;
+        a.w_pre[i] = p_old;
+        double alpha = 1.0;
+        if (p_old > 0.f) {
+            const double q = (double)__fdiv_rn(p_new, p_old);
+            alpha = (q < 1.0) ? q : 1.0;
+        }
+        const uint4 o = philox_draw4(a.seed, a.step, a.first_index + (uint64_t)i, 0u, MCL_STREAM_MH);
+        const bool acc = u53_from(o.x, o.y) < alpha;
+        a.nx[i] = acc ? a.px[i] : a.ox[i];
+        a.ny[i] = acc ? a.py[i] : a.oy[i];
+        a.nth[i] = acc ? a.pt[i] : a.ot[i];
+        a.w_out[i] = acc ? p_new : p_old;
+        const float s_new = acc ? s_prop : s_chain;
+        if (acc) score_chain[i] = s_prop;
+        smax = fmaxf(smax, s_new);
+    }
+    smax = warp_max(smax);
+    if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = smax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < FZ_THREADS / 32; ++k) smax = fmaxf(smax, shm[k]);
+        if (smax > -FLT_MAX) atomicMax(&a.hd->keymax[1], (unsigned long long)mcl_key_of_float(smax));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // central sums (node:590-597, pu:69-83) + inclusive scan of the quantised weights (pu:436-443 as integers).
 // Single pass: tiles take tickets in launch order, publish their aggregate, and look back over their
 // predecessors' descriptors (aggregate or inclusive prefix) -- Merrill & Garland's decoupled look-back.
@@ -506,6 +546,16 @@ int mcl_fused_resample(mcl_handle *h, int64_t n, double r, const double *nx, con
     a.idx = idx; a.gx = gx; a.gy = gy; a.gt = gt;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
     k_fz_search_gather<<<blocks, 256, p.nt <= FZ_SEARCH_SMEM_TILES ? (size_t)p.nt * 8 : 0, h->stream>>>(a);
+    MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// MH chain iteration: (ox, oy, ot) chain, (px, py, pt) proposal -> (nx, ny, nth); may alias the chain (in place)
+int mcl_fused_chain_accept(mcl_handle *h, const FusedStep &u, float *score_chain) {
+    FzArgs a;
+    fz_fill(h, u, a);
+    const int blocks = (int)std::min<int64_t>((u.n + FZ_THREADS - 1) / FZ_THREADS, (int64_t)h->sm_count * 16);
+    k_fz_chain_accept<<<blocks, FZ_THREADS, 0, h->stream>>>(a, score_chain);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }

@@ -31,6 +31,9 @@ struct MotionParams {
     double lv_ulo[10], lv_uhi[10], lv_hv[10];      // along-heading interval and half width of the sector box
     unsigned long long lv_thr[10];                  // an attempt can only succeed if radius word + 1 <= thr
     double inv_res;
+    // optional per-particle cache of the screening threshold (~0 = not computed yet): the MH chain proposes from
+    // the SAME poses with the SAME increment 31 more times, and the threshold depends on nothing else
+    unsigned long long *thr_cache;
 };
 
 struct Pose { double x, y, th; };
@@ -144,7 +147,12 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
         Pose c;
         if (motion_attempt(p, i, 0, x, y, th, c)) { out = c; att = 1; done = true; }
         else if (!p.normals) {
-            thr = screening_threshold(p, x, y, th);
+            if (p.thr_cache) {
+                thr = p.thr_cache[i];
+                if (thr == ~0ull) { thr = screening_threshold(p, x, y, th); p.thr_cache[i] = thr; }
+            } else {
+                thr = screening_threshold(p, x, y, th);
+            }
             if (thr == 0ull) done = true;                // provably stuck: att = 0, pose kept (pu:360-361)
         }
     }
@@ -262,6 +270,15 @@ extern "C" int mcl_predict(mcl_handle *h, const double *d_x, const double *d_y, 
                            int64_t n, const double delta[3], uint64_t seed, uint64_t step,
                            uint64_t first_index, const double *d_normals, int A, int max_attempts,
                            double *d_xo, double *d_yo, double *d_thetao, int32_t *d_attempts) {
+    return mcl_predict_cached(h, d_x, d_y, d_theta, n, delta, seed, step, first_index, d_normals, A, max_attempts, d_xo,
+                              d_yo, d_thetao, d_attempts, nullptr);
+}
+
+// internal: d_thr_cache (n values, ~0 = unknown) is valid for ONE set of source poses and ONE increment
+int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
+                       const double delta[3], uint64_t seed, uint64_t step, uint64_t first_index,
+                       const double *d_normals, int A, int max_attempts, double *d_xo, double *d_yo, double *d_thetao,
+                       int32_t *d_attempts, unsigned long long *d_thr_cache) {
     if (!h) return MCL_ERR_ARG;
     if (n < 0 || !delta || (n > 0 && (!d_x || !d_y || !d_theta || !d_xo || !d_yo || !d_thetao)))
         return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: bad argument");
@@ -284,6 +301,7 @@ extern "C" int mcl_predict(mcl_handle *h, const double *d_x, const double *d_y, 
     p.seed = seed; p.step = step; p.first_index = first_index;
     p.normals = d_normals; p.A = A; p.max_attempts = max_attempts;
     p.xo = d_xo; p.yo = d_yo; p.tho = d_thetao; p.attempts = d_attempts;
+    p.thr_cache = d_normals ? nullptr : d_thr_cache;
     // screening levels: every candidate with |z0|, |z1| <= rho has t in trans +- rho s2 and heading within
     // +- rho s1 of theta + rot1.  Valid only while t stays positive and the spread small; levels are nested.
     const double levels[10] = {1.0, 2.0, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.6605};
