@@ -52,6 +52,12 @@ struct mcl_handle {
     // the two clamped coordinates: index = minor | major << 8 (likelihood.cu).  win_ok = false when
     // neither axis fits in 256 columns (the table is then gathered from global memory / L2).
     int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
+    // Geometry of the staged window (mcl_prepare_table): window index i <-> map cell i + win_of per axis, largest
+    // index win_c.  A side of the free-space box that lies within beam reach of the map edge is an EDGE side: the
+    // window then runs to the map edge and its border holds "outside the map" (adds 0) instead of c0, so particles
+    // near that edge need no per-beam in-map test; on the low sides one extra column / row repeats cell 0, which is
+    // where int() sends coordinates in (-1, 0).  Bits of win_edge: 1 low x, 2 high x, 4 low y, 8 high y.
+    int win_ofx = 0, win_ofy = 0, win_cx = 0, win_cy = 0, win_edge = 0;
     bool win_ok = false, win_tpose = false;
     int win_rows = 0;            // (major extent + 2) rows of 256 cells
     int32_t *d_win = nullptr;

@@ -20,8 +20,9 @@
 // The table is staged in shared memory: the free-space window of the map (all cells outside
 // it hold one constant c0) plus a one-cell c0 border, so out-of-window lookups clamp onto the
 // border instead of branching.  Staging uses the bulk-copy engine (cp.async.bulk + mbarrier, "TMA"
-// 1-D form); CTAs are persistent and stage once.  If the window does not fit in shared memory the
-// table is gathered from global memory / L2.
+// 1-D form); CTAs are persistent and stage once.  If the window does not fit in shared memory even
+// byte-coded, the particles are binned by map tile and the neighbourhood of one tile is staged at a time
+// (k_likelihood_tiled); small particle counts on such maps gather from global memory / L2.
 // Mapping: G lanes per particle (G = 1 for large N: beam constants are then warp-uniform constant-bank
 // loads; G up to 32 for small N to fill the machine), beams strided over the G lanes and reduced
 // with __shfl_xor.
@@ -54,14 +55,16 @@ struct LikParams {
     const int32_t *lut;
     uint32_t win8_bytes, win_bytes;
     int32_t voff;              // shared-memory table values are v - voff (mcl_handle::voff)
-    int wofx, wofy;            // window origin incl. border: wx0 - 1, wy0 - 1
-    int cx, cy;                // largest window index per axis: ww + 1, wh + 1
+    int wofx, wofy;            // map cell of window index 0 per axis (mcl_handle::win_of*)
+    int cx, cy;                // largest window index per axis
     int tpose;                 // window stored with y as the minor (pitch-256) axis
     double M, lim;             // cell arithmetic: bias and validity limit (mcl_handle::cell_*)
     int K, S;
     double sigma_hit, z_hit, z_rand, max_range;
     double margin;     // rmax_cells + 2: particles further than this from every map edge cannot
                        // produce an out-of-map endpoint
+    double ilox, ihix, iloy, ihiy;   // "no per-beam in-map test needed" box of the particle position (cells): the
+                                     // margin on ordinary sides, unbounded on EDGE sides (mcl_handle::win_edge)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -119,7 +122,7 @@ __device__ __forceinline__ Pose load_pose(const LikParams &p, const double *__re
     q.far = !(fabs(wx) < p.lim && fabs(wy) < p.lim);                   // also catches NaN poses
     q.PX = __dadd_rn(q.far ? 0.0 : wx, p.M);
     q.PY = __dadd_rn(q.far ? 0.0 : wy, p.M);
-    q.interior = (px >= p.margin) && (px <= (double)p.W - p.margin) && (py >= p.margin) && (py <= (double)p.H - p.margin);
+    q.interior = !q.far && (px >= p.ilox) && (px <= p.ihix) && (py >= p.iloy) && (py <= p.ihiy);
     return q;
 }
 
@@ -140,7 +143,7 @@ __device__ __forceinline__ bool coord_in_map(double T, int Fm, int S, unsigned l
     return in;
 }
 __device__ __forceinline__ int map_coord(double T, int K, int S, int wof, int dim, bool &in) {
-    const int Fm = (__double2hiint(T) - K) + (wof << S);
+    const int Fm = (__double2hiint(T) - K) + wof * (1 << S);
     in = coord_in_map(T, Fm, S, (unsigned)(dim + 1) << S);
     return max(Fm >> S, 0);
 }
@@ -254,9 +257,9 @@ __global__ void __launch_bounds__(LIK_THREADS, 2) k_likelihood(const LikParams p
 // the beam table).  Per evaluation: 4 DFMA, 2 VIADDMNMX, 1 PRMT, 1 LEA, 1 LDS, ~0.75 integer adds and,
 // shared by the two particles of a thread, the uniform loads of the beam.
 //
-// Work split: every CTA owns an equal contiguous share of the particles and walks it in rows of one
-// particle per thread; a warp takes its 32-particle slices two rows at a time and a last odd slice alone,
-// so all warps of the grid carry the same number of slices +-1 (no tail of half-empty SMs).
+// Work split: every CTA owns an equal contiguous share of the particles, cut into pairs of adjacent
+// 32-particle slices dealt round-robin to its warps (a thread evaluates two particles per beam), so all
+// warps of the grid carry the same number of pairs +-1 (no tail of half-empty SMs).
 // Table values in shared memory are v - voff >= 0, so MCL_ACC_TERMS of them are summed in one unsigned
 // 32-bit register before the 64-bit accumulator is touched.
 // ---------------------------------------------------------------------------------------------
@@ -345,7 +348,7 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
             double PX[P], PY[P], ss[P], cc[P];
 #pragma unroll
             for (int u = 0; u < P; ++u) { uacc[u] = 0; PX[u] = q[u].PX; PY[u] = q[u].PY; ss[u] = q[u].s; cc[u] = q[u].c; }
-            const int negK = -p.K, Kmx = p.K - (wofx << 8), Kmy = p.K - (wofy << 8);
+            const int negK = -p.K, Kmx = p.K - wofx * 256, Kmy = p.K - wofy * 256;
             const unsigned limx = (unsigned)(p.W + 1) << 8, limy = (unsigned)(p.H + 1) << 8;
             const uint32_t zero_off = (uint32_t)(-p.voff);
             auto eval = [&](int u, const double2 b) -> uint32_t {
@@ -828,6 +831,8 @@ static int launch_tiled(mcl_handle *h, LikParams p, unsigned long long *keymax) 
     p.M = ldexp(1.5, 12); p.K = (int)(((uint32_t)(1023 + 12) << 20) + (1u << 19)); p.S = 8;
     p.lim = 2048.0 - (double)h->tile_margin - 4.0;
     p.x2 = nullptr; p.y2 = nullptr; p.th2 = nullptr; p.score2 = nullptr; p.keymax = keymax;
+    // staged sub-windows mark cells beyond the map but do not repeat cell 0 for the int() quirk: keep the margin test
+    p.ilox = p.margin; p.ihix = (double)p.W - p.margin; p.iloy = p.margin; p.ihiy = (double)p.H - p.margin;
     TiledArgs t;
     t.code8 = h->d_code8; t.lut = h->d_lut; t.perm = perm; t.offsets = offsets;
     t.tile_w = h->tile_w; t.tile_h = h->tile_h; t.margin = h->tile_margin; t.tiles_x = h->tiles_x; t.tiles_y = h->tiles_y;
@@ -892,10 +897,18 @@ static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, 
     p.win8 = h->d_win8; p.lut = h->d_lut; p.win8_bytes = (uint32_t)h->win8_bytes;
     p.win_bytes = (uint32_t)h->win_bytes;
     p.voff = h->voff;
-    p.wofx = h->wx0 - 1; p.wofy = h->wy0 - 1; p.cx = h->ww + 1; p.cy = h->wh + 1; p.tpose = h->win_tpose ? 1 : 0;
+    p.wofx = h->win_ofx; p.wofy = h->win_ofy; p.cx = h->win_cx; p.cy = h->win_cy; p.tpose = h->win_tpose ? 1 : 0;
     p.M = h->cell_M; p.lim = h->cell_lim; p.K = h->cell_K; p.S = h->cell_S;
     p.sigma_hit = h->sigma_hit; p.z_hit = h->z_hit; p.z_rand = h->z_rand; p.max_range = h->max_range;
     p.margin = h->rmax_cells + 2.0;
+    {   // EDGE sides (window runs to the map edge, border = outside) need no margin; only valid with the window
+        const bool win = h->win_ok;
+        const double big = 1e300;
+        p.ilox = (win && (h->win_edge & 1)) ? -big : p.margin;
+        p.ihix = (win && (h->win_edge & 2)) ? big : (double)h->W - p.margin;
+        p.iloy = (win && (h->win_edge & 4)) ? -big : p.margin;
+        p.ihiy = (win && (h->win_edge & 8)) ? big : (double)h->H - p.margin;
+    }
 
     const size_t beam_bytes = (size_t)nb * sizeof(BeamTable);
     const size_t smem_glob = 16 + beam_bytes;

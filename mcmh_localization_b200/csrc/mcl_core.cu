@@ -149,13 +149,7 @@ extern "C" int mcl_set_map(mcl_handle *h, const int8_t *h_occ, const float *h_di
     }
     if (x1 < 0) { h->wx0 = 0; h->wy0 = 0; h->ww = 0; h->wh = 0; }
     else { h->wx0 = x0; h->wy0 = y0; h->ww = x1 - x0 + 1; h->wh = y1 - y0 + 1; }
-    // pitch-256 layout: the minor axis is the larger extent that still fits in 256 columns (fewest rows)
-    const int ex = h->ww + 2, ey = h->wh + 2;
-    h->win_ok = std::min(ex, ey) <= 256;
-    h->win_tpose = h->win_ok && (ex > 256 || (ey <= 256 && ey > ex));
-    h->win_rows = h->win_tpose ? ex : ey;
-    h->win_bytes = h->win_ok ? (size_t)h->win_rows * 256 * sizeof(int32_t) : 0;
-    if (h->win_ok) MCL_CUDA(h, cudaMalloc((void **)&h->d_win, h->win_bytes));
+    h->win_ok = false; h->win_bytes = 0;      // the window is laid out by mcl_prepare_table (needs the beam reach)
     h->tab_dirty = true;
     return MCL_OK;
 }
@@ -193,14 +187,20 @@ __global__ void k_build_logtab(const float *__restrict__ dist, int32_t *__restri
         logtab[c] = quantise_logp(cell_logp(dist[c], sigma_hit, z_hit, z_rand, max_range, true));
 }
 
-__global__ void k_pack_window(const int32_t *__restrict__ logtab, int32_t *__restrict__ win, int W, int wx0,
-                              int wy0, int ww, int wh, int rows, int tpose, int32_t c0, int32_t voff) {
+// window cell (ix, iy) <-> map cell (ix + ofx, iy + ofy); see mcl_handle::win_edge for the EDGE sides
+__global__ void k_pack_window(const int32_t *__restrict__ logtab, int32_t *__restrict__ win, int W, int H, int ofx, int ofy,
+                              int edge, int rows, int tpose, int32_t c0, int32_t voff) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * 256; i += gridDim.x * blockDim.x) {
         const int major = i >> 8, minor = i & 255;
         const int ix = tpose ? major : minor, iy = tpose ? minor : major;
-        int32_t v = c0;
-        if (ix >= 1 && ix <= ww && iy >= 1 && iy <= wh)
-            v = logtab[(size_t)(wy0 + iy - 1) * W + (wx0 + ix - 1)];
+        int mx = ix + ofx, my = iy + ofy;
+        const bool outside = ((edge & 1) && mx <= -2) || ((edge & 2) && mx >= W) || ((edge & 4) && my <= -2) ||
+                             ((edge & 8) && my >= H);
+        if ((edge & 1) && mx == -1) mx = 0;          // int() sends (-1, 0) to cell 0
+        if ((edge & 4) && my == -1) my = 0;
+        int32_t v = c0;                               // in-map cells outside the free-space box
+        if (outside) v = 0;                           // beyond the map: the beam is skipped (pu:131-132), adds 0
+        else if (mx >= 0 && mx < W && my >= 0 && my < H) v = logtab[(size_t)my * W + mx];
         win[i] = v - voff;     // >= 0: see mcl_handle::voff
     }
 }
@@ -240,12 +240,46 @@ int mcl_prepare_table(mcl_handle *h) {
         h->cell_K = (int)(((uint32_t)(1023 + E) << 20) + (1u << 19));
         h->cell_lim = ldexp(1.0, E - 1) - rmax - 4.0;
     }
-    cudaFree(h->d_win8); cudaFree(h->d_lut);
-    h->d_win8 = nullptr; h->d_lut = nullptr; h->coded = false; h->win8_bytes = 0;
+    cudaFree(h->d_win8); cudaFree(h->d_lut); cudaFree(h->d_win);
+    h->d_win8 = nullptr; h->d_lut = nullptr; h->d_win = nullptr; h->coded = false; h->win8_bytes = 0;
+    {   // window layout: free-space box + border, extended to the map edge on the sides within beam reach of it
+        const int reach = (int)ceil(h->max_range / h->res) + 2;
+        const bool any = h->ww > 0 && h->wh > 0;
+        const int bx0 = h->wx0, bx1 = h->wx0 + h->ww - 1, by0 = h->wy0, by1 = h->wy0 + h->wh - 1;
+        int want = 0;
+        if (any) {
+            if (bx0 < reach) want |= 1;
+            if (bx1 > h->W - 1 - reach) want |= 2;
+            if (by0 < reach) want |= 4;
+            if (by1 > h->H - 1 - reach) want |= 8;
+        }
+        // extending the window costs shared memory and one axis must stay within 256 cells: take the EDGE sides
+        // of both axes if that fits, else those of one axis, else none
+        const int tries[4] = {want, want & 3, want & 12, 0};
+        const size_t limit = (size_t)h->smem_optin - 512;
+        for (int k = 0; k < 4; ++k) {
+            const int edge = tries[k];
+            h->win_edge = edge;
+            h->win_ofx = (edge & 1) ? -2 : h->wx0 - 1;
+            h->win_ofy = (edge & 4) ? -2 : h->wy0 - 1;
+            h->win_cx = ((edge & 2) ? h->W : (any ? bx1 + 1 : h->wx0)) - h->win_ofx;
+            h->win_cy = ((edge & 8) ? h->H : (any ? by1 + 1 : h->wy0)) - h->win_ofy;
+            // pitch-256 layout: the minor axis is the larger extent that still fits in 256 columns (fewest rows)
+            const int ex = h->win_cx + 1, ey = h->win_cy + 1;
+            h->win_ok = std::min(ex, ey) <= 256;
+            h->win_tpose = h->win_ok && (ex > 256 || (ey <= 256 && ey > ex));
+            h->win_rows = h->win_tpose ? ex : ey;
+            h->win_bytes = h->win_ok ? (size_t)h->win_rows * 256 * sizeof(int32_t) : 0;
+            const bool fits = h->win_ok && (16 + h->win_bytes <= limit || (size_t)h->win_rows * 256 + 16 + 32768 + 64 <= limit);
+            if (fits || edge == 0) break;
+        }
+        if (h->win_ok) MCL_CUDA(h, cudaMalloc((void **)&h->d_win, h->win_bytes));
+    }
     if (h->win_ok) {
         const int n = h->win_rows * 256;
         k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
-            h->d_logtab, h->d_win, h->W, h->wx0, h->wy0, h->ww, h->wh, h->win_rows, h->win_tpose ? 1 : 0, h->c0, h->voff);
+            h->d_logtab, h->d_win, h->W, h->H, h->win_ofx, h->win_ofy, h->win_edge, h->win_rows, h->win_tpose ? 1 : 0,
+            h->c0, h->voff);
         MCL_LAUNCH_CHECK(h);
         // coded window (uint8 + table of distinct values) when the int32 window does not fit in shared memory
         const size_t limit = (size_t)h->smem_optin - 512;

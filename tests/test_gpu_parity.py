@@ -780,7 +780,7 @@ def test_localizer_production_step_runs_and_is_deterministic():
     assert np.isfinite(outs[0][1][3]).all()
 
 
-@pytest.mark.parametrize("n", [1000, 33333, 400_003])
+@pytest.mark.parametrize("n", [1, 1000, 33333, 400_003])
 @pytest.mark.parametrize("mode", ["MHMCL", "MCL"])
 def test_fused_step_equals_standalone_sequence(mode, n):
     """Localizer.step() runs the step tail through the fused kernels (fused.cu: likelihood pair with max keys,
