@@ -267,11 +267,19 @@ __device__ __forceinline__ void normals3_from_words(uint32_t w_radius, const uin
     z1 = __dmul_rn(r1, s1);
     z2 = __dmul_rn(r2, c2);
 }
+// The radius word of attempt t: its HIGH half is half-word (t & 7) of the MOTION_R block (item, step, t >> 3) --
+// eight consecutive attempts share one Philox call, so the rejection loop screens eight attempts per call on the
+// high half alone -- and its low half is the low half of word 3 of the attempt's own MOTION block.
+__device__ __forceinline__ uint32_t radius_hi16(const uint4 &a, uint32_t k) {
+    const uint32_t w = pick_word(a, k >> 1);
+    return (k & 1u) ? (w >> 16) : (w & 0xffffu);
+}
+__device__ __forceinline__ uint32_t radius_word(uint32_t hi16, const uint4 &o) { return (hi16 << 16) | (o.w & 0xffffu); }
 __device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t step, uint64_t item,
                                                 uint32_t attempt, double &z0, double &z1, double &z2) {
-    const uint4 a = philox_draw4(seed, step, item, attempt >> 2, MCL_STREAM_MOTION_R);
+    const uint4 a = philox_draw4(seed, step, item, attempt >> 3, MCL_STREAM_MOTION_R);
     const uint4 o = philox_draw4(seed, step, item, attempt, MCL_STREAM_MOTION);
-    normals3_from_words(pick_word(a, attempt & 3u), o, z0, z1, z2);
+    normals3_from_words(radius_word(radius_hi16(a, attempt & 7u), o), o, z0, z1, z2);
 }
 
 // pu:388-396 is_valid_position: trunc-toward-zero cell index, cell == 0 only.

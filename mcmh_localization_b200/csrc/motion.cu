@@ -62,8 +62,8 @@ __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i,
 // proves (separating-axis test against every FREE cell near the sector, everything inflated by 1e-9 m)
 // that this sector touches no free cell.  Since |z0|, |z1| <= R1 = sqrt(-2 ln u1), an attempt whose
 // radius word gives R1 < rho cannot succeed -- an integer compare on the raw Philox word, no log / sqrt /
-// sincos.  The radius words of four consecutive attempts come from one Philox call, so a lane screens
-// four attempts per call and a warp 128 attempts per iteration; only attempts that pass are evaluated in
+// sincos.  The high halves of the radius words of eight consecutive attempts come from one Philox call, so a lane
+// screens eight attempts per call and a warp 256 attempts per iteration; only attempts that pass are evaluated in
 // full.  Results are identical to evaluating every attempt in order (tests: vs the oracle's plain loop).
 // ---------------------------------------------------------------------------------------------
 __device__ bool region_blocked(const MotionParams &p, double x, double y, double sn, double cs, int k) {
@@ -128,10 +128,10 @@ __device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x
     return is_valid_position_dev(cand.x, cand.y, p.occ, p.W, p.H, p.res, p.ox, p.oy);
 }
 
-#define MOTION_Q 192     // >= 31 leftover + 128 new candidates per screening round
+#define MOTION_Q 320     // >= 31 leftover + 256 new candidates per screening round
 __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
     __shared__ unsigned short q_att[8][MOTION_Q];
-    __shared__ unsigned q_word[8][MOTION_Q];
+    __shared__ unsigned short q_hi[8][MOTION_Q];
     const int lane = threadIdx.x & 31;
     const int64_t warp_base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
     if (warp_base >= p.n) return;                       // warp-uniform
@@ -178,23 +178,23 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
                 }
             }
         } else {
-            // Philox draws.  Screening: lane L reads the radius words of attempts 4g..4g+3 (g = g0 + L) from one
-            // Philox block and queues, in attempt order, the attempts whose word passes the threshold.  Full
-            // evaluation (log, sqrt, sincos, map lookup: ~1000 instructions) then takes 32 queued attempts at a
-            // time, lowest index first -- evaluating a passing attempt inside the screening loop would run it
-            // with one or two active lanes.
+            // Philox draws.  Screening: lane L reads the high halves of the radius words of attempts 8g..8g+7
+            // (g = g0 + L) from one Philox block and queues, in attempt order, the attempts whose radius can reach
+            // the threshold whatever the low half.  Full evaluation (log, sqrt, sincos, map lookup: ~1000
+            // instructions) then takes 32 queued attempts at a time, lowest index first -- evaluating a passing
+            // attempt inside the screening loop would run it with one or two active lanes.
             const unsigned long long T = __shfl_sync(0xffffffffu, thr, src);
             const uint64_t item = p.first_index + (uint64_t)si;
-            const int groups = (p.max_attempts + 3) >> 2;
+            const int groups = (p.max_attempts + 7) >> 3;
             unsigned short *qt = q_att[threadIdx.x >> 5];
-            unsigned *qw = q_word[threadIdx.x >> 5];
+            unsigned short *qw = q_hi[threadIdx.x >> 5];
             int qlen = 0, qhead = 0, g0 = 0;
             bool found = false;
             while (!found && (g0 < groups || qhead < qlen)) {
                 // fewer than 32 candidates left: move them to the front of the queue before screening more
                 if (qhead > 0 && g0 < groups && qlen - qhead < 32) {
                     const int left = qlen - qhead;
-                    unsigned short ta = 0; unsigned tw = 0;
+                    unsigned short ta = 0, tw = 0;
                     if (lane < left) { ta = qt[qhead + lane]; tw = qw[qhead + lane]; }
                     __syncwarp();
                     if (lane < left) { qt[lane] = ta; qw[lane] = tw; }
@@ -204,17 +204,19 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
                 // screen until 32 candidates are queued (or the attempts are exhausted)
                 while (g0 < groups && qlen - qhead < 32) {
                     const int g = g0 + lane;
-                    unsigned wv[4];
+                    uint4 a = make_uint4(0u, 0u, 0u, 0u);
                     int cnt = 0;
-                    bool pass[4] = {false, false, false, false};
+                    unsigned passm = 0;
                     if (g < groups) {
-                        const uint4 a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
-                        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+                        a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int t = 4 * g + k;
-                            pass[k] = t >= 1 && t < p.max_attempts && (unsigned long long)wv[k] + 1ull <= T;
-                            cnt += pass[k];
+                        for (int k = 0; k < 8; ++k) {
+                            const int t = 8 * g + k;
+                            // smallest radius word with this high half: (hi << 16); it must satisfy word + 1 <= T
+                            const bool ps = t >= 1 && t < p.max_attempts &&
+                                            ((unsigned long long)radius_hi16(a, (uint32_t)k) << 16) + 1ull <= T;
+                            passm |= (ps ? 1u : 0u) << k;
+                            cnt += ps;
                         }
                     }
                     if (__ballot_sync(0xffffffffu, cnt > 0) == 0u) {  // nothing passed (the usual outcome for a particle
@@ -227,8 +229,8 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
                     const int total = __shfl_sync(0xffffffffu, pre, 31);
                     int pos = qlen + pre - cnt;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (pass[k]) { qt[pos] = (unsigned short)(4 * g + k); qw[pos] = wv[k]; ++pos; }
+                    for (int k = 0; k < 8; ++k)
+                        if ((passm >> k) & 1u) { qt[pos] = (unsigned short)(8 * g + k); qw[pos] = (unsigned short)radius_hi16(a, (uint32_t)k); ++pos; }
                     qlen += total;
                     g0 += 32;
                     __syncwarp();
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
                     t = qt[e];
                     const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
                     double z0, z1, z2;
-                    normals3_from_words(qw[e], o, z0, z1, z2);
+                    normals3_from_words(radius_word((uint32_t)qw[e], o), o, z0, z1, z2);
                     ok = motion_candidate(p, sx, sy, sth, z0, z1, z2, c);
                 }
                 const unsigned okm = __ballot_sync(0xffffffffu, ok);

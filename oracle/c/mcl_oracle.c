@@ -196,15 +196,19 @@ double orc_uniform53(uint64_t seed, uint64_t step, uint64_t item, uint32_t sub, 
 }
 /* Three standard normals per (particle, attempt t): Box-Muller on 32-bit uniforms, u1 in (0,1],
  * u2 in [0,1):  z0 = R1 cos(2 pi u2), z1 = R1 sin(2 pi u2), z2 = R2 cos(2 pi u4), R = sqrt(-2 ln u).
- * The radius word of attempt t is word (t & 3) of the MOTION_R block (particle, step, t >> 2): four
- * consecutive attempts share one Philox call, which lets the GPU rejection loop screen four attempts
- * per call (|z0|, |z1| <= R1, so a small R1 cannot leave an all-blocked neighbourhood).  The other
- * three uniforms come from the MOTION block (particle, step, t). */
+ * The radius word of attempt t: high half = half-word (t & 7) of the MOTION_R block (particle, step, t >> 3)
+ * (eight consecutive attempts share one Philox call, which lets the GPU rejection loop screen eight attempts
+ * per call on the high half: |z0|, |z1| <= R1, so a small R1 cannot leave an all-blocked neighbourhood);
+ * low half = low half of word 3 of the MOTION block (particle, step, t), whose other three words give the
+ * remaining uniforms. */
 static inline void normals3(uint64_t seed, uint64_t step, uint64_t item, uint32_t attempt, double z[3]) {
     uint32_t a[4], o[4];
-    draw4(seed, step, item, attempt >> 2, ORC_STREAM_MOTION_R, a);
+    draw4(seed, step, item, attempt >> 3, ORC_STREAM_MOTION_R, a);
     draw4(seed, step, item, attempt, ORC_STREAM_MOTION, o);
-    const double u1 = ((double)a[attempt & 3u] + 1.0) * 2.3283064365386963e-10;
+    const uint32_t k = attempt & 7u, wk = a[k >> 1];
+    const uint32_t hi16 = (k & 1u) ? (wk >> 16) : (wk & 0xffffu);
+    const uint32_t wr = (hi16 << 16) | (o[3] & 0xffffu);
+    const double u1 = ((double)wr + 1.0) * 2.3283064365386963e-10;
     const double u2 = (double)o[0] * 2.3283064365386963e-10;
     const double u3 = ((double)o[1] + 1.0) * 2.3283064365386963e-10;
     const double u4 = (double)o[2] * 2.3283064365386963e-10;
