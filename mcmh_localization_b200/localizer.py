@@ -392,6 +392,17 @@ class Localizer:
             self._bind_stream()
             return self._aos(self.cur)
 
+    def particles_sample(self, max_count=2000):
+        """Every (n / max_count)-th particle with its weight, sliced on the device: what a visualisation topic needs
+        (the node builds one Marker per particle in Python, node:538-581 -- unusable at 1 M particles).
+        Returns ((k, 3) float64 poses, (k,) float32 weights)."""
+        with self._lock:
+            self._bind_stream()
+            stride = max(1, -(-self.n // max(1, int(max_count))))
+            x, y, t = (c[:self.n:stride] for c in self.cur)
+            poses = torch.stack((x, y, t), dim=1).cpu().numpy()
+            return poses, self.weights_t[:self.n:stride].cpu().numpy()
+
     def particles_prev(self):
         with self._lock:
             self._bind_stream()

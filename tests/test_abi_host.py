@@ -179,3 +179,12 @@ def test_likelihood_hot_loop_stays_on_the_uniform_datapath():
         assert ops.count("DFMA") == 4 * n_ev, name
         assert "F2I" not in ops and "DADD" not in ops, name
     assert checked >= 4
+
+
+def test_ros_adapter_example_is_valid_python():
+    """examples/ros_node_b200.py cannot run here (no ROS); keep it at least syntactically valid."""
+    import ast
+    src = open(os.path.join(ROOT, "examples", "ros_node_b200.py")).read()
+    tree = ast.parse(src)
+    names = {n.name for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+    assert {"B200LocalizerNode", "on_map", "on_odom", "on_scan", "publish_markers"} <= names

@@ -778,6 +778,11 @@ def test_localizer_production_step_runs_and_is_deterministic():
         outs.append((loc.particles(), est))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.isfinite(outs[0][1][3]).all()
+    # device-side sample for visualisation topics: every stride-th particle with its weight
+    poses, w = loc.particles_sample(300)
+    stride = -(-20000 // 300)
+    assert np.array_equal(poses, loc.particles()[::stride]) and np.array_equal(w, loc.weights()[::stride])
+    assert len(poses) <= 300
 
 
 @pytest.mark.parametrize("n", [1, 1000, 33333, 400_003])
