@@ -91,8 +91,10 @@ int mcl_set_scan_batch(mcl_handle *h, const float *h_ranges, const float *h_angl
 int mcl_use_scan(mcl_handle *h, int k);
 /* number of beams counted in valid_count (pu:123-124) for the current scan */
 int mcl_scan_valid_count(mcl_handle *h, int *valid_count);
-/* Likelihood-table staging: 0 = auto (shared-memory window when it fits), 1 = force global/L2
- * gather, 2 = force shared-memory window (error if it does not fit). For measurements. */
+/* Likelihood-table staging: 0 = auto (shared-memory window when it fits, int32 or byte-coded; else, for
+ * large particle counts, particles binned by map tile with one tile's neighbourhood staged at a time;
+ * else global/L2 gather), 1 = force global/L2 gather, 2 = force shared-memory window (error if it does
+ * not fit). For measurements. */
 int mcl_set_likelihood_path(mcl_handle *h, int path);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
@@ -287,7 +289,11 @@ int mcl_filter_update_chain(mcl_handle *h, int iters);
 int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]);                   /* node:586-597 */
 int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);                       /* node:488-492 */
 /* odom + scan -> predict (delta != NULL), update on pre-staged scan `scan_slot` (or the current scan
- * if < 0), estimate (to d_out18 and/or blocking into h_out16; both nullable), resample. */
+ * if < 0), estimate (to d_out18 and/or blocking into h_out16; both nullable), resample.
+ * With symmetric MH or plain MCL and MCL_RESAMPLE_FIXED_POINT the tail of the step runs through the fused
+ * kernels (6 launches per step; same results bit for bit as the calls above issued one by one; sharded
+ * handles exchange between the fused stages).  MCL_NO_FUSE=1 in the environment selects the stand-alone
+ * sequence (A/B measurements). */
 int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
                     double h_out16[16]);
 
