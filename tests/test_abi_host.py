@@ -163,7 +163,8 @@ def test_likelihood_hot_loop_stays_on_the_uniform_datapath():
     checked = 0
     for f in funcs:
         name = f.split("\n", 1)[0]
-        if not name.startswith("_Z15k_likelihood_g1ILb1E"):      # SMEM = true variants
+        # SMEM = true variants of the one-thread-per-particle kernel, and the tiled kernel (same slice code)
+        if not (name.startswith("_Z15k_likelihood_g1ILb1E") or name.startswith("_Z18k_likelihood_tiled")):
             continue
         checked += 1
         body = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4}\*/", l)]
@@ -178,7 +179,7 @@ def test_likelihood_hot_loop_stays_on_the_uniform_datapath():
         assert ops.count("LDCU") >= n_ev // 2 and ops.count("LDC") <= 1, (name, ops.count("LDCU"), ops.count("LDC"))
         assert ops.count("DFMA") == 4 * n_ev, name
         assert "F2I" not in ops and "DADD" not in ops, name
-    assert checked >= 4
+    assert checked >= 5
 
 
 def test_ros_adapter_example_is_valid_python():
