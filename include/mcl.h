@@ -309,6 +309,16 @@ int mcl_comm_init(mcl_handle *h, int rank, int world, void *d_mailbox, const uin
                   const uint64_t *h_peer_pose);
 int mcl_comm_status(mcl_handle *h, int *err);
 
+/* On one GPU mcl_filter_step runs the whole tail of the step (node:351-358 softmax x2, pu:208-236 MH accept,
+ * node:586-597 estimate sums, pu:416-446 resampling in either arithmetic) as ONE persistent cooperative kernel
+ * with grid-wide barriers (csrc/tail.cu).  Its waits are bounded; *err != 0 after a time-out (blocking call;
+ * the step's results are then invalid).  mcl_filter_step with a host estimate checks it itself.
+ * MCL_NO_TAIL=1 in the environment selects the multi-kernel sequence instead (A/B measurements). */
+int mcl_tail_status(mcl_handle *h, int *err);
+/* Test hook: systematic resampling (pu:416-446) of the given device weights through the resampling stages of
+ * that kernel alone; d_c (nullable) receives the running sums (n f32 in reference mode, n u64 in fixed point). */
+int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, double r, int mode, int32_t *d_idx, void *d_c);
+
 /* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */
 /* Random 4-byte gather rate, lookups/s: table_bytes resident in shared memory (where = 0) or in
  * global memory / L2 (where = 1); n_lookups per launch, iters launches timed with CUDA events. */

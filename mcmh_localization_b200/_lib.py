@@ -86,6 +86,8 @@ SIGNATURES = {
     "mcl_filter_step": (_i, [_vp, _pd, _i, _vp, _pd]),
     "mcl_comm_init": (_i, [_vp, _i, _i, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "mcl_comm_status": (_i, [_vp, _pi]),
+    "mcl_tail_status": (_i, [_vp, _pi]),
+    "mcl_debug_tail_resample": (_i, [_vp, _vp, _i64, _d, _i, _vp, _vp]),
     "mcl_bench_gather": (_i, [_vp, _i, _i64, _i64, _i, _pd]),
     "mcl_debug_seq_cumsum": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "mcl_launch_count": (_i64, [_vp]),

@@ -110,6 +110,10 @@ struct mcl_handle {
     size_t kld_bytes = 0;
     void *d_fused = nullptr;     // work area of the fused step tail (fused.cu)
     size_t fused_bytes = 0;
+    void *d_tail = nullptr;      // work area of the persistent step tail (tail.cu)
+    size_t tail_bytes = 0;
+    unsigned long long tail_bar = 0;   // grid-barrier arrivals consumed so far (base of the next launch)
+    int coop_launch = -1;        // cudaDevAttrCooperativeLaunch (-1: not queried yet)
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;
 
@@ -159,6 +163,11 @@ int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, const u
                            int tile, int64_t n_in, const uint64_t *d_totals_all, int rank, int world, double r,
                            int64_t n_global, int64_t n_per_rank, const double *d_x, const double *d_y,
                            const double *d_theta, const uint64_t *d_peer_ptrs);
+// tail.cu: the same tail as ONE persistent cooperative kernel, in either resampling arithmetic
+bool mcl_tail_available(mcl_handle *h, int64_t n);
+int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
+                  int32_t *idx, double *gx, double *gy, double *gt);
+const int *mcl_tail_err_ptr(mcl_handle *h);
 int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
                         const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
                         unsigned long long *d_keymax, bool *g1_used);

@@ -611,7 +611,11 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     *done = false;
     static int off = -1;
     if (off < 0) { const char *e = getenv("MCL_NO_FUSE"); off = (e && atoi(e)) ? 1 : 0; }
-    if (off || f->assym || f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
+    if (off || f->assym) return MCL_OK;
+    // single GPU: the whole tail is ONE persistent cooperative kernel (tail.cu), in either resampling arithmetic;
+    // sharded: four kernels with the peer-memory exchanges between them (fixed-point arithmetic only)
+    const bool tail = !f->comm && mcl_tail_available(h, f->n);
+    if (!tail && f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
     DeviceGuard guard(h->device);
     int rc = mcl_fused_prepare(h, f->n);
     if (rc) return rc;
@@ -647,6 +651,29 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
         res = cur;
     }
     u.step = f->tick;
+    if (tail) {
+        f->tick++;                                   // node:488-492 resample_lvr draws r
+        const double r = mcl_resample_offset(f->seed, f->tick, f->n);
+        const int dst = f->use_mh ? cur : spare;     // MH: the proposal set is free once the accept has read it
+        rc = mcl_tail_step(h, u, mcl_fused_keymax(h), f->resample_mode, r, f->idx, f->x[dst], f->y[dst], f->th[dst]);
+        if (rc) return rc;
+        // roles: particles = resampled set; the MH result (or, without MH, the old particles) becomes spare
+        f->cur = dst; f->spare = res;
+        if (d_out18) MCL_CUDA(h, cudaMemcpyAsync(d_out18, est, 18 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        if (h_out16) {
+            MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, est, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned + 20, mcl_tail_err_ptr(h), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            int terr = 0;
+            memcpy(&terr, h->h_pinned + 20, sizeof(int));
+            if (terr) return mcl_fail(h, MCL_ERR_CUDA, "step tail: a grid barrier / look-back wait timed out (mcl_tail_status)");
+            const double *o = h->h_pinned;
+            h_out16[0] = o[0]; h_out16[1] = o[1]; h_out16[2] = o[6]; h_out16[3] = o[7]; h_out16[4] = o[8];
+            for (int k = 0; k < 9; ++k) h_out16[5 + k] = o[9 + k];
+            h_out16[14] = 0; h_out16[15] = 0;
+        }
+        return MCL_OK;
+    }
     if (f->comm) { rc = comm_exchange(h, f, xp.keymax, 2, XCH_MAX_U64, xp.keymax); if (rc) return rc; }
     rc = mcl_fused_sumexp(h, u);
     if (rc) return rc;

@@ -69,57 +69,7 @@ __global__ void __launch_bounds__(32) k_cumsum_ref_f32(const float *__restrict__
 #define SEQ_ITEMS 8
 #define SEQ_TILE (SEQ_THREADS * SEQ_ITEMS)
 
-// increment if the incoming K is even / odd.  Increments saturate at SEQ_SAT (>= 2^25 > any in-binade K):
-// a saturated value means "the sum has left the binade", which is absorbing, so the composition stays
-// associative while everything fits in 32 bits (half the shuffles and registers of a 64-bit scan).
-#define SEQ_SAT 0x40000000u
-struct Pair64 { unsigned a0, a1; };
-
-__device__ __forceinline__ unsigned sat_add(unsigned a, unsigned b) { return min(a + b, SEQ_SAT); }   // a, b <= SEQ_SAT
-__device__ __forceinline__ Pair64 pair_compose(const Pair64 &f1, const Pair64 &f2) {   // first f1, then f2
-    Pair64 r;
-    r.a0 = sat_add(f1.a0, (f1.a0 & 1u) ? f2.a1 : f2.a0);
-    r.a1 = sat_add(f1.a1, ((1u + f1.a1) & 1u) ? f2.a1 : f2.a0);
-    return r;
-}
-__device__ __forceinline__ Pair64 pair_shfl_up(const Pair64 &v, int o) {
-    Pair64 r;
-    r.a0 = __shfl_up_sync(0xffffffffu, v.a0, o);
-    r.a1 = __shfl_up_sync(0xffffffffu, v.a1, o);
-    return r;
-}
-// element map for weight w when the running sum has unit exponent e (u = 2^(e-23), e >= -126)
-__device__ __forceinline__ Pair64 seq_decode(float w, int e) {
-    const unsigned b = __float_as_uint(w);
-    const unsigned ef = (b >> 23) & 0xffu, mf = b & 0x7fffffu;
-    Pair64 r; r.a0 = 0; r.a1 = 0;
-    if ((b & 0x7fffffffu) == 0u) return r;
-    const long long M = ef ? (long long)(mf | 0x800000u) : (long long)mf;
-    const int Ew = ef ? (int)ef - 127 : -126;
-    const int sh = e - Ew;
-    if (sh <= 0) {
-        const unsigned a = (-sh > 6) ? SEQ_SAT : (unsigned)min((long long)SEQ_SAT, M << (-sh));
-        r.a0 = a; r.a1 = a;
-    } else if (sh <= 24) {
-        const unsigned a = (unsigned)(M >> sh), rem = (unsigned)(M & ((1ll << sh) - 1)), half = 1u << (sh - 1);
-        if (rem < half) { r.a0 = a; r.a1 = a; }
-        else if (rem > half) { r.a0 = a + 1; r.a1 = a + 1; }
-        else { r.a0 = a + (a & 1u); r.a1 = a + ((1u + a) & 1u); }
-    }   // sh >= 25: w < u/2, the sum does not move
-    return r;
-}
-__device__ __forceinline__ int seq_exponent(float c) {      // unit exponent of c (denormals share e = -126)
-    const unsigned ef = (__float_as_uint(c) >> 23) & 0xffu;
-    return ef ? (int)ef - 127 : -126;
-}
-__device__ __forceinline__ long long seq_K(float c) {        // c = K * 2^(e-23)
-    const unsigned b = __float_as_uint(c);
-    const unsigned ef = (b >> 23) & 0xffu, mf = b & 0x7fffffu;
-    return ef ? (long long)(mf | 0x800000u) : (long long)mf;
-}
-__device__ __forceinline__ float seq_value(long long K, int e) {   // K < 2^24
-    return __uint_as_float((unsigned)(((long long)(e + 126) << 23) + K));
-}
+#include "seqsum.cuh"
 
 // w_eff[i] = divide ? w[i] / *div : w[i];  c_out (nullable) receives every partial sum, *total_out the last one
 __global__ void __launch_bounds__(SEQ_THREADS) k_seq_accumulate_exact(const float *__restrict__ w, int64_t n,
@@ -525,10 +475,12 @@ static int seq_accumulate(mcl_handle *h, const float *d_w, int64_t n, const floa
 }
 
 // idx[m] = min(first i in [0, limit] with c_i >= U_m, limit); U_m = r + m*step (two f64 roundings)
+// divide: U_m = r + m / n_out (pu:496 low_variance_resample_amcl) instead of r + m * (1 / n_out)
 __global__ void k_search_ref_f32(const float *__restrict__ c, int64_t limit, int64_t n_out, double r, double step,
-                                 int32_t *__restrict__ idx) {
+                                 int32_t *__restrict__ idx, bool divide = false) {
     for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < n_out; m += (int64_t)gridDim.x * blockDim.x) {
-        const double U = __dadd_rn(r, __dmul_rn((double)m, step));     // pu:440
+        const double U = divide ? __dadd_rn(r, __ddiv_rn((double)m, (double)n_out))
+                                : __dadd_rn(r, __dmul_rn((double)m, step));     // pu:440
         int64_t lo = 0, hi = limit;            // invariant: answer in [lo, hi]
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
@@ -724,6 +676,18 @@ extern "C" int mcl_resample_indices(mcl_handle *h, const float *d_w, int64_t n_i
             if (rc) return rc;
         }
         k_search_ref_f32<<<sblocks, 256, 0, h->stream>>>(c, limit, n_out, r, step, d_idx);
+        MCL_LAUNCH_CHECK(h);
+        return MCL_OK;
+    }
+    if (mode == MCL_RESAMPLE_AMCL_F32) {
+        // pu:486-502 low_variance_resample_amcl: the weights AS GIVEN (no normalisation), c a sequential f32 sum,
+        // U = r + m / target_size, walk bounded by len(particles) - 1
+        int rc = mcl_ensure_scratch(h, 64 + sizeof(float) * (size_t)n_in);
+        if (rc) return rc;
+        float *c = (float *)((char *)h->d_scratch + 64);
+        rc = seq_accumulate(h, d_w, n_in, nullptr, c, nullptr);
+        if (rc) return rc;
+        k_search_ref_f32<<<sblocks, 256, 0, h->stream>>>(c, n_in - 1, n_out, r, step, d_idx, true);
         MCL_LAUNCH_CHECK(h);
         return MCL_OK;
     }

@@ -1,0 +1,1070 @@
+// tail.cu -- the whole tail of a filter step in ONE persistent cooperative kernel:
+//   softmax x2 (node:351-358) -> MH accept (pu:208-236) -> estimate sums (node:586-597) -> systematic
+//   resampling (pu:416-446) in EITHER arithmetic: the reference's own (sequential f32 normalising sum, f32
+//   divide, sequential f32 running sum -- reproduced bit for bit) or the 64-bit fixed-point one.
+// One CTA per SM (1024 threads), grid-wide barriers between the stages instead of kernel boundaries:
+//   S1  exact 2^-40 sums of exp(s - max)                                  | barrier 1
+//   S2  weights, MH accept, new pose + weight, raw estimate sums per tile  | barrier 2
+//   S3  means; central sums; REFERENCE: exact sequential-f32 sum S of the weights (pass 1)
+//                            FIXED    : quantised tile totals              | barrier 3
+//   S4  REFERENCE: exact sequential-f32 running sums of w / S (pass 2);  FIXED: integer scan   | barrier 4
+//   S5  per output slot: search of the running sums (staged in shared memory) + pose gather
+//
+// The exact sequential-f32 passes.  c_i = fl32(c_{i-1} + w_i) is emulated with the integer maps of seqsum.cuh,
+// which need the binade of the running sum.  An fp64 prefix predicts it for every thread (8 consecutive
+// weights); threads whose prefix lies within 2^-11 (relative) of a power of two are not trusted: their
+// additions are replayed with real f32 adds.  Per tile a segmented scan composes the maps of every run of
+// trusted threads, so a tile is a short list of items (run map | replayed thread); one lane walks that list
+// from the tile's exact incoming sum, CHECKING every run (binade as predicted, no overflow) -- if a check fails
+// the tile is redone by the general restart loop, so the result never depends on the prediction.  Tiles are
+// chained by decoupled look-back (aggregate map of a clean tile | exact outgoing sum), so the serial part of a
+// pass is one short walk per binade crossing (~8 tiles at 1 M particles).
+// Every spin loop is bounded (~2 s): a lost peer sets hd->err instead of hanging the GPU.
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "seqsum.cuh"
+
+#define TL_THREADS 1024
+#define TL_WARPS 32
+#define TL_MAX_IPT 8
+#define TL_MAX_ROUNDS 64
+#define TL_MAX_ITEMS 160
+#define TL_MAX_SERIAL 256
+#define TL_NBAR 4
+#define TL_SPIN_LIMIT 4000000000ll
+#define TL_SOFTMAX_FIX 1099511627776.0   // 2^40 (mh_softmax.cu)
+#define TL_DELTA 4.8828125e-4            // 2^-11: distrust margin around a binade boundary
+#define TL_STAGE_BYTES 65536
+#define TL_COARSE_MAX 2048
+
+#define TL_F_AGG 1ull
+#define TL_F_INC 2ull
+#define TL_F_NOAGG 3ull
+#define TL_SERIAL_MARK (-100000)
+#define TL_FULL 0xffffffffu
+
+struct TailHeader {              // device, zero-initialised once
+    unsigned long long bar;      // grid barrier counter (monotone; the host tracks the base)
+    int err, pad;
+    float S, pad2;               // reference mode: exact sequential f32 sum of the weights (pu:430)
+    unsigned long long total;    // fixed-point mode: total of the quantised weights
+};
+
+struct TailArgs {
+    TailHeader *hd;
+    unsigned long long *keymax;  // [2] order-preserving keys of max(score), left by the likelihood kernel
+    unsigned long long bar_base;
+    int64_t n;
+    int nt, ipt, tile, use_mh;
+    int stop;                    // debug: return after stage `stop` (0 = run everything)
+    int raw;                     // test hook: w_out holds the weights already, no poses (S1, estimate, gather skipped)
+    const float *s_post, *s_pre;
+    float *w_out;
+    const double *px, *py, *pt, *ox, *oy, *ot;
+    double *nx, *ny, *nth;
+    uint64_t seed, step, first_index;
+    unsigned long long *part_q;  // [2][grid]
+    double *part_m;              // [nt][8]: six raw sums, weight maximum
+    double *part_c;              // [nt][9]
+    unsigned long long *st1, *st2;   // [nt] look-back records of the two exact passes
+    void *C;                     // [n]  f32 running sums (reference) / u64 cumulative sums (fixed)
+    void *tend;                  // [nt] value of C at the end of every tile
+    unsigned long long *ttot;    // [nt] fixed: tile totals
+    double *est18;
+    double r, rstep;
+    int32_t *idx;
+    double *gx, *gy, *gt;
+};
+
+struct TlItems {
+    int e[TL_MAX_ITEMS];             // unit exponent of a run, or TL_SERIAL_MARK
+    Pair64 map[TL_MAX_ITEMS];        // run: composed map; replayed thread: .a0 = slot in sw
+    float c[TL_MAX_ITEMS];           // exact sum entering the item (written by the walker)
+    float sw[TL_MAX_SERIAL * TL_MAX_IPT];
+};
+
+struct TlShared {
+    double d[9][TL_WARPS];
+    double par[12];
+    unsigned long long q[2][TL_WARPS];
+    unsigned long long sumq[2];
+    Pair64 pw[TL_WARPS];
+    int pwf[TL_WARPS];
+    int cnt[TL_WARPS];
+    int code[TL_THREADS];
+    Pair64 inc[TL_THREADS];
+    TlItems it;
+    double ownP[TL_MAX_ROUNDS], ownT[TL_MAX_ROUNDS];
+    unsigned long long ownE[TL_MAX_ROUNDS];
+    float c_in, c_out, cseg;
+    int fail, nitems, nserial;
+    long long cross;
+    int64_t seg0;
+    int64_t irange[2];
+};
+
+// ------------------------------------------------------------------------------------------------ primitives
+// Warp / lane index through inline PTX: nvcc 12.9 folds `&arr[tid >> 5]` to `base + (tid >> 2)` under a dominating
+// `lane == 0` test and then reuses that address for a `lane == 31` store of another helper (misaligned address at
+// run time); the opaque shifts keep the address computations apart.
+__device__ __forceinline__ int tl_warp() {
+    int w;
+    asm("shr.u32 %0, %1, 5;" : "=r"(w) : "r"(threadIdx.x));
+    return w;
+}
+__device__ __forceinline__ int tl_lane() {
+    int l;
+    asm("and.b32 %0, %1, 31;" : "=r"(l) : "r"(threadIdx.x));
+    return l;
+}
+__device__ __forceinline__ unsigned long long tl_ld_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tl_st_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void tl_grid_barrier(const TailArgs &a, int k) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long target = a.bar_base + (unsigned long long)k * gridDim.x;
+        __threadfence();
+        atomicAdd(&a.hd->bar, 1ull);
+        const long long t0 = clock64();
+        while (tl_ld_acquire(&a.hd->bar) < target) {
+            if (clock64() - t0 > TL_SPIN_LIMIT) { a.hd->err = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float tl_softmax_num(float s, float m) { return (float)exp((double)__fsub_rn(s, m)); }
+__device__ __forceinline__ unsigned long long tl_quantise(float w, double scale) {
+    const double v = __dmul_rn((double)w, scale);
+    return v > 0.0 ? __double2ull_rz(v) : 0ull;     // negative / NaN weights count as 0
+}
+__device__ __forceinline__ unsigned long long tl_warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(TL_FULL, v, o);
+    return v;
+}
+
+// sums of K doubles over the block; the totals are returned to every thread (fixed tree: deterministic)
+template <int K>
+__device__ __forceinline__ void tl_block_sum(double (&v)[K], TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < K; ++k) sh.d[k][warp] = v[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double t = warp_sum(sh.d[k][lane]);
+            if (lane == 0) sh.par[k] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = sh.par[k];
+    __syncthreads();
+}
+__device__ __forceinline__ float tl_block_max(float v, TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+    v = warp_max(v);
+    if (lane == 0) sh.d[0][warp] = (double)v;
+    __syncthreads();
+    if (warp == 0) {
+        const float t = warp_max((float)sh.d[0][lane]);
+        if (lane == 0) sh.par[0] = (double)t;
+    }
+    __syncthreads();
+    const float r = (float)sh.par[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ void tl_block_sum_u64x2(unsigned long long &a0, unsigned long long &a1, TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+    a0 = tl_warp_sum_u64(a0); a1 = tl_warp_sum_u64(a1);
+    if (lane == 0) { sh.q[0][warp] = a0; sh.q[1][warp] = a1; }
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long t0 = tl_warp_sum_u64(sh.q[0][lane]), t1 = tl_warp_sum_u64(sh.q[1][lane]);
+        if (lane == 0) { sh.sumq[0] = t0; sh.sumq[1] = t1; }
+    }
+    __syncthreads();
+    a0 = sh.sumq[0]; a1 = sh.sumq[1];
+    __syncthreads();
+}
+// exclusive scans over the block's threads (thread order); `total` is returned to every thread
+__device__ __forceinline__ double tl_block_excl_scan_d(double v, double &total, TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(TL_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sh.d[0][warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        double t = sh.d[0][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(TL_FULL, t, o); if (lane >= o) t += u; }
+        sh.d[1][lane] = t;
+    }
+    __syncthreads();
+    const double off = warp ? sh.d[1][warp - 1] : 0.0;
+    total = sh.d[1][TL_WARPS - 1];
+    const double r = off + inc - v;
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ unsigned long long tl_block_excl_scan_u64(unsigned long long v, unsigned long long &total,
+                                                                      TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(TL_FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sh.q[0][warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long t = sh.q[0][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(TL_FULL, t, o); if (lane >= o) t += u; }
+        sh.q[1][lane] = t;
+    }
+    __syncthreads();
+    const unsigned long long off = warp ? sh.q[1][warp - 1] : 0ull;
+    total = sh.q[1][TL_WARPS - 1];
+    const unsigned long long r = off + inc - v;
+    __syncthreads();
+    return r;
+}
+// exclusive scan of element maps (first the earlier thread, then the later one); aggregate to every thread
+__device__ __forceinline__ Pair64 tl_block_excl_scan_pair(const Pair64 &mine, Pair64 &aggregate, TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+    Pair64 inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Pair64 t = pair_shfl_up(inc, o);
+        if (lane >= o) inc = pair_compose(t, inc);
+    }
+    if (lane == 31) sh.pw[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        Pair64 t = sh.pw[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const Pair64 u = pair_shfl_up(t, o);
+            if (lane >= o) t = pair_compose(u, t);
+        }
+        sh.pw[lane] = t;                       // inclusive over warps
+    }
+    __syncthreads();
+    Pair64 excl = pair_shfl_up(inc, 1);
+    if (lane == 0) { excl.a0 = 0; excl.a1 = 0; }
+    if (warp > 0) excl = pair_compose(sh.pw[warp - 1], excl);
+    aggregate = sh.pw[TL_WARPS - 1];
+    __syncthreads();
+    return excl;
+}
+
+__device__ __forceinline__ long long tl_apply(long long K, const Pair64 &m) { return K + ((K & 1) ? m.a1 : m.a0); }
+
+// ------------------------------------------------------------------------------------------------ look-back
+__device__ __forceinline__ unsigned long long tl_rec_agg(int e, const Pair64 &m) {
+    return (TL_F_AGG << 62) | ((unsigned long long)((e + 126) & 0xff) << 52) | ((unsigned long long)m.a0 << 26) |
+           (unsigned long long)m.a1;
+}
+__device__ __forceinline__ unsigned long long tl_rec_inc(float c) { return (TL_F_INC << 62) | (unsigned long long)__float_as_uint(c); }
+
+// exact sum entering tile v (warp 0, all lanes; every lane returns the same value)
+__device__ float tl_lookback(unsigned long long *st, int v, int *err) {
+    const int lane = tl_lane();
+    if (v == 0) return 0.0f;
+    const long long t0 = clock64();
+    int top = v - 1, start = -1;
+    float c = 0.0f;
+    while (true) {                                       // backwards: the nearest tile with an exact outgoing sum
+        const int q = top - lane;
+        unsigned long long rec = TL_F_INC << 62;         // "tile -1": the sum starts at 0
+        bool dead = false;
+        if (q >= 0) {
+            while (true) {
+                rec = tl_ld_acquire(st + q);
+                const unsigned f = (unsigned)(rec >> 62);
+                if (f == TL_F_AGG || f == TL_F_INC) break;
+                if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
+            }
+        }
+        if (__any_sync(TL_FULL, dead)) { if (lane == 0) *err = 2; return 0.0f; }
+        const unsigned incm = __ballot_sync(TL_FULL, (rec >> 62) == TL_F_INC);
+        if (incm) {
+            const int j = __ffs(incm) - 1;
+            start = top - j;
+            c = __uint_as_float((unsigned)__shfl_sync(TL_FULL, rec, j));
+            break;
+        }
+        top -= 32;
+    }
+    for (int base = start + 1; base < v; base += 32) {   // forwards: apply the aggregate maps, checking each
+        const int q = base + lane;
+        unsigned long long rec = 0;
+        if (q < v) rec = tl_ld_acquire(st + q);
+        const int cnt = min(32, v - base);
+        for (int l = 0; l < cnt; ++l) {
+            unsigned long long r = __shfl_sync(TL_FULL, rec, l);
+            if ((r >> 62) == TL_F_AGG) {
+                const int e = (int)((r >> 52) & 0xff) - 126;
+                Pair64 m;
+                m.a0 = (unsigned)((r >> 26) & 0x3ffffffull); m.a1 = (unsigned)(r & 0x3ffffffull);
+                const long long Kn = tl_apply(seq_K(c), m);
+                if (seq_exponent(c) == e && Kn < (1ll << 24)) { c = seq_value(Kn, e); continue; }
+                // predicted binade wrong for that tile: it will find out itself and publish its exact sum
+                bool dead = false;
+                while (true) {
+                    r = tl_ld_acquire(st + base + l);
+                    if ((r >> 62) == TL_F_INC) break;
+                    if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
+                }
+                if (dead) { if (lane == 0) *err = 3; return 0.0f; }
+            }
+            c = __uint_as_float((unsigned)r);
+        }
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ exact tile
+// general path: exact running sums of one tile from c_start, one block scan per binade crossing
+template <bool WRITE>
+__device__ float tl_tile_general(const float (&wv)[TL_MAX_IPT], int ipt, int64_t first, int64_t tile_lo, int64_t end,
+                                 float c_start, float *C, TlShared &sh) {
+    const long long NONE = 0x7fffffffffffffffll;
+    if (threadIdx.x == 0) { sh.cseg = c_start; sh.seg0 = tile_lo; }
+    __syncthreads();
+    while (true) {
+        const float c0 = sh.cseg;
+        const int64_t seg0 = sh.seg0;
+        const int e = seq_exponent(c0);
+        const long long K0 = seq_K(c0);
+        Pair64 run; run.a0 = 0; run.a1 = 0;
+#pragma unroll
+        for (int k = 0; k < TL_MAX_IPT; ++k) {
+            const int64_t i = first + k;
+            if (k < ipt && i >= seg0 && i < end) run = pair_compose(run, seq_decode(wv[k], e));
+        }
+        if (threadIdx.x == 0) sh.cross = NONE;
+        Pair64 agg;
+        const Pair64 excl = tl_block_excl_scan_pair(run, agg, sh);
+        const long long Kstart = tl_apply(K0, excl);
+        long long my_cross = NONE, Kb = 0, Kw = Kstart;
+#pragma unroll
+        for (int k = 0; k < TL_MAX_IPT; ++k) {
+            const int64_t i = first + k;
+            if (k < ipt && i >= seg0 && i < end) {
+                const long long Kn = tl_apply(Kw, seq_decode(wv[k], e));
+                if (Kn >= (1ll << 24) && my_cross == NONE) { my_cross = i; Kb = Kw; }
+                Kw = Kn;
+            }
+        }
+        if (my_cross != NONE) atomicMin((unsigned long long *)&sh.cross, (unsigned long long)my_cross);
+        __syncthreads();
+        const long long cross = sh.cross;
+        const int64_t seg_end = cross == NONE ? end : (int64_t)cross;
+        if (WRITE) {
+            Kw = Kstart;
+#pragma unroll
+            for (int k = 0; k < TL_MAX_IPT; ++k) {
+                const int64_t i = first + k;
+                if (k < ipt && i >= seg0 && i < end) {
+                    Kw = tl_apply(Kw, seq_decode(wv[k], e));
+                    if (i < seg_end) C[i] = seq_value(Kw, e);
+                }
+            }
+        }
+        if (cross == NONE) {
+            const float r = seq_value(tl_apply(K0, agg), e);
+            __syncthreads();
+            return r;
+        }
+        if (my_cross == cross) {                      // this thread owns the addition that leaves the binade
+            const float cb = seq_value(Kb, e);
+            float cn = cb;
+#pragma unroll
+            for (int k = 0; k < TL_MAX_IPT; ++k)
+                if (first + k == cross) cn = __fadd_rn(cb, wv[k]);
+            if (WRITE) C[cross] = cn;
+            sh.cseg = cn;
+            sh.seg0 = cross + 1;
+        }
+        __syncthreads();
+        if (sh.seg0 >= end) {
+            const float r = sh.cseg;
+            __syncthreads();
+            return r;
+        }
+    }
+}
+
+// One exact pass over the tiles this CTA owns (v = blockIdx.x, + gridDim.x, ...).  P2: the weights are divided
+// by S first (pu:430) and every running sum is written to C (pu:436-443); otherwise only the total is wanted.
+template <bool P2>
+__device__ void tl_exact_pass(const TailArgs &a, TlShared &sh, float S) {
+    unsigned long long *st = P2 ? a.st2 : a.st1;
+    float *C = (float *)a.C;
+    const int t = threadIdx.x, lane = tl_lane(), warp = tl_warp();
+    const double invS = P2 ? 1.0 / (double)S : 1.0;
+    int rd = 0;
+    for (int v = blockIdx.x; v < a.nt; v += gridDim.x, ++rd) {
+        const int64_t tile_lo = (int64_t)v * a.tile;
+        const int64_t end = min(a.n, tile_lo + a.tile);
+        const int64_t first = tile_lo + (int64_t)t * a.ipt;
+        float wv[TL_MAX_IPT];
+        double ls = 0.0;
+#pragma unroll
+        for (int k = 0; k < TL_MAX_IPT; ++k) {
+            const int64_t i = first + k;
+            float w = 0.0f;                              // padding: + 0 leaves every sum unchanged
+            if (k < a.ipt && i < end) { w = a.w_out[i]; if (P2) w = __fdiv_rn(w, S); }
+            wv[k] = w;
+            ls += (double)w;
+        }
+        // predicted (fp64) sum entering / leaving this thread's weights
+        double ttot;
+        const double pe = tl_block_excl_scan_d(ls, ttot, sh);
+        if (a.stop == 33) return;
+        const double Pt = sh.ownP[rd] * invS + pe, Qt = Pt + ls;
+        int et = 0;
+        bool serial = true;
+        if (Pt > 0.0) {
+            et = ilogb(Pt);
+            const double lo = ldexp(1.0, et);
+            serial = !(et >= -126 && et < 127 && Pt >= lo * (1.0 + TL_DELTA) && Qt <= 2.0 * lo * (1.0 - TL_DELTA));
+        }
+        const int code = serial ? (TL_SERIAL_MARK - t) : et;
+        sh.code[t] = code;
+        __syncthreads();
+        if (a.stop == 34) return;
+        const bool head = t == 0 || serial || sh.code[t - 1] != code;
+        const bool last = t == TL_THREADS - 1 || serial || sh.code[t + 1] != code;
+        Pair64 F; F.a0 = 0; F.a1 = 0;
+        if (!serial) {
+#pragma unroll
+            for (int k = 0; k < TL_MAX_IPT; ++k) F = pair_compose(F, seq_decode(wv[k], et));
+        }
+        // segmented inclusive scan of the maps (segments start at heads) + counts of heads / replayed threads
+        Pair64 inc = F;
+        int hf = head ? 1 : 0;
+        int cnt = (head ? 1 : 0) | (serial ? 0x10000 : 0);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const Pair64 p2 = pair_shfl_up(inc, o);
+            const int h2 = __shfl_up_sync(TL_FULL, hf, o);
+            const int c2 = __shfl_up_sync(TL_FULL, cnt, o);
+            if (lane >= o) {
+                if (!hf) inc = pair_compose(p2, inc);
+                hf |= h2;
+                cnt += c2;
+            }
+        }
+        if (lane == 31) { sh.pw[warp] = inc; sh.pwf[warp] = hf; sh.cnt[warp] = cnt; }
+        __syncthreads();
+        if (warp == 0) {
+            Pair64 p = sh.pw[lane];
+            int f = sh.pwf[lane], c = sh.cnt[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const Pair64 p2 = pair_shfl_up(p, o);
+                const int h2 = __shfl_up_sync(TL_FULL, f, o);
+                const int c2 = __shfl_up_sync(TL_FULL, c, o);
+                if (lane >= o) {
+                    if (!f) p = pair_compose(p2, p);
+                    f |= h2;
+                    c += c2;
+                }
+            }
+            sh.pw[lane] = p; sh.cnt[lane] = c;
+        }
+        __syncthreads();
+        if (warp > 0) {
+            if (!hf) inc = pair_compose(sh.pw[warp - 1], inc);
+            cnt += sh.cnt[warp - 1];
+        }
+        if (a.stop == 35) return;
+        const int total_cnt = sh.cnt[TL_WARPS - 1];
+        const int nitems = total_cnt & 0xffff, nserial = total_cnt >> 16;
+        const bool overflow = nitems > TL_MAX_ITEMS || nserial > TL_MAX_SERIAL;
+        const int my_item = (cnt & 0xffff) - 1;
+        sh.inc[t] = inc;
+        if (!overflow && last) {
+            if (serial) {
+                const int slot = (cnt >> 16) - 1;
+                sh.it.e[my_item] = TL_SERIAL_MARK;
+                sh.it.map[my_item].a0 = (unsigned)slot;
+#pragma unroll
+                for (int k = 0; k < TL_MAX_IPT; ++k) sh.it.sw[slot * TL_MAX_IPT + k] = wv[k];
+            } else {
+                sh.it.e[my_item] = et;
+                sh.it.map[my_item] = inc;                // composed map of the whole run
+            }
+        }
+        __syncthreads();
+        if (a.stop == 36) return;
+        Pair64 ex; ex.a0 = 0; ex.a1 = 0;                 // map from the head of my run up to (excluding) me
+        if (!head) ex = sh.inc[t - 1];
+        const bool clean_tile = !overflow && nitems == 1 && sh.it.e[0] != TL_SERIAL_MARK &&
+                                sh.it.map[0].a0 < (1u << 24) && sh.it.map[0].a1 < (1u << 24);
+        if (warp == 0) {
+            if (lane == 0) tl_st_release(st + v, clean_tile ? tl_rec_agg(sh.it.e[0], sh.it.map[0]) : (TL_F_NOAGG << 62));
+            const float c_in = tl_lookback(st, v, &a.hd->err);
+            if (lane == 0) {
+                float c = c_in;
+                int fail = overflow ? 1 : 0;
+                if (!fail) {
+                    for (int it = 0; it < nitems; ++it) {
+                        sh.it.c[it] = c;
+                        const int e = sh.it.e[it];
+                        if (e == TL_SERIAL_MARK) {
+                            const float *w8 = sh.it.sw + sh.it.map[it].a0 * TL_MAX_IPT;
+#pragma unroll
+                            for (int k = 0; k < TL_MAX_IPT; ++k) c = __fadd_rn(c, w8[k]);
+                        } else {
+                            const long long Kn = tl_apply(seq_K(c), sh.it.map[it]);
+                            if (seq_exponent(c) != e || Kn >= (1ll << 24)) { fail = 1; break; }
+                            c = seq_value(Kn, e);
+                        }
+                    }
+                }
+                if (!fail) tl_st_release(st + v, tl_rec_inc(c));     // the chain goes on before this tile writes
+                sh.c_in = c_in; sh.c_out = c; sh.fail = fail;
+            }
+        }
+        __syncthreads();
+        if (a.stop == 37) return;
+        float c_out = sh.c_out;
+        if (sh.fail) {                                   // prediction off (or too many pieces): general path
+            c_out = tl_tile_general<P2>(wv, a.ipt, first, tile_lo, end, sh.c_in, C, sh);
+            if (t == 0) tl_st_release(st + v, tl_rec_inc(c_out));
+        } else if (P2) {
+            const float cs = sh.it.c[my_item];
+            if (serial) {
+                float c = cs;
+#pragma unroll
+                for (int k = 0; k < TL_MAX_IPT; ++k) {
+                    const int64_t i = first + k;
+                    c = __fadd_rn(c, wv[k]);
+                    if (k < a.ipt && i < end) C[i] = c;
+                }
+            } else {
+                long long K = tl_apply(seq_K(cs), ex);
+#pragma unroll
+                for (int k = 0; k < TL_MAX_IPT; ++k) {
+                    const int64_t i = first + k;
+                    K = tl_apply(K, seq_decode(wv[k], et));
+                    if (k < a.ipt && i < end) C[i] = seq_value(K, et);
+                }
+            }
+        }
+        if (t == 0) {
+            if (P2) ((float *)a.tend)[v] = c_out;
+            else if (v == a.nt - 1) a.hd->S = c_out;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ search helpers
+template <bool REF> struct TlCum;
+template <> struct TlCum<true> {
+    typedef float T;
+    typedef double Key;
+    static __device__ __forceinline__ bool gt(double U, float c) { return U > (double)c; }          // pu:441 "U > c"
+};
+template <> struct TlCum<false> {
+    typedef unsigned long long T;
+    typedef unsigned long long Key;
+    static __device__ __forceinline__ bool gt(unsigned long long T_, unsigned long long c) { return T_ > c; }
+};
+template <bool REF>
+__device__ __forceinline__ typename TlCum<REF>::Key tl_key(int64_t m, double r, double rstep, double totd);
+template <>
+__device__ __forceinline__ double tl_key<true>(int64_t m, double r, double rstep, double) {
+    return __dadd_rn(r, __dmul_rn((double)m, rstep));                                              // pu:440
+}
+template <>
+__device__ __forceinline__ unsigned long long tl_key<false>(int64_t m, double r, double rstep, double totd) {
+    const double U = __dadd_rn(r, __dmul_rn((double)m, rstep));
+    const double t = ceil(__dmul_rn(U, totd));
+    return t >= 18446744073709551616.0 ? 0xffffffffffffffffull : (t > 0.0 ? __double2ull_rz(t) : 0ull);
+}
+
+// first i in [lo, hi] with !(key > C[i]), else hi; one warp, 32 probes per round
+template <bool REF>
+__device__ int64_t tl_warp_search(const typename TlCum<REF>::T *C, int64_t lo, int64_t hi, typename TlCum<REF>::Key key) {
+    const int lane = tl_lane();
+    while (lo < hi) {
+        const int64_t span = hi - lo;
+        const int64_t p = lo + ((int64_t)lane * span) / 32;                  // p_0 = lo, p_31 < hi
+        const bool g = TlCum<REF>::gt(key, __ldcg(C + p));
+        const unsigned m = __ballot_sync(TL_FULL, g);
+        const int nt = __popc(m);                                            // predicates are monotone: true...false
+        if (nt == 0) { hi = lo; break; }
+        const int64_t p_last_true = lo + ((int64_t)(nt - 1) * span) / 32;
+        const int64_t p_first_false = nt < 32 ? lo + ((int64_t)nt * span) / 32 : hi;
+        lo = p_last_true + 1;
+        hi = p_first_false;
+        if (lo > hi) lo = hi;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <bool MH, bool REF>
+__global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
+    typedef typename TlCum<REF>::T CT;
+    typedef typename TlCum<REF>::Key KeyT;
+    __shared__ TlShared sh;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    const int64_t n = a.n;
+
+    // ---- S1: sums of the softmax numerators (node:355-357), exact 2^-40 integers ------------------------------
+    const unsigned key0 = (unsigned)((volatile unsigned long long *)a.keymax)[0];
+    const unsigned key1 = MH ? (unsigned)((volatile unsigned long long *)a.keymax)[1] : 0u;
+    const float m_post = key0 ? mcl_float_of_key(key0) : -FLT_MAX;
+    const float m_pre = key1 ? mcl_float_of_key(key1) : -FLT_MAX;
+    for (int v = b; v < a.nt; v += G) {                  // look-back records of both passes start empty
+        if (t == 0) { a.st1[v] = 0ull; a.st2[v] = 0ull; }
+    }
+    const bool raw = a.raw != 0;
+    if (!raw) {
+        unsigned long long acc0 = 0, acc1 = 0;
+        for (int v = b; v < a.nt; v += G) {
+            const int64_t base = (int64_t)v * a.tile + t;
+            for (int k = 0; k < a.ipt; ++k) {
+                const int64_t i = base + (int64_t)k * TL_THREADS;
+                if (i < n) {
+                    acc0 += __double2ull_rz(__dmul_rn((double)tl_softmax_num(a.s_post[i], m_post), TL_SOFTMAX_FIX));
+                    if (MH) acc1 += __double2ull_rz(__dmul_rn((double)tl_softmax_num(a.s_pre[i], m_pre), TL_SOFTMAX_FIX));
+                }
+            }
+        }
+        tl_block_sum_u64x2(acc0, acc1, sh);
+        if (t == 0) { a.part_q[b] = acc0; a.part_q[G + b] = acc1; }
+    }
+    if (a.stop == 1) return;
+    tl_grid_barrier(a, 1);
+    float sum_post = 1.0f, sum_pre = 1.0f;
+    if (!raw) {
+        unsigned long long q0 = 0, q1 = 0;
+        for (int u = t; u < G; u += TL_THREADS) { q0 += __ldcg(a.part_q + u); q1 += __ldcg(a.part_q + G + u); }
+        tl_block_sum_u64x2(q0, q1, sh);
+        // sum as f32 of the exact integer (node:356-357: f32 divide by the f32-rounded sum)
+        sum_post = (float)((double)q0 / TL_SOFTMAX_FIX);
+        sum_pre = MH ? (float)((double)q1 / TL_SOFTMAX_FIX) : 1.0f;
+        if (b == 0 && t == 0) { a.keymax[0] = 0ull; a.keymax[1] = 0ull; }    // every CTA has read the keys
+    }
+
+    // ---- S2: weights (node:356-357), MH accept (pu:229-233), raw estimate sums (node:586-589), weight maximum ---
+    for (int v = b; v < a.nt; v += G) {
+        double s6[6] = {0, 0, 0, 0, 0, 0};
+        float wmax = 0.0f;
+        const int64_t base = (int64_t)v * a.tile + t;
+#pragma unroll 2
+        for (int k = 0; k < a.ipt; ++k) {
+            const int64_t i = base + (int64_t)k * TL_THREADS;
+            if (i >= n) break;
+            if (raw) {
+                const float w = a.w_out[i];
+                s6[0] += (double)w;
+                wmax = fmaxf(wmax, w);
+                continue;
+            }
+            const float p_new = __fdiv_rn(tl_softmax_num(a.s_post[i], m_post), sum_post);
+            double x = a.px[i], y = a.py[i], th = a.pt[i];
+            float w = p_new;
+            if (MH) {
+                const float p_old = __fdiv_rn(tl_softmax_num(a.s_pre[i], m_pre), sum_pre);
+                double alpha = 1.0;
+                if (p_old > 0.f) {
+                    const double q = (double)__fdiv_rn(p_new, p_old);          // f32 divide, promoted
+                    alpha = (q < 1.0) ? q : 1.0;
+                }
+                const uint4 o = philox_draw4(a.seed, a.step, a.first_index + (uint64_t)i, 0u, MCL_STREAM_MH);
+                const bool acc = u53_from(o.x, o.y) < alpha;
+                if (!acc) { x = a.ox[i]; y = a.oy[i]; th = a.ot[i]; w = p_old; }
+                a.nx[i] = x; a.ny[i] = y; a.nth[i] = th;
+            }
+            a.w_out[i] = w;
+            const double wi = (double)w;
+            double sn, cs;
+            sincos(th, &sn, &cs);
+            s6[0] += wi; s6[1] += wi * wi; s6[2] += wi * x; s6[3] += wi * y; s6[4] += wi * cs; s6[5] += wi * sn;
+            wmax = fmaxf(wmax, w);
+        }
+        tl_block_sum<6>(s6, sh);
+        wmax = tl_block_max(wmax, sh);
+        if (t == 0) {
+            double *pm = a.part_m + (size_t)v * 8;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pm[k] = s6[k];
+            pm[6] = (double)wmax;
+        }
+    }
+    if (a.stop == 2) return;
+    tl_grid_barrier(a, 2);
+
+    // ---- S3: population sums (same order in every CTA), means, central sums; first resampling pass ------------
+    double mx, my, mt, scale = 0.0;
+    {
+        double tv[6] = {0, 0, 0, 0, 0, 0};
+        float wm = 0.0f;
+        for (int u = t; u < a.nt; u += TL_THREADS) {
+            const double *pm = a.part_m + (size_t)u * 8;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tv[k] += __ldcg(pm + k);
+            wm = fmaxf(wm, (float)__ldcg(pm + 6));
+        }
+        tl_block_sum<6>(tv, sh);
+        wm = tl_block_max(wm, sh);
+        mx = tv[2] / tv[0]; my = tv[3] / tv[0]; mt = atan2(tv[5], tv[4]);      // np.average; arctan2(sin, cos)
+        if (!REF) {
+            int e = 0;
+            if (wm > 0.0f) frexp((double)wm, &e);
+            int lg = 0;
+            while (((int64_t)1 << lg) < n) ++lg;
+            scale = ldexp(1.0, 62 - lg - e);               // resample.cu k_wmax, oracle orc_resample_scale
+        }
+        if (b == 0 && t == 0 && !raw) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.est18[k] = tv[k];
+            a.est18[6] = mx; a.est18[7] = my; a.est18[8] = mt;
+        }
+        if (REF) {
+            // fp64 prefix of the tile sums of w: the prediction the exact passes start from
+            double carry = 0.0;
+            for (int base = 0; base < a.nt; base += TL_THREADS) {
+                const int u = base + t;
+                const double val = u < a.nt ? __ldcg(a.part_m + (size_t)u * 8) : 0.0;
+                double tot;
+                const double ex = tl_block_excl_scan_d(val, tot, sh);
+                if (u < a.nt && u % G == b) { sh.ownP[u / G] = carry + ex; sh.ownT[u / G] = val; }
+                carry += tot;
+            }
+            __syncthreads();
+        }
+    }
+    if (a.stop == 31) return;
+    for (int v = b; v < a.nt && !raw; v += G) {          // central sums (node:590-597, pu:69-83)
+        double s9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int64_t base = (int64_t)v * a.tile + t;
+        for (int k = 0; k < a.ipt; ++k) {
+            const int64_t i = base + (int64_t)k * TL_THREADS;
+            if (i >= n) break;
+            const double wi = (double)a.w_out[i];
+            const double dx = a.nx[i] - mx, dy = a.ny[i] - my;
+            const double dt = (double)(float)normalize_angle_dev(__dadd_rn(a.nth[i], -mt));   // pu:80-82
+            s9[0] += wi * dx; s9[1] += wi * dy; s9[2] += wi * dt;
+            s9[3] += wi * dx * dx; s9[4] += wi * dx * dy; s9[5] += wi * dx * dt;
+            s9[6] += wi * dy * dy; s9[7] += wi * dy * dt; s9[8] += wi * dt * dt;
+        }
+        tl_block_sum<9>(s9, sh);
+        if (t == 0) {
+            double *pc = a.part_c + (size_t)v * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) pc[k] = s9[k];
+        }
+    }
+    if (REF) {
+        tl_exact_pass<false>(a, sh, 1.0f);               // pu:430 np.sum(weights): sequential f32
+    } else {
+        for (int v = b; v < a.nt; v += G) {
+            const int64_t first = (int64_t)v * a.tile + (int64_t)t * a.ipt, end = min(n, (int64_t)(v + 1) * a.tile);
+            unsigned long long s = 0, dummy = 0;
+            for (int k = 0; k < a.ipt; ++k)
+                if (first + k < end) s += tl_quantise(a.w_out[first + k], scale);
+            tl_block_sum_u64x2(s, dummy, sh);
+            if (t == 0) a.ttot[v] = s;
+        }
+    }
+    if (a.stop == 3) return;
+    tl_grid_barrier(a, 3);
+
+    // ---- S4: running sums of the normalised weights (reference) / of the quantised weights (fixed) ------------
+    double totd = 0.0;
+    if (b == 0 && !raw) {                                // central sums of the population -> est18[9..17]
+        double tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int u = t; u < a.nt; u += TL_THREADS) {
+            const double *pc = a.part_c + (size_t)u * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tc[k] += __ldcg(pc + k);
+        }
+        tl_block_sum<9>(tc, sh);
+        if (t == 0)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a.est18[9 + k] = tc[k];
+    }
+    if (REF) {
+        const float S = __ldcg(&a.hd->S);
+        tl_exact_pass<true>(a, sh, S);
+    } else {
+        unsigned long long carry = 0;
+        for (int base = 0; base < a.nt; base += TL_THREADS) {
+            const int u = base + t;
+            const unsigned long long val = u < a.nt ? __ldcg(a.ttot + u) : 0ull;
+            unsigned long long tot;
+            const unsigned long long ex = tl_block_excl_scan_u64(val, tot, sh);
+            if (u < a.nt && u % G == b) sh.ownE[u / G] = carry + ex;
+            carry += tot;
+        }
+        __syncthreads();
+        if (a.stop == 41) return;
+        totd = (double)carry;
+        if (b == 0 && t == 0) a.hd->total = carry;
+        unsigned long long *C = (unsigned long long *)a.C;
+        int rd = 0;
+        for (int v = b; v < a.nt; v += G, ++rd) {
+            const int64_t first = (int64_t)v * a.tile + (int64_t)t * a.ipt, end = min(n, (int64_t)(v + 1) * a.tile);
+            unsigned long long q[TL_MAX_IPT], s = 0;
+#pragma unroll
+            for (int k = 0; k < TL_MAX_IPT; ++k) {
+                q[k] = (k < a.ipt && first + k < end) ? tl_quantise(a.w_out[first + k], scale) : 0ull;
+                s += q[k];
+            }
+            unsigned long long tot;
+            unsigned long long run = sh.ownE[rd] + tl_block_excl_scan_u64(s, tot, sh);
+#pragma unroll
+            for (int k = 0; k < TL_MAX_IPT; ++k) {
+                run += q[k];
+                if (k < a.ipt && first + k < end) C[first + k] = run;
+            }
+            if (t == 0) ((unsigned long long *)a.tend)[v] = sh.ownE[rd] + tot;
+        }
+    }
+    if (a.stop == 4) return;
+    tl_grid_barrier(a, 4);
+
+    // ---- S5: idx[m] = min(first i with C_i >= key_m, n - 1) (pu:439-444 as a search) + pu:445 gather ----------
+    {
+        const CT *C = (const CT *)a.C;
+        const int64_t limit = n - 1;
+        const bool coarse = a.nt <= TL_COARSE_MAX;
+        CT *tendS = (CT *)dyn;
+        CT *stage = (CT *)(dyn + TL_COARSE_MAX * sizeof(unsigned long long));
+        const int stage_cap = (int)(TL_STAGE_BYTES / sizeof(CT));
+        if (coarse) {
+            for (int u = t; u < a.nt; u += TL_THREADS) tendS[u] = __ldcg((const CT *)a.tend + u);
+            __syncthreads();
+        }
+        const int warp = tl_warp(), lane = tl_lane();
+        for (int ov = b; ov < a.nt; ov += G) {
+            const int64_t m0 = (int64_t)ov * a.tile, m1 = min(n, m0 + a.tile);
+            if (warp < 2) {
+                const KeyT key = tl_key<REF>(warp == 0 ? m0 : m1 - 1, a.r, a.rstep, totd);
+                int64_t lo = 0, hi = limit;
+                if (coarse) {
+                    int tl = 0, th = a.nt - 1;               // first tile whose last running sum reaches the key
+                    while (tl < th) {
+                        const int mid = (tl + th) >> 1;
+                        if (TlCum<REF>::gt(key, tendS[mid])) tl = mid + 1; else th = mid;
+                    }
+                    lo = (int64_t)tl * a.tile;
+                    hi = min(limit, lo + a.tile - 1);
+                }
+                const int64_t i = tl_warp_search<REF>(C, lo, hi, key);
+                if (lane == 0) sh.irange[warp] = i;
+            }
+            __syncthreads();
+            const int64_t i_lo = sh.irange[0], i_hi = sh.irange[1];
+            const int64_t cnt = i_hi - i_lo + 1;
+            const bool staged = cnt <= stage_cap;
+            if (staged) {
+                for (int64_t j = t; j < cnt; j += TL_THREADS) stage[j] = __ldcg(C + i_lo + j);
+                __syncthreads();
+            }
+            for (int k = 0; k < a.ipt; ++k) {
+                const int64_t m = m0 + (int64_t)k * TL_THREADS + t;
+                if (m >= m1) break;
+                const KeyT key = tl_key<REF>(m, a.r, a.rstep, totd);
+                int64_t src;
+                if (staged) {
+                    int lo = 0, hi = (int)cnt - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (TlCum<REF>::gt(key, stage[mid])) lo = mid + 1; else hi = mid;
+                    }
+                    src = i_lo + lo;
+                } else {
+                    int64_t lo = i_lo, hi = i_hi;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (TlCum<REF>::gt(key, __ldcg(C + mid))) lo = mid + 1; else hi = mid;
+                    }
+                    src = lo;
+                }
+                a.idx[m] = (int32_t)src;
+                if (!raw) { a.gx[m] = a.nx[src]; a.gy[m] = a.ny[src]; a.gt[m] = a.nth[src]; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static size_t tl_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct TailPlan {
+    int ipt, tile, nt, grid;
+    size_t o_q, o_m, o_c, o_st1, o_st2, o_C, o_tend, o_ttot, bytes;
+};
+static TailPlan tail_plan(const mcl_handle *h, int64_t n) {
+    TailPlan p;
+    p.ipt = TL_MAX_IPT;
+    for (int k = 1; k <= TL_MAX_IPT; ++k)
+        if ((n + (int64_t)TL_THREADS * k - 1) / ((int64_t)TL_THREADS * k) <= h->sm_count) { p.ipt = k; break; }
+    p.tile = TL_THREADS * p.ipt;
+    p.nt = (int)((n + p.tile - 1) / p.tile);
+    p.grid = std::min(p.nt, h->sm_count);
+    size_t off = tl_align(sizeof(TailHeader));
+    p.o_q = off; off += tl_align((size_t)2 * h->sm_count * 8);
+    p.o_m = off; off += tl_align((size_t)p.nt * 8 * 8);
+    p.o_c = off; off += tl_align((size_t)p.nt * 9 * 8);
+    p.o_st1 = off; off += tl_align((size_t)p.nt * 8);
+    p.o_st2 = off; off += tl_align((size_t)p.nt * 8);
+    p.o_tend = off; off += tl_align((size_t)p.nt * 8);
+    p.o_ttot = off; off += tl_align((size_t)p.nt * 8);
+    p.o_C = off; off += tl_align((size_t)n * 8);
+    p.bytes = off;
+    return p;
+}
+
+static thread_local int g_tail_raw = 0;     // set by the test hook around its launch
+
+static int tail_disabled() {
+    static int off = -1;
+    if (off < 0) { const char *e = getenv("MCL_NO_TAIL"); off = (e && atoi(e)) ? 1 : 0; }
+    return off;
+}
+
+// can the persistent tail run this step?  (cooperative launch, every tile's round fits the per-CTA tables)
+bool mcl_tail_available(mcl_handle *h, int64_t n) {
+    if (tail_disabled() || n <= 0 || n > 0x7fffffffLL) return false;
+    if (h->coop_launch < 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device);
+        h->coop_launch = v ? 1 : 0;
+    }
+    if (!h->coop_launch) return false;
+    const TailPlan p = tail_plan(h, n);
+    return (p.nt + p.grid - 1) / p.grid <= TL_MAX_ROUNDS;
+}
+
+static int tail_prepare(mcl_handle *h, int64_t n) {
+    const TailPlan p = tail_plan(h, n);
+    if (p.bytes <= h->tail_bytes) return MCL_OK;
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_tail);
+    h->d_tail = nullptr; h->tail_bytes = 0;
+    MCL_CUDA(h, cudaMalloc(&h->d_tail, p.bytes + p.bytes / 4));
+    MCL_CUDA(h, cudaMemset(h->d_tail, 0, tl_align(sizeof(TailHeader))));
+    h->tail_bytes = p.bytes + p.bytes / 4;
+    h->tail_bar = 0;
+    return MCL_OK;
+}
+
+template <bool MH, bool REF>
+static cudaError_t tail_launch(const TailArgs &a, int grid, size_t dyn, cudaStream_t s) {
+    cudaFuncSetAttribute(k_tail<MH, REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    void *params[] = {(void *)&a};
+    return cudaLaunchCooperativeKernel((const void *)k_tail<MH, REF>, dim3(grid), dim3(TL_THREADS), params, dyn, s);
+}
+
+// softmax -> (MH) -> estimate sums -> resampling of one step; see the head of this file.  u.(nx, ny, nth) receives
+// the MH result (without MH it must be the particles themselves), (gx, gy, gt) the resampled set.
+int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
+                  int32_t *idx, double *gx, double *gy, double *gt) {
+    int rc = tail_prepare(h, u.n);
+    if (rc) return rc;
+    const TailPlan p = tail_plan(h, u.n);
+    char *b = (char *)h->d_tail;
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hd = (TailHeader *)b; a.keymax = d_keymax; a.bar_base = h->tail_bar;
+    a.n = u.n; a.nt = p.nt; a.ipt = p.ipt; a.tile = p.tile; a.use_mh = u.use_mh; a.raw = g_tail_raw;
+    { const char *e = getenv("MCL_TAIL_STOP"); a.stop = e ? atoi(e) : 0; }
+    a.s_post = u.s_post; a.s_pre = u.s_pre; a.w_out = u.w_out;
+    a.px = u.px; a.py = u.py; a.pt = u.pt; a.ox = u.ox; a.oy = u.oy; a.ot = u.ot; a.nx = u.nx; a.ny = u.ny; a.nth = u.nth;
+    a.seed = u.seed; a.step = u.step; a.first_index = u.first_index;
+    a.part_q = (unsigned long long *)(b + p.o_q); a.part_m = (double *)(b + p.o_m); a.part_c = (double *)(b + p.o_c);
+    a.st1 = (unsigned long long *)(b + p.o_st1); a.st2 = (unsigned long long *)(b + p.o_st2);
+    a.C = b + p.o_C; a.tend = b + p.o_tend; a.ttot = (unsigned long long *)(b + p.o_ttot);
+    a.est18 = u.est18;
+    a.r = r; a.rstep = 1.0 / (double)u.n;                       // pu:434
+    a.idx = idx; a.gx = gx; a.gy = gy; a.gt = gt;
+    const size_t dyn = (size_t)TL_COARSE_MAX * 8 + TL_STAGE_BYTES;
+    const bool ref = resample_mode == MCL_RESAMPLE_REFERENCE_F32;
+    cudaError_t e;
+    if (u.use_mh) e = ref ? tail_launch<true, true>(a, p.grid, dyn, h->stream) : tail_launch<true, false>(a, p.grid, dyn, h->stream);
+    else e = ref ? tail_launch<false, true>(a, p.grid, dyn, h->stream) : tail_launch<false, false>(a, p.grid, dyn, h->stream);
+    if (e != cudaSuccess) return mcl_fail(h, MCL_ERR_CUDA, std::string("k_tail launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    h->tail_bar += (unsigned long long)TL_NBAR * p.grid;
+    return MCL_OK;
+}
+
+// device address of the sticky error word of the tail kernel (0 = ok), or NULL before the first tail step
+const int *mcl_tail_err_ptr(mcl_handle *h) {
+    return h->d_tail ? &reinterpret_cast<TailHeader *>(h->d_tail)->err : nullptr;
+}
+
+// blocking: *err = 0 ok, != 0 a spin loop of the tail kernel timed out (the step's results are invalid)
+extern "C" int mcl_tail_status(mcl_handle *h, int *err) {
+    if (!h || !err) return MCL_ERR_ARG;
+    *err = 0;
+    if (!h->d_tail) return MCL_OK;
+    DeviceGuard guard(h->device);
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    TailHeader hd;
+    MCL_CUDA(h, cudaMemcpy(&hd, h->d_tail, sizeof(hd), cudaMemcpyDeviceToHost));
+    *err = hd.err;
+    if (hd.err) {       // the barrier counter is out of step after a time-out: start over
+        MCL_CUDA(h, cudaMemset(h->d_tail, 0, tl_align(sizeof(TailHeader))));
+        h->tail_bar = 0;
+    }
+    return MCL_OK;
+}
+
+// test hook: systematic resampling of the given weights through the tail kernel's resampling stages (S3-S5)
+// alone; d_c (nullable) receives the running sums (n f32, reference mode) / cumulative sums (n u64, fixed point)
+extern "C" int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, double r, int mode, int32_t *d_idx, void *d_c) {
+    if (!h) return MCL_ERR_ARG;
+    if (n <= 0 || !d_w || !d_idx) return mcl_fail(h, MCL_ERR_ARG, "mcl_debug_tail_resample: bad argument");
+    if (mode != MCL_RESAMPLE_REFERENCE_F32 && mode != MCL_RESAMPLE_FIXED_POINT)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_debug_tail_resample: unknown mode");
+    DeviceGuard guard(h->device);
+    if (!mcl_tail_available(h, n)) return mcl_fail(h, MCL_ERR_STATE, "mcl_debug_tail_resample: persistent tail not available");
+    int rc = mcl_fused_prepare(h, n);
+    if (rc) return rc;
+    FusedStep u;
+    memset(&u, 0, sizeof(u));
+    u.n = n; u.n_global = n; u.use_mh = 0; u.w_out = d_w;
+    g_tail_raw = 1;
+    rc = mcl_tail_step(h, u, mcl_fused_keymax(h), mode, r, d_idx, nullptr, nullptr, nullptr);
+    g_tail_raw = 0;
+    if (rc) return rc;
+    if (d_c) {
+        const TailPlan p = tail_plan(h, n);
+        MCL_CUDA(h, cudaMemcpyAsync(d_c, (char *)h->d_tail + p.o_C, (size_t)n * (mode == MCL_RESAMPLE_REFERENCE_F32 ? 4 : 8),
+                                    cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return MCL_OK;
+}

@@ -548,6 +548,153 @@ def test_sequential_f32_sum_exact_parallel_emulation(pu):
         assert torch.equal(a.view(torch.int32), b.view(torch.int32))
 
 
+def _tail_resample(pu, w, r, mode, want_c=False):
+    """Systematic resampling of host weights through the resampling stages of the persistent tail kernel."""
+    import ctypes as C
+    import torch
+    c = pu._ctx()
+    n = len(w)
+    wd = torch.from_numpy(np.ascontiguousarray(w, np.float32)).to(c.device)
+    idx = torch.empty(n, dtype=torch.int32, device=c.device)
+    cd = torch.empty(n, dtype=torch.float32 if mode == 0 else torch.int64, device=c.device) if want_c else None
+    c.h.call("mcl_debug_tail_resample", C.c_void_p(wd.data_ptr()), n, float(r), int(mode), C.c_void_p(idx.data_ptr()),
+             C.c_void_p(cd.data_ptr()) if want_c else None)
+    err = C.c_int(-1)
+    c.h.call("mcl_tail_status", C.byref(err))
+    assert err.value == 0, "tail kernel wait timed out: %d" % err.value
+    return idx.cpu().numpy(), (cd.cpu().numpy() if want_c else None)
+
+
+def test_tail_kernel_exact_sequential_sums_adversarial(pu):
+    """The persistent tail kernel's two exact passes (pu:430 sequential-f32 sum, pu:436-443 running sum of w / S)
+    against a NumPy float32 loop on adversarial weight sets: exact ties, powers of two, denormals, 2^-60..1
+    dynamic range, zeros, one huge weight, and EXACTLY uniform weights (every addition rounds the same way, so the
+    sum drifts systematically away from the fp64 prediction and the tiles fall back to the restart loop)."""
+    from mcmh_localization_b200 import RESAMPLE_REFERENCE_F32
+    rs = np.random.RandomState(12)
+    sets = {
+        "ties_pow2": np.full(70000, 2.0 ** -10, np.float32),
+        "ties_3x": (3.0 * 2.0 ** rs.randint(-30, -8, 60000)).astype(np.float32),
+        "uniform": rs.uniform(0, 1, 50000).astype(np.float32),
+        "softmax_like": np.exp(rs.normal(0, 3, 80000)).astype(np.float32),
+        "range": (rs.uniform(0.5, 1, 40000) * 2.0 ** rs.randint(-60, 0, 40000)).astype(np.float32),
+        "denormal": (rs.randint(0, 2 ** 22, 30000).astype(np.float64) * 2.0 ** -149).astype(np.float32),
+        "zeros_mixed": np.where(rs.uniform(0, 1, 50000) < 0.7, 0, rs.uniform(0, 1, 50000)).astype(np.float32),
+        "big_then_small": np.concatenate([[1e6], rs.uniform(0, 1e-3, 30000)]).astype(np.float32),
+        "exactly_uniform": np.full(200000, 1e-6, np.float32),
+        "one": np.array([0.3], np.float32),
+        "two": np.array([0.3, 0.9], np.float32),
+        "ragged": rs.uniform(0, 1, 1025).astype(np.float32),
+    }
+    for tag, w in sets.items():
+        n = len(w)
+        r = rs.uniform(0, 1.0 / n)
+        idx, c = _tail_resample(pu, w, r, RESAMPLE_REFERENCE_F32, want_c=True)
+        ref_c = _seq_cumsum_numpy(w, True)
+        assert np.array_equal(c.view(np.uint32), ref_c.view(np.uint32)), (tag, int((c != ref_c).sum()))
+        ref_idx = pu.low_variance_resample_indices(w, n, r)            # stand-alone kernels (pinned to the golden vectors)
+        assert np.array_equal(idx, ref_idx), tag
+
+
+@pytest.mark.parametrize("n", [1_000_000, 1_300_003, 3_000_001])
+def test_tail_kernel_resampling_large_vs_oracle(pu, orc, n):
+    """Both arithmetics of the tail kernel at full size (one tile per CTA; more tiles than CTAs, so every CTA
+    chains through several rounds) against the oracle: the reference's own walk (pu:416-446, sequential C) and
+    the fixed-point restatement; softmax-like, exactly uniform and sparse weights."""
+    from mcmh_localization_b200 import RESAMPLE_REFERENCE_F32, RESAMPLE_FIXED_POINT
+    rs = np.random.RandomState(n % 1000)
+    sets = {"softmax_like": np.exp(rs.normal(0, 0.2, n)).astype(np.float32) / n,
+            "exactly_uniform": np.full(n, 1.0 / n, np.float32)}
+    if n == 1_000_000:
+        sp = (rs.uniform(0, 1, n) ** 6).astype(np.float32)
+        sp[rs.randint(0, n, n // 3)] = 0.0
+        sets["sparse"] = sp
+    for tag, w in sets.items():
+        r = rs.uniform(0, 1.0 / n)
+        idx, _ = _tail_resample(pu, w, r, RESAMPLE_REFERENCE_F32)
+        assert np.array_equal(idx, orc.low_variance_resample_indices(w, n, r)), (tag, "reference arithmetic")
+        idx, _ = _tail_resample(pu, w, r, RESAMPLE_FIXED_POINT)
+        assert np.array_equal(idx, orc.systematic_resample_q(w, n, r)), (tag, "fixed point")
+
+
+def test_fixed_point_indices_diverge_from_reference_indices(pu, orc):
+    """States the divergence of the two resampling arithmetics (why the reference one is the default): the
+    reference's running sum is a SEQUENTIAL float32 sum, whose rounding drift moves thresholds across particle
+    boundaries; the fixed-point sum has no drift.  Same weights, same r: a handful of slots differ at 2 k
+    particles, a few per cent at 100 k, most of them at 1 M -- always by a small shift, never by mass."""
+    from mcmh_localization_b200 import RESAMPLE_FIXED_POINT
+    fr = {}
+    for n in (2000, 100_000, 1_000_000):
+        rs = np.random.RandomState(7)
+        s = rs.normal(-0.2, 0.08, n).astype(np.float32)                # mean log-likelihood scores (SURVEY A.5)
+        w = pu.convert_scores(s)
+        r = rs.uniform(0, 1.0 / n)
+        a = pu.low_variance_resample_indices(w, n, r)                  # reference arithmetic (pu:416-446)
+        b = pu.low_variance_resample_indices(w, n, r, mode=RESAMPLE_FIXED_POINT)
+        assert np.array_equal(a, orc.low_variance_resample_indices(w, n, r))
+        fr[n] = float((a != b).mean())
+        assert np.abs(a.astype(np.int64) - b).max() <= 64             # a shift of a few particles
+        ca, cb = np.bincount(a, minlength=n), np.bincount(b, minlength=n)
+        assert np.abs(ca - cb).max() <= 2                              # offspring counts agree to +-2
+    assert fr[2000] <= 0.01 and fr[1_000_000] > fr[2000]
+    print("fixed-point vs reference index mismatch fraction:", fr)
+
+
+def test_fused_reference_step_1m_vs_oracle(orc):
+    """BASELINE configs[1] through the production step (likelihood pair + persistent tail kernel, the
+    reference's resampling arithmetic), 1 M particles, NO teacher forcing: after every step the resampled indices
+    must equal the oracle's walk (pu:416-446) over the step's own weights and offset, the new particle set must
+    be the MH result gathered by those indices, and the MH result / weights must equal the oracle filter's on
+    the same Philox draws except for provable near-ties of the accept test."""
+    _need_gpu()
+    import os
+    import ctypes as C
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan, free_space_particles
+    from oracle import node_glue as ng
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    mp = ng.load_map(gm.occ, gm.resolution, gm.origin_x, gm.origin_y)
+    n = 1_000_000
+    p0 = free_space_particles(gm, n, seed=1234)
+    loc = Localizer(params=P, mode="MHMCL", seed=2024, resample_mode="reference")
+    loc.load_map(gm)
+    loc.set_particles(p0)
+    f = ng.ReferenceFilter(mp, P, p0, mode="MHMCL")
+    pose = np.array([-2.0, -0.5, 0.0])
+    loc.predict(pose); f.move_particles(pose)
+    for k in range(2):
+        pose = pose + np.array([0.02 * np.cos(pose[2]), 0.02 * np.sin(pose[2]), 0.01])
+        scan, angles = raycast_scan(gm, pose, noise_sigma=0.01, seed=50 + k)
+        f.particles = loc.particles(); f.particles_prev = loc.particles_prev()     # same state in (not a forced result)
+        t0 = loc.tick
+        loc.step(pose, scan, angles=angles)
+        err = C.c_int(-1)
+        loc.h.call("mcl_tail_status", C.byref(err))
+        assert err.value == 0
+        cur, prev, spare, ws, tick = loc._roles()
+        assert tick == t0 + 3                                           # predict, MH, resample
+        f.move_particles(pose, seed=2024, step=t0 + 1)
+        w_ref = f.update(scan, angles, seed=2024, step=t0 + 2)
+        mh = loc._aos(loc.sets[spare])                                  # the MH result the resampling gathered from
+        w = loc.weights()
+        same = np.isclose(mh, f.particles, rtol=0, atol=1e-9).all(axis=1)
+        # accept decisions may differ only where the uniform is within rounding of alpha (scores differ by <= 4e-7 rel)
+        bad = np.nonzero(~same)[0]
+        assert len(bad) <= 20, len(bad)
+        wpre = ng.convert_scores(f.scores_pre); wpost = ng.convert_scores(f.scores_post)
+        for i in bad:
+            u = orc.uniform53(2024, t0 + 2, int(i), 0, orc.STREAM_MH)
+            alpha = min(1.0, float(np.float32(wpost[i]) / np.float32(wpre[i]))) if wpre[i] > 0 else 1.0
+            assert abs(u - alpha) <= 1e-4 * alpha, (i, u, alpha)
+        np.testing.assert_allclose(w[same], w_ref[same], rtol=2e-6, atol=0)
+        r = loc.h.lib.mcl_resample_offset(2024, t0 + 3, n)
+        idx = loc.idx.cpu().numpy()
+        assert np.array_equal(idx, orc.low_variance_resample_indices(w, n, r))      # bit-exact (pu:416-446)
+        assert np.array_equal(loc.particles(), mh[idx])
+
+
 def test_resample_all_zero_weights(pu):
     w = np.zeros(100, np.float32)
     for mode in (0, 1):
@@ -787,7 +934,8 @@ def test_localizer_production_step_runs_and_is_deterministic():
 
 @pytest.mark.parametrize("n", [1, 1000, 33333, 400_003])
 @pytest.mark.parametrize("mode", ["MHMCL", "MCL"])
-def test_fused_step_equals_standalone_sequence(mode, n):
+@pytest.mark.parametrize("resample_mode", ["reference", "fixed"])
+def test_fused_step_equals_standalone_sequence(mode, n, resample_mode):
     """Localizer.step() runs the step tail through the fused kernels (fused.cu: likelihood pair with max keys,
     sum-exp, weights + MH + raw estimate sums, central sums + look-back scan, search + gather).  It must leave
     the SAME particles, weights and resampled indices, bit for bit, as predict/update/estimate/resample issued
@@ -804,7 +952,7 @@ def test_fused_step_equals_standalone_sequence(mode, n):
     p0 = free_space_particles(gm, n, seed=5)
     locs = []
     for _ in range(2):
-        loc = Localizer(params=P, mode=mode, seed=21, resample_mode="fixed")
+        loc = Localizer(params=P, mode=mode, seed=21, resample_mode=resample_mode)
         loc.load_map(gm)
         loc.set_particles(p0)
         locs.append(loc)
