@@ -47,8 +47,10 @@ typedef enum {
 enum {
     MCL_RESAMPLE_REFERENCE_F32 = 0, /* pu:416-446 bit-exact: sequential f32 normalising sum and f32
                                        running cumulative sum, f64 U = r + m/N */
-    MCL_RESAMPLE_FIXED_POINT = 1    /* production: same walk on 64-bit fixed-point weights (exact,
-                                       associative => identical for any block / rank split) */
+    MCL_RESAMPLE_FIXED_POINT = 1,   /* same walk on 64-bit fixed-point weights (exact, associative => identical
+                                       for any block / rank split): the sharded runs' arithmetic */
+    MCL_RESAMPLE_AMCL_F32 = 2       /* pu:486-502 low_variance_resample_amcl: weights as given (no normalisation),
+                                       sequential f32 running sum, U = r + m / n_out, walk bounded by n_in - 1 */
 };
 
 /* Philox stream ids (ctr[3] low byte). */
@@ -297,6 +299,25 @@ int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);        
 int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
                     double h_out16[16]);
 
+/* ---- functions the node imports (node:13) but never reaches from its callbacks ---------
+ * pu:369-386 compute_valid_indices: indices (ascending) of the particles whose cell (int() truncation) lies in the
+ * map with map_data <= 10.  Needs the occupancy grid (mcl_set_map).  Blocking; *h_count = how many. */
+int mcl_compute_valid_indices(mcl_handle *h, const double *d_x, const double *d_y, int64_t n, int32_t *d_idx,
+                              int64_t *h_count);
+/* pu:600-614 validate_samples (second half of initialize_gaussian_parallel, node:183): in place, a sample whose
+ * cell is outside the map or has distance_map >= 1.0 becomes (0, 0, 0).  Needs the distance map. */
+int mcl_validate_samples(mcl_handle *h, double *d_x, double *d_y, double *d_theta, int64_t n);
+/* pu:467-477 parallel_resample_simple: cum = np.cumsum(weights) as a sequential f32 sum, one uniform per output
+ * (d_u injected, or Philox(seed, step, output index)), idx = searchsorted(cum, u).  Where the reference reads out
+ * of bounds (u > cum[-1]) the last particle is taken. */
+int mcl_resample_multinomial(mcl_handle *h, const float *d_weights, int64_t n_in, int64_t n_out, const double *d_u,
+                             uint64_t seed, uint64_t step, int32_t *d_idx);
+/* pu:504-526 reinitialize_particles_numba: per new particle a uniformly chosen free cell (pose = its lower-left
+ * corner) and a uniform heading.  d_choice (index into the row-major list of free cells) / d_theta: injected draws
+ * or NULL for Philox(seed, step, particle).  Needs the occupancy grid.  Blocking; *h_n_free = free cells. */
+int mcl_reinitialize_particles(mcl_handle *h, int64_t n, const int64_t *d_choice, const double *d_theta, uint64_t seed,
+                               uint64_t step, double *d_x, double *d_y, double *d_theta_out, int64_t *h_n_free);
+
 /* Sharded operation, one process per GPU (call after mcl_filter_bind on every rank): the per-step scalar
  * exchanges (softmax max / sum, estimate sums, resampling scale and totals) and the resampling exchange then run
  * over NVLink peer memory inside the library's own kernels -- every mcl_filter_* call above becomes collective.
@@ -317,6 +338,9 @@ int mcl_comm_status(mcl_handle *h, int *err);
 int mcl_tail_status(mcl_handle *h, int *err);
 /* Test hook: systematic resampling (pu:416-446) of the given device weights through the resampling stages of
  * that kernel alone; d_c (nullable) receives the running sums (n f32 in reference mode, n u64 in fixed point). */
+/* Debug (MCL_TAIL_PROF=1 in the environment): globaltimer stamps [grid][32] of the stage boundaries of the last
+ * tail launch (out must hold 1024 * 32 values); *grid = CTAs of that launch. */
+int mcl_tail_prof(mcl_handle *h, unsigned long long *out, int *grid);
 int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, double r, int mode, int32_t *d_idx, void *d_c);
 
 /* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libmcl.so")
 
 RESAMPLE_REFERENCE_F32 = 0
 RESAMPLE_FIXED_POINT = 1
+RESAMPLE_AMCL_F32 = 2
 
 STREAM_MOTION, STREAM_MH, STREAM_RESAMPLE, STREAM_INIT, STREAM_KLD = 1, 2, 3, 4, 5
 
@@ -87,6 +88,11 @@ SIGNATURES = {
     "mcl_comm_init": (_i, [_vp, _i, _i, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "mcl_comm_status": (_i, [_vp, _pi]),
     "mcl_tail_status": (_i, [_vp, _pi]),
+    "mcl_compute_valid_indices": (_i, [_vp, _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "mcl_validate_samples": (_i, [_vp, _vp, _vp, _vp, _i64]),
+    "mcl_resample_multinomial": (_i, [_vp, _vp, _i64, _i64, _vp, _u64, _u64, _vp]),
+    "mcl_reinitialize_particles": (_i, [_vp, _i64, _vp, _vp, _u64, _u64, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "mcl_tail_prof": (_i, [_vp, C.POINTER(C.c_uint64), _pi]),
     "mcl_debug_tail_resample": (_i, [_vp, _vp, _i64, _d, _i, _vp, _vp]),
     "mcl_bench_gather": (_i, [_vp, _i, _i64, _i64, _i, _pd]),
     "mcl_debug_seq_cumsum": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libmcl.so")
 SOURCES = ["mcl_core.cu", "likelihood.cu", "motion.cu", "mh_softmax.cu", "resample.cu", "estimate.cu",
-           "init_misc.cu", "filter.cu", "amh.cu", "kld.cu", "raycast.cu", "edt.cu", "fused.cu", "tail.cu"]
+           "init_misc.cu", "filter.cu", "amh.cu", "kld.cu", "raycast.cu", "edt.cu", "fused.cu", "tail.cu", "alt.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "--fmad=true", "-Xptxas", "-v"]

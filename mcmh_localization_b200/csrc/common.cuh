@@ -113,6 +113,8 @@ struct mcl_handle {
     void *d_tail = nullptr;      // work area of the persistent step tail (tail.cu)
     size_t tail_bytes = 0;
     unsigned long long tail_bar = 0;   // grid-barrier arrivals consumed so far (base of the next launch)
+    void *d_tail_prof = nullptr; // MCL_TAIL_PROF=1: stage time stamps of the tail kernel
+    int tail_prof_grid = 0;
     int coop_launch = -1;        // cudaDevAttrCooperativeLaunch (-1: not queried yet)
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;

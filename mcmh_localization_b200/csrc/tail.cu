@@ -12,7 +12,7 @@
 //
 // The exact sequential-f32 passes.  c_i = fl32(c_{i-1} + w_i) is emulated with the integer maps of seqsum.cuh,
 // which need the binade of the running sum.  An fp64 prefix predicts it for every thread (8 consecutive
-// weights); threads whose prefix lies within 2^-11 (relative) of a power of two are not trusted: their
+// weights); threads whose prefix lies within 2^-13 (relative) of a power of two are not trusted: their
 // additions are replayed with real f32 adds.  Per tile a segmented scan composes the maps of every run of
 // trusted threads, so a tile is a short list of items (run map | replayed thread); one lane walks that list
 // from the tile's exact incoming sum, CHECKING every run (binade as predicted, no overflow) -- if a check fails
@@ -39,7 +39,8 @@
 #define TL_NBAR 4
 #define TL_SPIN_LIMIT 4000000000ll
 #define TL_SOFTMAX_FIX 1099511627776.0   // 2^40 (mh_softmax.cu)
-#define TL_DELTA 4.8828125e-4            // 2^-11: distrust margin around a binade boundary
+#define TL_DELTA 1.220703125e-4           // 2^-13: per-thread distrust margin around a binade boundary (MULTI tiles)
+#define TL_DELTA_TILE 1.953125e-3         // 2^-9: margin by which a tile's predicted sums are widened
 #define TL_STAGE_BYTES 65536
 #define TL_COARSE_MAX 2048
 
@@ -62,6 +63,7 @@ struct TailArgs {
     unsigned long long bar_base;
     int64_t n;
     int nt, ipt, tile, use_mh;
+    unsigned long long *prof;    // debug: [grid][32] globaltimer stamps of the stage boundaries (nullable)
     int stop;                    // debug: return after stage `stop` (0 = run everything)
     int raw;                     // test hook: w_out holds the weights already, no poses (S1, estimate, gather skipped)
     const float *s_post, *s_pre;
@@ -102,8 +104,8 @@ struct TlShared {
     TlItems it;
     double ownP[TL_MAX_ROUNDS], ownT[TL_MAX_ROUNDS];
     unsigned long long ownE[TL_MAX_ROUNDS];
-    float c_in, c_out, cseg;
-    int fail, nitems, nserial;
+    float c_in, c_out, cseg, cprime;
+    int fail, nitems, nserial, tstar;
     long long cross;
     int64_t seg0;
     int64_t irange[2];
@@ -130,6 +132,14 @@ __device__ __forceinline__ unsigned long long tl_ld_acquire(const unsigned long 
 }
 __device__ __forceinline__ void tl_st_release(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void tl_stamp(const TailArgs &a, int k) {
+    if (a.prof && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.prof[(size_t)blockIdx.x * 32 + k] = t;
+    }
 }
 
 __device__ __forceinline__ void tl_grid_barrier(const TailArgs &a, int k) {
@@ -286,36 +296,11 @@ __device__ __forceinline__ unsigned long long tl_rec_agg(int e, const Pair64 &m)
 }
 __device__ __forceinline__ unsigned long long tl_rec_inc(float c) { return (TL_F_INC << 62) | (unsigned long long)__float_as_uint(c); }
 
-// exact sum entering tile v (warp 0, all lanes; every lane returns the same value)
-__device__ float tl_lookback(unsigned long long *st, int v, int *err) {
+// serial form: from the exact sum c leaving tile `start`, apply the records of tiles start+1 .. v-1 one by one; a
+// record that does not apply (binade not as predicted, overflow) is waited for until its tile has published its sum
+__device__ __noinline__ float tl_lookback_serial(unsigned long long *st, int v, int start, float c, long long t0, int *err) {
     const int lane = tl_lane();
-    if (v == 0) return 0.0f;
-    const long long t0 = clock64();
-    int top = v - 1, start = -1;
-    float c = 0.0f;
-    while (true) {                                       // backwards: the nearest tile with an exact outgoing sum
-        const int q = top - lane;
-        unsigned long long rec = TL_F_INC << 62;         // "tile -1": the sum starts at 0
-        bool dead = false;
-        if (q >= 0) {
-            while (true) {
-                rec = tl_ld_acquire(st + q);
-                const unsigned f = (unsigned)(rec >> 62);
-                if (f == TL_F_AGG || f == TL_F_INC) break;
-                if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
-            }
-        }
-        if (__any_sync(TL_FULL, dead)) { if (lane == 0) *err = 2; return 0.0f; }
-        const unsigned incm = __ballot_sync(TL_FULL, (rec >> 62) == TL_F_INC);
-        if (incm) {
-            const int j = __ffs(incm) - 1;
-            start = top - j;
-            c = __uint_as_float((unsigned)__shfl_sync(TL_FULL, rec, j));
-            break;
-        }
-        top -= 32;
-    }
-    for (int base = start + 1; base < v; base += 32) {   // forwards: apply the aggregate maps, checking each
+    for (int base = start + 1; base < v; base += 32) {
         const int q = base + lane;
         unsigned long long rec = 0;
         if (q < v) rec = tl_ld_acquire(st + q);
@@ -328,26 +313,98 @@ __device__ float tl_lookback(unsigned long long *st, int v, int *err) {
                 m.a0 = (unsigned)((r >> 26) & 0x3ffffffull); m.a1 = (unsigned)(r & 0x3ffffffull);
                 const long long Kn = tl_apply(seq_K(c), m);
                 if (seq_exponent(c) == e && Kn < (1ll << 24)) { c = seq_value(Kn, e); continue; }
-                // predicted binade wrong for that tile: it will find out itself and publish its exact sum
-                bool dead = false;
-                while (true) {
-                    r = tl_ld_acquire(st + base + l);
-                    if ((r >> 62) == TL_F_INC) break;
-                    if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
-                }
-                if (dead) { if (lane == 0) *err = 3; return 0.0f; }
             }
+            bool dead = false;
+            while ((r >> 62) != TL_F_INC) {
+                r = tl_ld_acquire(st + base + l);
+                if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
+            }
+            if (dead) { if (lane == 0) *err = 3; return 0.0f; }
             c = __uint_as_float((unsigned)r);
         }
     }
     return c;
 }
 
+// exact sum entering tile v (warp 0, all lanes; every lane returns the same value).  Backwards in windows of 32
+// tiles: the aggregate maps of clean tiles are composed by a shuffle reduction while the window's nearest dirty
+// tile is still being waited for, so that once an exact sum arrives it takes ONE checked application.
+__device__ float tl_lookback(unsigned long long *st, int v, int *err) {
+    const int lane = tl_lane();
+    if (v == 0) return 0.0f;
+    const long long t0 = clock64();
+    int top = v - 1;
+    Pair64 suffix; suffix.a0 = 0; suffix.a1 = 0;         // composed map of the clean tiles (top, v-1]
+    int e_suf = 1000;                                    // their common unit exponent (1000: none yet)
+    bool composable = true;
+    while (true) {
+        const int q = top - lane;
+        unsigned long long rec = TL_F_INC << 62;         // "tile -1": the sum starts at 0
+        bool dead = false;
+        if (q >= 0) {
+            while (true) {
+                rec = tl_ld_acquire(st + q);
+                const unsigned f = (unsigned)(rec >> 62);
+                if (f == TL_F_AGG || f == TL_F_INC) break;
+                if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
+            }
+        }
+        if (__any_sync(TL_FULL, dead)) { if (lane == 0) *err = 2; return 0.0f; }
+        // a clean tile predicted in ANOTHER binade than the tiles composed so far ends the composable stretch
+        // like a dirty one: its own exact sum is waited for (it publishes it right after its own look-back)
+        const int e = (int)((rec >> 52) & 0xff) - 126;
+        const bool isinc = (rec >> 62) == TL_F_INC;
+        int e_ref = e_suf;
+        if (e_ref == 1000) {
+            const int e0 = __shfl_sync(TL_FULL, e, 0);
+            const bool inc0 = __shfl_sync(TL_FULL, isinc ? 1 : 0, 0) != 0;
+            if (!inc0) e_ref = e0;
+        }
+        const unsigned stopm = __ballot_sync(TL_FULL, isinc || e != e_ref);
+        const int j = stopm ? __ffs(stopm) - 1 : 32;     // lanes 0 .. j-1: clean tiles of one binade, nearer than any stop
+        if (j < 32) {
+            unsigned long long rj = __shfl_sync(TL_FULL, rec, j);
+            bool dead2 = false;
+            while ((rj >> 62) != TL_F_INC) {             // (uniform) the stop tile's exact sum
+                rj = tl_ld_acquire(st + (top - j));
+                if (clock64() - t0 > TL_SPIN_LIMIT) { dead2 = true; break; }
+            }
+            if (dead2) { if (lane == 0) *err = 4; return 0.0f; }
+            if (lane == j) rec = rj;
+        }
+        const unsigned incm = j < 32 ? (1u << j) : 0u;
+        const bool isagg = lane < j;
+        Pair64 m; m.a0 = 0; m.a1 = 0;
+        if (isagg) { m.a0 = (unsigned)((rec >> 26) & 0x3ffffffull); m.a1 = (unsigned)(rec & 0x3ffffffull); }
+        if (j > 0 && e_suf == 1000) e_suf = e_ref;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {               // lane 0 <- first the farthest tile, ..., last the nearest
+            Pair64 other;
+            other.a0 = __shfl_down_sync(TL_FULL, m.a0, o);
+            other.a1 = __shfl_down_sync(TL_FULL, m.a1, o);
+            if (lane + o < 32) m = pair_compose(other, m);
+        }
+        Pair64 win;
+        win.a0 = __shfl_sync(TL_FULL, m.a0, 0); win.a1 = __shfl_sync(TL_FULL, m.a1, 0);
+        suffix = pair_compose(win, suffix);
+        if (incm) {
+            const float c = __uint_as_float((unsigned)__shfl_sync(TL_FULL, rec, j));
+            if (e_suf == 1000) return c;                 // no clean tile in between
+            if (composable) {
+                const long long Kn = tl_apply(seq_K(c), suffix);
+                if (seq_exponent(c) == e_suf && Kn < (1ll << 24)) return seq_value(Kn, e_suf);
+            }
+            return tl_lookback_serial(st, v, top - j, c, t0, err);
+        }
+        top -= 32;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ exact tile
-// general path: exact running sums of one tile from c_start, one block scan per binade crossing
-template <bool WRITE>
-__device__ float tl_tile_general(const float (&wv)[TL_MAX_IPT], int ipt, int64_t first, int64_t tile_lo, int64_t end,
-                                 float c_start, float *C, TlShared &sh) {
+// general path: exact running sums of one tile from c_start, one block scan per binade crossing.  The thread's
+// weights are read from the shared-memory copy wt[0 .. ipt) (rolled loops: this path is cold, keep it small).
+__device__ __noinline__ float tl_tile_general(bool write, const float *wt, int ipt, int64_t first, int64_t tile_lo,
+                                              int64_t end, float c_start, float *C, TlShared &sh) {
     const long long NONE = 0x7fffffffffffffffll;
     if (threadIdx.x == 0) { sh.cseg = c_start; sh.seg0 = tile_lo; }
     __syncthreads();
@@ -357,22 +414,24 @@ __device__ float tl_tile_general(const float (&wv)[TL_MAX_IPT], int ipt, int64_t
         const int e = seq_exponent(c0);
         const long long K0 = seq_K(c0);
         Pair64 run; run.a0 = 0; run.a1 = 0;
-#pragma unroll
-        for (int k = 0; k < TL_MAX_IPT; ++k) {
+#pragma unroll 1
+        for (int k = 0; k < ipt; ++k) {
             const int64_t i = first + k;
-            if (k < ipt && i >= seg0 && i < end) run = pair_compose(run, seq_decode(wv[k], e));
+            if (i >= seg0 && i < end) run = pair_compose(run, seq_decode(wt[k], e));
         }
         if (threadIdx.x == 0) sh.cross = NONE;
         Pair64 agg;
         const Pair64 excl = tl_block_excl_scan_pair(run, agg, sh);
         const long long Kstart = tl_apply(K0, excl);
         long long my_cross = NONE, Kb = 0, Kw = Kstart;
-#pragma unroll
-        for (int k = 0; k < TL_MAX_IPT; ++k) {
+        float w_cross = 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < ipt; ++k) {
             const int64_t i = first + k;
-            if (k < ipt && i >= seg0 && i < end) {
-                const long long Kn = tl_apply(Kw, seq_decode(wv[k], e));
-                if (Kn >= (1ll << 24) && my_cross == NONE) { my_cross = i; Kb = Kw; }
+            if (i >= seg0 && i < end) {
+                const float w = wt[k];
+                const long long Kn = tl_apply(Kw, seq_decode(w, e));
+                if (Kn >= (1ll << 24) && my_cross == NONE) { my_cross = i; Kb = Kw; w_cross = w; }
                 Kw = Kn;
             }
         }
@@ -380,13 +439,13 @@ __device__ float tl_tile_general(const float (&wv)[TL_MAX_IPT], int ipt, int64_t
         __syncthreads();
         const long long cross = sh.cross;
         const int64_t seg_end = cross == NONE ? end : (int64_t)cross;
-        if (WRITE) {
+        if (write) {
             Kw = Kstart;
-#pragma unroll
-            for (int k = 0; k < TL_MAX_IPT; ++k) {
+#pragma unroll 1
+            for (int k = 0; k < ipt; ++k) {
                 const int64_t i = first + k;
-                if (k < ipt && i >= seg0 && i < end) {
-                    Kw = tl_apply(Kw, seq_decode(wv[k], e));
+                if (i >= seg0 && i < end) {
+                    Kw = tl_apply(Kw, seq_decode(wt[k], e));
                     if (i < seg_end) C[i] = seq_value(Kw, e);
                 }
             }
@@ -397,12 +456,8 @@ __device__ float tl_tile_general(const float (&wv)[TL_MAX_IPT], int ipt, int64_t
             return r;
         }
         if (my_cross == cross) {                      // this thread owns the addition that leaves the binade
-            const float cb = seq_value(Kb, e);
-            float cn = cb;
-#pragma unroll
-            for (int k = 0; k < TL_MAX_IPT; ++k)
-                if (first + k == cross) cn = __fadd_rn(cb, wv[k]);
-            if (WRITE) C[cross] = cn;
+            const float cn = __fadd_rn(seq_value(Kb, e), w_cross);
+            if (write) C[cross] = cn;
             sh.cseg = cn;
             sh.seg0 = cross + 1;
         }
@@ -415,12 +470,103 @@ __device__ float tl_tile_general(const float (&wv)[TL_MAX_IPT], int ipt, int64_t
     }
 }
 
+// central sums of this CTA's tiles around the population means (node:590-597, pu:69-83) -> part_c
+__device__ __forceinline__ void tl_central_sums(const TailArgs &a, TlShared &sh, double mx, double my, double mt) {
+    const int t = threadIdx.x;
+    for (int v = blockIdx.x; v < a.nt; v += gridDim.x) {
+        double s9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int64_t base = (int64_t)v * a.tile + t;
+        for (int k = 0; k < a.ipt; ++k) {
+            const int64_t i = base + (int64_t)k * TL_THREADS;
+            if (i >= a.n) break;
+            const double wi = (double)a.w_out[i];
+            const double dx = a.nx[i] - mx, dy = a.ny[i] - my;
+            const double dt = (double)(float)normalize_angle_dev(__dadd_rn(a.nth[i], -mt));   // pu:80-82
+            s9[0] += wi * dx; s9[1] += wi * dy; s9[2] += wi * dt;
+            s9[3] += wi * dx * dx; s9[4] += wi * dx * dy; s9[5] += wi * dx * dt;
+            s9[6] += wi * dy * dy; s9[7] += wi * dy * dt; s9[8] += wi * dt * dt;
+        }
+        tl_block_sum<9>(s9, sh);
+        if (t == 0) {
+            double *pc = a.part_c + (size_t)v * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) pc[k] = s9[k];
+        }
+    }
+}
+
+// exclusive SUFFIX scan of element maps: the composition of the maps of threads t+1 .. 1023 (t+1 applied first);
+// `aggregate` (all threads, in order) is returned to every thread
+__device__ __forceinline__ Pair64 tl_block_suffix_scan_pair(const Pair64 &mine, Pair64 &aggregate, TlShared &sh) {
+    const int warp = tl_warp(), lane = tl_lane();
+    Pair64 inc = mine;                                   // lanes lane .. 31 of this warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Pair64 other;
+        other.a0 = __shfl_down_sync(TL_FULL, inc.a0, o);
+        other.a1 = __shfl_down_sync(TL_FULL, inc.a1, o);
+        if (lane + o < 32) inc = pair_compose(inc, other);
+    }
+    if (lane == 0) sh.pw[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        Pair64 p = sh.pw[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Pair64 other;
+            other.a0 = __shfl_down_sync(TL_FULL, p.a0, o);
+            other.a1 = __shfl_down_sync(TL_FULL, p.a1, o);
+            if (lane + o < 32) p = pair_compose(p, other);
+        }
+        sh.pw[lane] = p;                                 // warps lane .. 31
+    }
+    __syncthreads();
+    Pair64 excl;
+    excl.a0 = __shfl_down_sync(TL_FULL, inc.a0, 1);
+    excl.a1 = __shfl_down_sync(TL_FULL, inc.a1, 1);
+    if (lane == 31) { excl.a0 = 0; excl.a1 = 0; }
+    if (warp < TL_WARPS - 1) excl = pair_compose(excl, sh.pw[warp + 1]);
+    aggregate = sh.pw[0];
+    __syncthreads();
+    return excl;
+}
+
+#define TL_WSTRIDE 9      // shared-memory words per thread (odd: thread-consecutive reads are bank-conflict free)
+
+#define TL_CENTRAL_EARLY 8      // CTAs below this do their central sums after the first pass (they head the chain)
+#define TL_KIND_CLEAN 0
+#define TL_KIND_TWO 1
+#define TL_KIND_MULTI 2
+#define TL_WSM_BYTES (TL_THREADS * TL_WSTRIDE * 4)
+
 // One exact pass over the tiles this CTA owns (v = blockIdx.x, + gridDim.x, ...).  P2: the weights are divided
 // by S first (pu:430) and every running sum is written to C (pu:436-443); otherwise only the total is wanted.
+// A tile is prepared BEFORE its exact incoming sum is known, according to where the fp64 prediction of its sums
+// (widened by 2^-9: real filter weights repeat, so the f32 sum drifts systematically) lies:
+//   CLEAN  inside one binade e: plain scan of the maps under e; the aggregate map is published for the look-back
+//   TWO    may cross from e to e+1: prefix scan under e and suffix scan under e+1; with the exact incoming sum one
+//          lane finds the crossing thread by binary search, replays its <= 8 additions in real f32 and applies the
+//          suffix map -- whatever the drift, as long as the crossing falls inside the tile (or not at all)
+//   MULTI  several binades (the first tiles, where the sum is still tiny and the prediction sharp): per-thread
+//          prediction, runs of trusted threads composed by a segmented scan, the others replayed one by one
+// Every shortcut is CHECKED against the exact sum (binade as assumed, no overflow); a tile that fails is redone by
+// the general restart loop, so no result depends on a prediction.
+// composition of the maps of this thread's weights wt[0 .. ipt) under unit exponent e (rolled: code size)
+__device__ __forceinline__ Pair64 tl_thread_map(const float *wt, int ipt, int e) {
+    Pair64 F; F.a0 = 0; F.a1 = 0;
+#pragma unroll
+    for (int k = 0; k < TL_MAX_IPT; ++k)
+        if (k < ipt) F = pair_compose(F, seq_decode(wt[k], e));
+    return F;
+}
+
 template <bool P2>
-__device__ void tl_exact_pass(const TailArgs &a, TlShared &sh, float S) {
+__device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, float S, unsigned char *dyn, bool central,
+                                              double mx, double my, double mt) {
     unsigned long long *st = P2 ? a.st2 : a.st1;
     float *C = (float *)a.C;
+    float *wsm = (float *)dyn;
+    Pair64 *pfs = (Pair64 *)(dyn + TL_WSM_BYTES), *sxs = pfs + TL_THREADS;
     const int t = threadIdx.x, lane = tl_lane(), warp = tl_warp();
     const double invS = P2 ? 1.0 / (double)S : 1.0;
     int rd = 0;
@@ -428,151 +574,270 @@ __device__ void tl_exact_pass(const TailArgs &a, TlShared &sh, float S) {
         const int64_t tile_lo = (int64_t)v * a.tile;
         const int64_t end = min(a.n, tile_lo + a.tile);
         const int64_t first = tile_lo + (int64_t)t * a.ipt;
-        float wv[TL_MAX_IPT];
+        // coalesced loads -> shared memory -> ipt consecutive weights per thread (padding: + 0 changes no sum)
+        for (int k = 0; k < a.ipt; ++k) {
+            const int j = k * TL_THREADS + t;
+            const int64_t i = tile_lo + j;
+            float w = 0.0f;
+            if (i < end) { w = __ldcg(a.w_out + i); if (P2) w = __fdiv_rn(w, S); }
+            const int tj = j / a.ipt;
+            wsm[tj * TL_WSTRIDE + (j - tj * a.ipt)] = w;
+        }
+        __syncthreads();
+        const float *wt = wsm + t * TL_WSTRIDE;          // this thread's weights: wt[0 .. ipt)
         double ls = 0.0;
 #pragma unroll
-        for (int k = 0; k < TL_MAX_IPT; ++k) {
-            const int64_t i = first + k;
-            float w = 0.0f;                              // padding: + 0 leaves every sum unchanged
-            if (k < a.ipt && i < end) { w = a.w_out[i]; if (P2) w = __fdiv_rn(w, S); }
-            wv[k] = w;
-            ls += (double)w;
-        }
-        // predicted (fp64) sum entering / leaving this thread's weights
+        for (int k = 0; k < TL_MAX_IPT; ++k)
+            if (k < a.ipt) ls += (double)wt[k];
+        if (rd == 0) tl_stamp(a, P2 ? 26 : 29);
         double ttot;
-        const double pe = tl_block_excl_scan_d(ls, ttot, sh);
-        if (a.stop == 33) return;
-        const double Pt = sh.ownP[rd] * invS + pe, Qt = Pt + ls;
-        int et = 0;
-        bool serial = true;
-        if (Pt > 0.0) {
-            et = ilogb(Pt);
-            const double lo = ldexp(1.0, et);
-            serial = !(et >= -126 && et < 127 && Pt >= lo * (1.0 + TL_DELTA) && Qt <= 2.0 * lo * (1.0 - TL_DELTA));
+        const double pe = tl_block_excl_scan_d(ls, ttot, sh);     // predicted (fp64) sum entering this thread's weights
+        if (rd == 0) tl_stamp(a, P2 ? 27 : 30);
+        const double lo_v = sh.ownP[rd] * invS, hi_v = lo_v + ttot;
+        int kind = TL_KIND_MULTI, e1 = 0;
+        if (lo_v > 0.0 && hi_v < 1e38) {
+            const int ea = ilogb(lo_v * (1.0 - TL_DELTA_TILE)), eb = ilogb(hi_v * (1.0 + TL_DELTA_TILE));
+            if (ea >= -126 && eb < 127) { e1 = ea; kind = eb == ea ? TL_KIND_CLEAN : (eb == ea + 1 ? TL_KIND_TWO : TL_KIND_MULTI); }
         }
-        const int code = serial ? (TL_SERIAL_MARK - t) : et;
-        sh.code[t] = code;
-        __syncthreads();
-        if (a.stop == 34) return;
-        const bool head = t == 0 || serial || sh.code[t - 1] != code;
-        const bool last = t == TL_THREADS - 1 || serial || sh.code[t + 1] != code;
-        Pair64 F; F.a0 = 0; F.a1 = 0;
-        if (!serial) {
-#pragma unroll
-            for (int k = 0; k < TL_MAX_IPT; ++k) F = pair_compose(F, seq_decode(wv[k], et));
-        }
-        // segmented inclusive scan of the maps (segments start at heads) + counts of heads / replayed threads
-        Pair64 inc = F;
-        int hf = head ? 1 : 0;
-        int cnt = (head ? 1 : 0) | (serial ? 0x10000 : 0);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const Pair64 p2 = pair_shfl_up(inc, o);
-            const int h2 = __shfl_up_sync(TL_FULL, hf, o);
-            const int c2 = __shfl_up_sync(TL_FULL, cnt, o);
-            if (lane >= o) {
-                if (!hf) inc = pair_compose(p2, inc);
-                hf |= h2;
-                cnt += c2;
+        // per-kind state that the write phase needs
+        Pair64 EX; EX.a0 = 0; EX.a1 = 0;                 // CLEAN / TWO: map of the threads before me (under e1); MULTI: inside my run
+        Pair64 G; G.a0 = 0; G.a1 = 0;                    // TWO: my map under e1 + 1
+        int et = e1, my_item = 0, nitems = 1;
+        bool serial = false;
+        if (kind == TL_KIND_CLEAN) {
+            const Pair64 F = tl_thread_map(wt, a.ipt, e1);
+            Pair64 agg;
+            EX = tl_block_excl_scan_pair(F, agg, sh);
+            if (rd == 0) tl_stamp(a, P2 ? 20 : 16);
+            if (t == 0) {
+                const bool pub = agg.a0 < (1u << 24) && agg.a1 < (1u << 24);
+                tl_st_release(st + v, pub ? tl_rec_agg(e1, agg) : (TL_F_NOAGG << 62));
             }
-        }
-        if (lane == 31) { sh.pw[warp] = inc; sh.pwf[warp] = hf; sh.cnt[warp] = cnt; }
-        __syncthreads();
-        if (warp == 0) {
-            Pair64 p = sh.pw[lane];
-            int f = sh.pwf[lane], c = sh.cnt[lane];
+            if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);      // hidden behind the chain
+            if (warp == 0) {
+                const float c_in = tl_lookback(st, v, &a.hd->err);
+                if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
+                if (lane == 0) {
+                    const long long Kn = tl_apply(seq_K(c_in), agg);
+                    const int fail = !(seq_exponent(c_in) == e1 && Kn < (1ll << 24));
+                    const float c = fail ? c_in : seq_value(Kn, e1);
+                    if (!fail) tl_st_release(st + v, tl_rec_inc(c));
+                    sh.c_in = c_in; sh.c_out = c; sh.fail = fail;
+                }
+                if (rd == 0) tl_stamp(a, P2 ? 22 : 18);
+            }
+        } else if (kind == TL_KIND_TWO) {
+            const Pair64 F = tl_thread_map(wt, a.ipt, e1);
+            G = tl_thread_map(wt, a.ipt, e1 + 1);
+            Pair64 aggF, aggG;
+            EX = tl_block_excl_scan_pair(F, aggF, sh);
+            const Pair64 SX = tl_block_suffix_scan_pair(G, aggG, sh);
+            pfs[t] = pair_compose(EX, F);                // through my last weight, under e1
+            sxs[t] = SX;                                 // everything behind me, under e1 + 1
+            __syncthreads();
+            if (rd == 0) tl_stamp(a, P2 ? 20 : 16);
+            if (t == 0) tl_st_release(st + v, TL_F_NOAGG << 62);
+            if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);      // hidden behind the chain
+            if (warp == 0) {
+                const float c_in = tl_lookback(st, v, &a.hd->err);
+                if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
+                if (lane == 0) {
+                    const long long K0 = seq_K(c_in);
+                    const int ec = seq_exponent(c_in);
+                    int fail = 1, ts = TL_THREADS;
+                    float c = c_in, cp = c_in;
+                    if (ec == e1) {
+                        int lo = 0, hi = TL_THREADS;     // first thread whose last sum leaves the binade
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (tl_apply(K0, pfs[mid]) >= (1ll << 24)) hi = mid; else lo = mid + 1;
+                        }
+                        ts = lo;
+                        if (ts == TL_THREADS) { c = seq_value(tl_apply(K0, pfs[TL_THREADS - 1]), e1); fail = 0; }
+                        else {
+                            cp = seq_value(ts ? tl_apply(K0, pfs[ts - 1]) : K0, e1);
+                            float w8[TL_MAX_IPT];
+#pragma unroll
+                            for (int k = 0; k < TL_MAX_IPT; ++k) w8[k] = k < a.ipt ? wsm[ts * TL_WSTRIDE + k] : 0.0f;
+#pragma unroll
+                            for (int k = 0; k < TL_MAX_IPT; ++k) cp = __fadd_rn(cp, w8[k]);
+                            const long long Kn = tl_apply(seq_K(cp), sxs[ts]);
+                            if (seq_exponent(cp) == e1 + 1 && Kn < (1ll << 24)) { c = seq_value(Kn, e1 + 1); fail = 0; }
+                        }
+                    } else if (ec == e1 + 1) {           // the crossing already happened before this tile
+                        ts = -1;
+                        const long long Kn = tl_apply(K0, aggG);
+                        if (Kn < (1ll << 24)) { c = seq_value(Kn, e1 + 1); fail = 0; }
+                    }
+                    if (!fail) tl_st_release(st + v, tl_rec_inc(c));
+                    sh.c_in = c_in; sh.c_out = c; sh.fail = fail; sh.tstar = ts; sh.cprime = cp;
+                }
+                if (rd == 0) tl_stamp(a, P2 ? 22 : 18);
+            }
+        } else {
+            // ---- MULTI: per-thread prediction; threads within 2^-13 of a power of two are replayed -------------
+            const double Pt = lo_v + pe, Qt = Pt + ls;
+            serial = true;
+            if (Pt > 0.0) {
+                et = ilogb(Pt);
+                const double lo = ldexp(1.0, et);
+                serial = !(et >= -126 && et < 127 && Pt >= lo * (1.0 + TL_DELTA) && Qt <= 2.0 * lo * (1.0 - TL_DELTA));
+            }
+            // threads behind the last weight of a ragged tile hold nothing: they never start a piece of their own
+            const bool beyond = first >= end && t > 0;
+            const int last_real = (int)((end - tile_lo - 1) / a.ipt);
+            if (beyond) serial = false;
+            const int code = serial ? (TL_SERIAL_MARK - t) : et;
+            sh.code[t] = code;
+            __syncthreads();
+            const bool head = !beyond && (t == 0 || serial || sh.code[t - 1] != code);
+            const bool last = !beyond && (t == last_real || serial || sh.code[t + 1] != code);
+            Pair64 F; F.a0 = 0; F.a1 = 0;
+            if (!serial && !beyond) F = tl_thread_map(wt, a.ipt, et);
+            // segmented inclusive scan of the maps (segments start at heads) + counts of heads / replayed threads
+            Pair64 inc = F;
+            int hf = head ? 1 : 0;
+            int cnt = (head ? 1 : 0) | (serial ? 0x10000 : 0);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const Pair64 p2 = pair_shfl_up(p, o);
-                const int h2 = __shfl_up_sync(TL_FULL, f, o);
-                const int c2 = __shfl_up_sync(TL_FULL, c, o);
+                const Pair64 p2 = pair_shfl_up(inc, o);
+                const int h2 = __shfl_up_sync(TL_FULL, hf, o);
+                const int c2 = __shfl_up_sync(TL_FULL, cnt, o);
                 if (lane >= o) {
-                    if (!f) p = pair_compose(p2, p);
-                    f |= h2;
-                    c += c2;
+                    if (!hf) inc = pair_compose(p2, inc);
+                    hf |= h2;
+                    cnt += c2;
                 }
             }
-            sh.pw[lane] = p; sh.cnt[lane] = c;
-        }
-        __syncthreads();
-        if (warp > 0) {
-            if (!hf) inc = pair_compose(sh.pw[warp - 1], inc);
-            cnt += sh.cnt[warp - 1];
-        }
-        if (a.stop == 35) return;
-        const int total_cnt = sh.cnt[TL_WARPS - 1];
-        const int nitems = total_cnt & 0xffff, nserial = total_cnt >> 16;
-        const bool overflow = nitems > TL_MAX_ITEMS || nserial > TL_MAX_SERIAL;
-        const int my_item = (cnt & 0xffff) - 1;
-        sh.inc[t] = inc;
-        if (!overflow && last) {
-            if (serial) {
-                const int slot = (cnt >> 16) - 1;
-                sh.it.e[my_item] = TL_SERIAL_MARK;
-                sh.it.map[my_item].a0 = (unsigned)slot;
+            if (lane == 31) { sh.pw[warp] = inc; sh.pwf[warp] = hf; sh.cnt[warp] = cnt; }
+            __syncthreads();
+            if (warp == 0) {
+                Pair64 p = sh.pw[lane];
+                int f = sh.pwf[lane], c = sh.cnt[lane];
 #pragma unroll
-                for (int k = 0; k < TL_MAX_IPT; ++k) sh.it.sw[slot * TL_MAX_IPT + k] = wv[k];
-            } else {
-                sh.it.e[my_item] = et;
-                sh.it.map[my_item] = inc;                // composed map of the whole run
-            }
-        }
-        __syncthreads();
-        if (a.stop == 36) return;
-        Pair64 ex; ex.a0 = 0; ex.a1 = 0;                 // map from the head of my run up to (excluding) me
-        if (!head) ex = sh.inc[t - 1];
-        const bool clean_tile = !overflow && nitems == 1 && sh.it.e[0] != TL_SERIAL_MARK &&
-                                sh.it.map[0].a0 < (1u << 24) && sh.it.map[0].a1 < (1u << 24);
-        if (warp == 0) {
-            if (lane == 0) tl_st_release(st + v, clean_tile ? tl_rec_agg(sh.it.e[0], sh.it.map[0]) : (TL_F_NOAGG << 62));
-            const float c_in = tl_lookback(st, v, &a.hd->err);
-            if (lane == 0) {
-                float c = c_in;
-                int fail = overflow ? 1 : 0;
-                if (!fail) {
-                    for (int it = 0; it < nitems; ++it) {
-                        sh.it.c[it] = c;
-                        const int e = sh.it.e[it];
-                        if (e == TL_SERIAL_MARK) {
-                            const float *w8 = sh.it.sw + sh.it.map[it].a0 * TL_MAX_IPT;
-#pragma unroll
-                            for (int k = 0; k < TL_MAX_IPT; ++k) c = __fadd_rn(c, w8[k]);
-                        } else {
-                            const long long Kn = tl_apply(seq_K(c), sh.it.map[it]);
-                            if (seq_exponent(c) != e || Kn >= (1ll << 24)) { fail = 1; break; }
-                            c = seq_value(Kn, e);
-                        }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const Pair64 p2 = pair_shfl_up(p, o);
+                    const int h2 = __shfl_up_sync(TL_FULL, f, o);
+                    const int c2 = __shfl_up_sync(TL_FULL, c, o);
+                    if (lane >= o) {
+                        if (!f) p = pair_compose(p2, p);
+                        f |= h2;
+                        c += c2;
                     }
                 }
-                if (!fail) tl_st_release(st + v, tl_rec_inc(c));     // the chain goes on before this tile writes
-                sh.c_in = c_in; sh.c_out = c; sh.fail = fail;
+                sh.pw[lane] = p; sh.cnt[lane] = c;
+            }
+            __syncthreads();
+            if (warp > 0) {
+                if (!hf) inc = pair_compose(sh.pw[warp - 1], inc);
+                cnt += sh.cnt[warp - 1];
+            }
+            const int total_cnt = sh.cnt[TL_WARPS - 1];
+            nitems = total_cnt & 0xffff;
+            const int nserial = total_cnt >> 16;
+            const bool overflow = nitems > TL_MAX_ITEMS || nserial > TL_MAX_SERIAL;
+            my_item = (cnt & 0xffff) - 1;
+            sh.inc[t] = inc;
+            if (!overflow && last) {
+                if (serial) {
+                    const int slot = (cnt >> 16) - 1;
+                    sh.it.e[my_item] = TL_SERIAL_MARK;
+                    sh.it.map[my_item].a0 = (unsigned)slot;
+#pragma unroll 1
+                    for (int k = 0; k < TL_MAX_IPT; ++k) sh.it.sw[slot * TL_MAX_IPT + k] = k < a.ipt ? wt[k] : 0.0f;
+                } else {
+                    sh.it.e[my_item] = et;
+                    sh.it.map[my_item] = inc;            // composed map of the whole run
+                }
+            }
+            __syncthreads();
+            if (!head) EX = sh.inc[t - 1];               // map from the head of my run up to (excluding) me
+            if (rd == 0) tl_stamp(a, P2 ? 20 : 16);
+            if (t == 0) tl_st_release(st + v, TL_F_NOAGG << 62);
+            if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);      // hidden behind the chain
+            if (warp == 0) {
+                const float c_in = tl_lookback(st, v, &a.hd->err);
+                if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
+                if (lane == 0) {
+                    float c = c_in;
+                    int fail = overflow ? 1 : 0;
+                    if (!fail) {
+                        for (int it = 0; it < nitems; ++it) {
+                            sh.it.c[it] = c;
+                            const int e = sh.it.e[it];
+                            if (e == TL_SERIAL_MARK) {
+                                const float *w8 = sh.it.sw + sh.it.map[it].a0 * TL_MAX_IPT;
+#pragma unroll
+                                for (int k = 0; k < TL_MAX_IPT; ++k) c = __fadd_rn(c, w8[k]);
+                            } else {
+                                const long long Kn = tl_apply(seq_K(c), sh.it.map[it]);
+                                if (seq_exponent(c) != e || Kn >= (1ll << 24)) { fail = 1; break; }
+                                c = seq_value(Kn, e);
+                            }
+                        }
+                    }
+                    if (!fail) tl_st_release(st + v, tl_rec_inc(c));     // the chain goes on before this tile writes
+                    sh.c_in = c_in; sh.c_out = c; sh.fail = fail;
+                }
+                if (rd == 0) tl_stamp(a, P2 ? 22 : 18);
             }
         }
         __syncthreads();
-        if (a.stop == 37) return;
         float c_out = sh.c_out;
-        if (sh.fail) {                                   // prediction off (or too many pieces): general path
-            c_out = tl_tile_general<P2>(wv, a.ipt, first, tile_lo, end, sh.c_in, C, sh);
+        const int failed = sh.fail;
+        if (failed) {                                    // a check failed (or too many pieces): general path
+            c_out = tl_tile_general(P2, wt, a.ipt, first, tile_lo, end, sh.c_in, C, sh);
             if (t == 0) tl_st_release(st + v, tl_rec_inc(c_out));
         } else if (P2) {
-            const float cs = sh.it.c[my_item];
-            if (serial) {
+            // ---- every running sum of the tile, from the exact sum that enters it --------------------------------
+            bool replay = false;
+            float cs = sh.c_in;
+            long long K = 0;
+            int ew = e1;
+            if (kind == TL_KIND_CLEAN) {
+                K = tl_apply(seq_K(cs), EX);
+            } else if (kind == TL_KIND_TWO) {
+                const int ts = sh.tstar;                 // -1: the whole tile is in e1 + 1; 1024: all of it in e1
+                Pair64 EXG; EXG.a0 = 0; EXG.a1 = 0;
+                if (ts < TL_THREADS) {                   // (uniform) maps under e1 + 1 of the threads behind the crossing
+                    Pair64 mine; mine.a0 = 0; mine.a1 = 0;
+                    if (t > ts) mine = G;
+                    Pair64 dummy;
+                    EXG = tl_block_excl_scan_pair(mine, dummy, sh);
+                }
+                if (t < ts) K = tl_apply(seq_K(cs), EX);
+                else if (t == ts) { replay = true; cs = seq_value(tl_apply(seq_K(cs), EX), e1); }
+                else { ew = e1 + 1; K = tl_apply(seq_K(sh.cprime), EXG); }
+            } else {
+                cs = sh.it.c[my_item];
+                replay = serial;
+                ew = et;
+                K = tl_apply(seq_K(cs), EX);
+            }
+            if (replay) {
                 float c = cs;
 #pragma unroll
                 for (int k = 0; k < TL_MAX_IPT; ++k) {
                     const int64_t i = first + k;
-                    c = __fadd_rn(c, wv[k]);
-                    if (k < a.ipt && i < end) C[i] = c;
+                    if (k < a.ipt) {
+                        c = __fadd_rn(c, wt[k]);
+                        if (i < end) C[i] = c;
+                    }
                 }
             } else {
-                long long K = tl_apply(seq_K(cs), ex);
 #pragma unroll
                 for (int k = 0; k < TL_MAX_IPT; ++k) {
                     const int64_t i = first + k;
-                    K = tl_apply(K, seq_decode(wv[k], et));
-                    if (k < a.ipt && i < end) C[i] = seq_value(K, et);
+                    if (k < a.ipt) {
+                        K = tl_apply(K, seq_decode(wt[k], ew));
+                        if (i < end) C[i] = seq_value(K, ew);
+                    }
                 }
             }
+        }
+        if (rd == 0) {
+            tl_stamp(a, P2 ? 23 : 19);
+            if (t == 0 && a.prof) a.prof[(size_t)blockIdx.x * 32 + (P2 ? 25 : 24)] = (unsigned long long)(failed * 1000 + kind * 100000 + nitems);
         }
         if (t == 0) {
             if (P2) ((float *)a.tend)[v] = c_out;
@@ -646,6 +911,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         if (t == 0) { a.st1[v] = 0ull; a.st2[v] = 0ull; }
     }
     const bool raw = a.raw != 0;
+    tl_stamp(a, 0);
     if (!raw) {
         unsigned long long acc0 = 0, acc1 = 0;
         for (int v = b; v < a.nt; v += G) {
@@ -662,7 +928,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         if (t == 0) { a.part_q[b] = acc0; a.part_q[G + b] = acc1; }
     }
     if (a.stop == 1) return;
+    tl_stamp(a, 1);
     tl_grid_barrier(a, 1);
+    tl_stamp(a, 2);
     float sum_post = 1.0f, sum_pre = 1.0f;
     if (!raw) {
         unsigned long long q0 = 0, q1 = 0;
@@ -721,7 +989,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         }
     }
     if (a.stop == 2) return;
+    tl_stamp(a, 3);
     tl_grid_barrier(a, 2);
+    tl_stamp(a, 4);
 
     // ---- S3: population sums (same order in every CTA), means, central sums; first resampling pass ------------
     double mx, my, mt, scale = 0.0;
@@ -764,28 +1034,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         }
     }
     if (a.stop == 31) return;
-    for (int v = b; v < a.nt && !raw; v += G) {          // central sums (node:590-597, pu:69-83)
-        double s9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        const int64_t base = (int64_t)v * a.tile + t;
-        for (int k = 0; k < a.ipt; ++k) {
-            const int64_t i = base + (int64_t)k * TL_THREADS;
-            if (i >= n) break;
-            const double wi = (double)a.w_out[i];
-            const double dx = a.nx[i] - mx, dy = a.ny[i] - my;
-            const double dt = (double)(float)normalize_angle_dev(__dadd_rn(a.nth[i], -mt));   // pu:80-82
-            s9[0] += wi * dx; s9[1] += wi * dy; s9[2] += wi * dt;
-            s9[3] += wi * dx * dx; s9[4] += wi * dx * dy; s9[5] += wi * dx * dt;
-            s9[6] += wi * dy * dy; s9[7] += wi * dy * dt; s9[8] += wi * dt * dt;
-        }
-        tl_block_sum<9>(s9, sh);
-        if (t == 0) {
-            double *pc = a.part_c + (size_t)v * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) pc[k] = s9[k];
-        }
-    }
+    tl_stamp(a, 5);
+    // central sums: in reference mode the CTAs whose first tile is far down the look-back chain compute them while
+    // they wait for it (inside the first exact pass), the first few after their pass; fixed point: here
+    const bool central_in_pass = REF && !raw && b >= TL_CENTRAL_EARLY;
+    if (!raw && !REF) tl_central_sums(a, sh, mx, my, mt);
+    tl_stamp(a, 6);
     if (REF) {
-        tl_exact_pass<false>(a, sh, 1.0f);               // pu:430 np.sum(weights): sequential f32
+        tl_exact_pass<false>(a, sh, 1.0f, dyn, central_in_pass, mx, my, mt);   // pu:430 np.sum(weights): sequential f32
+        if (!raw && !central_in_pass) tl_central_sums(a, sh, mx, my, mt);
     } else {
         for (int v = b; v < a.nt; v += G) {
             const int64_t first = (int64_t)v * a.tile + (int64_t)t * a.ipt, end = min(n, (int64_t)(v + 1) * a.tile);
@@ -797,25 +1054,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         }
     }
     if (a.stop == 3) return;
+    tl_stamp(a, 7);
     tl_grid_barrier(a, 3);
+    tl_stamp(a, 8);
 
     // ---- S4: running sums of the normalised weights (reference) / of the quantised weights (fixed) ------------
     double totd = 0.0;
-    if (b == 0 && !raw) {                                // central sums of the population -> est18[9..17]
-        double tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int u = t; u < a.nt; u += TL_THREADS) {
-            const double *pc = a.part_c + (size_t)u * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) tc[k] += __ldcg(pc + k);
-        }
-        tl_block_sum<9>(tc, sh);
-        if (t == 0)
-#pragma unroll
-            for (int k = 0; k < 9; ++k) a.est18[9 + k] = tc[k];
-    }
     if (REF) {
         const float S = __ldcg(&a.hd->S);
-        tl_exact_pass<true>(a, sh, S);
+        tl_exact_pass<true>(a, sh, S, dyn, false, 0.0, 0.0, 0.0);
     } else {
         unsigned long long carry = 0;
         for (int base = 0; base < a.nt; base += TL_THREADS) {
@@ -850,8 +1097,22 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             if (t == 0) ((unsigned long long *)a.tend)[v] = sh.ownE[rd] + tot;
         }
     }
+    if (b == G - 1 && !raw) {                            // central sums of the population -> est18[9..17]
+        double tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // (after this CTA's own tiles: off the look-back chain)
+        for (int u = t; u < a.nt; u += TL_THREADS) {
+            const double *pc = a.part_c + (size_t)u * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) tc[k] += __ldcg(pc + k);
+        }
+        tl_block_sum<9>(tc, sh);
+        if (t == 0)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a.est18[9 + k] = tc[k];
+    }
     if (a.stop == 4) return;
+    tl_stamp(a, 9);
     tl_grid_barrier(a, 4);
+    tl_stamp(a, 10);
 
     // ---- S5: idx[m] = min(first i with C_i >= key_m, n - 1) (pu:439-444 as a search) + pu:445 gather ----------
     {
@@ -917,6 +1178,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             __syncthreads();
         }
     }
+    tl_stamp(a, 11);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1001,6 +1263,15 @@ int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keyma
     a.hd = (TailHeader *)b; a.keymax = d_keymax; a.bar_base = h->tail_bar;
     a.n = u.n; a.nt = p.nt; a.ipt = p.ipt; a.tile = p.tile; a.use_mh = u.use_mh; a.raw = g_tail_raw;
     { const char *e = getenv("MCL_TAIL_STOP"); a.stop = e ? atoi(e) : 0; }
+    {
+        static int prof = -1;
+        if (prof < 0) { const char *e = getenv("MCL_TAIL_PROF"); prof = (e && atoi(e)) ? 1 : 0; }
+        if (prof) {
+            if (!h->d_tail_prof) MCL_CUDA(h, cudaMalloc((void **)&h->d_tail_prof, (size_t)1024 * 32 * 8));
+            a.prof = (unsigned long long *)h->d_tail_prof;
+            h->tail_prof_grid = p.grid;
+        }
+    }
     a.s_post = u.s_post; a.s_pre = u.s_pre; a.w_out = u.w_out;
     a.px = u.px; a.py = u.py; a.pt = u.pt; a.ox = u.ox; a.oy = u.oy; a.ot = u.ot; a.nx = u.nx; a.ny = u.ny; a.nth = u.nth;
     a.seed = u.seed; a.step = u.step; a.first_index = u.first_index;
@@ -1066,5 +1337,17 @@ extern "C" int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, dou
         MCL_CUDA(h, cudaMemcpyAsync(d_c, (char *)h->d_tail + p.o_C, (size_t)n * (mode == MCL_RESAMPLE_REFERENCE_F32 ? 4 : 8),
                                     cudaMemcpyDeviceToDevice, h->stream));
     }
+    return MCL_OK;
+}
+
+// debug (MCL_TAIL_PROF=1): globaltimer stamps [grid][16] of the last tail launch; returns the grid size in *grid
+extern "C" int mcl_tail_prof(mcl_handle *h, unsigned long long *out, int *grid) {
+    if (!h || !out || !grid) return MCL_ERR_ARG;
+    *grid = 0;
+    if (!h->d_tail_prof) return MCL_OK;
+    DeviceGuard guard(h->device);
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    MCL_CUDA(h, cudaMemcpy(out, h->d_tail_prof, (size_t)h->tail_prof_grid * 32 * 8, cudaMemcpyDeviceToHost));
+    *grid = h->tail_prof_grid;
     return MCL_OK;
 }

@@ -301,3 +301,77 @@ def estimate(particles, weights):
     out = (C.c_double * 16)()
     c.h.call("mcl_estimate", _p(x), _p(y), _p(t), _p(w), x.shape[0], out)
     return assemble_estimate(list(out))
+
+
+# ---- names the node imports at node:13 without reaching them from its callbacks --------
+def compute_valid_indices(particles, map_data, map_resolution, origin_x, origin_y, width, height):
+    """pu:369-386 -> int32 indices (ascending) of the particles on in-map cells with map_data <= 10."""
+    c = _ctx()
+    c.set_map(map_data, None, width, height, map_resolution, origin_x, origin_y)
+    n = len(particles)
+    if n == 0:
+        return np.zeros(0, np.int32)
+    x, y, _ = c.soa(particles)
+    idx = torch.empty(n, dtype=torch.int32, device=c.device)
+    cnt = C.c_int64(0)
+    c.h.call("mcl_compute_valid_indices", _p(x), _p(y), n, _p(idx), C.byref(cnt))
+    return idx[:cnt.value].cpu().numpy()
+
+
+def validate_samples(samples, distance_map, resolution, origin):
+    """pu:600-614 -> (N,3) float64 copy of samples, the invalid ones zeroed.  distance_map is (H, W)."""
+    c = _ctx()
+    d = np.asarray(distance_map)
+    c.set_map(None, d, d.shape[1], d.shape[0], resolution, origin[0], origin[1])
+    x, y, t = c.soa(samples)
+    c.h.call("mcl_validate_samples", _p(x), _p(y), _p(t), x.shape[0])
+    return c.aos(x, y, t)
+
+
+def initialize_gaussian_parallel(mean, cov, num_particles, distance_map, resolution, origin):
+    """pu:594-598 (node:183): the samples come from NumPy's global generator exactly like the reference's (it is
+    plain Python there); the validation kernel zeroes the invalid ones."""
+    samples = np.random.multivariate_normal(mean, cov, size=num_particles)
+    return validate_samples(samples, distance_map, resolution, origin)
+
+
+def parallel_resample_simple(particles, weights, N, uniforms=None):
+    """pu:467-477 multinomial resampling -> new particles (same shape/dtype as `particles`).  uniforms: optional
+    injected (N,) draws.  Where the reference would read out of bounds (Appendix C #7) the last particle is taken."""
+    c = _ctx()
+    w = _dev(c, weights, np.float32)
+    N = int(N)
+    u = _dev(c, uniforms, np.float64) if uniforms is not None else None
+    idx = torch.empty(N, dtype=torch.int32, device=c.device)
+    c.h.call("mcl_resample_multinomial", _p(w), w.shape[0], N, _p(u), _state["seed"], _tick(), _p(idx))
+    particles = np.asarray(particles)
+    out = np.empty_like(particles)
+    out[:N] = particles[idx.cpu().numpy()]
+    return out
+
+
+def low_variance_resample_amcl(particles, weights, target_size, r=None):
+    """pu:486-502 -> ((target_size, 3) float32 particles, float64 weights 1/target_size)."""
+    c = _ctx()
+    w = _dev(c, weights, np.float32)
+    T = int(target_size)
+    if r is None:
+        r = c.h.lib.mcl_resample_offset(_state["seed"], _tick(), T)
+    idx = torch.empty(T, dtype=torch.int32, device=c.device)
+    c.h.call("mcl_resample_indices", _p(w), w.shape[0], T, float(r), _lib.RESAMPLE_AMCL_F32, _p(idx))
+    return np.asarray(particles)[idx.cpu().numpy()].astype(np.float32), np.full(T, 1.0 / T)
+
+
+def reinitialize_particles_numba(num_new, occupancy_map, res, origin_x, origin_y, choice=None, theta=None):
+    """pu:504-526 -> (num_new, 3) float32 poses on the corners of uniformly chosen free cells.  occupancy_map is
+    (H, W); choice / theta: optional injected draws (index into the row-major free-cell list, heading)."""
+    c = _ctx()
+    occ = np.asarray(occupancy_map)
+    c.set_map(occ, None, occ.shape[1], occ.shape[0], res, origin_x, origin_y)
+    n = int(num_new)
+    x, y, t = (torch.empty(n, dtype=torch.float64, device=c.device) for _ in range(3))
+    ch = _dev(c, choice, np.int64) if choice is not None else None
+    th = _dev(c, theta, np.float64) if theta is not None else None
+    nf = C.c_int64(0)
+    c.h.call("mcl_reinitialize_particles", n, _p(ch), _p(th), _state["seed"], _tick(), _p(x), _p(y), _p(t), C.byref(nf))
+    return c.aos(x, y, t).astype(np.float32)

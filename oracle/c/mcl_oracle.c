@@ -485,3 +485,83 @@ void orc_compute_likelihoods_raycast(const float *scan, const float *angles, int
         scores[i] = valid_count > 0 ? (float)(log_score / (double)valid_count) : -INFINITY;
     }
 }
+
+/* ---------------------------------------------------------------------- */
+/* Functions the node imports (node:13) but its callbacks never reach      */
+/* (SURVEY 8(a) row a14).                                                  */
+/* ---------------------------------------------------------------------- */
+
+/* pu:369-386 compute_valid_indices: int() truncation, cell in the map, map_data[cell] <= 10 */
+int64_t orc_compute_valid_indices(const double *particles, int64_t N, const int8_t *map, int W, int H, double res,
+                                  double ox, double oy, int32_t *out) {
+    int64_t k = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        const int64_t mx = (int64_t)((particles[3 * i] - ox) / res);
+        const int64_t my = (int64_t)((particles[3 * i + 1] - oy) / res);
+        if (0 <= mx && mx < W && 0 <= my && my < H && map[my * (int64_t)W + mx] <= 10) out[k++] = (int32_t)i;
+    }
+    return k;
+}
+
+/* pu:467-477 parallel_resample_simple with the uniforms passed in: cum = np.cumsum(weights) (numba: sequential,
+ * float32 accumulator), idx = np.searchsorted(cum, u) (left: first i with cum[i] >= u, compared in f64).
+ * The reference reads particles[N] when u > cum[-1]; here that case takes N - 1. */
+void orc_parallel_resample_simple(const float *weights, int64_t n, const double *u, int64_t N, int32_t *idx) {
+    float *cum = (float *)malloc(sizeof(float) * (size_t)n);
+    float c = 0.0f;
+    for (int64_t i = 0; i < n; ++i) { c += weights[i]; cum[i] = c; }
+    for (int64_t m = 0; m < N; ++m) {
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((double)cum[mid] < u[m]) lo = mid + 1; else hi = mid;
+        }
+        idx[m] = (int32_t)(lo < n ? lo : n - 1);
+    }
+    free(cum);
+}
+
+/* pu:486-502 low_variance_resample_amcl: weights as given, c a sequential f32 sum starting at weights[0],
+ * U = r + m / target_size (int / int true division), walk bounded by len(particles) - 1 */
+void orc_low_variance_resample_amcl(const float *weights, int64_t n_in, int64_t target, double r, int32_t *idx) {
+    float c = weights[0];
+    int64_t i = 0;
+    for (int64_t m = 0; m < target; ++m) {
+        const double U = r + (double)m / (double)target;
+        while (U > (double)c && i < n_in - 1) {
+            i += 1;
+            c += weights[i];
+        }
+        idx[m] = (int32_t)(i % n_in);
+    }
+}
+
+/* pu:504-526 reinitialize_particles_numba with the draws passed in: choice[i] indexes np.argwhere(map == 0)
+ * (row-major), pose = lower-left corner of that cell, float32 output */
+int64_t orc_reinitialize_particles(int64_t n, const int8_t *occ, int W, int H, double res, double ox, double oy,
+                                   const int64_t *choice, const double *theta, float *out) {
+    const int64_t cells = (int64_t)W * H;
+    int32_t *free_cells = (int32_t *)malloc(sizeof(int32_t) * (size_t)(cells > 0 ? cells : 1));
+    int64_t nf = 0;
+    for (int64_t c = 0; c < cells; ++c) if (occ[c] == 0) free_cells[nf++] = (int32_t)c;
+    for (int64_t i = 0; i < n; ++i) {
+        if (nf == 0) { out[3 * i] = (float)ox; out[3 * i + 1] = (float)oy; out[3 * i + 2] = (float)theta[i]; continue; }
+        const int cell = free_cells[choice[i]];
+        const int my = cell / W, mx = cell % W;
+        out[3 * i] = (float)((double)mx * res + ox);
+        out[3 * i + 1] = (float)((double)my * res + oy);
+        out[3 * i + 2] = (float)theta[i];
+    }
+    free(free_cells);
+    return nf;
+}
+
+/* pu:600-614 validate_samples: in place; a sample outside the map or with distance_map >= 1.0 becomes (0, 0, 0) */
+void orc_validate_samples(double *samples, int64_t n, const float *dist, int W, int H, double res, double ox, double oy) {
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t mx = (int64_t)((samples[3 * i] - ox) / res);
+        const int64_t my = (int64_t)((samples[3 * i + 1] - oy) / res);
+        if (!(0 <= mx && mx < W && 0 <= my && my < H && dist[my * (int64_t)W + mx] < 1.0f))
+            samples[3 * i] = samples[3 * i + 1] = samples[3 * i + 2] = 0.0;
+    }
+}

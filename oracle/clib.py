@@ -289,3 +289,59 @@ def normals3(seed, step, item, attempt):
     lib().orc_normals3(C.c_uint64(int(seed)), C.c_uint64(int(step)), C.c_uint64(int(item)),
                        C.c_uint32(int(attempt)), _p(z, C.c_double))
     return z
+
+
+# ---- functions the node imports but its callbacks never reach -------------------------
+def compute_valid_indices(particles, map_data, map_resolution, origin_x, origin_y, width, height):
+    """pu:369-386 -> int32 indices of the particles on cells with map_data <= 10."""
+    p = _f64(particles)
+    m = np.ascontiguousarray(map_data, np.int8)
+    out = np.empty(p.shape[0], np.int32)
+    lib().orc_compute_valid_indices.restype = C.c_int64
+    k = lib().orc_compute_valid_indices(_p(p, C.c_double), C.c_int64(p.shape[0]), _p(m, C.c_int8), C.c_int(int(width)),
+                                        C.c_int(int(height)), C.c_double(float(map_resolution)),
+                                        C.c_double(float(origin_x)), C.c_double(float(origin_y)), _p(out, C.c_int32))
+    return out[:k].copy()
+
+
+def parallel_resample_simple_indices(weights, N, uniforms):
+    """pu:467-477 with injected uniforms -> source index per output."""
+    w = _f32(weights)
+    u = _f64(uniforms)
+    idx = np.empty(int(N), np.int32)
+    lib().orc_parallel_resample_simple(_p(w, C.c_float), C.c_int64(w.shape[0]), _p(u, C.c_double), C.c_int64(int(N)),
+                                       _p(idx, C.c_int32))
+    return idx
+
+
+def low_variance_resample_amcl_indices(weights, target_size, r):
+    """pu:486-502 -> source index per output (r = the one uniform draw in [0, 1/target_size))."""
+    w = _f32(weights)
+    idx = np.empty(int(target_size), np.int32)
+    lib().orc_low_variance_resample_amcl(_p(w, C.c_float), C.c_int64(w.shape[0]), C.c_int64(int(target_size)),
+                                         C.c_double(float(r)), _p(idx, C.c_int32))
+    return idx
+
+
+def reinitialize_particles(num_new, occupancy_map, res, origin_x, origin_y, choice, theta):
+    """pu:504-526 with injected draws (choice into the row-major list of free cells, theta) -> (num_new, 3) float32."""
+    occ = np.ascontiguousarray(occupancy_map, np.int8)
+    H, W = occ.shape
+    ch = np.ascontiguousarray(choice, np.int64)
+    th = _f64(theta)
+    out = np.empty((int(num_new), 3), np.float32)
+    lib().orc_reinitialize_particles.restype = C.c_int64
+    lib().orc_reinitialize_particles(C.c_int64(int(num_new)), _p(occ, C.c_int8), C.c_int(W), C.c_int(H),
+                                     C.c_double(float(res)), C.c_double(float(origin_x)), C.c_double(float(origin_y)),
+                                     _p(ch, C.c_int64), _p(th, C.c_double), _p(out, C.c_float))
+    return out
+
+
+def validate_samples(samples, distance_map, resolution, origin):
+    """pu:600-614 -> copy of samples with the invalid ones zeroed (distance_map is (H, W))."""
+    s = _f64(samples).copy()
+    d = np.ascontiguousarray(distance_map, np.float32)
+    H, W = d.shape
+    lib().orc_validate_samples(_p(s, C.c_double), C.c_int64(s.shape[0]), _p(d, C.c_float), C.c_int(W), C.c_int(H),
+                               C.c_double(float(resolution)), C.c_double(float(origin[0])), C.c_double(float(origin[1])))
+    return s

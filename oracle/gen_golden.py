@@ -384,8 +384,76 @@ def gen_filter_run():
     print("filter run: final estimate", est[-1][:3], "true pose", odoms[-1])
 
 
+@njit(parallel=True)
+def _reinit_draws(n, L):
+    """The draws reinitialize_particles_numba consumes (pu:517, 522), exposed: same calls in the same order on the
+    same (seeded, single-thread) stream."""
+    ci = np.empty(n, np.int64)
+    th = np.empty(n, np.float64)
+    for i in prange(n):
+        ci[i] = np.random.randint(0, L)
+        th[i] = np.random.uniform(-np.pi, np.pi)
+    return ci, th
+
+
+def gen_alt():
+    """The functions the node imports (node:13) but never reaches from its callbacks:
+    compute_valid_indices pu:369-386, parallel_resample_simple pu:467-477, low_variance_resample_amcl pu:486-502,
+    reinitialize_particles_numba pu:504-526."""
+    occ, res, ox, oy = load_ref_map("map_world")
+    mp = ng.load_map(occ, res, ox, oy)
+    rs = np.random.RandomState(77)
+    out = {}
+    # compute_valid_indices: free, occupied, unknown, outside, and (-1, 0)-cell particles
+    p = free_particles(mp, 600, rs)
+    p[::7, 0] += rs.uniform(-3, 3, len(p[::7]))
+    p[5] = [ox - 0.03, oy + 4.0, 0.1]; p[6] = [ox + 4.0, oy - 0.02, 0.2]; p[7] = [ox - 0.07, oy - 0.2, 0.0]
+    p[8] = [ox + 384 * res + 0.01, oy + 1.0, 0.0]
+    vi = pu.compute_valid_indices(p, mp["map_data"], mp["resolution"], ox, oy, mp["width"], mp["height"])
+    out["cvi_particles"] = p; out["cvi_out"] = vi
+    print("compute_valid_indices", len(vi), "of", len(p))
+    # parallel_resample_simple (multinomial): seeds chosen so that no draw exceeds cum[-1] (Appendix C #7)
+    g = np.load(os.path.join(OUT, "mh_map_world.npz"))
+    w = (g["mh_weights_a"] / np.sum(g["mh_weights_a"])).astype(np.float32)
+    parts = np.ascontiguousarray(g["mh_particles_a"])
+    N = len(w)
+    cum = np.cumsum(w)
+    seed = 500
+    while np.random.RandomState(seed).random_sample(N).max() >= cum[-1]:
+        seed += 1
+    seed_reference(seed)
+    res_p = pu.parallel_resample_simple(parts, w, N)
+    out["prs_particles"] = parts; out["prs_w"] = w; out["prs_seed"] = seed; out["prs_out"] = res_p
+    # low_variance_resample_amcl: target_size below, equal to and above N; weights as given
+    for tag, target, ww in (("eq", N, w), ("small", 700, w), ("big", 2 * N + 3, w),
+                            ("unnorm", N, (w * np.float32(0.37)).astype(np.float32))):
+        seed_reference(520 + len(tag))
+        a, b = pu.low_variance_resample_amcl(parts, ww, target)
+        out["amcl_w_" + tag] = ww; out["amcl_target_" + tag] = target; out["amcl_seed_" + tag] = 520 + len(tag)
+        out["amcl_out_" + tag] = a; out["amcl_wout_" + tag] = b
+        print("amcl lvr", tag, a.shape, a.dtype, b.dtype)
+    out["amcl_particles"] = parts
+    # reinitialize_particles_numba: the draws are read off the same stream by _reinit_draws
+    occ2d = mp["map_data"].reshape(mp["height"], mp["width"])
+    L = int((occ2d == 0).sum())
+    seed_reference(540)
+    rp = pu.reinitialize_particles_numba(500, occ2d, res, ox, oy)
+    seed_reference(540)
+    ci, th = _reinit_draws(500, L)
+    cells = np.argwhere(occ2d == 0)
+    exp = np.column_stack((cells[ci, 1] * res + ox, cells[ci, 0] * res + oy, th)).astype(np.float32)
+    assert np.array_equal(exp, rp), "draw recovery does not reproduce reinitialize_particles_numba"
+    out["reinit_choice"] = ci; out["reinit_theta"] = th; out["reinit_out"] = rp
+    np.savez_compressed(os.path.join(OUT, "alt_functions.npz"), **out)
+    print("alt functions written")
+
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "alt":        # only the fixtures added in round 2
+        gen_alt()
+        return
     gen_maps()
     gen_likelihood()
     gen_motion()
@@ -395,6 +463,7 @@ def main():
     gen_raycast_likelihood()
     gen_kld()
     gen_filter_run()
+    gen_alt()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes", tot)
 

@@ -189,3 +189,36 @@ def test_ros_adapter_example_is_valid_python():
     tree = ast.parse(src)
     names = {n.name for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
     assert {"B200LocalizerNode", "on_map", "on_odom", "on_scan", "publish_markers"} <= names
+
+
+def test_node_import_line_resolves_against_the_shim():
+    """SURVEY 8(b) level 0: the node's own import statement (amcmh_localizer.py:13), verbatim, with only the module
+    name pointed at the shim -- every one of its 14 names must resolve (no GPU needed to import)."""
+    from mcmh_localization_b200.parallel_utils import compute_likelihoods, mh_resampling, apply_motion_model_parallel, normalize_angle, compute_valid_indices, generate_valid_particles, low_variance_resample_numba, normalize_angle_array, kld_sampling_amcl, initialize_gaussian_parallel, parallel_resample_simple, compute_likelihoods_raycast, assym_mh_resampling, motion_model_odometry_parallel  # noqa: E501,F401
+    # the node's unused wrappers (node:441-487) call two more
+    from mcmh_localization_b200.parallel_utils import low_variance_resample_amcl, reinitialize_particles_numba  # noqa: F401
+    import inspect
+    from mcmh_localization_b200 import parallel_utils as shim
+    # positional signatures of the reference (pu:86-88, 208, 333, 370, 417, 452, 468, 487, 505, 530-531, 594)
+    want = {
+        "compute_likelihoods": ["scan_ranges", "angles", "particles", "distance_map", "map_resolution", "map_origin",
+                                "width", "height", "sigma_hit", "z_hit", "z_rand", "max_range", "step"],
+        "mh_resampling": ["particles", "proposed_particles", "likelihoods", "old_weights"],
+        "apply_motion_model_parallel": ["particles", "delta", "alpha", "map_data", "map_resolution", "origin_x", "origin_y",
+                                        "width", "height"],
+        "compute_valid_indices": ["particles", "map_data", "map_resolution", "origin_x", "origin_y", "width", "height"],
+        "generate_valid_particles": ["num_particles", "map_data", "map_resolution", "origin_x", "origin_y", "width", "height"],
+        "low_variance_resample_numba": ["particles", "weights", "N"],
+        "parallel_resample_simple": ["particles", "weights", "N"],
+        "low_variance_resample_amcl": ["particles", "weights", "target_size"],
+        "reinitialize_particles_numba": ["num_new", "occupancy_map", "res", "origin_x", "origin_y"],
+        "kld_sampling_amcl": ["particles", "weights", "bin_size_xy", "bin_size_theta", "epsilon", "z", "max_samples",
+                              "min_particles"],
+        "initialize_gaussian_parallel": ["mean", "cov", "num_particles", "distance_map", "resolution", "origin"],
+        "assym_mh_resampling": ["particles", "proposed_particles", "likelihoods", "old_weights", "trans_forward",
+                                "trans_backward"],
+        "motion_model_odometry_parallel": ["particles_prev", "particles_curr", "delta", "alpha"],
+    }
+    for name, args in want.items():
+        got = list(inspect.signature(getattr(shim, name)).parameters)
+        assert got[:len(args)] == args, (name, got)

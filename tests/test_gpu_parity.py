@@ -1062,3 +1062,56 @@ def test_gpu_edt_bit_identical_to_scipy():
     ref = map_from_occupancy(occ, 0.05, 0.0, 0.0)
     loc.load_map(occ, 0.05, (0.0, 0.0), gpu_edt=True)
     assert np.array_equal(loc.map.dist, ref.dist)
+
+
+# --------------------------------------------------------------------------- a14: imported but never reached
+def test_alt_functions_golden_bitexact(pu, orc, oracle_map_world):
+    """compute_valid_indices pu:369-386, parallel_resample_simple pu:467-477, low_variance_resample_amcl pu:486-502,
+    reinitialize_particles_numba pu:504-526, initialize_gaussian_parallel / validate_samples pu:594-614: the GPU
+    forms behind the shim against the unmodified reference's outputs (injected draws), and against the oracle on
+    larger inputs."""
+    mp = oracle_map_world
+    g = golden("alt_functions.npz")
+    vi = pu.compute_valid_indices(g["cvi_particles"], mp["map_data"], mp["resolution"], mp["origin_np"][0],
+                                  mp["origin_np"][1], mp["width"], mp["height"])
+    assert vi.dtype == np.int32 and np.array_equal(vi, g["cvi_out"])
+    n = len(g["prs_w"])
+    u = np.random.RandomState(int(g["prs_seed"])).random_sample(n)
+    out = pu.parallel_resample_simple(g["prs_particles"], g["prs_w"], n, uniforms=u)
+    assert np.array_equal(out, g["prs_out"])
+    for tag in ("eq", "small", "big", "unnorm"):
+        target = int(g["amcl_target_" + tag])
+        r = np.random.RandomState(int(g["amcl_seed_" + tag])).uniform(0.0, 1.0 / target)
+        p32, w64 = pu.low_variance_resample_amcl(g["amcl_particles"], g["amcl_w_" + tag], target, r=r)
+        assert p32.dtype == np.float32 and np.array_equal(p32, g["amcl_out_" + tag]), tag
+        assert w64.dtype == np.float64 and np.array_equal(w64, g["amcl_wout_" + tag])
+    occ2d = mp["map_data"].reshape(mp["height"], mp["width"])
+    rp = pu.reinitialize_particles_numba(len(g["reinit_choice"]), occ2d, mp["resolution"], mp["origin_np"][0],
+                                         mp["origin_np"][1], choice=g["reinit_choice"], theta=g["reinit_theta"])
+    assert rp.dtype == np.float32 and np.array_equal(rp, g["reinit_out"])
+    # Philox mode: every pose is the corner of a free cell
+    rq = pu.reinitialize_particles_numba(5000, occ2d, mp["resolution"], mp["origin_np"][0], mp["origin_np"][1])
+    mx = np.rint((rq[:, 0].astype(np.float64) - mp["origin_np"][0]) / mp["resolution"]).astype(int)
+    my = np.rint((rq[:, 1].astype(np.float64) - mp["origin_np"][1]) / mp["resolution"]).astype(int)
+    assert np.all(occ2d[my, mx] == 0) and len(np.unique(my * 384 + mx)) > 2000
+    gi = golden("init_gaussian.npz")
+    for k in (0, 1):
+        np.random.seed(int(gi["seed_%d" % k]))
+        p = pu.initialize_gaussian_parallel(gi["mean_%d" % k], gi["cov_%d" % k], 500,
+                                            mp["distance_map"].reshape(mp["height"], mp["width"]), mp["resolution"],
+                                            mp["origin_np"])
+        assert np.array_equal(p, gi["out_%d" % k])
+    # larger inputs against the oracle
+    rs = np.random.RandomState(3)
+    big = np.column_stack((rs.uniform(-11, 10, 300_000), rs.uniform(-11, 10, 300_000), rs.uniform(-3, 3, 300_000)))
+    assert np.array_equal(pu.compute_valid_indices(big, mp["map_data"], mp["resolution"], -10.0, -10.0, 384, 384),
+                          orc.compute_valid_indices(big, mp["map_data"], mp["resolution"], -10.0, -10.0, 384, 384))
+    w = np.exp(rs.normal(0, 1.5, 200_000)).astype(np.float32)
+    w /= w.sum()
+    u = rs.random_sample(150_000) * 0.999
+    idx = pu.parallel_resample_simple(np.arange(200_000), w, 150_000, uniforms=u)[:150_000]
+    assert np.array_equal(idx, orc.parallel_resample_simple_indices(w, 150_000, u))
+    r = rs.uniform(0, 1.0 / 123_457)
+    p32, _ = pu.low_variance_resample_amcl(np.arange(200_000 * 3).reshape(-1, 3) % 1000, w, 123_457, r=r)
+    ref = orc.low_variance_resample_amcl_indices(w, 123_457, r)
+    assert np.array_equal(p32, (np.arange(200_000 * 3).reshape(-1, 3) % 1000)[ref].astype(np.float32))
