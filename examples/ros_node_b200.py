@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
 """ROS 1 adapter: the reference node's message handling around the device-resident filter.
 
-SURVEY 8(f) rank 2.  NOT exercised in the build image (no rospy / tf there): it shows where the calls of
-`mcmh_localization_b200.Localizer` go in a node shaped like app/scripts/amcmh_localizer.py -- topic names and
-parameters as in the reference's launch files -- and is kept syntactically valid by tests/test_abi_host.py.
+SURVEY 8(f) rank 2: where the calls of `mcmh_localization_b200.Localizer` go in a node shaped like
+app/scripts/amcmh_localizer.py -- the reference's topics (/scan, /odom, /map in; /mcmh_estimated_pose, /mcmh_particles
+out: node:104-110, 126) and rosparam keys (app/params/amhmcl.yaml).  There is no ROS in the build image, so
+tests/test_ros_adapter.py runs these callbacks under stub rospy / message modules with synthetic messages.
 
-    rosrun <pkg> ros_node_b200.py _mode:=MHMCL _num_particles:=100000
+    rosrun <pkg> ros_node_b200.py _localization_mode:=MHMCL _init_particles:=100000
 """
 import math
 
@@ -23,7 +24,8 @@ except ImportError:                     # pragma: no cover
 
 from mcmh_localization_b200 import Localizer
 
-PARAM_KEYS = ("alpha1", "alpha2", "alpha3", "alpha4", "sigma_hit", "z_hit", "z_rand", "max_range", "step")
+PARAM_KEYS = ("alpha1", "alpha2", "alpha3", "alpha4", "sigma_hit", "z_hit", "z_rand", "max_range", "step", "kld_epsilon", "kld_z",
+              "kld_bin_size_xy", "kld_bin_size_theta", "min_particles", "alpha_slow", "alpha_fast")      # amhmcl.yaml
 
 
 def yaw_of(q):
@@ -33,11 +35,12 @@ def yaw_of(q):
 class B200LocalizerNode:
     def __init__(self):
         params = {k: rospy.get_param("~" + k) for k in PARAM_KEYS if rospy.has_param("~" + k)}
-        self.n = int(rospy.get_param("~num_particles", 100000))
+        self.n = int(rospy.get_param("~init_particles", 2000))                      # node:26
         self.max_markers = int(rospy.get_param("~max_markers", 2000))
-        self.loc = Localizer(params=params, mode=rospy.get_param("~mode", "MHMCL"), resample_mode="fixed")
+        # node:18 localization_mode; the resampling arithmetic is the reference's own (pu:416-446, bit-exact)
+        self.loc = Localizer(params=params, mode=rospy.get_param("~localization_mode", "MHAMCL"))
         self.ready = False
-        self.pose_pub = rospy.Publisher("/mcmh_pose", PoseWithCovarianceStamped, queue_size=1)
+        self.pose_pub = rospy.Publisher("/mcmh_estimated_pose", PoseWithCovarianceStamped, queue_size=1)     # node:109
         self.marker_pub = rospy.Publisher("/mcmh_particles", MarkerArray, queue_size=1)
         rospy.Subscriber("/map", OccupancyGrid, self.on_map, queue_size=1)
         rospy.Subscriber("/odom", Odometry, self.on_odom, queue_size=10)
@@ -59,8 +62,11 @@ class B200LocalizerNode:
         if not self.ready:
             return
         self.loc.update(np.asarray(msg.ranges, dtype=np.float32), msg.angle_min, msg.angle_max)
-        mx, my, mt, cov = self.loc.estimate()    # node:586-597
-        self.loc.resample()                      # node:488-492
+        est = self.loc.estimate()                # node:586-597
+        self.loc.resample()                      # node:488-492 / node:496-527 by mode
+        if est is None:                          # node:594-596: fewer than two particles, nothing is published
+            return
+        mx, my, mt, cov = est
         out = PoseWithCovarianceStamped()
         out.header.stamp, out.header.frame_id = msg.header.stamp, "map"
         out.pose.pose.position.x, out.pose.pose.position.y = mx, my

@@ -98,7 +98,7 @@ struct mcl_handle {
     std::vector<ScanMeta> batch_meta;
     int batch_stride = 0;
     const BeamTable *d_beams_active = nullptr;
-    uint64_t scan_gen = 0;       // bumped whenever the active scan table changes
+    uint64_t scan_gen = 0;       // process-wide unique id of the active scan table's contents (mcl_next_scan_uid)
 
     // scratch for reductions / scans
     void *d_scratch = nullptr;
@@ -128,6 +128,8 @@ struct mcl_handle {
 extern thread_local std::string g_create_err;
 
 int mcl_fail(mcl_handle *h, int code, const std::string &msg);
+uint64_t mcl_next_scan_uid();
+void mcl_raycast_forget(const mcl_handle *h);
 int mcl_ensure_scratch(mcl_handle *h, size_t bytes);
 int mcl_prepare_table(mcl_handle *h);   // rebuild logtab/window if dirty
 void mcl_filter_forget(const mcl_handle *h);

@@ -99,6 +99,7 @@ extern "C" int mcl_filter_bind(mcl_handle *h, int64_t n, double *const x[3], dou
     if (!h) return MCL_ERR_ARG;
     if (n <= 0 || !x || !y || !th || !score_pre || !score_post || !w_pre || !w_post || !w_a || !w_b || !idx)
         return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_bind: bad argument");
+    if (max_attempts > 65535) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_bind: max_attempts > 65535");
     FilterState *f = filter_of(h, true);
     for (int k = 0; k < 3; ++k) {
         if (!x[k] || !y[k] || !th[k]) return mcl_fail(h, MCL_ERR_ARG, "mcl_filter_bind: null pose buffer");
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(32) k_exchange(const XchArgs a, const unsigned
                                                  unsigned long long *out, unsigned long long *out2) {
     const int t = threadIdx.x;
     const int par = (int)(a.epoch & 1ull);
+    if (*(volatile int *)a.err) return;        // a peer was lost earlier: sticky, the host reports it (comm_check)
     if (t < a.world) {
         unsigned long long *peer = reinterpret_cast<unsigned long long *>(a.peers[t]);
         unsigned long long *slot = peer + 32 + ((size_t)par * 16 + a.rank) * XCH_MAXV;
@@ -324,6 +326,18 @@ static int sharded_softmax_arrays(mcl_handle *h, FilterState *f, const float *s_
     if (rc) return rc;
     if (both) rc = mcl_softmax_weights(h, s_pre, f->n, st_pre, w_pre);
     return rc;
+}
+
+// after a host read-back that has synchronised the stream: a timed-out exchange invalidates everything since
+static int comm_check(mcl_handle *h, FilterState *f) {
+    if (!f->comm) return MCL_OK;
+    int e = 0;
+    MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned + 22, f->d_comm_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(&e, h->h_pinned + 22, sizeof(int));
+    if (e) return mcl_fail(h, MCL_ERR_CUDA, "sharded step: a peer-memory exchange timed out (a rank died?); the particle sets "
+                                            "are no longer consistent -- rebuild the ShardedLocalizer");
+    return MCL_OK;
 }
 
 #define FILTER_OR_FAIL(name)                                                                          \
@@ -554,6 +568,7 @@ extern "C" int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out1
             h_out16[0] = r[0]; h_out16[1] = r[1]; h_out16[2] = r[6]; h_out16[3] = r[7]; h_out16[4] = r[8];
             for (int k = 0; k < 9; ++k) h_out16[5 + k] = r[9 + k];
             h_out16[14] = 0; h_out16[15] = 0;
+            return comm_check(h, f);
         }
         return MCL_OK;
     }
@@ -716,6 +731,7 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
         h_out16[0] = o[0]; h_out16[1] = o[1]; h_out16[2] = o[6]; h_out16[3] = o[7]; h_out16[4] = o[8];
         for (int k = 0; k < 9; ++k) h_out16[5 + k] = o[9 + k];
         h_out16[14] = 0; h_out16[15] = 0;
+        return comm_check(h, f);
     }
     return MCL_OK;
 }

@@ -851,9 +851,59 @@ static int launch_tiled(mcl_handle *h, LikParams p, unsigned long long *keymax) 
     return MCL_OK;
 }
 
-// the constant-bank beam table is module-global: re-upload when the active scan (or handle) changed
-static const void *g_cbeams_src = nullptr;
-static uint64_t g_cbeams_gen = 0;
+// The constant-bank beam table is one __constant__ symbol per device, shared by every handle on that device.  What it
+// holds is identified by the scan's process-wide unique id (mcl_next_scan_uid: never reused, so a new handle at a
+// recycled address can never match a stale entry); a handle on ANOTHER stream waits for the previous user's kernels
+// (event recorded after every launch that reads the table) before it overwrites the symbol.
+#include <mutex>
+struct CbeamState { uint64_t uid = 0; cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr; };
+static CbeamState g_cbeams[64];
+static std::mutex g_cbeams_mu;
+
+static int cbeams_upload(mcl_handle *h, size_t beam_bytes) {
+    std::lock_guard<std::mutex> lk(g_cbeams_mu);
+    CbeamState &c = g_cbeams[h->device & 63];
+    if (c.uid == h->scan_gen && c.stream == h->stream) return MCL_OK;
+    if (c.ev && c.stream != h->stream) MCL_CUDA(h, cudaStreamWaitEvent(h->stream, c.ev, 0));
+    if (c.uid != h->scan_gen)
+        MCL_CUDA(h, cudaMemcpyToSymbolAsync(c_beams_raw, h->d_beams_active, beam_bytes, 0, cudaMemcpyDeviceToDevice, h->stream));
+    c.uid = h->scan_gen;
+    c.stream = h->stream;
+    return MCL_OK;
+}
+static int cbeams_used(mcl_handle *h) {         // after the launches that read the table
+    std::lock_guard<std::mutex> lk(g_cbeams_mu);
+    CbeamState &c = g_cbeams[h->device & 63];
+    if (!c.ev) MCL_CUDA(h, cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+    MCL_CUDA(h, cudaEventRecord(c.ev, h->stream));
+    return MCL_OK;
+}
+
+// the one-thread-per-particle launches (tiled / coded window / int32 window / global path); they read the beam
+// table from the constant bank
+static int likelihood_g1_dispatch(mcl_handle *h, const LikParams &p, unsigned long long *d_keymax, const double *d_x2,
+                                  const double *d_y2, const double *d_theta2, float *d_score2, int64_t n, bool use_smem,
+                                  bool use_coded) {
+    int rc;
+    static int notile = -1;
+    if (notile < 0) { const char *e = getenv("MCL_NO_TILED"); notile = (e && atoi(e)) ? 1 : 0; }
+    if (!use_smem && !use_coded && h->tiled_ok && !notile && h->lik_path != 1 &&
+        n >= 64 * (int64_t)h->tiles_x * h->tiles_y && h->rmax_cells + 2.0 <= (double)h->tile_margin) {
+        rc = launch_tiled(h, p, d_keymax);
+        if (rc || !d_x2) return rc;
+        LikParams p2 = p;
+        p2.x = d_x2; p2.y = d_y2; p2.th = d_theta2; p2.score = d_score2;
+        return launch_tiled(h, p2, d_keymax ? d_keymax + 1 : nullptr);
+    }
+    if (use_coded) {
+        const size_t sm = 16 + 32768 + h->win8_bytes;
+        return h->win_tpose ? launch_g1<true, true, true>(h, p, sm) : launch_g1<true, true, false>(h, p, sm);
+    }
+    if (use_smem && h->cell_S == 8)
+        return h->win_tpose ? launch_g1<true, false, true>(h, p, 16 + h->win_bytes)
+                            : launch_g1<true, false, false>(h, p, 16 + h->win_bytes);
+    return launch_g1<false, false, false>(h, p, 16);
+}
 
 static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, int64_t n,
                            float *d_score, const double *d_x2, const double *d_y2, const double *d_theta2,
@@ -929,30 +979,11 @@ static int likelihood_impl(mcl_handle *h, const double *d_x, const double *d_y, 
     while (G < 32 && n * G < target) G *= 2;
     if (G == 1 && nb <= MAX_CBEAMS && h->acc_terms_ok) {
         if (g1_used) *g1_used = true;
-        if (g_cbeams_src != (const void *)h->d_beams_active || g_cbeams_gen != h->scan_gen) {
-            MCL_CUDA(h, cudaMemcpyToSymbolAsync(c_beams_raw, h->d_beams_active, beam_bytes, 0, cudaMemcpyDeviceToDevice,
-                                                h->stream));
-            g_cbeams_src = (const void *)h->d_beams_active;
-            g_cbeams_gen = h->scan_gen;
-        }
-        static int notile = -1;
-        if (notile < 0) { const char *e = getenv("MCL_NO_TILED"); notile = (e && atoi(e)) ? 1 : 0; }
-        if (!use_smem && !use_coded && h->tiled_ok && !notile && h->lik_path != 1 &&
-            n >= 64 * (int64_t)h->tiles_x * h->tiles_y && h->rmax_cells + 2.0 <= (double)h->tile_margin) {
-            rc = launch_tiled(h, p, d_keymax);
-            if (rc || !d_x2) return rc;
-            LikParams p2 = p;
-            p2.x = d_x2; p2.y = d_y2; p2.th = d_theta2; p2.score = d_score2;
-            return launch_tiled(h, p2, d_keymax ? d_keymax + 1 : nullptr);
-        }
-        if (use_coded) {
-            const size_t sm = 16 + 32768 + h->win8_bytes;
-            return h->win_tpose ? launch_g1<true, true, true>(h, p, sm) : launch_g1<true, true, false>(h, p, sm);
-        }
-        if (use_smem && h->cell_S == 8)
-            return h->win_tpose ? launch_g1<true, false, true>(h, p, 16 + h->win_bytes)
-                                : launch_g1<true, false, false>(h, p, 16 + h->win_bytes);
-        return launch_g1<false, false, false>(h, p, 16);
+        rc = cbeams_upload(h, beam_bytes);
+        if (rc) return rc;
+        rc = likelihood_g1_dispatch(h, p, d_keymax, d_x2, d_y2, d_theta2, d_score2, n, use_smem, use_coded);
+        if (rc) return rc;
+        return cbeams_used(h);
     }
     if (g1_used) *g1_used = true;   // the lanes-per-particle kernels implement the pair / key form as well
     if (use_coded && !use_smem && h->lik_path == 2)

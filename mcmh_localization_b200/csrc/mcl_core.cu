@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <atomic>
+
 #include "common.cuh"
 
 thread_local std::string g_create_err;
@@ -63,6 +65,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
     mcl_filter_forget(h);
+    mcl_raycast_forget(h);
     cudaFree(h->d_est18); cudaFree(h->d_fused); cudaFree(h->d_code8); cudaFree(h->d_tiled);
     cudaFree(h->d_kld);
     cudaFree(h->d_seq);
@@ -74,6 +77,12 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     for (auto &p : h->lik_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete h;
     return MCL_OK;
+}
+
+// process-wide unique id of "what the active beam table holds" (likelihood.cu keys its constant-bank copy on it)
+uint64_t mcl_next_scan_uid() {
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
 }
 
 extern "C" int mcl_set_stream(mcl_handle *h, void *s) {
@@ -399,7 +408,7 @@ extern "C" int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h
         MCL_CUDA(h, cudaMemcpyAsync(h->d_beams, h->h_beams, (size_t)(n_pos + n_neg) * sizeof(BeamTable),
                                     cudaMemcpyHostToDevice, h->stream));
     h->d_beams_active = h->d_beams;
-    h->scan_gen++;
+    h->scan_gen = mcl_next_scan_uid();
     h->scan_set = true;
     return MCL_OK;
 }
@@ -430,7 +439,7 @@ extern "C" int mcl_use_scan(mcl_handle *h, int k) {
     if (!h) return MCL_ERR_ARG;
     if (k < 0 || k >= (int)h->batch_meta.size()) return mcl_fail(h, MCL_ERR_ARG, "mcl_use_scan: no such pre-staged scan");
     h->d_beams_active = h->d_batch + (size_t)k * h->batch_stride;
-    h->scan_gen++;
+    h->scan_gen = mcl_next_scan_uid();
     h->n_pos = h->batch_meta[k].n_pos; h->n_neg = h->batch_meta[k].n_neg; h->rmax_cells = h->batch_meta[k].rmax_cells;
     h->scan_set = true;
     return MCL_OK;

@@ -284,6 +284,8 @@ int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, cons
     if (!h) return MCL_ERR_ARG;
     if (n < 0 || !delta || (n > 0 && (!d_x || !d_y || !d_theta || !d_xo || !d_yo || !d_thetao)))
         return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: bad argument");
+    // the cooperative retry queue keeps attempt indices in 16 bits (pu:339 uses 1000)
+    if (max_attempts > 65535) return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: max_attempts > 65535");
     if (d_normals && A <= 0) return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: injected normals need A > 0");
     if (!h->d_occ) return mcl_fail(h, MCL_ERR_STATE, "mcl_predict: map not set");
     if (!h->motion_set) return mcl_fail(h, MCL_ERR_STATE, "mcl_predict: motion noise not set (mcl_set_motion)");

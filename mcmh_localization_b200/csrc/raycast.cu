@@ -86,6 +86,14 @@ static RcState *rc_of(mcl_handle *h) {
     std::lock_guard<std::mutex> lk(g_rc_mu);
     return &g_rc[h];
 }
+// mcl_destroy: free the grid and drop the entry (a later handle at the same address must not inherit it)
+void mcl_raycast_forget(const mcl_handle *h) {
+    std::lock_guard<std::mutex> lk(g_rc_mu);
+    auto it = g_rc.find(h);
+    if (it == g_rc.end()) return;
+    cudaFree(it->second.d_bits); cudaFree(it->second.d_scan);
+    g_rc.erase(it);
+}
 
 extern "C" int mcl_set_raycast_grid(mcl_handle *h, const uint8_t *h_blocked, int W, int H, double res, double x_min,
                                     double y_min) {

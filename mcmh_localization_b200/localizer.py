@@ -15,6 +15,7 @@ libmcl.so kernel (include/mcl.h); torch only allocates buffers.  No CPU fallback
 """
 import ctypes as C
 import threading
+import warnings
 
 import numpy as np
 import torch
@@ -324,7 +325,11 @@ class Localizer:
 
     # ------------------------------------------------------------------ estimate / resample
     def estimate(self):
-        """node:586-597 -> (mean_x, mean_y, mean_theta, cov 3x3) with np.cov(aweights) semantics."""
+        """node:586-597 -> (mean_x, mean_y, mean_theta, cov 3x3) with np.cov(aweights) semantics, or None with
+        fewer than two particles (node:594-596 logs a warning and publishes nothing)."""
+        if self.n < 2:
+            warnings.warn("not enough particles for an estimate (node:594-596)")
+            return None
         with self._lock:
             self._bind_stream()
             out = (C.c_double * 16)()
@@ -367,6 +372,8 @@ class Localizer:
                 self._push_transition()
                 d = None
             self.h.call("mcl_filter_step", d, -1, None, out)
+        if self.n < 2:                                   # node:594-596: no estimate is published
+            return None
         return assemble_estimate(list(out))
 
     def step_staged(self, odom, k, out18=None):
@@ -409,13 +416,19 @@ class Localizer:
             return self._aos(self.prev)
 
     def weights(self):
-        return self.weights_t[:self.n].cpu().numpy()
+        with self._lock:
+            self._bind_stream()
+            return self.weights_t[:self.n].cpu().numpy()
 
     def set_weights(self, w):
-        self.weights_t[:self.n].copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
+        with self._lock:
+            self._bind_stream()
+            self.weights_t[:self.n].copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
 
     def scores(self):
-        return self.score_pre[:self.n].cpu().numpy(), self.score_post[:self.n].cpu().numpy()
+        with self._lock:
+            self._bind_stream()
+            return self.score_pre[:self.n].cpu().numpy(), self.score_post[:self.n].cpu().numpy()
 
     def sync(self):
         self.h.call("mcl_sync")

@@ -92,7 +92,11 @@ class ShardedLocalizer(Localizer):
     """Localizer whose particle set is the union over ranks of equally sized shards."""
 
     def __init__(self, device=0, params=None, mode=None, seed=0, resample_mode="fixed", max_attempts=1000,
-                 group=None, peer_push=True, native_comm=True):
+                 group=None, peer_push=True, native_comm=True, allow_fallback=False):
+        """peer_push / native_comm select the exchange implementation explicitly.  If the selected one cannot be set
+        up (no symmetric memory, ...) construction RAISES unless allow_fallback=True, in which case the next
+        simpler one is used and the reason is kept in `symm_error`."""
+        self.allow_fallback = allow_fallback
         if resample_mode != "fixed":
             raise ValueError("sharded resampling uses the fixed-point arithmetic (decomposition-independent)")
         self.group = group
@@ -121,7 +125,10 @@ class ShardedLocalizer(Localizer):
                 self.peer_tab = tab.to(self.device)                      # [set][component][rank]
                 self.symm, self.symm_buf = hdl, buf
                 return [[buf[(3 * j + k) * n:(3 * j + k + 1) * n] for k in range(3)] for j in range(3)]
-            except Exception as e:      # noqa: BLE001 -- any failure means: use the all-to-all path
+            except Exception as e:      # noqa: BLE001
+                if not self.allow_fallback:
+                    raise RuntimeError("ShardedLocalizer: symmetric (peer-mapped) pose buffers unavailable: %r; pass "
+                                       "peer_push=False or allow_fallback=True for the NCCL all-to-all path" % (e,)) from e
                 self.symm_error = repr(e)
                 self.symm = None
         return super()._make_sets(n)
@@ -134,7 +141,10 @@ class ShardedLocalizer(Localizer):
         if self.symm is not None and self.use_native_comm:
             try:
                 self._init_native_comm(n)
-            except Exception as e:      # noqa: BLE001 -- fall back to NCCL through torch.distributed
+            except Exception as e:      # noqa: BLE001
+                if not self.allow_fallback:
+                    raise RuntimeError("ShardedLocalizer: peer-memory mailboxes unavailable: %r; pass native_comm=False "
+                                       "or allow_fallback=True for NCCL scalar exchanges" % (e,)) from e
                 self.symm_error = repr(e)
                 self.native = False
         d = self.device

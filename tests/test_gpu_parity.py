@@ -972,8 +972,11 @@ def test_fused_step_equals_standalone_sequence(mode, n, resample_mode):
         assert np.array_equal(fused.idx.cpu().numpy(), plain.idx.cpu().numpy()), k
         sf, sp = fused.scores(), plain.scores()
         assert np.array_equal(sf[1], sp[1]) and (mode == "MCL" or np.array_equal(sf[0], sp[0]))
-        np.testing.assert_allclose(e_f[:3], e_p[:3], rtol=1e-12, atol=1e-13)
-        np.testing.assert_allclose(e_f[3], e_p[3], rtol=1e-9, atol=1e-15)
+        if n < 2:                                        # node:594-596: no estimate with fewer than two particles
+            assert e_f is None and e_p is None
+        else:
+            np.testing.assert_allclose(e_f[:3], e_p[:3], rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(e_f[3], e_p[3], rtol=1e-9, atol=1e-15)
         pose = pose + np.array([0.02 * np.cos(pose[2]), 0.02 * np.sin(pose[2]), 0.01])
 
 
@@ -1115,3 +1118,60 @@ def test_alt_functions_golden_bitexact(pu, orc, oracle_map_world):
     p32, _ = pu.low_variance_resample_amcl(np.arange(200_000 * 3).reshape(-1, 3) % 1000, w, 123_457, r=r)
     ref = orc.low_variance_resample_amcl_indices(w, 123_457, r)
     assert np.array_equal(p32, (np.arange(200_000 * 3).reshape(-1, 3) % 1000)[ref].astype(np.float32))
+
+
+# --------------------------------------------------------------------------- does it localise?
+@pytest.mark.parametrize("mode", ["MCL", "AMCL", "MHMCL", "MHAMCL", "AMHMCL", "AMHAMCL"])
+def test_filter_converges_to_the_true_pose(mode):
+    """End-to-end function, not just arithmetic: from a Gaussian cloud centred 0.35 m / 0.15 rad off the true pose
+    (node:183 initialize_gaussian_parallel with the launch files' initial covariance) the estimate must move onto
+    the robot while it drives 30 steps through map_world.  The reference's weights are a softmax of MEAN
+    log-likelihoods, i.e. deliberately flat, so convergence is gradual (the CPU oracle goes 0.29 m -> 0.10 m on
+    the same run); the bar is: final position error < 0.15 m and less than half the initial one, yaw < 0.1 rad."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    true = np.array([-2.0, -0.5, 0.0])
+    loc = Localizer(params=P, mode=mode, seed=5)
+    loc.load_map(gm)
+    loc.init_gaussian(true + np.array([0.25, -0.2, 0.15]), np.diag([0.05, 0.05, 0.1]), 2000, seed=3)
+    loc.predict(true)
+    errs = []
+    for k in range(30):
+        true = true + np.array([0.05 * np.cos(true[2]), 0.05 * np.sin(true[2]), 0.03])
+        scan, angles = raycast_scan(gm, true, noise_sigma=0.01, seed=100 + k)
+        mx, my, mt, cov = loc.step(true, scan, angles=angles)
+        errs.append(float(np.hypot(mx - true[0], my - true[1])))
+        yaw_err = abs((mt - true[2] + np.pi) % (2 * np.pi) - np.pi)
+    assert errs[-1] < 0.15 and errs[-1] < 0.5 * errs[0], errs[::5]
+    assert yaw_err < 0.1
+    assert np.all(np.isfinite(cov)) and np.all(np.linalg.eigvalsh(cov) > 0)
+
+
+def test_filter_converges_at_one_million_particles():
+    """The same run at BASELINE configs[1]'s size through the production step (persistent tail kernel, the
+    reference's resampling arithmetic)."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    true = np.array([-2.0, -0.5, 0.0])
+    loc = Localizer(params=P, mode="MHMCL", seed=5)
+    loc.load_map(gm)
+    loc.init_gaussian(true + np.array([0.25, -0.2, 0.15]), np.diag([0.05, 0.05, 0.1]), 1_000_000, seed=3)
+    loc.predict(true)
+    errs = []
+    for k in range(30):
+        true = true + np.array([0.05 * np.cos(true[2]), 0.05 * np.sin(true[2]), 0.03])
+        scan, angles = raycast_scan(gm, true, noise_sigma=0.01, seed=100 + k)
+        mx, my, mt, cov = loc.step(true, scan, angles=angles)
+        errs.append(float(np.hypot(mx - true[0], my - true[1])))
+    assert errs[-1] < 0.15 and errs[-1] < 0.5 * errs[0], errs[::5]
+    assert abs((mt - true[2] + np.pi) % (2 * np.pi) - np.pi) < 0.1
