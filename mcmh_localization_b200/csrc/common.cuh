@@ -169,8 +169,20 @@ int mcl_resample_push_from(mcl_handle *h, const unsigned long long *d_C, const u
                            const double *d_theta, const uint64_t *d_peer_ptrs);
 // tail.cu: the same tail as ONE persistent cooperative kernel, in either resampling arithmetic
 bool mcl_tail_available(mcl_handle *h, int64_t n);
+// comm != NULL: sharded step -- the kernel exchanges its five global quantities over NVLink peer memory itself
+// (TAIL_EXCHANGES epochs of filter.cu's mailbox) and pushes every offspring into the destination rank's set
+struct TailComm {
+    int rank, world;
+    int64_t n_global;
+    unsigned long long *mailbox;
+    unsigned long long peers[16];
+    unsigned long long epoch0;
+    int *d_err;
+    const unsigned long long *d_peer_pose_dst;   // device [3][world]
+};
+#define TAIL_EXCHANGES 5
 int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
-                  int32_t *idx, double *gx, double *gy, double *gt);
+                  int32_t *idx, double *gx, double *gy, double *gt, const TailComm *comm);
 const int *mcl_tail_err_ptr(mcl_handle *h);
 int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
                         const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,

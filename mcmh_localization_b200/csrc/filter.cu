@@ -629,7 +629,7 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     if (off || f->assym) return MCL_OK;
     // single GPU: the whole tail is ONE persistent cooperative kernel (tail.cu), in either resampling arithmetic;
     // sharded: four kernels with the peer-memory exchanges between them (fixed-point arithmetic only)
-    const bool tail = !f->comm && mcl_tail_available(h, f->n);
+    const bool tail = mcl_tail_available(h, f->n) && (!f->comm || f->resample_mode == MCL_RESAMPLE_FIXED_POINT);
     if (!tail && f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
     DeviceGuard guard(h->device);
     int rc = mcl_fused_prepare(h, f->n);
@@ -668,9 +668,18 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     u.step = f->tick;
     if (tail) {
         f->tick++;                                   // node:488-492 resample_lvr draws r
-        const double r = mcl_resample_offset(f->seed, f->tick, f->n);
+        const double r = mcl_resample_offset(f->seed, f->tick, f->comm ? f->n_global : f->n);
         const int dst = f->use_mh ? cur : spare;     // MH: the proposal set is free once the accept has read it
-        rc = mcl_tail_step(h, u, mcl_fused_keymax(h), f->resample_mode, r, f->idx, f->x[dst], f->y[dst], f->th[dst]);
+        TailComm tc;
+        if (f->comm) {
+            tc.rank = f->rank; tc.world = f->world; tc.n_global = f->n_global; tc.mailbox = f->mailbox;
+            for (int d = 0; d < 16; ++d) tc.peers[d] = f->peer_mailbox[d];
+            tc.epoch0 = f->epoch; tc.d_err = f->d_comm_err;
+            tc.d_peer_pose_dst = (const unsigned long long *)(f->d_peer_pose + (size_t)dst * 3 * f->world);
+            f->epoch += TAIL_EXCHANGES;
+        }
+        rc = mcl_tail_step(h, u, mcl_fused_keymax(h), f->resample_mode, r, f->idx, f->x[dst], f->y[dst], f->th[dst],
+                           f->comm ? &tc : nullptr);
         if (rc) return rc;
         // roles: particles = resampled set; the MH result (or, without MH, the old particles) becomes spare
         f->cur = dst; f->spare = res;
@@ -682,6 +691,7 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
             int terr = 0;
             memcpy(&terr, h->h_pinned + 20, sizeof(int));
             if (terr) return mcl_fail(h, MCL_ERR_CUDA, "step tail: a grid barrier / look-back wait timed out (mcl_tail_status)");
+            if (f->comm) { rc = comm_check(h, f); if (rc) return rc; }
             const double *o = h->h_pinned;
             h_out16[0] = o[0]; h_out16[1] = o[1]; h_out16[2] = o[6]; h_out16[3] = o[7]; h_out16[4] = o[8];
             for (int k = 0; k < 9; ++k) h_out16[5 + k] = o[9 + k];

@@ -82,6 +82,14 @@ struct TailArgs {
     double r, rstep;
     int32_t *idx;
     double *gx, *gy, *gt;
+    // sharded operation (SH kernels): exchanges over NVLink peer memory, offspring pushed to their destination rank
+    int rank, world;
+    int64_t n_global;                        // particles of the whole population (= world * n)
+    unsigned long long *mailbox;             // this rank's mailbox (filter.cu: flags[2][16] | slots[2][16][16])
+    unsigned long long peers[16];            // every rank's mailbox as mapped here
+    unsigned long long epoch0;               // exchanges consumed before this launch
+    int *comm_err;                           // sticky: a peer did not answer
+    const unsigned long long *peer_pose;     // device [3][world]: x / y / theta of the destination set on every rank
 };
 
 struct TlItems {
@@ -106,6 +114,10 @@ struct TlShared {
     unsigned long long ownE[TL_MAX_ROUNDS];
     float c_in, c_out, cseg, cprime;
     int fail, nitems, nserial, tstar;
+    unsigned long long xpay[16];             // exchange payload of this rank (CTA 0 publishes it)
+    unsigned long long xch[16 * 16];         // [rank][value] what every rank published
+    unsigned long long poff[17];             // cumulative weight before every rank (and the grand total)
+    long long pcnt[17], m_lo, m_hi;          // output slots whose threshold lies below every rank / owned by this rank
     long long cross;
     int64_t seg0;
     int64_t irange[2];
@@ -154,6 +166,67 @@ __device__ __forceinline__ void tl_grid_barrier(const TailArgs &a, int k) {
         }
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void tl_st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long tl_ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Cross-rank exchange k of this launch (all threads of all CTAs call it): CTA 0 stores this rank's payload sh.xpay[0 ..
+// nvals) into every peer's mailbox over NVLink and raises its flag; every CTA (or only CTA 0) waits for the flags of
+// all ranks on its OWN mailbox and copies what they published into sh.xch[rank][value].  Same mailbox, parities and
+// epochs as filter.cu's k_exchange, so both forms can alternate on one stream.
+__device__ void tl_exchange(const TailArgs &a, TlShared &sh, int k, int nvals, bool all_wait) {
+    const int lane = tl_lane(), warp = tl_warp();
+    const unsigned long long epoch = a.epoch0 + (unsigned long long)k;
+    const int par = (int)(epoch & 1ull);
+    __syncthreads();
+    if (warp == 0) {
+        if (blockIdx.x == 0 && lane < a.world) {
+            unsigned long long *peer = reinterpret_cast<unsigned long long *>(a.peers[lane]);
+            unsigned long long *slot = peer + 32 + ((size_t)par * 16 + a.rank) * 16;
+            for (int v = 0; v < nvals; ++v) slot[v] = sh.xpay[v];
+            __threadfence_system();
+            tl_st_release_sys(peer + par * 16 + a.rank, epoch);
+        }
+        if (all_wait || blockIdx.x == 0) {
+            bool dead = *(volatile int *)a.comm_err != 0;      // a peer was lost earlier: do not wait again
+            if (!dead && lane < a.world) {
+                const unsigned long long *flag = a.mailbox + par * 16 + lane;
+                const long long t0 = clock64();
+                while (tl_ld_acquire_sys(flag) < epoch) {
+                    if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
+                }
+            }
+            if (__any_sync(TL_FULL, dead) && lane == 0) *a.comm_err = 1;
+            const volatile unsigned long long *slots = a.mailbox + 32 + (size_t)par * 16 * 16;
+            for (int q = lane; q < a.world * nvals; q += 32) {
+                const int r = q / nvals, v = q - r * nvals;
+                sh.xch[r * 16 + v] = slots[r * 16 + v];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// thresholds of the global systematic resampling (resample.cu push_threshold / count_thresholds_le_dev)
+__device__ __forceinline__ unsigned long long tl_threshold(long long m, double r, double step, double totd) {
+    const double U = __dadd_rn(r, __dmul_rn((double)m, step));
+    const double t = ceil(__dmul_rn(U, totd));
+    return t >= 18446744073709551616.0 ? 0xffffffffffffffffull : (t > 0.0 ? __double2ull_rz(t) : 0ull);
+}
+__device__ long long tl_count_thresholds_le(unsigned long long x, double r, double step, double totd, long long n_out) {
+    long long lo = 0, hi = n_out;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (tl_threshold(mid, r, step, totd) <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
 
 __device__ __forceinline__ float tl_softmax_num(float s, float m) { return (float)exp((double)__fsub_rn(s, m)); }
@@ -893,7 +966,7 @@ __device__ int64_t tl_warp_search(const typename TlCum<REF>::T *C, int64_t lo, i
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <bool MH, bool REF>
+template <bool MH, bool REF, bool SH>
 __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     typedef typename TlCum<REF>::T CT;
     typedef typename TlCum<REF>::Key KeyT;
@@ -903,8 +976,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     const int64_t n = a.n;
 
     // ---- S1: sums of the softmax numerators (node:355-357), exact 2^-40 integers ------------------------------
-    const unsigned key0 = (unsigned)((volatile unsigned long long *)a.keymax)[0];
-    const unsigned key1 = MH ? (unsigned)((volatile unsigned long long *)a.keymax)[1] : 0u;
+    unsigned key0 = (unsigned)((volatile unsigned long long *)a.keymax)[0];
+    unsigned key1 = MH ? (unsigned)((volatile unsigned long long *)a.keymax)[1] : 0u;
+    if (SH) {                                            // exchange 1: the population's score maxima
+        if (t == 0) { sh.xpay[0] = key0; sh.xpay[1] = key1; }
+        tl_exchange(a, sh, 1, 2, true);
+        for (int r = 0; r < a.world; ++r) {
+            key0 = max(key0, (unsigned)sh.xch[r * 16]);
+            key1 = max(key1, (unsigned)sh.xch[r * 16 + 1]);
+        }
+    }
     const float m_post = key0 ? mcl_float_of_key(key0) : -FLT_MAX;
     const float m_pre = key1 ? mcl_float_of_key(key1) : -FLT_MAX;
     for (int v = b; v < a.nt; v += G) {                  // look-back records of both passes start empty
@@ -936,6 +1017,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         unsigned long long q0 = 0, q1 = 0;
         for (int u = t; u < G; u += TL_THREADS) { q0 += __ldcg(a.part_q + u); q1 += __ldcg(a.part_q + G + u); }
         tl_block_sum_u64x2(q0, q1, sh);
+        if (SH) {                                        // exchange 2: the exact softmax sums
+            if (t == 0) { sh.xpay[0] = q0; sh.xpay[1] = q1; }
+            tl_exchange(a, sh, 2, 2, true);
+            q0 = 0; q1 = 0;
+            for (int r = 0; r < a.world; ++r) { q0 += sh.xch[r * 16]; q1 += sh.xch[r * 16 + 1]; }
+        }
         // sum as f32 of the exact integer (node:356-357: f32 divide by the f32-rounded sum)
         sum_post = (float)((double)q0 / TL_SOFTMAX_FIX);
         sum_pre = MH ? (float)((double)q1 / TL_SOFTMAX_FIX) : 1.0f;
@@ -1006,12 +1093,27 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         }
         tl_block_sum<6>(tv, sh);
         wm = tl_block_max(wm, sh);
+        if (SH) {                                        // exchange 3: raw estimate sums (rank order) + weight maximum
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sh.xpay[k] = (unsigned long long)__double_as_longlong(tv[k]);
+                sh.xpay[6] = (unsigned long long)__double_as_longlong((double)wm);
+            }
+            tl_exchange(a, sh, 3, 7, true);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double acc = __longlong_as_double((long long)sh.xch[k]);
+                for (int r = 1; r < a.world; ++r) acc += __longlong_as_double((long long)sh.xch[r * 16 + k]);
+                tv[k] = acc;
+            }
+            for (int r = 0; r < a.world; ++r) wm = fmaxf(wm, (float)__longlong_as_double((long long)sh.xch[r * 16 + 6]));
+        }
         mx = tv[2] / tv[0]; my = tv[3] / tv[0]; mt = atan2(tv[5], tv[4]);      // np.average; arctan2(sin, cos)
         if (!REF) {
             int e = 0;
             if (wm > 0.0f) frexp((double)wm, &e);
             int lg = 0;
-            while (((int64_t)1 << lg) < n) ++lg;
+            while (((int64_t)1 << lg) < (SH ? a.n_global : n)) ++lg;
             scale = ldexp(1.0, 62 - lg - e);               // resample.cu k_wmax, oracle orc_resample_scale
         }
         if (b == 0 && t == 0 && !raw) {
@@ -1077,6 +1179,55 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         if (a.stop == 41) return;
         totd = (double)carry;
         if (b == 0 && t == 0) a.hd->total = carry;
+        if (SH) {                                        // exchange 4: central sums (rank order) + every rank's total
+            double tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (b == 0) {
+                for (int u = t; u < a.nt; u += TL_THREADS) {
+                    const double *pc = a.part_c + (size_t)u * 9;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) tc[k] += __ldcg(pc + k);
+                }
+                tl_block_sum<9>(tc, sh);
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sh.xpay[k] = (unsigned long long)__double_as_longlong(tc[k]);
+                sh.xpay[9] = carry;
+            }
+            tl_exchange(a, sh, 4, 10, true);
+            if (b == 0 && t < 9) {
+                double acc = __longlong_as_double((long long)sh.xch[t]);
+                for (int r = 1; r < a.world; ++r) acc += __longlong_as_double((long long)sh.xch[r * 16 + t]);
+                a.est18[9 + t] = acc;
+            }
+            if (tl_warp() == 0) {                        // which output slots this rank emits (sharded.plan_resample)
+                const int lane = tl_lane();
+                if (lane == 0) {
+                    unsigned long long acc = 0;
+                    for (int r = 0; r < a.world; ++r) { sh.poff[r] = acc; acc += sh.xch[r * 16 + 9]; }
+                    sh.poff[a.world] = acc;
+                }
+                __syncwarp();
+                const double gt = (double)sh.poff[a.world];
+                if (lane <= a.world) sh.pcnt[lane] = tl_count_thresholds_le(sh.poff[lane], a.r, a.rstep, gt, (long long)a.n_global);
+                __syncwarp();
+                if (lane == 0) {
+                    long long prev_hi = 0, my_lo = 0, my_hi = 0;
+                    for (int r = 0; r < a.world; ++r) {
+                        long long lo = r == 0 ? 0 : sh.pcnt[r];
+                        long long hi = r == a.world - 1 ? (long long)a.n_global : sh.pcnt[r + 1];
+                        if (hi < lo) hi = lo;
+                        if (r > 0) { if (lo < prev_hi) lo = prev_hi; if (hi < lo) hi = lo; }
+                        if (r == a.world - 1) hi = (long long)a.n_global;
+                        if (r == a.rank) { my_lo = lo; my_hi = hi; }
+                        prev_hi = hi;
+                    }
+                    sh.m_lo = my_lo; sh.m_hi = my_hi;
+                }
+            }
+            __syncthreads();
+            totd = (double)sh.poff[a.world];
+        }
         unsigned long long *C = (unsigned long long *)a.C;
         int rd = 0;
         for (int v = b; v < a.nt; v += G, ++rd) {
@@ -1097,7 +1248,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             if (t == 0) ((unsigned long long *)a.tend)[v] = sh.ownE[rd] + tot;
         }
     }
-    if (b == G - 1 && !raw) {                            // central sums of the population -> est18[9..17]
+    if (b == G - 1 && !raw && !SH) {                     // central sums of the population -> est18[9..17]
         double tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // (after this CTA's own tiles: off the look-back chain)
         for (int u = t; u < a.nt; u += TL_THREADS) {
             const double *pc = a.part_c + (size_t)u * 9;
@@ -1115,6 +1266,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     tl_stamp(a, 10);
 
     // ---- S5: idx[m] = min(first i with C_i >= key_m, n - 1) (pu:439-444 as a search) + pu:445 gather ----------
+    // Sharded: this rank emits the output slots [m_lo, m_hi) whose thresholds fall into its own stretch of the
+    // population's cumulative weight and stores every offspring straight into the destination rank's set.
     {
         const CT *C = (const CT *)a.C;
         const int64_t limit = n - 1;
@@ -1127,10 +1280,17 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             __syncthreads();
         }
         const int warp = tl_warp(), lane = tl_lane();
-        for (int ov = b; ov < a.nt; ov += G) {
-            const int64_t m0 = (int64_t)ov * a.tile, m1 = min(n, m0 + a.tile);
+        const int64_t out_lo = SH ? (int64_t)sh.m_lo : 0, out_hi = SH ? (int64_t)sh.m_hi : n;
+        const unsigned long long koff = SH ? sh.poff[a.rank] : 0ull;       // cumulative weight of the ranks before this one
+        const int64_t n_per_rank = n;
+        if (SH && t < 3 * a.world) sh.xch[t] = a.peer_pose[t];
+        if (SH) __syncthreads();
+        const int ntile_out = (int)((out_hi - out_lo + a.tile - 1) / a.tile);
+        for (int ov = b; ov < ntile_out; ov += G) {
+            const int64_t m0 = out_lo + (int64_t)ov * a.tile, m1 = min(out_hi, m0 + a.tile);
             if (warp < 2) {
-                const KeyT key = tl_key<REF>(warp == 0 ? m0 : m1 - 1, a.r, a.rstep, totd);
+                KeyT key = tl_key<REF>(warp == 0 ? m0 : m1 - 1, a.r, a.rstep, totd);
+                if (SH) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
                 int64_t lo = 0, hi = limit;
                 if (coarse) {
                     int tl = 0, th = a.nt - 1;               // first tile whose last running sum reaches the key
@@ -1155,7 +1315,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             for (int k = 0; k < a.ipt; ++k) {
                 const int64_t m = m0 + (int64_t)k * TL_THREADS + t;
                 if (m >= m1) break;
-                const KeyT key = tl_key<REF>(m, a.r, a.rstep, totd);
+                KeyT key = tl_key<REF>(m, a.r, a.rstep, totd);
+                if (SH) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
                 int64_t src;
                 if (staged) {
                     int lo = 0, hi = (int)cnt - 1;
@@ -1172,11 +1333,25 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
                     }
                     src = lo;
                 }
-                a.idx[m] = (int32_t)src;
-                if (!raw) { a.gx[m] = a.nx[src]; a.gy[m] = a.ny[src]; a.gt[m] = a.nth[src]; }
+                if (SH) {
+                    int64_t d = m / n_per_rank;
+                    if (d > a.world - 1) d = a.world - 1;
+                    const int64_t j = m - d * n_per_rank;
+                    reinterpret_cast<double *>(sh.xch[d])[j] = a.nx[src];
+                    reinterpret_cast<double *>(sh.xch[a.world + d])[j] = a.ny[src];
+                    reinterpret_cast<double *>(sh.xch[2 * a.world + d])[j] = a.nth[src];
+                } else {
+                    a.idx[m] = (int32_t)src;
+                    if (!raw) { a.gx[m] = a.nx[src]; a.gy[m] = a.ny[src]; a.gt[m] = a.nth[src]; }
+                }
             }
             __syncthreads();
         }
+    }
+    if (SH) {                                            // exchange 5: every rank's offspring have landed everywhere
+        __threadfence_system();
+        tl_grid_barrier(a, 5);
+        tl_exchange(a, sh, 5, 0, false);
     }
     tl_stamp(a, 11);
 }
@@ -1243,17 +1418,19 @@ static int tail_prepare(mcl_handle *h, int64_t n) {
     return MCL_OK;
 }
 
-template <bool MH, bool REF>
+template <bool MH, bool REF, bool SH>
 static cudaError_t tail_launch(const TailArgs &a, int grid, size_t dyn, cudaStream_t s) {
-    cudaFuncSetAttribute(k_tail<MH, REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tail<MH, REF, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     void *params[] = {(void *)&a};
-    return cudaLaunchCooperativeKernel((const void *)k_tail<MH, REF>, dim3(grid), dim3(TL_THREADS), params, dyn, s);
+    return cudaLaunchCooperativeKernel((const void *)k_tail<MH, REF, SH>, dim3(grid), dim3(TL_THREADS), params, dyn, s);
 }
 
 // softmax -> (MH) -> estimate sums -> resampling of one step; see the head of this file.  u.(nx, ny, nth) receives
 // the MH result (without MH it must be the particles themselves), (gx, gy, gt) the resampled set.
 int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
-                  int32_t *idx, double *gx, double *gy, double *gt) {
+                  int32_t *idx, double *gx, double *gy, double *gt, const TailComm *comm) {
+    if (comm && resample_mode != MCL_RESAMPLE_FIXED_POINT)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_tail_step: sharded runs use the fixed-point resampling arithmetic");
     int rc = tail_prepare(h, u.n);
     if (rc) return rc;
     const TailPlan p = tail_plan(h, u.n);
@@ -1279,16 +1456,23 @@ int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keyma
     a.st1 = (unsigned long long *)(b + p.o_st1); a.st2 = (unsigned long long *)(b + p.o_st2);
     a.C = b + p.o_C; a.tend = b + p.o_tend; a.ttot = (unsigned long long *)(b + p.o_ttot);
     a.est18 = u.est18;
-    a.r = r; a.rstep = 1.0 / (double)u.n;                       // pu:434
+    a.r = r; a.rstep = 1.0 / (double)(comm ? comm->n_global : u.n);     // pu:434
+    if (comm) {
+        a.rank = comm->rank; a.world = comm->world; a.n_global = comm->n_global;
+        a.mailbox = comm->mailbox;
+        for (int d = 0; d < 16; ++d) a.peers[d] = comm->peers[d];
+        a.epoch0 = comm->epoch0; a.comm_err = comm->d_err; a.peer_pose = comm->d_peer_pose_dst;
+    }
     a.idx = idx; a.gx = gx; a.gy = gy; a.gt = gt;
     const size_t dyn = (size_t)TL_COARSE_MAX * 8 + TL_STAGE_BYTES;
     const bool ref = resample_mode == MCL_RESAMPLE_REFERENCE_F32;
     cudaError_t e;
-    if (u.use_mh) e = ref ? tail_launch<true, true>(a, p.grid, dyn, h->stream) : tail_launch<true, false>(a, p.grid, dyn, h->stream);
-    else e = ref ? tail_launch<false, true>(a, p.grid, dyn, h->stream) : tail_launch<false, false>(a, p.grid, dyn, h->stream);
+    if (comm) e = u.use_mh ? tail_launch<true, false, true>(a, p.grid, dyn, h->stream) : tail_launch<false, false, true>(a, p.grid, dyn, h->stream);
+    else if (u.use_mh) e = ref ? tail_launch<true, true, false>(a, p.grid, dyn, h->stream) : tail_launch<true, false, false>(a, p.grid, dyn, h->stream);
+    else e = ref ? tail_launch<false, true, false>(a, p.grid, dyn, h->stream) : tail_launch<false, false, false>(a, p.grid, dyn, h->stream);
     if (e != cudaSuccess) return mcl_fail(h, MCL_ERR_CUDA, std::string("k_tail launch: ") + cudaGetErrorString(e));
     h->launches++;
-    h->tail_bar += (unsigned long long)TL_NBAR * p.grid;
+    h->tail_bar += (unsigned long long)(comm ? TL_NBAR + 1 : TL_NBAR) * p.grid;
     return MCL_OK;
 }
 
@@ -1329,7 +1513,7 @@ extern "C" int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, dou
     memset(&u, 0, sizeof(u));
     u.n = n; u.n_global = n; u.use_mh = 0; u.w_out = d_w;
     g_tail_raw = 1;
-    rc = mcl_tail_step(h, u, mcl_fused_keymax(h), mode, r, d_idx, nullptr, nullptr, nullptr);
+    rc = mcl_tail_step(h, u, mcl_fused_keymax(h), mode, r, d_idx, nullptr, nullptr, nullptr, nullptr);
     g_tail_raw = 0;
     if (rc) return rc;
     if (d_c) {
