@@ -174,6 +174,16 @@ int mcl_assym_mh_accept(mcl_handle *h, const double *d_x, const double *d_y, con
                         double *d_xo, double *d_yo, double *d_thetao, float *d_weights_out,
                         uint8_t *d_accept);
 
+/* mcl_assym_mh_accept with corrected != 0: the Metropolis-Hastings ratio applied unconditionally (see
+ * mcl_filter_set_assym). */
+int mcl_assym_mh_accept_ex(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                           const double *d_px, const double *d_py, const double *d_ptheta,
+                           const float *d_likelihoods, const float *d_old_weights,
+                           const double *d_trans_forward, const double *d_trans_backward, int64_t n,
+                           const double *d_uniforms, uint64_t seed, uint64_t step, uint64_t first_index,
+                           double *d_xo, double *d_yo, double *d_thetao, float *d_weights_out,
+                           uint8_t *d_accept, int corrected);
+
 /* pu:416-446 low_variance_resample_numba -> source index per output (d_idx[n_out], int32).
  * r is the single uniform draw in [0, 1/n_out) (see mcl_resample_offset). */
 int mcl_resample_indices(mcl_handle *h, const float *d_weights, int64_t n_in, int64_t n_out,
@@ -273,7 +283,11 @@ int mcl_filter_configure(mcl_handle *h, int use_mh, int resample_mode, uint64_t 
                          uint64_t first_index, int64_t tick /* < 0: keep */);
 /* asymmetric MH (localization_mode containing "AMH", node:21): update() then runs node:424-439
  * transition_probability + pu:238-276.  set_transition overrides the increments stored by predict
- * (delta_b NULL = derive it with node:429-434's formula). */
+ * (delta_b NULL = derive it with node:429-434's formula).
+ * assym = 1: the reference, quirks included (pu:269 only applies the ratio when
+ * log_den > 0, i.e. never, so every proposal is accepted; node:429-434 treats (rot1, trans, rot2) as (dx, dy, dtheta)).
+ * assym = 2: corrected variant -- alpha = min(1, exp(log_alpha)) unconditionally and the backward increment is the
+ * odometry increment that undoes the forward one, (pi - rot2, trans, -rot1 - pi). */
 int mcl_filter_set_assym(mcl_handle *h, int assym);
 int mcl_filter_set_transition(mcl_handle *h, const double delta[3], const double delta_b[3]);
 /* roles = {particles, particles_prev, spare (indices into x/y/th), weights slot (0 = w_a)} */

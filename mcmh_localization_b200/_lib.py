@@ -51,6 +51,8 @@ SIGNATURES = {
     "mcl_scale_by_sum": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_assym_mh_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u64,
                                  _vp, _vp, _vp, _vp, _vp]),
+    "mcl_assym_mh_accept_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _u64, _u64, _u64,
+                                 _vp, _vp, _vp, _vp, _vp, _i]),
     "mcl_resample_indices": (_i, [_vp, _vp, _i64, _i64, _d, _i, _vp]),
     "mcl_weights_max": (_i, [_vp, _vp, _i64, _vp]),
     "mcl_resample_scan": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),

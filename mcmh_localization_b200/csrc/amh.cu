@@ -121,7 +121,7 @@ __global__ void k_assym_mh(const double *x, const double *y, const double *th, c
                            const double *pth, const float *__restrict__ lik, const float *__restrict__ oldw,
                            const double *__restrict__ tf, const double *__restrict__ tb, int64_t n,
                            const double *__restrict__ uniforms, uint64_t seed, uint64_t step, uint64_t first_index,
-                           double *xo, double *yo, double *tho, float *wo, uint8_t *accept) {
+                           double *xo, double *yo, double *tho, float *wo, uint8_t *accept, bool corrected) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double log_pre = log(__dadd_rn((double)oldw[i], 1e-10));       // pu:259
         const double log_post = log(__dadd_rn((double)lik[i], 1e-10));       // pu:260
@@ -130,7 +130,9 @@ __global__ void k_assym_mh(const double *x, const double *y, const double *th, c
         const double log_num = __dadd_rn(log_post, log_tb);
         const double log_den = __dadd_rn(log_pre, log_tf);
         double alpha = 1.0;
-        if (log_den > 0) {                                                   // pu:269 (reference quirk)
+        // pu:269 tests log_den > 0, which never holds for probabilities < 1: the reference accepts everything
+        // (SURVEY Appendix C #1).  corrected: the Metropolis-Hastings ratio is applied unconditionally.
+        if (corrected || log_den > 0) {
             const double e = exp(__dadd_rn(log_num, -log_den));
             alpha = e < 1.0 ? e : 1.0;
         }
@@ -154,6 +156,16 @@ extern "C" int mcl_assym_mh_accept(mcl_handle *h, const double *d_x, const doubl
                                    int64_t n, const double *d_uniforms, uint64_t seed, uint64_t step,
                                    uint64_t first_index, double *d_xo, double *d_yo, double *d_thetao, float *d_wo,
                                    uint8_t *d_accept) {
+    return mcl_assym_mh_accept_ex(h, d_x, d_y, d_theta, d_px, d_py, d_ptheta, d_lik, d_oldw, d_tf, d_tb, n, d_uniforms, seed,
+                                  step, first_index, d_xo, d_yo, d_thetao, d_wo, d_accept, 0);
+}
+
+extern "C" int mcl_assym_mh_accept_ex(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta,
+                                      const double *d_px, const double *d_py, const double *d_ptheta,
+                                      const float *d_lik, const float *d_oldw, const double *d_tf, const double *d_tb,
+                                      int64_t n, const double *d_uniforms, uint64_t seed, uint64_t step,
+                                      uint64_t first_index, double *d_xo, double *d_yo, double *d_thetao, float *d_wo,
+                                      uint8_t *d_accept, int corrected) {
     if (!h) return MCL_ERR_ARG;
     if (n <= 0 || !d_x || !d_y || !d_theta || !d_px || !d_py || !d_ptheta || !d_lik || !d_oldw || !d_tf || !d_tb ||
         !d_xo || !d_yo || !d_thetao || !d_wo)
@@ -161,7 +173,8 @@ extern "C" int mcl_assym_mh_accept(mcl_handle *h, const double *d_x, const doubl
     DeviceGuard guard(h->device);
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
     k_assym_mh<<<blocks, 256, 0, h->stream>>>(d_x, d_y, d_theta, d_px, d_py, d_ptheta, d_lik, d_oldw, d_tf, d_tb, n,
-                                              d_uniforms, seed, step, first_index, d_xo, d_yo, d_thetao, d_wo, d_accept);
+                                              d_uniforms, seed, step, first_index, d_xo, d_yo, d_thetao, d_wo, d_accept,
+                                              corrected != 0);
     MCL_LAUNCH_CHECK(h);
     return MCL_OK;
 }

@@ -73,12 +73,24 @@ static void backward_delta(const double d[3], double out[3]) {
     out[1] = d[0] * sin(d[2]) - d[1] * cos(d[2]);
     out[2] = -d[2];
 }
+// corrected variant: the odometry increment that undoes (rot1, trans, rot2) -- turn to face
+// back along the travelled segment, drive it, turn to the old heading
+static double wrap_pi(double a) {
+    a = fmod(a + MCL_PI, MCL_TWO_PI);
+    if (a < 0) a += MCL_TWO_PI;
+    return a - MCL_PI;
+}
+static void backward_delta_corrected(const double d[3], double out[3]) {
+    out[0] = wrap_pi(MCL_PI - d[2]);
+    out[1] = d[1];
+    out[2] = wrap_pi(-d[0] - MCL_PI);
+}
 
 extern "C" int mcl_filter_set_assym(mcl_handle *h, int assym) {
     if (!h) return MCL_ERR_ARG;
     FilterState *f = filter_of(h, false);
     if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_set_assym: no filter bound");
-    f->assym = assym ? 1 : 0;
+    f->assym = assym == 2 ? 2 : (assym ? 1 : 0);     // 2: corrected variant (see include/mcl.h)
     return MCL_OK;
 }
 
@@ -88,7 +100,9 @@ extern "C" int mcl_filter_set_transition(mcl_handle *h, const double delta[3], c
     FilterState *f = filter_of(h, false);
     if (!f || !f->bound) return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_set_transition: no filter bound");
     memcpy(f->delta, delta, sizeof(f->delta));
-    if (delta_b) memcpy(f->delta_b, delta_b, sizeof(f->delta_b)); else backward_delta(delta, f->delta_b);
+    if (delta_b) memcpy(f->delta_b, delta_b, sizeof(f->delta_b));
+    else if (f->assym == 2) backward_delta_corrected(delta, f->delta_b);
+    else backward_delta(delta, f->delta_b);
     return MCL_OK;
 }
 
@@ -349,7 +363,7 @@ static int comm_check(mcl_handle *h, FilterState *f) {
 extern "C" int mcl_filter_predict(mcl_handle *h, const double delta[3], const double *d_normals, int A) {
     FILTER_OR_FAIL("mcl_filter_predict");
     memcpy(f->delta, delta, sizeof(f->delta));
-    backward_delta(delta, f->delta_b);
+    if (f->assym == 2) backward_delta_corrected(delta, f->delta_b); else backward_delta(delta, f->delta_b);
     f->tick++;
     int rc = mcl_predict(h, f->x[f->cur], f->y[f->cur], f->th[f->cur], f->n, delta, f->seed, f->tick, f->first_index,
                          d_normals, A, f->max_attempts, f->x[f->spare], f->y[f->spare], f->th[f->spare], nullptr);
@@ -413,10 +427,10 @@ extern "C" int mcl_filter_update(mcl_handle *h, const double *d_uniforms) {
                                     f->th[f->prev], f->n, f->delta_b, f->tb, nullptr, 1);
             if (rc) return rc;
         }
-        rc = mcl_assym_mh_accept(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
-                                 f->th[f->cur], f->w_post, f->w_pre, f->tf, f->tb, f->n, d_uniforms, f->seed,
-                                 f->tick, f->first_index, f->x[f->spare], f->y[f->spare], f->th[f->spare],
-                                 f->w[f->wslot], nullptr);
+        rc = mcl_assym_mh_accept_ex(h, f->x[f->prev], f->y[f->prev], f->th[f->prev], f->x[f->cur], f->y[f->cur],
+                                    f->th[f->cur], f->w_post, f->w_pre, f->tf, f->tb, f->n, d_uniforms, f->seed,
+                                    f->tick, f->first_index, f->x[f->spare], f->y[f->spare], f->th[f->spare],
+                                    f->w[f->wslot], nullptr, f->assym == 2);
         if (rc) return rc;
         const int t = f->cur; f->cur = f->spare; f->spare = t;
         return MCL_OK;

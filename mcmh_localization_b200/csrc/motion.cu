@@ -129,7 +129,7 @@ __device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x
 }
 
 #define MOTION_Q 320     // >= 31 leftover + 256 new candidates per screening round
-__global__ void __launch_bounds__(256) k_motion(const MotionParams p) {
+__global__ void __launch_bounds__(256, 4) k_motion(const MotionParams p) {
     __shared__ unsigned short q_att[8][MOTION_Q];
     __shared__ unsigned short q_hi[8][MOTION_Q];
     const int lane = threadIdx.x & 31;

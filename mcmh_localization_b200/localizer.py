@@ -37,7 +37,11 @@ def _dbl3(v):
 
 class Localizer:
     def __init__(self, device=0, params=None, mode=None, seed=0, resample_mode="reference",
-                 max_attempts=1000):
+                 max_attempts=1000, amh_corrected=False):
+        """amh_corrected: in the asymmetric-MH modes use the corrected accept rule and backward increment instead
+        of the reference's (see mcl_filter_set_assym in include/mcl.h).  Default: the
+        reference's behaviour, quirks included."""
+        self.amh_corrected = bool(amh_corrected)
         if not torch.cuda.is_available():
             raise RuntimeError("mcmh_localization_b200.Localizer needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", int(device))
@@ -76,7 +80,7 @@ class Localizer:
         self.h.call("mcl_set_motion", self.alpha.ctypes.data_as(C.POINTER(C.c_float)))
         if self.n:
             self.h.call("mcl_filter_configure", int(self.use_mh), self.resample_mode, self.seed, self.first_index, -1)
-            self.h.call("mcl_filter_set_assym", int(self.assym))
+            self.h.call("mcl_filter_set_assym", (2 if self.amh_corrected else 1) if self.assym else 0)
 
     def load_map(self, occ, resolution=None, origin_xy=None, gpu_edt=False):
         """occ: (H,W) int8 OccupancyGrid payload, or a GridMap (maps.load_map_yaml / map_from_occupancy).
@@ -118,7 +122,7 @@ class Localizer:
         self.h.call("mcl_filter_bind", n, arr(0), arr(1), arr(2), _ptr(self.score_pre), _ptr(self.score_post),
                     _ptr(self.w_pre), _ptr(self.w_post), _ptr(self.wbuf[0]), _ptr(self.wbuf[1]), _ptr(self.idx),
                     int(self.use_mh), self.resample_mode, self.seed, self.first_index, self.max_attempts)
-        self.h.call("mcl_filter_set_assym", int(self.assym))
+        self.h.call("mcl_filter_set_assym", (2 if self.amh_corrected else 1) if self.assym else 0)
 
     def _make_sets(self, n):
         mk = lambda: [torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3)]
@@ -259,7 +263,9 @@ class Localizer:
 
     def _push_transition(self):
         """node:429-434 backward increment with the node's own NumPy calls (bit-exact), for AMH modes."""
-        if self.assym:
+        if self.assym and self.amh_corrected:
+            self.h.call("mcl_filter_set_transition", _dbl3(self.delta), None)     # the library derives the true inverse
+        elif self.assym:
             dx, dy, dth = self.delta
             db = (-dx * np.cos(dth) - dy * np.sin(dth), dx * np.sin(dth) - dy * np.cos(dth), -dth)
             self.h.call("mcl_filter_set_transition", _dbl3(self.delta), _dbl3(db))

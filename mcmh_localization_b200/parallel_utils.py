@@ -196,8 +196,9 @@ def motion_model_odometry_parallel(particles_prev, particles_curr, delta, alpha)
 
 
 def assym_mh_resampling(particles, proposed_particles, likelihoods, old_weights, trans_forward, trans_backward,
-                        uniforms=None, return_accept=False):
-    """pu:238-276 -> (new_particles, new_weights); the reference's always-accept quirk included."""
+                        uniforms=None, return_accept=False, corrected=False):
+    """pu:238-276 -> (new_particles, new_weights); the reference's always-accept quirk included.
+    corrected=True: the Metropolis-Hastings ratio applied unconditionally (SURVEY Appendix C #1)."""
     c = _ctx()
     n = len(particles)
     x, y, t = c.soa(particles)
@@ -208,8 +209,8 @@ def assym_mh_resampling(particles, proposed_particles, likelihoods, old_weights,
     xo, yo, to = (torch.empty_like(x) for _ in range(3))
     wo = torch.empty_like(lk)
     acc = torch.empty(n, dtype=torch.uint8, device=c.device)
-    c.h.call("mcl_assym_mh_accept", _p(x), _p(y), _p(t), _p(px), _p(py), _p(pt), _p(lk), _p(ow), _p(tf), _p(tb), n,
-             _p(u), _state["seed"], _tick(), 0, _p(xo), _p(yo), _p(to), _p(wo), _p(acc))
+    c.h.call("mcl_assym_mh_accept_ex", _p(x), _p(y), _p(t), _p(px), _p(py), _p(pt), _p(lk), _p(ow), _p(tf), _p(tb), n,
+             _p(u), _state["seed"], _tick(), 0, _p(xo), _p(yo), _p(to), _p(wo), _p(acc), 1 if corrected else 0)
     out = (c.aos(xo, yo, to), wo.cpu().numpy())
     return out + (acc.cpu().numpy(),) if return_accept else out
 

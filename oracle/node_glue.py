@@ -135,6 +135,20 @@ def synthetic_scan(pose, mp, num_beams=360, sensor_max=3.5, noise=None):
     return r.astype(np.float32), angles
 
 
+def mh_near_ties(w_new, w_old, seed, step, first_index=0, rel=1e-5, uniforms=None):
+    """Particles whose MH accept decision (pu:229-231: u < min(1, f32(p_new / p_old))) could legitimately differ
+    between two implementations whose weights agree to a few 1e-6 relative: the uniform lies within `rel` (relative)
+    of alpha.  Tests require every mismatch to be inside this set instead of tolerating a fraction."""
+    w_new, w_old = np.asarray(w_new, np.float32), np.asarray(w_old, np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = np.where(w_old > 0, np.minimum(1.0, (w_new / w_old).astype(np.float64)), 1.0)
+    if uniforms is None:
+        u = np.array([clib.uniform53(seed, step, first_index + i, 0, clib.STREAM_MH) for i in range(len(w_new))])
+    else:
+        u = np.asarray(uniforms, np.float64)
+    return (np.abs(u - alpha) <= rel * np.maximum(alpha, 1e-300)) & (alpha < 1.0)
+
+
 # --------------------------------------------------------------------------- filter
 class ReferenceFilter:
     """ROS-free replay of node.odom_callback (node:379-408) and node.lidar_callback

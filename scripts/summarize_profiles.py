@@ -62,8 +62,36 @@ def full(rep, out):
                 out.write("  %-88s %-12s %s\n" % (k, units[col[k]], d[col[k]]))
 
 
+def traffic_json(rep, tag, particles, sets):
+    """profiles/likelihood_traffic.json: DRAM bytes per k_likelihood_g1 launch from the --set full capture (bench.py
+    reads it for roofline.traffic instead of a literal)."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: j for j, h in enumerate(hdr)}
+    vals = []
+    for d in data:
+        if "k_likelihood_g1" in d[col["Kernel Name"]]:
+            def num(k):
+                v = float(d[col[k]].replace(",", ""))
+                u = units[col[k]].lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+            vals.append(num("dram__bytes_read.sum") + num("dram__bytes_write.sum"))
+    if not vals:
+        return
+    out = {"kernel": "k_likelihood_g1", "dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals),
+           "particles_per_launch": particles, "sets_per_launch": sets,
+           "source": "profiles/%s_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum per k_likelihood_g1 launch, ncu --set full "
+                     "--clock-control none, mean of %d launches (%d particles x %d sets per launch)" % (tag, len(vals), particles, sets)}
+    json.dump(out, open("profiles/likelihood_traffic.json", "w"), indent=1)
+    print(out)
+
+
 if __name__ == "__main__":
     lpath, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+    if len(sys.argv) > 4:
+        traffic_json(rep, tag, int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 2)
     os.makedirs("profiles", exist_ok=True)
     with open("profiles/%s_summary.txt" % tag, "w") as out:
         out.write("profile summary %s  (command: python bench.py --steps 3 --warmup 10 --quick, 1M particles x 360 beams)\n\n" % tag)

@@ -110,7 +110,7 @@ def test_likelihood_vs_oracle_sizes(pu, orc, n, oracle_map_house):
 
 def test_likelihood_full_size_properties(pu, oracle_map_world):
     """BASELINE config 2 size (1M x 360): shared-memory path == global path bit-for-bit, permutation
-    equivariance, and a 20k-particle slice against the oracle."""
+    equivariance, and ALL one million scores against the oracle (the C oracle needs ~1 s for them)."""
     from oracle import clib
     mp = oracle_map_world
     g = golden("mh_map_world.npz")
@@ -131,10 +131,11 @@ def test_likelihood_full_size_properties(pu, oracle_map_world):
     perm = rs.permutation(n)
     gg2 = dict(gg, particles=parts[perm])
     assert np.array_equal(_lik(pu, gg2, mp, *sensor), s_smem[perm])
-    sl = slice(500_000, 520_000)
-    ref = clib.compute_likelihoods(g["scan"], g["angles"], parts[sl], mp["distance_map"], mp["resolution"],
+    ref = clib.compute_likelihoods(g["scan"], g["angles"], parts, mp["distance_map"], mp["resolution"],
                                    mp["origin_np"], mp["width"], mp["height"], *sensor)
-    assert lik_close(s_smem[sl], ref).all()
+    assert lik_close(s_smem, ref).all()
+    # measured: the fixed-point table keeps the error three orders of magnitude below the 1e-4 bar
+    assert (np.abs(s_smem.astype(np.float64) - ref) / np.maximum(np.abs(ref), 1e-2)).max() < 5e-6
 
 
 def test_likelihood_house_coded_window_full_size(pu, oracle_map_house):
@@ -159,10 +160,9 @@ def test_likelihood_house_coded_window_full_size(pu, oracle_map_house):
     s_auto = _lik(pu, gg, mp, *sensor, path=2)      # shared memory required: only the coded window fits
     s_glob = _lik(pu, gg, mp, *sensor, path=1)
     assert np.array_equal(s_auto, s_glob)
-    sl = slice(0, 20_000)
-    ref = clib.compute_likelihoods(g["scan"], g["angles"], parts[sl], mp["distance_map"], mp["resolution"],
-                                   mp["origin_np"], mp["width"], mp["height"], *sensor)
-    assert lik_close(s_auto[sl], ref, rel=2e-6).all()
+    ref = clib.compute_likelihoods(g["scan"], g["angles"], parts, mp["distance_map"], mp["resolution"],
+                                   mp["origin_np"], mp["width"], mp["height"], *sensor)        # all of them
+    assert lik_close(s_auto, ref, rel=2e-6).all()
 
 
 def test_likelihood_large_tiled_map_vs_oracle(pu):
@@ -436,6 +436,7 @@ def test_mh_chain_equals_composition_of_reference_primitives():
         tick = loc.tick
         loc.update_chain(g["scans"][1], angles=g["angles"], iters=iters)
         chain, w = prev.copy(), None
+        excused = np.zeros(len(prev), bool)      # chains that met a provable near-tie of the accept test on the way
         for it in range(iters):
             if it > 0:
                 tick += 1
@@ -445,10 +446,14 @@ def test_mh_chain_equals_composition_of_reference_primitives():
             w_prop = ng.convert_scores(lik(prop, g["scans"][1]))
             w_chain = ng.convert_scores(lik(chain, g["scans"][1]))
             tick += 1
+            excused |= ng.mh_near_ties(w_prop, w_chain, 31, tick)
             chain, w = clib.mh_resampling(chain, prop, w_prop, w_chain, seed=31, step=tick)
         assert loc.tick == tick
         same = np.isclose(loc.particles(), chain, rtol=0, atol=1e-12).all(axis=1)
-        assert same.mean() >= 0.998, (iters, same.mean())
+        # a chain may differ from the oracle's only if one of its accept tests was a near-tie (u within 1e-5 of alpha:
+        # the two softmax sums differ in the last bits); everything else is identical
+        assert not np.any(~same & ~excused), (iters, int((~same).sum()), int(excused.sum()))
+        assert excused.mean() < 1e-3
         np.testing.assert_allclose(loc.weights()[same], w[same], rtol=3e-6, atol=0)
     # k = 1 is the plain update
     a = Localizer(params=P, mode="MHMCL", seed=31); a.load_map(gm); a.set_particles(g["particles0"])
@@ -886,6 +891,9 @@ def test_localizer_lockstep_with_reference_filter():
         s_pre, s_post = loc.scores()
         assert lik_close(s_pre, f.scores_pre).all() and lik_close(s_post, f.scores_post).all()
         same = np.isclose(loc.particles(), f.particles, rtol=0, atol=1e-12).all(axis=1)
+        if had_odom:      # every differing accept decision must be a provable near-tie (u within 1e-5 of alpha)
+            ties = ng.mh_near_ties(ng.convert_scores(f.scores_post), ng.convert_scores(f.scores_pre), 11, loc.tick)
+            assert not np.any(~same & ~ties), (k, int((~same).sum()), int(ties.sum()))
         mism += int((~same).sum())
         np.testing.assert_allclose(loc.weights()[same], w_ref[same], rtol=2e-6, atol=0)
         # estimate of the GPU's own (particles, weights) == NumPy's
@@ -1138,7 +1146,12 @@ def test_filter_converges_to_the_true_pose(mode):
     true = np.array([-2.0, -0.5, 0.0])
     loc = Localizer(params=P, mode=mode, seed=5)
     loc.load_map(gm)
-    loc.init_gaussian(true + np.array([0.25, -0.2, 0.15]), np.diag([0.05, 0.05, 0.1]), 2000, seed=3)
+    # Adaptive (AMCL) modes: the reference's recovery term is p_random = max(0, 1 - w_fast / w_slow) with
+    # w_avg == 1 / N always and both averages starting at 1e-3 (node:86-87), so with more than
+    # 1000 particles it injects uniformly random particles for the first scans -- reproduced here, and it drags the
+    # estimate across the map.  Start those modes below that threshold, where the reference localises.
+    n0 = 800 if "AMCL" in mode else 2000
+    loc.init_gaussian(true + np.array([0.25, -0.2, 0.15]), np.diag([0.05, 0.05, 0.1]), n0, seed=3)
     loc.predict(true)
     errs = []
     for k in range(30):
@@ -1147,6 +1160,7 @@ def test_filter_converges_to_the_true_pose(mode):
         mx, my, mt, cov = loc.step(true, scan, angles=angles)
         errs.append(float(np.hypot(mx - true[0], my - true[1])))
         yaw_err = abs((mt - true[2] + np.pi) % (2 * np.pi) - np.pi)
+    print(mode, "particles", loc.n, "errors", ["%.3f" % e for e in errs[::3]])
     assert errs[-1] < 0.15 and errs[-1] < 0.5 * errs[0], errs[::5]
     assert yaw_err < 0.1
     assert np.all(np.isfinite(cov)) and np.all(np.linalg.eigvalsh(cov) > 0)
@@ -1175,3 +1189,72 @@ def test_filter_converges_at_one_million_particles():
         errs.append(float(np.hypot(mx - true[0], my - true[1])))
     assert errs[-1] < 0.15 and errs[-1] < 0.5 * errs[0], errs[::5]
     assert abs((mt - true[2] + np.pi) % (2 * np.pi) - np.pi) < 0.1
+
+
+def test_adaptive_mode_injects_random_particles_above_1000_like_the_reference():
+    """The other side of the quirk above (node:276-286, 497): with N = 2000 > 1000 the first
+    adaptive resampling replaces a share p_random of the cloud by uniformly drawn particles, exactly as the
+    reference's arithmetic says: w_slow = 1e-3 + 0.04 (1/N - 1e-3), w_fast = 1e-3 + 0.6 (1/N - 1e-3)."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    true = np.array([-2.0, -0.5, 0.0])
+    loc = Localizer(params=P, mode="AMCL", seed=5)
+    loc.load_map(gm)
+    loc.init_gaussian(true, np.diag([0.01, 0.01, 0.01]), 2000, seed=3)
+    loc.predict(true)
+    scan, angles = raycast_scan(gm, true)
+    loc.step(true + np.array([0.02, 0.0, 0.0]), scan, angles=angles)
+    w_slow = 1e-3 + loc.params["alpha_slow"] * (np.float32(1 / 2000.0) - 1e-3)
+    w_fast = 1e-3 + loc.params["alpha_fast"] * (np.float32(1 / 2000.0) - 1e-3)
+    assert abs(loc.w_slow - w_slow) < 1e-12 and abs(loc.w_fast - w_fast) < 1e-12
+    n_random = int(max(0.0, 1.0 - w_fast / (w_slow + 1e-9)) * 2000)
+    assert n_random > 50
+    p = loc.particles()
+    far = np.hypot(p[:, 0] - true[0], p[:, 1] - true[1]) > 1.0          # the cloud itself has sigma 0.1 m
+    assert abs(int(far.sum()) - n_random) <= 0.15 * n_random + 5         # (a few random particles land nearby)
+
+
+def test_corrected_asymmetric_mh_variant(pu):
+    """SURVEY 8(f) rank 3, second half: behind a flag, the asymmetric MH step WITHOUT the reference's two quirks
+    (Appendix C #1: pu:269 never applies the ratio; #2: node:429-434's backward increment).  The accept rule must
+    equal alpha = min(1, exp(log_num - log_den)) on the golden inputs, reject some proposals, and the filter must
+    still localise; the default stays the reference's behaviour (always accept)."""
+    g = golden("mh_map_world.npz")
+    n = len(g["w_post"])
+    u = np.random.RandomState(9).random_sample(n)
+    args = (g["prev"], g["cur"], g["w_post"], g["w_pre"], g["amh_tf"], g["amh_tb"])
+    _, _, acc_ref = pu.assym_mh_resampling(*args, uniforms=u, return_accept=True)
+    assert acc_ref.all()                                                  # the reference: every proposal accepted
+    newp, neww, acc = pu.assym_mh_resampling(*args, uniforms=u, return_accept=True, corrected=True)
+    log_num = np.log(g["w_post"].astype(np.float64) + 1e-10) + np.log(g["amh_tb"] + 1e-10)
+    log_den = np.log(g["w_pre"].astype(np.float64) + 1e-10) + np.log(g["amh_tf"] + 1e-10)
+    alpha = np.minimum(1.0, np.exp(log_num - log_den))
+    want = u < alpha
+    near = np.abs(u - alpha) < 1e-12
+    assert np.array_equal(acc.astype(bool)[~near], want[~near]) and 0.05 < acc.mean() < 0.999
+    assert np.array_equal(newp[acc.astype(bool)], g["cur"][acc.astype(bool)])
+    assert np.array_equal(newp[~acc.astype(bool)], g["prev"][~acc.astype(bool)])
+    # through the filter: corrected AMH localises like the other modes
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import raycast_scan
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    true = np.array([-2.0, -0.5, 0.0])
+    loc = Localizer(params=P, mode="AMHMCL", seed=5, amh_corrected=True)
+    loc.load_map(gm)
+    loc.init_gaussian(true + np.array([0.25, -0.2, 0.15]), np.diag([0.05, 0.05, 0.1]), 2000, seed=3)
+    loc.predict(true)
+    errs = []
+    for k in range(30):
+        true = true + np.array([0.05 * np.cos(true[2]), 0.05 * np.sin(true[2]), 0.03])
+        scan, angles = raycast_scan(gm, true, noise_sigma=0.01, seed=100 + k)
+        mx, my, mt, cov = loc.step(true, scan, angles=angles)
+        errs.append(float(np.hypot(mx - true[0], my - true[1])))
+    assert errs[-1] < 0.2 and errs[-1] < 0.7 * errs[0], errs[::5]
