@@ -75,6 +75,7 @@ struct mcl_handle {
     // one map tile at a time; particles are binned by tile first (likelihood.cu, k_likelihood_tiled).
     bool tiled_ok = false;
     uint8_t *d_code8 = nullptr;      // W * H
+    uint8_t *d_code8p = nullptr;     // (H + 1) x (W + 16): the same with an apron (mcl_prepare_table), for k_likelihood_tiled2
     int tile_w = 0, tile_h = 0, tile_margin = 0, tiles_x = 0, tiles_y = 0;
     void *d_tiled = nullptr;         // per-call binning buffers
     size_t tiled_bytes = 0;

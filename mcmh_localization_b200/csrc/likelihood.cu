@@ -272,7 +272,18 @@ struct G1Ctx {
     const uint8_t *swin8;
     int lane, nb, cmx, cmy;
     int wofx, wofy;            // tiled kernel only: origin of the staged sub-window (map cells)
+    uint32_t swin8_s, slut_s;  // PERM == 2: the sub-window (column 0 of row 0) and this lane's column of the value table
+                               // as 32-bit shared-memory addresses (the buffer changes per item: no 64-bit pointer math)
 };
+
+// PERM == 2 fetch: rows of 272 bytes; index, pitch and buffer base in one 3-input add
+__device__ __forceinline__ uint32_t g1_fetch_t2(const G1Ctx &k, unsigned cell) {
+    uint32_t code, v;
+    const uint32_t a = cell + ((cell >> 4) & 0xfffffff0u) + k.swin8_s;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(code) : "r"(a));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(code * 128u + k.slut_s));
+    return v;
+}
 
 template <bool CODED>
 __device__ __forceinline__ uint32_t g1_fetch(const G1Ctx &k, int cell) {
@@ -281,7 +292,8 @@ __device__ __forceinline__ uint32_t g1_fetch(const G1Ctx &k, int cell) {
 
 // P slices (rows i0, i0 + row, ...) of one warp; lanes whose particle index is >= end idle on a copy of end - 1
 // PERM: i0 / end are positions in a tile-sorted order and perm[] maps them to particle indices (tiled kernel)
-template <bool SMEM, bool CODED, bool TPOSE, int P, bool PERM = false>
+// PERM: 0 no; 1 tiled kernel with rows of 260 bytes (manual staging); 2 tiled kernel with rows of 272 bytes (bulk copies)
+template <bool SMEM, bool CODED, bool TPOSE, int P, int PERM = 0>
 __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, const double *__restrict__ xs,
                                           const double *__restrict__ ys, const double *__restrict__ ts,
                                           float *__restrict__ score, int64_t i0, int64_t row, int64_t end, float &smax,
@@ -317,7 +329,8 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
             const int rx = __viaddmin_s32_relu(__double2hiint(TX), negK, k.cmx);
             const int ry = __viaddmin_s32_relu(__double2hiint(TY), negK, k.cmy);
             unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
-            if (PERM) cell += (cell >> 8) << 2;     // tiled kernel: rows of 260 bytes (see k_likelihood_tiled)
+            if (PERM == 1) cell += (cell >> 8) << 2;     // tiled kernel: rows of 260 bytes (see k_likelihood_tiled)
+            if (PERM == 2) return g1_fetch_t2(k, cell);  // rows of 272 bytes (k_likelihood_tiled2)
             return g1_fetch<CODED>(k, (int)cell);
         };
         int j = 0;
@@ -359,8 +372,8 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
                 const int rx = __viaddmin_s32_relu(hx - min(fx, 0), negK, k.cmx);
                 const int ry = __viaddmin_s32_relu(hy - min(fy, 0), negK, k.cmy);
                 unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
-                if (PERM) cell += (cell >> 8) << 2;
-                const uint32_t v = g1_fetch<CODED>(k, (int)cell);
+                if (PERM == 1) cell += (cell >> 8) << 2;
+                const uint32_t v = PERM == 2 ? g1_fetch_t2(k, cell) : g1_fetch<CODED>(k, (int)cell);
                 const bool in = coord_in_map(TX, fx, 8, limx) && coord_in_map(TY, fy, 8, limy);
                 return in ? v : zero_off;
             };
@@ -498,6 +511,7 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
 // the same beam loop.  Coordinates are taken relative to the staged sub-window with S = 8.
 // ---------------------------------------------------------------------------------------------
 struct TiledArgs {
+    const uint8_t *code8p;                // (H + 1) x (W + 16) padded coded map (k_likelihood_tiled2)
     const uint8_t *code8;
     const int32_t *lut;
     const int32_t *perm, *offsets;        // particle index by sorted position; first sorted position of every tile
@@ -657,13 +671,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_likelihood_tiled(const LikParams
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(d)),
                                  "l"(t.code8 + (size_t)my * p.W + mx) : "memory");
                 } else {
-                    uint32_t v = 0xffffffffu;                          // code 255: outside the map
+                    uint32_t v = 0u;                                   // code 0: outside the map
                     if ((unsigned)my < (unsigned)p.H && !aligned) {
                         const uint8_t *row = t.code8 + (size_t)my * p.W;
                         v = 0;
 #pragma unroll
                         for (int b = 0; b < 4; ++b)
-                            v |= (uint32_t)((unsigned)(mx + b) < (unsigned)p.W ? row[mx + b] : 255) << (8 * b);
+                            v |= (uint32_t)((unsigned)(mx + b) < (unsigned)p.W ? row[mx + b] : 0) << (8 * b);
                     }
                     *d = v;
                 }
@@ -677,9 +691,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_likelihood_tiled(const LikParams
         // warps of a CTA stay busy on tiles with few particles (the uniform beam loads are no longer shared)
         int64_t pos = seg_lo + 32 * warp;
         for (; pos < seg_hi; pos += 32 * (THREADS / 32))
-            g1_slices<true, true, false, 1, true>(p, k, p.x, p.y, p.th, p.score, pos + k.lane, 0, seg_hi, smax, t.perm);
+            g1_slices<true, true, false, 1, 1>(p, k, p.x, p.y, p.th, p.score, pos + k.lane, 0, seg_hi, smax, t.perm);
         // never taken: keeps the hot copy of the slice code on the uniform datapath (see k_likelihood_g1)
-        if (p.n < 0) g1_slices<true, true, false, 2, true>(p, k, p.x, p.y, p.th, p.score, pos + k.lane, 32, seg_hi, smax, t.perm);
+        if (p.n < 0) g1_slices<true, true, false, 2, 1>(p, k, p.x, p.y, p.th, p.score, pos + k.lane, 32, seg_hi, smax, t.perm);
     }
     if (p.keymax) {
         __shared__ float smx[32];
@@ -690,6 +704,136 @@ __global__ void __launch_bounds__(THREADS, 2) k_likelihood_tiled(const LikParams
             float v = k.lane < (THREADS >> 5) ? smx[k.lane] : -FLT_MAX;
             v = warp_max(v);
             if (k.lane == 0 && v > -FLT_MAX) atomicMax(p.keymax, (unsigned long long)mcl_key_of_float(v));
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Tiled kernel, second form: one persistent CTA per SM, NCONS consumer warps + one producer warp, TWO sub-window
+// buffers.  The producer takes the next work item and copies the byte-coded neighbourhood of its tile row by row
+// with bulk asynchronous copies (cp.async.bulk, the TMA engine: 272-byte rows so that the bank depends on the row;
+// rows / columns beyond the map are zero-filled = code 0 = "outside, adds 0") while the consumers are still on
+// the previous item; full / empty mbarriers hand the buffers over, there is no __syncthreads in the loop.  The
+// consumers take 32-particle slices of the item from a shared counter (no static imbalance) and a warp that finds
+// none left moves on to the next item on its own.
+// ---------------------------------------------------------------------------------------------
+#define T2_PITCH 272
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NCONS>
+__global__ void __launch_bounds__((NCONS + 1) * 32, 1) k_likelihood_tiled2(const LikParams p, const TiledArgs t) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // [0,32) full[2], empty[2] | [64,96) ring[2][4] | [96,104) slice counters | [1024, +32 KB) value table per lane |
+    // two sub-window buffers of sub_rows x 272 bytes
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem), *empty = full + 2;
+    int *ring = reinterpret_cast<int *>(smem + 64);
+    int *sctr = reinterpret_cast<int *>(smem + 96);
+    int32_t *slut = reinterpret_cast<int32_t *>(smem + 1024);
+    unsigned char *bufs = smem + 1024 + 32768;
+    const uint32_t buf_bytes = (uint32_t)t.sub_rows * T2_PITCH;
+    // REDUX results live in uniform registers: every value that steers a loop below goes through one, so that ptxas
+    // keeps the beam loop on the uniform datapath (LDCU + UR operands; see k_likelihood_g1)
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+    const int lpad = (16 - (t.margin & 15)) & 15;                     // bytes in front of column 0: 16-byte aligned sources
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1); mbar_init(full + 1, 1);
+        mbar_init(empty, NCONS); mbar_init(empty + 1, NCONS);
+    }
+    for (int e = threadIdx.x; e < 256 * 32; e += (NCONS + 1) * 32) slut[e] = __ldg(t.lut + (e >> 5));
+    __syncthreads();
+    const int nitems = t.counters[0];
+    float smax = -FLT_MAX;
+    if (warp == NCONS) {
+        // ------------------------------------------------------------------ producer
+        for (int s = 0;; ++s) {
+            const int b = s & 1;
+            if (s >= 2) mbar_wait(empty + b, ((s >> 1) - 1) & 1);      // every consumer warp is done with use s - 2
+            int item = 0;
+            if (lane == 0) item = atomicAdd(t.counters + 1, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= nitems) {
+                if (lane == 0) { ring[b * 4] = -1; mbar_arrive(full + b); }
+                break;
+            }
+            const int tile = __ldg(t.items + 3 * item);
+            const int sub_x0 = (tile % t.tiles_x) * t.tile_w - t.margin, sub_y0 = (tile / t.tiles_x) * t.tile_h - t.margin;
+            unsigned char *dst = bufs + (size_t)b * buf_bytes;
+            // columns [xs, xe) of every row come from the padded map (x >= -16, y >= -1; 16-byte aligned), the rest is
+            // zero-filled
+            const int x_start = sub_x0 - lpad;
+            const int xs = max(x_start, -16), xe = min(x_start + T2_PITCH, p.W);
+            const int y_lo = max(sub_y0, -1), y_hi = min(sub_y0 + t.sub_rows, p.H);
+            const uint32_t row_bytes = xe > xs ? (uint32_t)(xe - xs) : 0u;
+            const uint32_t total = row_bytes * (uint32_t)max(y_hi - y_lo, 0);
+            if (row_bytes < T2_PITCH || y_lo > sub_y0 || y_hi < sub_y0 + t.sub_rows) {
+                // edge tile: zero what the copies will not write (whole rows above / below, strips left / right)
+                for (int r = 0; r < t.sub_rows; ++r) {
+                    const int my = sub_y0 + r;
+                    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)r * T2_PITCH);
+                    if (my < y_lo || my >= y_hi || row_bytes == 0) {
+                        for (int w = lane; w < T2_PITCH / 4; w += 32) row[w] = 0u;
+                    } else {
+                        const int a = (xs - x_start) >> 2, z = (xe - x_start) >> 2;
+                        for (int w = lane; w < T2_PITCH / 4; w += 32)
+                            if (w < a || w >= z) row[w] = 0u;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+                ring[b * 4] = tile; ring[b * 4 + 1] = __ldg(t.items + 3 * item + 1); ring[b * 4 + 2] = __ldg(t.items + 3 * item + 2);
+                sctr[b] = 0;
+                if (total) mbar_expect_tx(full + b, total); else mbar_arrive(full + b);
+            }
+            __syncwarp();
+            if (row_bytes)
+                for (int my = y_lo + lane; my < y_hi; my += 32)
+                    bulk_g2s(dst + (size_t)(my - sub_y0) * T2_PITCH + (xs - x_start),
+                             t.code8p + (size_t)(my + 1) * (p.W + 16) + (xs + 16), row_bytes, full + b);
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        G1Ctx k;
+        k.swin = nullptr; k.slut = slut;
+        k.lane = lane;
+        k.nb = p.n_pos + p.n_neg;
+        k.cmx = (255 << 8) | 255; k.cmy = ((t.sub_rows - 1) << 8) | 255;
+        k.slut_s = smem_u32(slut) + 4u * (uint32_t)lane;
+        for (int s = 0;; ++s) {
+            const int b = s & 1;
+            mbar_wait(full + b, (s >> 1) & 1);
+            const int tile = __reduce_min_sync(0xffffffffu, ring[b * 4]);
+            if (tile < 0) break;
+            const int seg_lo = __reduce_min_sync(0xffffffffu, ring[b * 4 + 1]), seg_hi = __reduce_min_sync(0xffffffffu, ring[b * 4 + 2]);
+            k.swin8 = bufs + (size_t)b * buf_bytes + lpad;
+            k.swin8_s = smem_u32(k.swin8);
+            k.wofx = (tile % t.tiles_x) * t.tile_w - t.margin; k.wofy = (tile / t.tiles_x) * t.tile_h - t.margin;
+            int pos = 0;
+            for (;;) {                                    // pairs of adjacent 32-particle slices from the shared counter
+                const int sl = __reduce_max_sync(0xffffffffu, lane == 0 ? atomicAdd(sctr + b, 2) : 0);
+                pos = seg_lo + 32 * sl;
+                if (pos >= seg_hi) break;
+                g1_slices<true, true, false, 2, 2>(p, k, p.x, p.y, p.th, p.score, (int64_t)pos + lane, 32, (int64_t)seg_hi, smax, t.perm);
+            }
+            // never taken: keeps the hot copy of the slice code on the uniform datapath (see k_likelihood_g1)
+            if (p.n < 0) g1_slices<true, true, false, 1, 2>(p, k, p.x, p.y, p.th, p.score, (int64_t)pos + lane, 0, (int64_t)seg_hi, smax, t.perm);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + b);
+        }
+    }
+    if (p.keymax) {
+        __shared__ float smx[32];
+        smax = warp_max(smax);
+        if (lane == 0) smx[warp] = smax;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = lane < NCONS + 1 ? smx[lane] : -FLT_MAX;
+            v = warp_max(v);
+            if (lane == 0 && v > -FLT_MAX) atomicMax(p.keymax, (unsigned long long)mcl_key_of_float(v));
         }
     }
 }
@@ -837,11 +981,33 @@ static int launch_tiled(mcl_handle *h, LikParams p, unsigned long long *keymax) 
     // staged sub-windows mark cells beyond the map but do not repeat cell 0 for the int() quirk: keep the margin test
     p.ilox = p.margin; p.ihix = (double)p.W - p.margin; p.iloy = p.margin; p.ihiy = (double)p.H - p.margin;
     TiledArgs t;
-    t.code8 = h->d_code8; t.lut = h->d_lut; t.perm = perm; t.offsets = offsets;
+    t.code8 = h->d_code8; t.code8p = h->d_code8p; t.lut = h->d_lut; t.perm = perm; t.offsets = offsets;
     t.tile_w = h->tile_w; t.tile_h = h->tile_h; t.margin = h->tile_margin; t.tiles_x = h->tiles_x; t.tiles_y = h->tiles_y;
     t.ntiles = ntiles; t.sub_rows = sub_rows; t.piece = PIECE; t.items = items; t.counters = counters;
-    const int blocks = h->sm_count * 2;
-    kern<<<blocks, THREADS, smem_bytes, h->stream>>>(p, t);
+    // second form (double-buffered bulk copies, one CTA per SM) when its two buffers fit and the rows can be copied
+    // 16 bytes aligned; MCL_TILED_OLD=1 keeps the first form (A/B measurements)
+    static int old_form = -1;
+    if (old_form < 0) { const char *e = getenv("MCL_TILED_OLD"); old_form = (e && atoi(e)) ? 1 : 0; }
+    constexpr int NCONS = 27;
+    const size_t smem2 = 1024 + 32768 + 2 * (size_t)sub_rows * T2_PITCH;
+    if (!old_form && (h->W & 15) == 0 && (h->tile_w & 15) == 0 && smem2 + 1024 <= (size_t)h->smem_optin) {
+        auto kern2 = k_likelihood_tiled2<NCONS>;
+        static thread_local int attr2_dev = -1;
+        if (attr2_dev != h->device) {
+            cudaFuncAttributes fa;
+            MCL_CUDA(h, cudaFuncGetAttributes(&fa, kern2));
+            MCL_CUDA(h, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             h->smem_optin - (int)fa.sharedSizeBytes));
+            attr2_dev = h->device;
+        }
+        // the staged sub-windows carry the map border (zero = outside, apron for the int() quirk): no particle needs the
+        // per-beam in-map test
+        p.ilox = -1e300; p.ihix = 1e300; p.iloy = -1e300; p.ihiy = 1e300;
+        kern2<<<h->sm_count, (NCONS + 1) * 32, smem2, h->stream>>>(p, t);
+    } else {
+        const int blocks = h->sm_count * 2;
+        kern<<<blocks, THREADS, smem_bytes, h->stream>>>(p, t);
+    }
     MCL_LAUNCH_CHECK(h);
     if (h->timing) {
         MCL_CUDA(h, cudaEventRecord(e1, h->stream));

@@ -66,7 +66,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     cudaStreamSynchronize(h->stream);
     mcl_filter_forget(h);
     mcl_raycast_forget(h);
-    cudaFree(h->d_est18); cudaFree(h->d_fused); cudaFree(h->d_code8); cudaFree(h->d_tiled);
+    cudaFree(h->d_est18); cudaFree(h->d_fused); cudaFree(h->d_code8); cudaFree(h->d_code8p); cudaFree(h->d_tiled);
     cudaFree(h->d_kld);
     cudaFree(h->d_seq);
     cudaFree(h->d_tail); cudaFree(h->d_tail_prof);
@@ -321,7 +321,8 @@ int mcl_prepare_table(mcl_handle *h) {
     if (!window_in_smem && h->cell_S >= 0) {
         const int margin = (((int)ceil(h->max_range / h->res) + 2) + 3) & ~3;       // multiple of 4: word-aligned staging
         // tile height: the largest multiple of 32 (at most 96) whose sub-window lets two CTAs share an SM
-        const int tw = (256 - 2 * margin) & ~3;
+        int tw = (256 - 2 * margin) & ~15;            // multiple of 16: tile origins stay 16-byte aligned (bulk copies)
+        if (tw < 16) tw = (256 - 2 * margin) & ~3;
         int th = 96;
         while (th > 32 && 2 * (16 + 32768 + (size_t)(th + 2 * margin) * 260 + 1536) > (size_t)h->smem_optin) th -= 32;
         const int tx = tw > 0 ? (h->W + tw - 1) / tw : 0, ty = (h->H + th - 1) / th;
@@ -344,11 +345,29 @@ int mcl_prepare_table(mcl_handle *h) {
                 std::sort(uniq.begin(), uniq.end());
                 for (size_t k = 0; k < uniq.size(); ++k) hcode[slot_of(uniq[k])] = (int)k;
                 std::vector<uint8_t> codes((size_t)cells);
-                for (int64_t c = 0; c < cells; ++c) codes[c] = (uint8_t)hcode[slot_of(tab[c])];
-                std::vector<int32_t> lut(256, -h->voff);                  // code 255: outside the map, adds 0
-                for (size_t k = 0; k < uniq.size(); ++k) lut[k] = uniq[k] - h->voff;
+                // code 0 = outside the map (adds 0): what a zero-filled staging area means; values are codes 1 .. 255
+                for (int64_t c = 0; c < cells; ++c) codes[c] = (uint8_t)(hcode[slot_of(tab[c])] + 1);
+                std::vector<int32_t> lut(256, -h->voff);
+                for (size_t k = 0; k < uniq.size(); ++k) lut[k + 1] = uniq[k] - h->voff;
                 MCL_CUDA(h, cudaMalloc((void **)&h->d_code8, (size_t)cells));
                 MCL_CUDA(h, cudaMemcpy(h->d_code8, codes.data(), (size_t)cells, cudaMemcpyHostToDevice));
+                // padded copy for the bulk-copy kernel: 16 columns in front of every row and one row in front of the
+                // map, zero (= outside) except the cells at x = -1 / y = -1, which repeat column / row 0: int() sends a
+                // coordinate in (-1, 0) to cell 0 (pu:128-129), so a staged sub-window then needs no in-map test at all
+                {
+                    const size_t Wp = (size_t)h->W + 16, Hp = (size_t)h->H + 1;
+                    std::vector<uint8_t> pad(Wp * Hp, 0);
+                    for (int y = -1; y < h->H; ++y) {
+                        const uint8_t *src = codes.data() + (size_t)(y < 0 ? 0 : y) * h->W;
+                        uint8_t *dst = pad.data() + (size_t)(y + 1) * Wp + 16;
+                        memcpy(dst, src, (size_t)h->W);
+                        dst[-1] = src[0];
+                    }
+                    cudaFree(h->d_code8p);
+                    h->d_code8p = nullptr;
+                    MCL_CUDA(h, cudaMalloc((void **)&h->d_code8p, Wp * Hp));
+                    MCL_CUDA(h, cudaMemcpy(h->d_code8p, pad.data(), Wp * Hp, cudaMemcpyHostToDevice));
+                }
                 cudaFree(h->d_lut);
                 h->d_lut = nullptr;
                 MCL_CUDA(h, cudaMalloc((void **)&h->d_lut, 256 * sizeof(int32_t)));
