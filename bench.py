@@ -12,7 +12,9 @@ e2e    : the same steps through the public Localizer API with HOST scan/odom buf
          host estimate out, wall clock per step (copies and sync inside the timed region).
 Resampling arithmetic: on one GPU the REFERENCE'S OWN (pu:416-446: sequential float32 sums, reproduced bit for
 bit by the persistent tail kernel); the time of the fixed-point arithmetic is reported beside it.  Sharded runs
-(N > 1) use the fixed-point arithmetic, which is what makes them bit-identical for any number of ranks.
+(N > 1) default to the fixed-point arithmetic (exact sums: cheapest exchanges, results independent of the number of
+ranks) and report the time of the reference's arithmetic -- continued from rank to rank inside the same kernel,
+bit-identical to one GPU -- beside it (`step_ms_other_resampling`; `--resample reference` makes it the timed mode).
 One process per GPU (torchrun for N > 1); particles are sharded (weak scaling: per-GPU N fixed),
 the map is replicated; timing = barrier + synchronize on both sides, max over ranks.  For N > 1 the run ends with
 a parity check (sharded == single GPU of the same total size) whose result is printed and decides the exit code.
@@ -257,8 +259,6 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     # one GPU: the reference's own resampling arithmetic; sharded: fixed point (rank-count independent)
     resample = args.resample or ("reference" if world == 1 else "fixed")
-    if world > 1 and resample != "fixed":
-        raise SystemExit("bench.py: sharded runs use the fixed-point resampling arithmetic (--resample fixed)")
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -377,13 +377,15 @@ def run_native(args):
 
     # ---- the same step with the OTHER resampling arithmetic, for comparison (one GPU) ------------------------
     other_mode_ms, other_mode = None, None
-    if world == 1 and not args.quick and iters == 1:
+    if not args.quick and iters == 1:
         other_mode = "fixed" if resample == "reference" else "reference"
         loc.h.call("mcl_filter_configure", 1, RESAMPLE_FIXED_POINT if other_mode == "fixed" else RESAMPLE_REFERENCE_F32,
-                   loc.seed, 0, -1)
-        other_mode_ms = timed_steps(min(K, 40))
+                   loc.seed, loc.first_index, -1)
+        barrier()
+        other_mode_ms = max_over_ranks(timed_steps(min(K, 40)))
         loc.h.call("mcl_filter_configure", 1, RESAMPLE_REFERENCE_F32 if resample == "reference" else RESAMPLE_FIXED_POINT,
-                   loc.seed, 0, -1)
+                   loc.seed, loc.first_index, -1)
+        barrier()
     tail_err = C.c_int(0)
     if world == 1:
         loc.h.call("mcl_tail_status", C.byref(tail_err))

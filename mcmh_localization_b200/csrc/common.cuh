@@ -181,7 +181,8 @@ struct TailComm {
     int *d_err;
     const unsigned long long *d_peer_pose_dst;   // device [3][world]
 };
-#define TAIL_EXCHANGES 5
+#define TAIL_EXCHANGES 5          /* fixed-point arithmetic */
+#define TAIL_EXCHANGES_REF 7      /* the reference's arithmetic: + the two rank-to-rank hand-offs of the exact sums */
 int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
                   int32_t *idx, double *gx, double *gy, double *gt, const TailComm *comm);
 const int *mcl_tail_err_ptr(mcl_handle *h);

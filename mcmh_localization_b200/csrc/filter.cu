@@ -595,6 +595,9 @@ extern "C" int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out1
 extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
     FILTER_OR_FAIL("mcl_filter_resample");
     f->tick++;
+    if (f->comm && f->resample_mode != MCL_RESAMPLE_FIXED_POINT)
+        return mcl_fail(h, MCL_ERR_STATE, "mcl_filter_resample: on sharded particles the reference's resampling arithmetic "
+                                          "exists only inside the persistent step (mcl_filter_step, MCL / MHMCL modes)");
     if (f->comm) {
         // global systematic resampling (fixed-point arithmetic): scale from the global weight maximum, local
         // cumulative sums, all-gather of the totals, offspring pushed into the destination ranks' spare set
@@ -643,7 +646,7 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
     if (off || f->assym) return MCL_OK;
     // single GPU: the whole tail is ONE persistent cooperative kernel (tail.cu), in either resampling arithmetic;
     // sharded: four kernels with the peer-memory exchanges between them (fixed-point arithmetic only)
-    const bool tail = mcl_tail_available(h, f->n) && (!f->comm || f->resample_mode == MCL_RESAMPLE_FIXED_POINT);
+    const bool tail = mcl_tail_available(h, f->n);
     if (!tail && f->resample_mode != MCL_RESAMPLE_FIXED_POINT) return MCL_OK;
     DeviceGuard guard(h->device);
     int rc = mcl_fused_prepare(h, f->n);
@@ -690,7 +693,7 @@ static int fused_tail(mcl_handle *h, FilterState *f, double *d_out18, double h_o
             for (int d = 0; d < 16; ++d) tc.peers[d] = f->peer_mailbox[d];
             tc.epoch0 = f->epoch; tc.d_err = f->d_comm_err;
             tc.d_peer_pose_dst = (const unsigned long long *)(f->d_peer_pose + (size_t)dst * 3 * f->world);
-            f->epoch += TAIL_EXCHANGES;
+            f->epoch += f->resample_mode == MCL_RESAMPLE_REFERENCE_F32 ? TAIL_EXCHANGES_REF : TAIL_EXCHANGES;
         }
         rc = mcl_tail_step(h, u, mcl_fused_keymax(h), f->resample_mode, r, f->idx, f->x[dst], f->y[dst], f->th[dst],
                            f->comm ? &tc : nullptr);

@@ -181,6 +181,53 @@ __device__ __forceinline__ unsigned long long tl_ld_acquire_sys(const unsigned l
 // nvals) into every peer's mailbox over NVLink and raises its flag; every CTA (or only CTA 0) waits for the flags of
 // all ranks on its OWN mailbox and copies what they published into sh.xch[rank][value].  Same mailbox, parities and
 // epochs as filter.cu's k_exchange, so both forms can alternate on one stream.
+// warp 0 of any CTA: wait until every rank has published exchange k, copy the payloads into sh.xch[rank][value]
+__device__ void tl_wait_all(const TailArgs &a, TlShared &sh, int k, int nvals) {
+    const int lane = tl_lane();
+    const unsigned long long epoch = a.epoch0 + (unsigned long long)k;
+    const int par = (int)(epoch & 1ull);
+    bool dead = *(volatile int *)a.comm_err != 0;      // a peer was lost earlier: do not wait again
+    if (!dead && lane < a.world) {
+        const unsigned long long *flag = a.mailbox + par * 16 + lane;
+        const long long t0 = clock64();
+        while (tl_ld_acquire_sys(flag) < epoch) {
+            if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
+        }
+    }
+    if (__any_sync(TL_FULL, dead) && lane == 0) *a.comm_err = 1;
+    const volatile unsigned long long *slots = a.mailbox + 32 + (size_t)par * 16 * 16;
+    for (int q = lane; q < a.world * nvals; q += 32) {
+        const int r = q / nvals, v = q - r * nvals;
+        sh.xch[r * 16 + v] = slots[r * 16 + v];
+    }
+}
+// one thread: publish ONE value as this rank's payload of exchange k (the hand-off of an exact running sum to the
+// next rank; everybody reads it later through tl_wait_all)
+__device__ void tl_publish_one(const TailArgs &a, int k, unsigned long long value) {
+    const unsigned long long epoch = a.epoch0 + (unsigned long long)k;
+    const int par = (int)(epoch & 1ull);
+    for (int d = 0; d < a.world; ++d) {
+        unsigned long long *peer = reinterpret_cast<unsigned long long *>(a.peers[d]);
+        peer[32 + ((size_t)par * 16 + a.rank) * 16] = value;
+    }
+    __threadfence_system();
+    for (int d = 0; d < a.world; ++d)
+        tl_st_release_sys(reinterpret_cast<unsigned long long *>(a.peers[d]) + par * 16 + a.rank, epoch);
+}
+// any thread(s): the value rank `src` published for exchange k (spins until it is there)
+__device__ unsigned long long tl_wait_one(const TailArgs &a, int k, int src) {
+    const unsigned long long epoch = a.epoch0 + (unsigned long long)k;
+    const int par = (int)(epoch & 1ull);
+    const unsigned long long *flag = a.mailbox + par * 16 + src;
+    if (*(volatile int *)a.comm_err == 0) {
+        const long long t0 = clock64();
+        while (tl_ld_acquire_sys(flag) < epoch) {
+            if (clock64() - t0 > TL_SPIN_LIMIT) { *a.comm_err = 1; break; }
+        }
+    }
+    return ((const volatile unsigned long long *)a.mailbox)[32 + ((size_t)par * 16 + src) * 16];
+}
+
 __device__ void tl_exchange(const TailArgs &a, TlShared &sh, int k, int nvals, bool all_wait) {
     const int lane = tl_lane(), warp = tl_warp();
     const unsigned long long epoch = a.epoch0 + (unsigned long long)k;
@@ -194,22 +241,7 @@ __device__ void tl_exchange(const TailArgs &a, TlShared &sh, int k, int nvals, b
             __threadfence_system();
             tl_st_release_sys(peer + par * 16 + a.rank, epoch);
         }
-        if (all_wait || blockIdx.x == 0) {
-            bool dead = *(volatile int *)a.comm_err != 0;      // a peer was lost earlier: do not wait again
-            if (!dead && lane < a.world) {
-                const unsigned long long *flag = a.mailbox + par * 16 + lane;
-                const long long t0 = clock64();
-                while (tl_ld_acquire_sys(flag) < epoch) {
-                    if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
-                }
-            }
-            if (__any_sync(TL_FULL, dead) && lane == 0) *a.comm_err = 1;
-            const volatile unsigned long long *slots = a.mailbox + 32 + (size_t)par * 16 * 16;
-            for (int q = lane; q < a.world * nvals; q += 32) {
-                const int r = q / nvals, v = q - r * nvals;
-                sh.xch[r * 16 + v] = slots[r * 16 + v];
-            }
-        }
+        if (all_wait || blockIdx.x == 0) tl_wait_all(a, sh, k, nvals);
     }
     __syncthreads();
 }
@@ -402,9 +434,12 @@ __device__ __noinline__ float tl_lookback_serial(unsigned long long *st, int v, 
 // exact sum entering tile v (warp 0, all lanes; every lane returns the same value).  Backwards in windows of 32
 // tiles: the aggregate maps of clean tiles are composed by a shuffle reduction while the window's nearest dirty
 // tile is still being waited for, so that once an exact sum arrives it takes ONE checked application.
-__device__ float tl_lookback(unsigned long long *st, int v, int *err) {
+// xk != 0 (sharded, reference arithmetic): the sum does not start at 0 but at the exact sum leaving the previous
+// rank, which that rank hands over as exchange xk
+__device__ float tl_lookback(unsigned long long *st, int v, int *err, const TailArgs &a, int xk) {
     const int lane = tl_lane();
-    if (v == 0) return 0.0f;
+    const bool handoff = xk != 0 && a.rank > 0;
+    if (v == 0) return handoff ? __uint_as_float((unsigned)tl_wait_one(a, xk, a.rank - 1)) : 0.0f;
     const long long t0 = clock64();
     int top = v - 1;
     Pair64 suffix; suffix.a0 = 0; suffix.a1 = 0;         // composed map of the clean tiles (top, v-1]
@@ -412,7 +447,7 @@ __device__ float tl_lookback(unsigned long long *st, int v, int *err) {
     bool composable = true;
     while (true) {
         const int q = top - lane;
-        unsigned long long rec = TL_F_INC << 62;         // "tile -1": the sum starts at 0
+        unsigned long long rec = TL_F_INC << 62;         // "tile -1": the sum starts at 0 ...
         bool dead = false;
         if (q >= 0) {
             while (true) {
@@ -421,6 +456,8 @@ __device__ float tl_lookback(unsigned long long *st, int v, int *err) {
                 if (f == TL_F_AGG || f == TL_F_INC) break;
                 if (clock64() - t0 > TL_SPIN_LIMIT) { dead = true; break; }
             }
+        } else if (handoff) {                            // ... or at what the previous rank hands over
+            rec = (TL_F_INC << 62) | (tl_wait_one(a, xk, a.rank - 1) & 0xffffffffull);
         }
         if (__any_sync(TL_FULL, dead)) { if (lane == 0) *err = 2; return 0.0f; }
         // a clean tile predicted in ANOTHER binade than the tiles composed so far ends the composable stretch
@@ -635,7 +672,7 @@ __device__ __forceinline__ Pair64 tl_thread_map(const float *wt, int ipt, int e)
 
 template <bool P2>
 __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, float S, unsigned char *dyn, bool central,
-                                              double mx, double my, double mt) {
+                                              double mx, double my, double mt, int xk) {
     unsigned long long *st = P2 ? a.st2 : a.st1;
     float *C = (float *)a.C;
     float *wsm = (float *)dyn;
@@ -688,7 +725,7 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
             }
             if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);      // hidden behind the chain
             if (warp == 0) {
-                const float c_in = tl_lookback(st, v, &a.hd->err);
+                const float c_in = tl_lookback(st, v, &a.hd->err, a, xk);
                 if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
                 if (lane == 0) {
                     const long long Kn = tl_apply(seq_K(c_in), agg);
@@ -712,7 +749,7 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
             if (t == 0) tl_st_release(st + v, TL_F_NOAGG << 62);
             if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);      // hidden behind the chain
             if (warp == 0) {
-                const float c_in = tl_lookback(st, v, &a.hd->err);
+                const float c_in = tl_lookback(st, v, &a.hd->err, a, xk);
                 if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
                 if (lane == 0) {
                     const long long K0 = seq_K(c_in);
@@ -829,7 +866,7 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
             if (t == 0) tl_st_release(st + v, TL_F_NOAGG << 62);
             if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);      // hidden behind the chain
             if (warp == 0) {
-                const float c_in = tl_lookback(st, v, &a.hd->err);
+                const float c_in = tl_lookback(st, v, &a.hd->err, a, xk);
                 if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
                 if (lane == 0) {
                     float c = c_in;
@@ -915,6 +952,7 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
         if (t == 0) {
             if (P2) ((float *)a.tend)[v] = c_out;
             else if (v == a.nt - 1) a.hd->S = c_out;
+            if (xk && v == a.nt - 1) tl_publish_one(a, xk, (unsigned long long)__float_as_uint(c_out));   // to the next rank
         }
         __syncthreads();
     }
@@ -1081,7 +1119,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     tl_stamp(a, 4);
 
     // ---- S3: population sums (same order in every CTA), means, central sums; first resampling pass ------------
-    double mx, my, mt, scale = 0.0;
+    double mx, my, mt, scale = 0.0, rank_prefix = 0.0;     // rank_prefix: fp64 sum of the weights of the ranks before this one
     {
         double tv[6] = {0, 0, 0, 0, 0, 0};
         float wm = 0.0f;
@@ -1107,6 +1145,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
                 tv[k] = acc;
             }
             for (int r = 0; r < a.world; ++r) wm = fmaxf(wm, (float)__longlong_as_double((long long)sh.xch[r * 16 + 6]));
+            for (int r = 0; r < a.rank; ++r) rank_prefix += __longlong_as_double((long long)sh.xch[r * 16]);
         }
         mx = tv[2] / tv[0]; my = tv[3] / tv[0]; mt = atan2(tv[5], tv[4]);      // np.average; arctan2(sin, cos)
         if (!REF) {
@@ -1129,7 +1168,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
                 const double val = u < a.nt ? __ldcg(a.part_m + (size_t)u * 8) : 0.0;
                 double tot;
                 const double ex = tl_block_excl_scan_d(val, tot, sh);
-                if (u < a.nt && u % G == b) { sh.ownP[u / G] = carry + ex; sh.ownT[u / G] = val; }
+                if (u < a.nt && u % G == b) { sh.ownP[u / G] = rank_prefix + carry + ex; sh.ownT[u / G] = val; }
                 carry += tot;
             }
             __syncthreads();
@@ -1143,7 +1182,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     if (!raw && !REF) tl_central_sums(a, sh, mx, my, mt);
     tl_stamp(a, 6);
     if (REF) {
-        tl_exact_pass<false>(a, sh, 1.0f, dyn, central_in_pass, mx, my, mt);   // pu:430 np.sum(weights): sequential f32
+        tl_exact_pass<false>(a, sh, 1.0f, dyn, central_in_pass, mx, my, mt, SH ? 4 : 0);   // pu:430 np.sum(weights): sequential f32
         if (!raw && !central_in_pass) tl_central_sums(a, sh, mx, my, mt);
     } else {
         for (int v = b; v < a.nt; v += G) {
@@ -1163,8 +1202,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     // ---- S4: running sums of the normalised weights (reference) / of the quantised weights (fixed) ------------
     double totd = 0.0;
     if (REF) {
-        const float S = __ldcg(&a.hd->S);
-        tl_exact_pass<true>(a, sh, S, dyn, false, 0.0, 0.0, 0.0);
+        float S = __ldcg(&a.hd->S);
+        if (SH) {                                        // exchange 4 (handed from rank to rank during pass 1): the
+            if (tl_warp() == 0) tl_wait_all(a, sh, 4, 1);    // population's sum is what left the LAST rank
+            __syncthreads();
+            S = __uint_as_float((unsigned)sh.xch[(a.world - 1) * 16]);
+            __syncthreads();
+        }
+        tl_exact_pass<true>(a, sh, S, dyn, false, 0.0, 0.0, 0.0, SH ? 5 : 0);
     } else {
         unsigned long long carry = 0;
         for (int base = 0; base < a.nt; base += TL_THREADS) {
@@ -1264,6 +1309,57 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     tl_stamp(a, 9);
     tl_grid_barrier(a, 4);
     tl_stamp(a, 10);
+    if (SH && REF) {
+        // exchange 5 (handed from rank to rank during pass 2): the exact running sum at the end of every rank = the
+        // stretch of the population's cumulative weight each rank owns.  Exchange 6: central sums, rank order.
+        if (tl_warp() == 0) tl_wait_all(a, sh, 5, 1);
+        __syncthreads();
+        if (t <= a.world) sh.poff[t] = t == 0 ? 0ull : (sh.xch[(t - 1) * 16] & 0xffffffffull);     // float bits of the bounds
+        double tc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (b == 0) {
+            for (int u = t; u < a.nt; u += TL_THREADS) {
+                const double *pc = a.part_c + (size_t)u * 9;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) tc[k] += __ldcg(pc + k);
+            }
+            tl_block_sum<9>(tc, sh);
+        }
+        if (t == 0)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sh.xpay[k] = (unsigned long long)__double_as_longlong(tc[k]);
+        tl_exchange(a, sh, 6, 9, true);
+        if (b == 0 && t < 9) {
+            double acc = __longlong_as_double((long long)sh.xch[t]);
+            for (int r = 1; r < a.world; ++r) acc += __longlong_as_double((long long)sh.xch[r * 16 + t]);
+            a.est18[9 + t] = acc;
+        }
+        if (tl_warp() == 0) {                            // output slots m with bound[rank-1] < U_m <= bound[rank] (pu:441)
+            const int lane = tl_lane();
+            if (lane <= a.world) {
+                const double cb = (double)__uint_as_float((unsigned)sh.poff[lane]);
+                long long lo = 0, hi = (long long)a.n_global;
+                while (lo < hi) {                        // number of slots with U_m <= cb
+                    const long long mid = (lo + hi) >> 1;
+                    if (__dadd_rn(a.r, __dmul_rn((double)mid, a.rstep)) <= cb) lo = mid + 1; else hi = mid;
+                }
+                sh.pcnt[lane] = lo;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                long long prev_hi = 0, my_lo = 0, my_hi = 0;
+                for (int r = 0; r < a.world; ++r) {
+                    long long lo = r == 0 ? 0 : sh.pcnt[r];
+                    long long hi = r == a.world - 1 ? (long long)a.n_global : sh.pcnt[r + 1];     // pu:441 "i < N - 1": the rest
+                    if (hi < lo) hi = lo;
+                    if (r > 0) { if (lo < prev_hi) lo = prev_hi; if (hi < lo) hi = lo; }
+                    if (r == a.rank) { my_lo = lo; my_hi = hi; }
+                    prev_hi = hi;
+                }
+                sh.m_lo = my_lo; sh.m_hi = my_hi;
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- S5: idx[m] = min(first i with C_i >= key_m, n - 1) (pu:439-444 as a search) + pu:445 gather ----------
     // Sharded: this rank emits the output slots [m_lo, m_hi) whose thresholds fall into its own stretch of the
@@ -1281,7 +1377,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         }
         const int warp = tl_warp(), lane = tl_lane();
         const int64_t out_lo = SH ? (int64_t)sh.m_lo : 0, out_hi = SH ? (int64_t)sh.m_hi : n;
-        const unsigned long long koff = SH ? sh.poff[a.rank] : 0ull;       // cumulative weight of the ranks before this one
+        const unsigned long long koff = (SH && !REF) ? sh.poff[a.rank] : 0ull;     // fixed point: cumulative weight of the ranks before this one
         const int64_t n_per_rank = n;
         if (SH && t < 3 * a.world) sh.xch[t] = a.peer_pose[t];
         if (SH) __syncthreads();
@@ -1290,7 +1386,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             const int64_t m0 = out_lo + (int64_t)ov * a.tile, m1 = min(out_hi, m0 + a.tile);
             if (warp < 2) {
                 KeyT key = tl_key<REF>(warp == 0 ? m0 : m1 - 1, a.r, a.rstep, totd);
-                if (SH) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
+                if (SH && !REF) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
                 int64_t lo = 0, hi = limit;
                 if (coarse) {
                     int tl = 0, th = a.nt - 1;               // first tile whose last running sum reaches the key
@@ -1316,7 +1412,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
                 const int64_t m = m0 + (int64_t)k * TL_THREADS + t;
                 if (m >= m1) break;
                 KeyT key = tl_key<REF>(m, a.r, a.rstep, totd);
-                if (SH) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
+                if (SH && !REF) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
                 int64_t src;
                 if (staged) {
                     int lo = 0, hi = (int)cnt - 1;
@@ -1351,7 +1447,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     if (SH) {                                            // exchange 5: every rank's offspring have landed everywhere
         __threadfence_system();
         tl_grid_barrier(a, 5);
-        tl_exchange(a, sh, 5, 0, false);
+        tl_exchange(a, sh, REF ? 7 : 5, 0, false);
     }
     tl_stamp(a, 11);
 }
@@ -1429,8 +1525,8 @@ static cudaError_t tail_launch(const TailArgs &a, int grid, size_t dyn, cudaStre
 // the MH result (without MH it must be the particles themselves), (gx, gy, gt) the resampled set.
 int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
                   int32_t *idx, double *gx, double *gy, double *gt, const TailComm *comm) {
-    if (comm && resample_mode != MCL_RESAMPLE_FIXED_POINT)
-        return mcl_fail(h, MCL_ERR_ARG, "mcl_tail_step: sharded runs use the fixed-point resampling arithmetic");
+    if (comm && resample_mode != MCL_RESAMPLE_FIXED_POINT && resample_mode != MCL_RESAMPLE_REFERENCE_F32)
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_tail_step: unknown resampling arithmetic");
     int rc = tail_prepare(h, u.n);
     if (rc) return rc;
     const TailPlan p = tail_plan(h, u.n);
@@ -1467,7 +1563,8 @@ int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keyma
     const size_t dyn = (size_t)TL_COARSE_MAX * 8 + TL_STAGE_BYTES;
     const bool ref = resample_mode == MCL_RESAMPLE_REFERENCE_F32;
     cudaError_t e;
-    if (comm) e = u.use_mh ? tail_launch<true, false, true>(a, p.grid, dyn, h->stream) : tail_launch<false, false, true>(a, p.grid, dyn, h->stream);
+    if (comm && ref) e = u.use_mh ? tail_launch<true, true, true>(a, p.grid, dyn, h->stream) : tail_launch<false, true, true>(a, p.grid, dyn, h->stream);
+    else if (comm) e = u.use_mh ? tail_launch<true, false, true>(a, p.grid, dyn, h->stream) : tail_launch<false, false, true>(a, p.grid, dyn, h->stream);
     else if (u.use_mh) e = ref ? tail_launch<true, true, false>(a, p.grid, dyn, h->stream) : tail_launch<true, false, false>(a, p.grid, dyn, h->stream);
     else e = ref ? tail_launch<false, true, false>(a, p.grid, dyn, h->stream) : tail_launch<false, false, false>(a, p.grid, dyn, h->stream);
     if (e != cudaSuccess) return mcl_fail(h, MCL_ERR_CUDA, std::string("k_tail launch: ") + cudaGetErrorString(e));

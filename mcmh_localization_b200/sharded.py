@@ -97,14 +97,19 @@ class ShardedLocalizer(Localizer):
         up (no symmetric memory, ...) construction RAISES unless allow_fallback=True, in which case the next
         simpler one is used and the reason is kept in `symm_error`."""
         self.allow_fallback = allow_fallback
-        if resample_mode != "fixed":
-            raise ValueError("sharded resampling uses the fixed-point arithmetic (decomposition-independent)")
+        # "fixed": 64-bit fixed-point sums (the default: independent of the decomposition, cheapest exchanges);
+        # "reference": pu:416-446's sequential float32 sums, continued from rank to rank inside the persistent step
+        # kernel -- bit-identical to the single-GPU reference arithmetic; step() / step_staged() only, native exchanges
+        if resample_mode not in ("fixed", "reference"):
+            raise ValueError(resample_mode)
+        if resample_mode == "reference" and not (peer_push and native_comm):
+            raise ValueError("sharded reference-arithmetic resampling needs the native peer-memory exchanges")
         self.group = group
         self.use_peer_push = peer_push
         self.use_native_comm = native_comm and peer_push
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        super().__init__(device=device, params=params, mode=mode, seed=seed, resample_mode="fixed",
+        super().__init__(device=device, params=params, mode=mode, seed=seed, resample_mode=resample_mode,
                          max_attempts=max_attempts)
 
     # -- buffers -----------------------------------------------------------------------------

@@ -1,6 +1,7 @@
 """Multi-GPU check (run under torchrun, one rank per GPU): a ShardedLocalizer over R ranks must
 reproduce a single-GPU Localizer of the same total size -- same Philox streams (keyed by the global
-particle index), same softmax statistics, same fixed-point global resampling."""
+particle index), same softmax statistics, same global resampling -- in the fixed-point arithmetic or
+(MCL_RESAMPLE=reference) in the reference's own sequential-float32 arithmetic continued from rank to rank."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,13 +25,14 @@ def main():
     scans, angles = bench.make_scans(gm, poses, 360)
     parts = free_space_particles(gm, n, seed=5)
     mode = os.environ.get("MCL_EXCHANGE", "native")      # native | push | nccl
+    arith = os.environ.get("MCL_RESAMPLE", "fixed")      # fixed | reference (native exchanges only)
     sh = ShardedLocalizer(device=local, params=P, mode="MHMCL", seed=99, peer_push=mode != "nccl",
-                          native_comm=mode == "native")
+                          native_comm=mode == "native", resample_mode=arith)
     sh.load_map(gm)
     sh.set_particles(parts[rank * n_local:(rank + 1) * n_local])
     ref = None
     if rank == 0:
-        ref = Localizer(device=local, params=P, mode="MHMCL", seed=99, resample_mode="fixed")
+        ref = Localizer(device=local, params=P, mode="MHMCL", seed=99, resample_mode=arith)
         ref.load_map(gm)
         ref.set_particles(parts)
     ok = True
@@ -48,7 +50,7 @@ def main():
             dc = np.abs(est[3] - rest[3]).max()
             print("step %d: identical particles %.6f  |d mean| %.2e  |d cov| %.2e" % (k, same, de, dc), flush=True)
             ok = ok and same > 0.9999 and de < 1e-9 and dc < 1e-9
-    if mode == "native":
+    if mode == "native" and arith == "fixed":
         # asymmetric MH and the MH chain (BASELINE config 4) on sharded particles == single GPU
         for lm, chain in (("AMHMCL", 0), ("MHMCL", 4)):
             sh2 = ShardedLocalizer(device=local, params=P, mode=lm, seed=7)

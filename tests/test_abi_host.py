@@ -186,7 +186,7 @@ def test_likelihood_hot_loop_stays_on_the_uniform_datapath():
     assert "UBLKCP" in t2 and "SYNCS" in t2 and "LDGSTS" not in t2
     # the persistent step tail: one cooperative kernel per configuration, system-scope acquire/release in the sharded ones
     tails = [f for f in funcs if f.startswith("_Z6k_tailIL")]
-    assert len(tails) == 6
+    assert len(tails) == 8      # {MCL, MH} x {fixed point, reference arithmetic} x {one GPU, sharded}
 
 
 def test_ros_adapter_example_is_valid_python():

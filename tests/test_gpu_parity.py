@@ -1013,6 +1013,15 @@ def test_sharded_two_gpus_equals_single_gpu():
                         os.path.join(ROOT, "scripts", "dist_check.py"), "320000"],
                        capture_output=True, text=True, timeout=900, env=dict(os.environ, MCL_EXCHANGE="native"))
     assert "DIST_CHECK OK" in r.stdout, ("native/fused", r.stdout[-2000:] + r.stderr[-2000:])
+    # the reference's own resampling arithmetic (sequential float32 sums) continued from rank to rank: the sharded
+    # run must equal the single-GPU run in that arithmetic, i.e. pu:416-446 bit for bit on two GPUs
+    for n_local in ("20000", "320000"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29541",
+                            os.path.join(ROOT, "scripts", "dist_check.py"), n_local],
+                           capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, MCL_EXCHANGE="native", MCL_RESAMPLE="reference"))
+        assert "DIST_CHECK OK" in r.stdout, ("native/reference arithmetic", n_local, r.stdout[-2000:] + r.stderr[-2000:])
 
 
 def test_c_abi_error_behaviour():
