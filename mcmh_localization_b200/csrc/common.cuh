@@ -186,6 +186,12 @@ struct TailComm {
 int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, int resample_mode, double r,
                   int32_t *idx, double *gx, double *gy, double *gt, const TailComm *comm);
 const int *mcl_tail_err_ptr(mcl_handle *h);
+// MH chain iteration as one cooperative launch (k_chain_tail); TAIL_CHAIN_EXCHANGES epochs when sharded
+#define TAIL_CHAIN_EXCHANGES 2
+unsigned long long *mcl_tail_chain_key(mcl_handle *h, int64_t n, int slot);
+int mcl_tail_chain_iteration(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, float *score_chain, int it,
+                             const TailComm *comm);
+int mcl_tail_chain_finish(mcl_handle *h);
 int mcl_likelihood_pair(mcl_handle *h, const double *d_x, const double *d_y, const double *d_theta, float *d_score,
                         const double *d_x2, const double *d_y2, const double *d_theta2, float *d_score2, int64_t n,
                         unsigned long long *d_keymax, bool *g1_used);

@@ -489,6 +489,68 @@ extern "C" int mcl_filter_update_chain(mcl_handle *h, int iters) {
     if (nofuse < 0) { const char *e = getenv("MCL_NO_FUSE"); nofuse = (e && atoi(e)) ? 1 : 0; }
     bool fused = !f->comm && !nofuse;
     int rc;
+    // every iteration after its likelihood launch = ONE cooperative kernel (tail.cu k_chain_tail): softmax sums of
+    // both score sets, accept, carried score and its maximum; sharded: with the two exchanges inside
+    const bool ctail = !nofuse && mcl_tail_available(h, f->n);
+    if (ctail) {
+        rc = mcl_fused_prepare(h, f->n);
+        if (rc) return rc;
+        unsigned long long *ck0 = mcl_tail_chain_key(h, f->n, 0);
+        if (!ck0) return mcl_fail(h, MCL_ERR_NOMEM, "mcl_filter_update_chain: work area");
+        bool ok = false;
+        rc = mcl_likelihood_pair(h, f->x[prev], f->y[prev], f->th[prev], score_chain, nullptr, nullptr, nullptr, nullptr, f->n,
+                                 ck0, &ok);                                                  // chain_0 = particles_prev
+        if (rc) return rc;
+        // (a scan without a valid beam launches nothing: !ok, the stand-alone sequence below scores -50, pu:147)
+        if (ok && iters > 1) {
+            if (f->thr_cap < f->n) {
+                MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+                cudaFree(f->thr); f->thr = nullptr; f->thr_cap = 0;
+                MCL_CUDA(h, cudaMalloc((void **)&f->thr, (size_t)f->n * sizeof(unsigned long long)));
+                f->thr_cap = f->n;
+            }
+            MCL_CUDA(h, cudaMemsetAsync(f->thr, 0xff, (size_t)f->n * sizeof(unsigned long long), h->stream));
+        }
+        for (int it = 0; ok && it < iters; ++it) {
+            if (it > 0) {   // fresh proposal from particles_prev
+                f->tick++;
+                rc = mcl_predict_cached(h, f->x[prev], f->y[prev], f->th[prev], f->n, f->delta, f->seed, f->tick,
+                                        f->first_index, nullptr, 0, f->max_attempts, f->x[prop], f->y[prop], f->th[prop],
+                                        nullptr, f->thr);
+                if (rc) return rc;
+            }
+            const int src = it == 0 ? prev : chain;
+            bool ok2 = false;
+            rc = mcl_likelihood_pair(h, f->x[prop], f->y[prop], f->th[prop], score_prop, nullptr, nullptr, nullptr, nullptr,
+                                     f->n, mcl_fused_keymax(h), &ok2);
+            if (rc) return rc;
+            f->tick++;
+            FusedStep u;
+            memset(&u, 0, sizeof(u));
+            u.n = f->n; u.n_global = f->comm ? f->n_global : f->n; u.use_mh = 1;
+            u.s_post = score_prop; u.w_out = f->w[f->wslot];
+            u.px = f->x[prop]; u.py = f->y[prop]; u.pt = f->th[prop];
+            u.ox = f->x[src]; u.oy = f->y[src]; u.ot = f->th[src];
+            u.nx = f->x[chain]; u.ny = f->y[chain]; u.nth = f->th[chain];
+            u.seed = f->seed; u.step = f->tick; u.first_index = f->first_index;
+            TailComm tc;
+            if (f->comm) {
+                tc.rank = f->rank; tc.world = f->world; tc.n_global = f->n_global; tc.mailbox = f->mailbox;
+                for (int d = 0; d < 16; ++d) tc.peers[d] = f->peer_mailbox[d];
+                tc.epoch0 = f->epoch; tc.d_err = f->d_comm_err; tc.d_peer_pose_dst = nullptr;
+                f->epoch += TAIL_CHAIN_EXCHANGES;
+            }
+            rc = mcl_tail_chain_iteration(h, u, mcl_fused_keymax(h), score_chain, it, f->comm ? &tc : nullptr);
+            if (rc) return rc;
+        }
+        if (ok) {
+            rc = mcl_tail_chain_finish(h);
+            if (rc) return rc;
+            f->cur = chain; f->spare = prop;              // self.particles = chain
+            return MCL_OK;
+        }
+        fused = false;
+    }
     if (fused) {
         rc = mcl_fused_prepare(h, f->n);
         if (rc) return rc;

@@ -52,6 +52,7 @@
 
 struct TailHeader {              // device, zero-initialised once
     unsigned long long bar;      // grid barrier counter (monotone; the host tracks the base)
+    unsigned long long ckey[2];  // MH chain: max(carried score) as a key, slot = iteration parity (read | written)
     int err, pad;
     float S, pad2;               // reference mode: exact sequential f32 sum of the weights (pu:430)
     unsigned long long total;    // fixed-point mode: total of the quantised weights
@@ -90,6 +91,9 @@ struct TailArgs {
     unsigned long long epoch0;               // exchanges consumed before this launch
     int *comm_err;                           // sticky: a peer did not answer
     const unsigned long long *peer_pose;     // device [3][world]: x / y / theta of the destination set on every rank
+    // MH chain iteration (k_chain_tail)
+    float *score_chain;                      // carried scores (read and updated in place)
+    unsigned long long *ckey_in, *ckey_out;  // key of max(carried score): of this iteration / for the next one
 };
 
 struct TlItems {
@@ -1452,6 +1456,73 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     tl_stamp(a, 11);
 }
 
+// ------------------------------------------------------------------------------------------------ MH chain iteration
+// One iteration of the MH refinement chain (filter.cu mcl_filter_update_chain, BASELINE config 4) after its
+// likelihood launch: weights of the proposal and of the chain from two separately normalised softmaxes
+// (node:254-270), accept (pu:229-233), carried score and its maximum for the next iteration -- one cooperative
+// launch with one grid barrier; sharded: the two exchanges (score maxima, exact softmax sums) inside.
+//   a.s_post = proposal scores, a.score_chain = carried scores, (px..) proposal, (ox..) chain, (nx..) result
+template <bool SH>
+__global__ void __launch_bounds__(TL_THREADS, 1) k_chain_tail(const TailArgs a) {
+    __shared__ TlShared sh;
+    const int t = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+    const int64_t n = a.n;
+    unsigned key0 = (unsigned)((volatile unsigned long long *)a.keymax)[0];
+    unsigned key1 = (unsigned)((volatile unsigned long long *)a.ckey_in)[0];
+    if (SH) {
+        if (t == 0) { sh.xpay[0] = key0; sh.xpay[1] = key1; }
+        tl_exchange(a, sh, 1, 2, true);
+        for (int r = 0; r < a.world; ++r) {
+            key0 = max(key0, (unsigned)sh.xch[r * 16]);
+            key1 = max(key1, (unsigned)sh.xch[r * 16 + 1]);
+        }
+    }
+    const float m_prop = key0 ? mcl_float_of_key(key0) : -FLT_MAX;
+    const float m_chain = key1 ? mcl_float_of_key(key1) : -FLT_MAX;
+    {
+        unsigned long long acc0 = 0, acc1 = 0;
+        for (int64_t i = (int64_t)b * TL_THREADS + t; i < n; i += (int64_t)G * TL_THREADS) {
+            acc0 += __double2ull_rz(__dmul_rn((double)tl_softmax_num(a.s_post[i], m_prop), TL_SOFTMAX_FIX));
+            acc1 += __double2ull_rz(__dmul_rn((double)tl_softmax_num(a.score_chain[i], m_chain), TL_SOFTMAX_FIX));
+        }
+        tl_block_sum_u64x2(acc0, acc1, sh);
+        if (t == 0) { a.part_q[b] = acc0; a.part_q[G + b] = acc1; }
+    }
+    tl_grid_barrier(a, 1);
+    unsigned long long q0 = 0, q1 = 0;
+    for (int u = t; u < G; u += TL_THREADS) { q0 += __ldcg(a.part_q + u); q1 += __ldcg(a.part_q + G + u); }
+    tl_block_sum_u64x2(q0, q1, sh);
+    if (SH) {
+        if (t == 0) { sh.xpay[0] = q0; sh.xpay[1] = q1; }
+        tl_exchange(a, sh, 2, 2, true);
+        q0 = 0; q1 = 0;
+        for (int r = 0; r < a.world; ++r) { q0 += sh.xch[r * 16]; q1 += sh.xch[r * 16 + 1]; }
+    }
+    if (b == 0 && t == 0) { a.keymax[0] = 0ull; a.ckey_in[0] = 0ull; }     // every CTA has read both keys
+    const float sum_prop = (float)((double)q0 / TL_SOFTMAX_FIX), sum_chain = (float)((double)q1 / TL_SOFTMAX_FIX);
+    float smax = -FLT_MAX;
+    for (int64_t i = (int64_t)b * TL_THREADS + t; i < n; i += (int64_t)G * TL_THREADS) {
+        const float s_prop = a.s_post[i], s_chain = a.score_chain[i];
+        const float p_new = __fdiv_rn(tl_softmax_num(s_prop, m_prop), sum_prop);
+        const float p_old = __fdiv_rn(tl_softmax_num(s_chain, m_chain), sum_chain);
+        double alpha = 1.0;
+        if (p_old > 0.f) {
+            const double q = (double)__fdiv_rn(p_new, p_old);
+            alpha = (q < 1.0) ? q : 1.0;
+        }
+        const uint4 o = philox_draw4(a.seed, a.step, a.first_index + (uint64_t)i, 0u, MCL_STREAM_MH);
+        const bool acc = u53_from(o.x, o.y) < alpha;
+        a.nx[i] = acc ? a.px[i] : a.ox[i];
+        a.ny[i] = acc ? a.py[i] : a.oy[i];
+        a.nth[i] = acc ? a.pt[i] : a.ot[i];
+        a.w_out[i] = acc ? p_new : p_old;
+        if (acc) a.score_chain[i] = s_prop;
+        smax = fmaxf(smax, acc ? s_prop : s_chain);
+    }
+    smax = tl_block_max(smax, sh);
+    if (t == 0 && smax > -FLT_MAX) atomicMax(a.ckey_out, (unsigned long long)mcl_key_of_float(smax));
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static size_t tl_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -1630,5 +1701,47 @@ extern "C" int mcl_tail_prof(mcl_handle *h, unsigned long long *out, int *grid) 
     MCL_CUDA(h, cudaStreamSynchronize(h->stream));
     MCL_CUDA(h, cudaMemcpy(out, h->d_tail_prof, (size_t)h->tail_prof_grid * 32 * 8, cudaMemcpyDeviceToHost));
     *grid = h->tail_prof_grid;
+    return MCL_OK;
+}
+
+// MH chain (mcl_filter_update_chain): where the likelihood of chain_0 leaves its maximum; one iteration
+unsigned long long *mcl_tail_chain_key(mcl_handle *h, int64_t n, int slot) {
+    if (tail_prepare(h, n)) return nullptr;
+    return &reinterpret_cast<TailHeader *>(h->d_tail)->ckey[slot & 1];
+}
+
+int mcl_tail_chain_iteration(mcl_handle *h, const FusedStep &u, unsigned long long *d_keymax, float *score_chain, int it,
+                             const TailComm *comm) {
+    int rc = tail_prepare(h, u.n);
+    if (rc) return rc;
+    const TailPlan p = tail_plan(h, u.n);
+    char *b = (char *)h->d_tail;
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hd = (TailHeader *)b; a.keymax = d_keymax; a.bar_base = h->tail_bar;
+    a.n = u.n; a.s_post = u.s_post; a.w_out = u.w_out; a.score_chain = score_chain;
+    a.px = u.px; a.py = u.py; a.pt = u.pt; a.ox = u.ox; a.oy = u.oy; a.ot = u.ot; a.nx = u.nx; a.ny = u.ny; a.nth = u.nth;
+    a.seed = u.seed; a.step = u.step; a.first_index = u.first_index;
+    a.part_q = (unsigned long long *)(b + p.o_q);
+    a.ckey_in = &a.hd->ckey[it & 1]; a.ckey_out = &a.hd->ckey[(it + 1) & 1];
+    if (comm) {
+        a.rank = comm->rank; a.world = comm->world; a.n_global = comm->n_global; a.mailbox = comm->mailbox;
+        for (int d = 0; d < 16; ++d) a.peers[d] = comm->peers[d];
+        a.epoch0 = comm->epoch0; a.comm_err = comm->d_err;
+    }
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((u.n + TL_THREADS * 4 - 1) / (TL_THREADS * 4), h->sm_count));
+    void *params[] = {(void *)&a};
+    cudaError_t e = comm ? cudaLaunchCooperativeKernel((const void *)k_chain_tail<true>, dim3(grid), dim3(TL_THREADS), params, 0, h->stream)
+                         : cudaLaunchCooperativeKernel((const void *)k_chain_tail<false>, dim3(grid), dim3(TL_THREADS), params, 0, h->stream);
+    if (e != cudaSuccess) return mcl_fail(h, MCL_ERR_CUDA, std::string("k_chain_tail launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    h->tail_bar += (unsigned long long)grid;
+    return MCL_OK;
+}
+
+// after the last iteration: both chain-key slots back to zero
+int mcl_tail_chain_finish(mcl_handle *h) {
+    if (!h->d_tail) return MCL_OK;
+    MCL_CUDA(h, cudaMemsetAsync(reinterpret_cast<TailHeader *>(h->d_tail)->ckey, 0, 2 * sizeof(unsigned long long), h->stream));
     return MCL_OK;
 }
