@@ -306,10 +306,11 @@ int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]);    
 int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);                       /* node:488-492 */
 /* odom + scan -> predict (delta != NULL), update on pre-staged scan `scan_slot` (or the current scan
  * if < 0), estimate (to d_out18 and/or blocking into h_out16; both nullable), resample.
- * With symmetric MH or plain MCL and MCL_RESAMPLE_FIXED_POINT the tail of the step runs through the fused
- * kernels (6 launches per step; same results bit for bit as the calls above issued one by one; sharded
- * handles exchange between the fused stages).  MCL_NO_FUSE=1 in the environment selects the stand-alone
- * sequence (A/B measurements). */
+ * With symmetric MH or plain MCL the step is three launches: motion, likelihood of both particle sets, and the
+ * persistent tail kernel (csrc/tail.cu: softmax x2, MH accept, estimate sums, resampling in either arithmetic;
+ * on sharded handles also the cross-rank exchanges and the peer push) -- same results bit for bit as the calls
+ * above issued one by one.  MCL_NO_TAIL=1 in the environment selects round 1's four fused kernels (fixed point)
+ * or the stand-alone sequence, MCL_NO_FUSE=1 the stand-alone sequence (A/B measurements). */
 int mcl_filter_step(mcl_handle *h, const double delta[3], int scan_slot, double *d_out18,
                     double h_out16[16]);
 
@@ -344,7 +345,7 @@ int mcl_comm_init(mcl_handle *h, int rank, int world, void *d_mailbox, const uin
                   const uint64_t *h_peer_pose);
 int mcl_comm_status(mcl_handle *h, int *err);
 
-/* On one GPU mcl_filter_step runs the whole tail of the step (node:351-358 softmax x2, pu:208-236 MH accept,
+/* mcl_filter_step runs the whole tail of the step (node:351-358 softmax x2, pu:208-236 MH accept,
  * node:586-597 estimate sums, pu:416-446 resampling in either arithmetic) as ONE persistent cooperative kernel
  * with grid-wide barriers (csrc/tail.cu).  Its waits are bounded; *err != 0 after a time-out (blocking call;
  * the step's results are then invalid).  mcl_filter_step with a host estimate checks it itself.
@@ -356,6 +357,10 @@ int mcl_tail_status(mcl_handle *h, int *err);
  * tail launch (out must hold 1024 * 32 values); *grid = CTAs of that launch. */
 int mcl_tail_prof(mcl_handle *h, unsigned long long *out, int *grid);
 int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, double r, int mode, int32_t *d_idx, void *d_c);
+/* Debug (MCL_MOTION_STATS=1 in the environment): counters of the motion kernel's rejection loop since the last
+ * call: [0] attempt 0 failed, [1] provably stuck, [2] particles retried, [3] screening rounds, [4] evaluation rounds,
+ * [5] retries that found a pose, [6] retried with threshold <= 2^28, [7] attempts evaluated, [8] warps with a retry. */
+int mcl_debug_motion_stats(mcl_handle *h, unsigned long long out[16]);
 
 /* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */
 /* Random 4-byte gather rate, lookups/s: table_bytes resident in shared memory (where = 0) or in

@@ -116,6 +116,7 @@ struct mcl_handle {
     unsigned long long tail_bar = 0;   // grid-barrier arrivals consumed so far (base of the next launch)
     void *d_tail_prof = nullptr; // MCL_TAIL_PROF=1: stage time stamps of the tail kernel
     int tail_prof_grid = 0;
+    void *d_motion_stats = nullptr; // MCL_MOTION_STATS=1: counters of the motion kernel's rejection loop
     int coop_launch = -1;        // cudaDevAttrCooperativeLaunch (-1: not queried yet)
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;

@@ -34,7 +34,10 @@ struct MotionParams {
     // optional per-particle cache of the screening threshold (~0 = not computed yet): the MH chain proposes from
     // the SAME poses with the SAME increment 31 more times, and the threshold depends on nothing else
     unsigned long long *thr_cache;
+    // MCL_MOTION_STATS=1: counters of the rejection loop (mcl_debug_motion_stats), else null
+    unsigned long long *stats;
 };
+#define MOTION_STAT(p, k, v) do { if ((p).stats) atomicAdd((p).stats + (k), (unsigned long long)(v)); } while (0)
 
 struct Pose { double x, y, th; };
 
@@ -129,9 +132,12 @@ __device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x
 }
 
 #define MOTION_Q 320     // >= 31 leftover + 256 new candidates per screening round
-__global__ void __launch_bounds__(256, 4) k_motion(const MotionParams p) {
-    __shared__ unsigned short q_att[8][MOTION_Q];
-    __shared__ unsigned short q_hi[8][MOTION_Q];
+// Small CTAs: a CTA stays resident until its slowest warp is done, and the warps that hold stuck particles run
+// 10-100x longer than the others -- with 8 warps per CTA the SM averaged 13 resident warps (ncu r2a: 20 %).
+template <int MOTION_BLOCK>
+__global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(const MotionParams p) {
+    __shared__ unsigned short q_att[MOTION_BLOCK / 32][MOTION_Q];
+    __shared__ unsigned short q_hi[MOTION_BLOCK / 32][MOTION_Q];
     const int lane = threadIdx.x & 31;
     const int64_t warp_base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
     if (warp_base >= p.n) return;                       // warp-uniform
@@ -157,6 +163,15 @@ __global__ void __launch_bounds__(256, 4) k_motion(const MotionParams p) {
         }
     }
     unsigned pending = __ballot_sync(0xffffffffu, !done);
+    if (p.stats) {
+        const unsigned f0 = __ballot_sync(0xffffffffu, live && att == 0 && p.max_attempts > 0);
+        const unsigned ps = __ballot_sync(0xffffffffu, live && att == 0 && thr == 0ull);
+        const unsigned hard = __ballot_sync(0xffffffffu, !done && thr <= (1ull << 28));
+        if (lane == 0) {
+            MOTION_STAT(p, 0, __popc(f0)); MOTION_STAT(p, 1, __popc(ps)); MOTION_STAT(p, 2, __popc(pending));
+            MOTION_STAT(p, 6, __popc(hard)); MOTION_STAT(p, 8, pending ? 1 : 0);
+        }
+    }
     while (pending) {
         const int src = __ffs(pending) - 1;
         const double sx = shfl_d(x, src), sy = shfl_d(y, src), sth = shfl_d(th, src);
@@ -207,6 +222,7 @@ __global__ void __launch_bounds__(256, 4) k_motion(const MotionParams p) {
                     uint4 a = make_uint4(0u, 0u, 0u, 0u);
                     int cnt = 0;
                     unsigned passm = 0;
+                    if (lane == 0) MOTION_STAT(p, 3, 1);
                     if (g < groups) {
                         a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
 #pragma unroll
@@ -240,6 +256,7 @@ __global__ void __launch_bounds__(256, 4) k_motion(const MotionParams p) {
                 Pose c = {0, 0, 0};
                 bool ok = false;
                 int t = 0;
+                if (lane == 0 && qlen > qhead) { MOTION_STAT(p, 4, 1); MOTION_STAT(p, 7, min(32, qlen - qhead)); }
                 if (e < qlen) {
                     t = qt[e];
                     const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
@@ -259,6 +276,7 @@ __global__ void __launch_bounds__(256, 4) k_motion(const MotionParams p) {
                 __syncwarp();
             }
         }
+        if (lane == 0 && watt) MOTION_STAT(p, 5, 1);
         if (lane == src) { out = win; att = watt; }       // watt == 0: keep the old pose (pu:360-361)
         pending &= pending - 1;
     }
@@ -306,6 +324,12 @@ int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, cons
     p.normals = d_normals; p.A = A; p.max_attempts = max_attempts;
     p.xo = d_xo; p.yo = d_yo; p.tho = d_thetao; p.attempts = d_attempts;
     p.thr_cache = d_normals ? nullptr : d_thr_cache;
+    static const bool want_stats = getenv("MCL_MOTION_STATS") != nullptr;
+    if (want_stats && !h->d_motion_stats) {
+        MCL_CUDA(h, cudaMalloc((void **)&h->d_motion_stats, 16 * 8));
+        MCL_CUDA(h, cudaMemsetAsync(h->d_motion_stats, 0, 16 * 8, h->stream));
+    }
+    p.stats = (unsigned long long *)h->d_motion_stats;
     // screening levels: every candidate with |z0|, |z1| <= rho has t in trans +- rho s2 and heading within
     // +- rho s1 of theta + rot1.  Valid only while t stays positive and the spread small; levels are nested.
     const double levels[10] = {1.0, 2.0, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.6605};
@@ -324,8 +348,33 @@ int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, cons
                                  : (unsigned long long)(4294967296.0 * exp(-0.5 * rho * rho) * (1.0 + 1e-9)) + 2ull;
         p.n_levels = k + 1;
     }
-    const int blocks = (int)((n + 255) / 256);
-    k_motion<<<blocks, 256, 0, h->stream>>>(p);
+    static const int block = [] {                        // MCL_MOTION_BLOCK=32|64|128|256 for A/B measurements
+        const char *e = getenv("MCL_MOTION_BLOCK");
+        const int v = e ? atoi(e) : 64;
+        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 64;
+    }();
+    const int blocks = (int)((n + block - 1) / block);
+    switch (block) {
+    case 32:  k_motion<32><<<blocks, 32, 0, h->stream>>>(p); break;
+    case 128: k_motion<128><<<blocks, 128, 0, h->stream>>>(p); break;
+    case 256: k_motion<256><<<blocks, 256, 0, h->stream>>>(p); break;
+    default:  k_motion<64><<<blocks, 64, 0, h->stream>>>(p); break;
+    }
     MCL_LAUNCH_CHECK(h);
+    return MCL_OK;
+}
+
+// Debug (MCL_MOTION_STATS=1): counters of the rejection loop since the last call, then reset.
+// [0] attempt 0 failed, [1] provably stuck, [2] particles retried, [3] screening rounds (one Philox call per lane),
+// [4] evaluation rounds, [5] retries that found a pose, [6] retried with threshold <= 2^28, [7] attempts evaluated,
+// [8] warps with a retry.
+int mcl_debug_motion_stats(mcl_handle *h, unsigned long long out[16]) {
+    if (!h || !out) return MCL_ERR_ARG;
+    for (int k = 0; k < 16; ++k) out[k] = 0;
+    if (!h->d_motion_stats) return MCL_OK;
+    DeviceGuard guard(h->device);
+    MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    MCL_CUDA(h, cudaMemcpy(out, h->d_motion_stats, 16 * 8, cudaMemcpyDeviceToHost));
+    MCL_CUDA(h, cudaMemset(h->d_motion_stats, 0, 16 * 8));
     return MCL_OK;
 }
