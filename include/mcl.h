@@ -55,7 +55,7 @@ enum {
 
 /* Philox stream ids (ctr[3] low byte). */
 enum { MCL_STREAM_MOTION = 1, MCL_STREAM_MH = 2, MCL_STREAM_RESAMPLE = 3, MCL_STREAM_INIT = 4,
-       MCL_STREAM_KLD = 5, MCL_STREAM_MOTION_RADIUS = 6 };
+       MCL_STREAM_KLD = 5, MCL_STREAM_MOTION_RADIUS = 6, MCL_STREAM_MOTION_RADIUS2 = 7 };
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int mcl_create(mcl_handle **out, int device);
@@ -361,6 +361,10 @@ int mcl_debug_tail_resample(mcl_handle *h, float *d_w, int64_t n, double r, int 
  * call: [0] attempt 0 failed, [1] provably stuck, [2] particles retried, [3] screening rounds, [4] evaluation rounds,
  * [5] retries that found a pose, [6] retried with threshold <= 2^28, [7] attempts evaluated, [8] warps with a retry. */
 int mcl_debug_motion_stats(mcl_handle *h, unsigned long long out[16]);
+/* Test hook for the motion kernel's rejection loop: screening thresholds below min_thr are raised to it (a looser
+ * screen is still exact; 2^28 makes every zero top nibble a candidate, 2^32 disables the screen) and small_queue = 1
+ * selects a 64-entry candidate queue, so that the paths a production run reaches with probability ~0 are tested. */
+int mcl_debug_motion(mcl_handle *h, unsigned long long min_thr, int small_queue);
 
 /* ---- measurement helpers (bench.py roofline denominators; not on the product path) ------- */
 /* Random 4-byte gather rate, lookups/s: table_bytes resident in shared memory (where = 0) or in

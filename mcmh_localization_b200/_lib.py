@@ -97,6 +97,7 @@ SIGNATURES = {
     "mcl_tail_prof": (_i, [_vp, C.POINTER(C.c_uint64), _pi]),
     "mcl_debug_tail_resample": (_i, [_vp, _vp, _i64, _d, _i, _vp, _vp]),
     "mcl_debug_motion_stats": (_i, [_vp, _vp]),
+    "mcl_debug_motion": (_i, [_vp, C.c_ulonglong, _i]),
     "mcl_bench_gather": (_i, [_vp, _i, _i64, _i64, _i, _pd]),
     "mcl_debug_seq_cumsum": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "mcl_launch_count": (_i64, [_vp]),

@@ -117,6 +117,12 @@ struct mcl_handle {
     void *d_tail_prof = nullptr; // MCL_TAIL_PROF=1: stage time stamps of the tail kernel
     int tail_prof_grid = 0;
     void *d_motion_stats = nullptr; // MCL_MOTION_STATS=1: counters of the motion kernel's rejection loop
+    unsigned long long motion_min_thr = 0;   // mcl_debug_motion (tests)
+    bool motion_small_queue = false;
+    int32_t *d_retry_idx = nullptr;           // motion kernel's retry list (particle, threshold), counters {count, done}
+    unsigned long long *d_retry_thr = nullptr;
+    unsigned *d_retry_ctr = nullptr;
+    int64_t retry_cap = 0;
     int coop_launch = -1;        // cudaDevAttrCooperativeLaunch (-1: not queried yet)
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;
@@ -281,10 +287,22 @@ __device__ __forceinline__ uint4 philox_draw4(uint64_t seed, uint64_t step, uint
 __device__ __forceinline__ double u53_from(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
-// three standard normals by Box-Muller on 32-bit uniforms (u1 in (0,1], u2 in [0,1)); layout as in
-// oracle/c/mcl_oracle.c normals3(): the radius word of attempt t is word (t & 3) of the MOTION_R block
-// (particle, step, t >> 2), the other uniforms come from the MOTION block (particle, step, t).
+// Three standard normals by Box-Muller on 32-bit uniforms (u1 in (0,1], u2 in [0,1)); same construction as
+// oracle/c/mcl_oracle.c normals3().  The attempt's own MOTION block (particle, step, t) gives the angle of the first
+// pair (word 0), the second pair (words 1, 2) and, in word 3, the part of the RADIUS WORD that is not dealt out by
+// the two screening streams below.
+//
+// Radius word of attempt t (uniform on [0, 2^32), independent over t -- every bit is used once):
+//   t = 0 : word 3 of the own block.
+//   t >= 1: top nibble = nibble (t & 31) of the MOTION_R block (particle, step, t >> 5): one Philox call deals the
+//           top nibbles of 32 attempts, so a warp screens 1024 attempts of the rejection loop with one call per lane.
+//           nibble != 0: the other 28 bits are the top 28 bits of word 3 of the own block.
+//           nibble == 0 (one attempt in 16; the only ones that can pass a screening threshold <= 2^28): the next
+//           16 bits are half-word (c & 7) of the MOTION_R2 block (particle, step, c >> 3), c = number of attempts
+//           1 <= s < t with a zero nibble (dealt by RANK, so the survivors of the first level cost one call per eight);
+//           the low 12 bits are the low 12 bits of word 3 of the own block.
 #define MCL_STREAM_MOTION_R 6
+#define MCL_STREAM_MOTION_R2 7
 __device__ __forceinline__ uint32_t pick_word(const uint4 &a, uint32_t k) {
     return k == 0 ? a.x : (k == 1 ? a.y : (k == 2 ? a.z : a.w));
 }
@@ -301,19 +319,24 @@ __device__ __forceinline__ void normals3_from_words(uint32_t w_radius, const uin
     z1 = __dmul_rn(r1, s1);
     z2 = __dmul_rn(r2, c2);
 }
-// The radius word of attempt t: its HIGH half is half-word (t & 7) of the MOTION_R block (item, step, t >> 3) --
-// eight consecutive attempts share one Philox call, so the rejection loop screens eight attempts per call on the
-// high half alone -- and its low half is the low half of word 3 of the attempt's own MOTION block.
-__device__ __forceinline__ uint32_t radius_hi16(const uint4 &a, uint32_t k) {
+__device__ __forceinline__ uint32_t half_word(const uint4 &a, uint32_t k) {     // k = 0..7
     const uint32_t w = pick_word(a, k >> 1);
     return (k & 1u) ? (w >> 16) : (w & 0xffffu);
 }
-__device__ __forceinline__ uint32_t radius_word(uint32_t hi16, const uint4 &o) { return (hi16 << 16) | (o.w & 0xffffu); }
-__device__ __forceinline__ void philox_normals3(uint64_t seed, uint64_t step, uint64_t item,
-                                                uint32_t attempt, double &z0, double &z1, double &z2) {
-    const uint4 a = philox_draw4(seed, step, item, attempt >> 3, MCL_STREAM_MOTION_R);
-    const uint4 o = philox_draw4(seed, step, item, attempt, MCL_STREAM_MOTION);
-    normals3_from_words(radius_word(radius_hi16(a, attempt & 7u), o), o, z0, z1, z2);
+// bit 4k set <=> nibble k of x is zero
+__device__ __forceinline__ uint32_t zero_nibble_flags(uint32_t x) {
+    return ((x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u) ^ 0x11111111u;
+}
+// radius word of an attempt t >= 1 from its top nibble, its MOTION_R2 half-word (used when the nibble is zero) and
+// its own block
+__device__ __forceinline__ uint32_t radius_word(uint32_t nibble, uint32_t mid16, const uint4 &o) {
+    return nibble ? ((nibble << 28) | (o.w >> 4)) : ((mid16 << 12) | (o.w & 0xfffu));
+}
+// attempt 0 (every particle, every step): one Philox call
+__device__ __forceinline__ void philox_normals3_first(uint64_t seed, uint64_t step, uint64_t item, double &z0,
+                                                      double &z1, double &z2) {
+    const uint4 o = philox_draw4(seed, step, item, 0u, MCL_STREAM_MOTION);
+    normals3_from_words(o.w, o, z0, z1, z2);
 }
 
 // pu:388-396 is_valid_position: trunc-toward-zero cell index, cell == 0 only.

@@ -69,7 +69,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     cudaFree(h->d_est18); cudaFree(h->d_fused); cudaFree(h->d_code8); cudaFree(h->d_code8p); cudaFree(h->d_tiled);
     cudaFree(h->d_kld);
     cudaFree(h->d_seq);
-    cudaFree(h->d_tail); cudaFree(h->d_tail_prof); cudaFree(h->d_motion_stats);
+    cudaFree(h->d_tail); cudaFree(h->d_tail_prof); cudaFree(h->d_motion_stats); cudaFree(h->d_retry_idx); cudaFree(h->d_retry_thr); cudaFree(h->d_retry_ctr);
     if (h->ev_est) cudaEventDestroy(h->ev_est);
     cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
     cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch); cudaFree(h->d_win8); cudaFree(h->d_lut);

@@ -36,6 +36,12 @@ struct MotionParams {
     unsigned long long *thr_cache;
     // MCL_MOTION_STATS=1: counters of the rejection loop (mcl_debug_motion_stats), else null
     unsigned long long *stats;
+    unsigned long long min_thr;   // test hook (mcl_debug_motion): screening thresholds below it are raised to it
+    // retry list (Philox draws): particles whose attempt 0 failed and that are not provably stuck
+    int32_t *retry_idx;
+    unsigned long long *retry_thr;
+    unsigned *retry_count, *retry_done;      // retry_count[0]: thresholds <= 2^28 (front), [1]: the others (back)
+    unsigned *retry_ticket;                  // [0] dense, [1] sparse: next entry to hand out
 };
 #define MOTION_STAT(p, k, v) do { if ((p).stats) atomicAdd((p).stats + (k), (unsigned long long)(v)); } while (0)
 
@@ -52,7 +58,8 @@ __device__ __forceinline__ bool motion_attempt(const MotionParams &p, int64_t i,
         const double *z = p.normals + ((size_t)i * p.A + (size_t)(t % p.A)) * 3;
         z0 = z[0]; z1 = z[1]; z2 = z[2];
     } else {
-        philox_normals3(p.seed, p.step, p.first_index + (uint64_t)i, (uint32_t)t, z0, z1, z2);
+        // Philox mode: only attempt 0 comes through here (the retries are screened in k_motion)
+        philox_normals3_first(p.seed, p.step, p.first_index + (uint64_t)i, z0, z1, z2);
     }
     return motion_candidate(p, x, y, th, z0, z1, z2, cand);
 }
@@ -131,13 +138,232 @@ __device__ __forceinline__ bool motion_candidate(const MotionParams &p, double x
     return is_valid_position_dev(cand.x, cand.y, p.occ, p.W, p.H, p.res, p.ox, p.oy);
 }
 
-#define MOTION_Q 320     // >= 31 leftover + 256 new candidates per screening round
-// Small CTAs: a CTA stays resident until its slowest warp is done, and the warps that hold stuck particles run
-// 10-100x longer than the others -- with 8 warps per CTA the SM averaged 13 resident warps (ncu r2a: 20 %).
-template <int MOTION_BLOCK>
+// Per-warp scratch of the rejection loop: the queue of attempts that passed the screen (attempt index + the top 20
+// bits of its radius word) and the MOTION_R2 half-words of one screening round (<= 1024 zero nibbles + alignment).
+template <int Q>
+struct MotionWarpScratch {
+    uint4 r2[130];                       // 1040 half-words
+    uint32_t q_top[Q];
+    unsigned short q_att[Q];
+};
+#define MOTION_BLOCK 128
+#define MOTION_RETRY_BLOCK 256
+#define MOTION_RETRY_BLOCKS_PER_SM 4
+
+// pu:350-352 only: x, y of the candidate and its validity -- what decides whether an attempt is the accepted one.
+// Same operations in the same order as motion_candidate (the heading and the third normal do not enter).
+__device__ __forceinline__ bool motion_candidate_xy(const MotionParams &p, double x, double y, double th, double z0,
+                                                    double z1) {
+    const double r1_hat = __dadd_rn(p.rot1, __dadd_rn(0.0, __dmul_rn(p.s1, z0)));
+    const double t_hat = __dadd_rn(p.trans, __dadd_rn(0.0, __dmul_rn(p.s2, z1)));
+    double sn, cs;
+    sincos(__dadd_rn(th, r1_hat), &sn, &cs);
+    return is_valid_position_dev(__dadd_rn(x, __dmul_rn(t_hat, cs)), __dadd_rn(y, __dmul_rn(t_hat, sn)), p.occ, p.W, p.H,
+                                 p.res, p.ox, p.oy);
+}
+// first pair of normals3_from_words (identical operations)
+__device__ __forceinline__ void normals2_from_words(uint32_t w_radius, const uint4 &o, double &z0, double &z1) {
+    const double k = 2.3283064365386963e-10;  // 2^-32
+    const double u1 = __dmul_rn(__dadd_rn((double)w_radius, 1.0), k), u2 = __dmul_rn((double)o.x, k);
+    const double r1 = sqrt(__dmul_rn(-2.0, log(u1)));
+    double s1, c1;
+    sincos(__dmul_rn(MCL_TWO_PI, u2), &s1, &c1);
+    z0 = __dmul_rn(r1, c1);
+    z1 = __dmul_rn(r1, s1);
+}
+
+// The retries 1 .. max_attempts - 1 of ONE particle with a screening threshold T <= 2^28 by a warp (Philox draws):
+// returns the 1-based index of the first valid attempt (0: none) and its pose.  Identical to evaluating the attempts
+// one by one in order.
+template <int Q>
+__device__ __forceinline__ int retry_particle(const MotionParams &p, MotionWarpScratch<Q> &ws, const int lane,
+                                              const uint64_t item, const double sx, const double sy, const double sth,
+                                              const unsigned long long T, Pose &win) {
+    int watt = 0;
+    uint32_t wwr = 0u;                                    // radius word of the accepted attempt
+    // Philox draws, screened on the radius word (common.cuh): an attempt can only succeed if word + 1 <= T.
+    // Level 1: lane L takes the MOTION_R block of attempts 32 g .. 32 g + 31 (g = g0 + L): one call per lane
+    // deals the top nibbles of up to 1024 attempts.  With T <= 2^28 (a particle facing a wall) only zero
+    // nibbles survive, one attempt in 16.  Level 2: the survivors' next 16 bits come from the MOTION_R2
+    // stream in RANK order, eight per call.  What passes both is queued in attempt order and evaluated for validity
+    // (x, y only: log, sqrt, two sincos, map lookup) 32 queued attempts at a time, lowest first; the accepted attempt
+    // is then evaluated in full.
+    const int nblk = (p.max_attempts + 31) >> 5;                // T <= 2^28 here: only zero nibbles can pass
+    const uint32_t hmax = (uint32_t)((T - 1ull) >> 12);         // ... and of those the ones with (half << 12) + 1 <= T
+    const unsigned short *r2h = reinterpret_cast<const unsigned short *>(ws.r2);
+    int qlen = 0, qhead = 0, g0 = 0;
+    unsigned rank_base = 0;                                    // zero nibbles among attempts 1 .. 32 g0 - 1
+    bool found = false;
+    while (!found && (g0 < nblk || qhead < qlen)) {
+        // fewer than 32 candidates left: move them to the front of the queue before screening more
+        if (qhead > 0 && g0 < nblk && qlen - qhead < 32) {
+            const int left = qlen - qhead;
+            unsigned short ta = 0; uint32_t tw = 0;
+            if (lane < left) { ta = ws.q_att[qhead + lane]; tw = ws.q_top[qhead + lane]; }
+            __syncwarp();
+            if (lane < left) { ws.q_att[lane] = ta; ws.q_top[lane] = tw; }
+            __syncwarp();
+            qlen = left; qhead = 0;
+        }
+        // screen until 32 candidates are queued (or the attempts are exhausted)
+        while (g0 < nblk && qlen - qhead < 32) {
+            const int active = min(32, nblk - g0);
+            const int g = g0 + lane;
+            uint32_t zf[4] = {0u, 0u, 0u, 0u};
+            int zc = 0;
+            if (lane == 0) MOTION_STAT(p, 3, 1);
+            if (lane < active) {
+                const uint4 a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
+                if (g > 0 && 32 * g + 32 <= p.max_attempts) {           // all 32 attempts of the block are retries
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { zf[w] = zero_nibble_flags(pick_word(a, (uint32_t)w)); zc += __popc(zf[w]); }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int lo = 32 * g + 8 * w;                  // attempts lo .. lo + 7
+                        const int nv = min(8, max(0, p.max_attempts - lo));
+                        uint32_t valid = nv == 8 ? 0x11111111u : (((1u << (4 * nv)) - 1u) & 0x11111111u);
+                        if (lo == 0) valid &= ~1u;                      // attempt 0 is not part of the retry
+                        zf[w] = zero_nibble_flags(pick_word(a, (uint32_t)w)) & valid;
+                        zc += __popc(zf[w]);
+                    }
+                }
+            }
+            int zpre = zc;                                   // inclusive prefix of the zero-nibble counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, zpre, o); if (lane >= o) zpre += v; }
+            const int ztot = __shfl_sync(0xffffffffu, zpre, 31);
+            // level 2: MOTION_R2 blocks of ranks rank_base .. rank_base + ztot - 1.  Usually <= 32 blocks (a round has
+            // ~64 zero nibbles): lane j tests the eight half-words of block b_first + j in registers, and as a rule
+            // none can reach the threshold -- the particle is done with this round without touching shared memory.
+            const unsigned b_first = rank_base >> 3;
+            const int nb2 = ztot ? (int)(((rank_base + (unsigned)ztot - 1u) >> 3) - b_first) + 1 : 0;
+            if (nb2 <= 32) {
+                uint4 b = make_uint4(0u, 0u, 0u, 0u);
+                bool any = false;
+                if (lane < nb2) {
+                    b = philox_draw4(p.seed, p.step, item, b_first + (uint32_t)lane, MCL_STREAM_MOTION_R2);
+                    const unsigned r0 = 8u * (b_first + (unsigned)lane);        // rank of half-word 0 of this block
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const unsigned r = r0 + (unsigned)k;
+                        any |= r >= rank_base && r < rank_base + (unsigned)ztot && half_word(b, (uint32_t)k) <= hmax;
+                    }
+                }
+                if (__ballot_sync(0xffffffffu, any) == 0u) {  // nothing passed (the usual outcome for a particle facing
+                    g0 += active;                            // a wall)
+                    rank_base += (unsigned)ztot;
+                    continue;
+                }
+                if (lane < nb2) ws.r2[lane] = b;
+            } else {
+                for (int j0 = 0; j0 < nb2; j0 += 32)
+                    if (j0 + lane < nb2) ws.r2[j0 + lane] = philox_draw4(p.seed, p.step, item, b_first + (uint32_t)(j0 + lane), MCL_STREAM_MOTION_R2);
+            }
+            __syncwarp();
+            // pass flags: zero nibbles whose next 16 bits can still reach the threshold
+            uint32_t ff[4];
+            int cnt = 0;
+            {
+                unsigned r = rank_base + (unsigned)(zpre - zc) - 8u * b_first;      // index into r2h of this lane's first zero nibble
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t f = 0u, z = zf[w];
+                    while (z) {
+                        const uint32_t b = z & (0u - z);
+                        if ((uint32_t)r2h[r] <= hmax) f |= b;
+                        ++r;
+                        z ^= b;
+                    }
+                    ff[w] = f;
+                    cnt += __popc(f);
+                }
+            }
+            if (__ballot_sync(0xffffffffu, cnt > 0) == 0u) {  // nothing passed (the usual outcome for a particle
+                g0 += active;                                // facing a wall): skip the queue bookkeeping
+                rank_base += (unsigned)ztot;
+                __syncwarp();
+                continue;
+            }
+            int pre = cnt;                                   // inclusive prefix over lanes -> queue order = attempt order
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+            // a round may not fit the queue (every nibble zero and passing: probability ~ 0, but the loop
+            // must be exact): take the leading blocks that fit -- the first always does -- and redo the others
+            const int space = Q - qlen;
+            const int fit = min(active, __popc(__ballot_sync(0xffffffffu, pre <= space)));
+            if (lane < fit) {
+                int pos = qlen + pre - cnt;
+                unsigned r = rank_base + (unsigned)(zpre - zc) - 8u * b_first;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t z = zf[w];
+                    const uint32_t f = ff[w];
+                    while (z) {                               // ascending over the zero nibbles of this word
+                        const uint32_t b = z & (0u - z);
+                        if (f & b) {
+                            ws.q_att[pos] = (unsigned short)(32 * g + 8 * w + ((__ffs(b) - 1) >> 2));
+                            ws.q_top[pos] = (uint32_t)r2h[r];  // top nibble 0 | the 16 bits dealt by rank
+                            ++pos;
+                        }
+                        ++r;
+                        z ^= b;
+                    }
+                }
+            }
+            qlen += __shfl_sync(0xffffffffu, pre, fit - 1);
+            rank_base += (unsigned)__shfl_sync(0xffffffffu, zpre, fit - 1);
+            g0 += fit;
+            __syncwarp();
+        }
+        // evaluate up to 32 queued attempts, lowest attempt index first
+        const int e = qhead + lane;
+        bool ok = false;
+        int t = 0;
+        if (lane == 0 && qlen > qhead) { MOTION_STAT(p, 4, 1); MOTION_STAT(p, 7, min(32, qlen - qhead)); }
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t wr = 0u;
+        bool pass = false;
+        if (e < qlen) {
+            t = ws.q_att[e];
+            const uint32_t top = ws.q_top[e];
+            o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
+            wr = radius_word(top >> 16, top & 0xffffu, o);
+            pass = (unsigned long long)wr + 1ull <= T;         // the exact word: drop what the screen let through
+        }
+        if (__ballot_sync(0xffffffffu, pass)) {
+            if (pass) {
+                double z0, z1;
+                normals2_from_words(wr, o, z0, z1);
+                ok = motion_candidate_xy(p, sx, sy, sth, z0, z1);
+            }
+        }
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (okm) {
+            const int w = __ffs(okm) - 1;                    // queue order = attempt order: lowest valid attempt
+            wwr = __shfl_sync(0xffffffffu, wr, w);
+            watt = __shfl_sync(0xffffffffu, t, w) + 1;
+            found = true;
+        }
+        qhead += 32;
+        if (qhead >= qlen) { qhead = 0; qlen = 0; }          // queue drained: reuse it from the start
+        __syncwarp();
+    }
+    if (watt) {                                           // the accepted attempt in full (every lane: same values)
+        const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)(watt - 1), MCL_STREAM_MOTION);
+        double z0, z1, z2;
+        normals3_from_words(wwr, o, z0, z1, z2);
+        motion_candidate(p, sx, sy, sth, z0, z1, z2, win);
+    }
+    return watt;
+}
+
+// Kernel 1: attempt 0 of every particle.  A particle whose attempt 0 fails is proved stuck by the geometric screen
+// (no draws: pose kept), or appended with its threshold to the retry list, which kernel 2 works off one particle
+// per warp: the cloud is ordered by ancestor after resampling, so the particles facing a wall sit in runs, and a warp
+// that retried its own 32 particles one after the other set the duration of the whole kernel (measured: 0.15-0.3 ms
+// for the slowest warp against 0.03 ms for attempt 0).  Injected draws (parity tests) retry in place.
 __global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(const MotionParams p) {
-    __shared__ unsigned short q_att[MOTION_BLOCK / 32][MOTION_Q];
-    __shared__ unsigned short q_hi[MOTION_BLOCK / 32][MOTION_Q];
     const int lane = threadIdx.x & 31;
     const int64_t warp_base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31;
     if (warp_base >= p.n) return;                       // warp-uniform
@@ -152,7 +378,8 @@ __global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(co
     if (!done) {
         Pose c;
         if (motion_attempt(p, i, 0, x, y, th, c)) { out = c; att = 1; done = true; }
-        else if (!p.normals) {
+        if (!done && !p.normals && !p.retry_count) done = true;      // max_attempts == 1: nothing to retry
+        if (!done && !p.normals) {
             if (p.thr_cache) {
                 thr = p.thr_cache[i];
                 if (thr == ~0ull) { thr = screening_threshold(p, x, y, th); p.thr_cache[i] = thr; }
@@ -160,6 +387,7 @@ __global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(co
                 thr = screening_threshold(p, x, y, th);
             }
             if (thr == 0ull) done = true;                // provably stuck: att = 0, pose kept (pu:360-361)
+            else if (thr < p.min_thr) thr = p.min_thr;   // test hook: a looser screen is still exact
         }
     }
     unsigned pending = __ballot_sync(0xffffffffu, !done);
@@ -172,14 +400,35 @@ __global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(co
             MOTION_STAT(p, 6, __popc(hard)); MOTION_STAT(p, 8, pending ? 1 : 0);
         }
     }
-    while (pending) {
-        const int src = __ffs(pending) - 1;
-        const double sx = shfl_d(x, src), sy = shfl_d(y, src), sth = shfl_d(th, src);
-        const int64_t si = warp_base + src;
-        Pose win = {sx, sy, sth};
-        int watt = 0;
-        if (p.normals) {
+    if (!p.normals) {
+        if (pending) {
+            // append to the retry lists (order is irrelevant): thresholds <= 2^28 from the front of the arrays (a warp
+            // each in kernel 2), the others -- one attempt in 16 or more passes the screen -- from the back (a CTA each)
+            const unsigned dense = __ballot_sync(0xffffffffu, !done && thr > (1ull << 28));
+            const unsigned sparse = pending & ~dense;
+            unsigned bs = 0, bd = 0;
+            if (lane == 0) {
+                if (sparse) bs = atomicAdd(p.retry_count, (unsigned)__popc(sparse));
+                if (dense) bd = atomicAdd(p.retry_count + 1, (unsigned)__popc(dense));
+            }
+            bs = __shfl_sync(0xffffffffu, bs, 0); bd = __shfl_sync(0xffffffffu, bd, 0);
+            if (!done) {
+                const unsigned below = (1u << lane) - 1u;
+                const bool isd = (dense >> lane) & 1u;
+                const int64_t slot = isd ? p.n - 1 - (int64_t)(bd + (unsigned)__popc(dense & below))
+                                         : (int64_t)(bs + (unsigned)__popc(sparse & below));
+                p.retry_idx[slot] = (int32_t)i;
+                p.retry_thr[slot] = thr;
+            }
+        }
+    } else {
+        while (pending) {
             // injected draws: the lanes evaluate attempts t0..t0+31 of this particle, lowest valid wins
+            const int src = __ffs(pending) - 1;
+            const double sx = shfl_d(x, src), sy = shfl_d(y, src), sth = shfl_d(th, src);
+            const int64_t si = warp_base + src;
+            Pose win = {sx, sy, sth};
+            int watt = 0;
             for (int t0 = 1; t0 < p.max_attempts; t0 += 32) {
                 const int t = t0 + lane;
                 Pose c = {0, 0, 0};
@@ -192,97 +441,196 @@ __global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(co
                     break;
                 }
             }
-        } else {
-            // Philox draws.  Screening: lane L reads the high halves of the radius words of attempts 8g..8g+7
-            // (g = g0 + L) from one Philox block and queues, in attempt order, the attempts whose radius can reach
-            // the threshold whatever the low half.  Full evaluation (log, sqrt, sincos, map lookup: ~1000
-            // instructions) then takes 32 queued attempts at a time, lowest index first -- evaluating a passing
-            // attempt inside the screening loop would run it with one or two active lanes.
-            const unsigned long long T = __shfl_sync(0xffffffffu, thr, src);
-            const uint64_t item = p.first_index + (uint64_t)si;
-            const int groups = (p.max_attempts + 7) >> 3;
-            unsigned short *qt = q_att[threadIdx.x >> 5];
-            unsigned short *qw = q_hi[threadIdx.x >> 5];
-            int qlen = 0, qhead = 0, g0 = 0;
-            bool found = false;
-            while (!found && (g0 < groups || qhead < qlen)) {
-                // fewer than 32 candidates left: move them to the front of the queue before screening more
-                if (qhead > 0 && g0 < groups && qlen - qhead < 32) {
-                    const int left = qlen - qhead;
-                    unsigned short ta = 0, tw = 0;
-                    if (lane < left) { ta = qt[qhead + lane]; tw = qw[qhead + lane]; }
-                    __syncwarp();
-                    if (lane < left) { qt[lane] = ta; qw[lane] = tw; }
-                    __syncwarp();
-                    qlen = left; qhead = 0;
-                }
-                // screen until 32 candidates are queued (or the attempts are exhausted)
-                while (g0 < groups && qlen - qhead < 32) {
-                    const int g = g0 + lane;
-                    uint4 a = make_uint4(0u, 0u, 0u, 0u);
-                    int cnt = 0;
-                    unsigned passm = 0;
-                    if (lane == 0) MOTION_STAT(p, 3, 1);
-                    if (g < groups) {
-                        a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int t = 8 * g + k;
-                            // smallest radius word with this high half: (hi << 16); it must satisfy word + 1 <= T
-                            const bool ps = t >= 1 && t < p.max_attempts &&
-                                            ((unsigned long long)radius_hi16(a, (uint32_t)k) << 16) + 1ull <= T;
-                            passm |= (ps ? 1u : 0u) << k;
-                            cnt += ps;
-                        }
-                    }
-                    if (__ballot_sync(0xffffffffu, cnt > 0) == 0u) {  // nothing passed (the usual outcome for a particle
-                        g0 += 32;                                    // facing a wall): skip the queue bookkeeping
-                        continue;
-                    }
-                    int pre = cnt;                                   // exclusive prefix over lanes -> queue order = attempt order
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-                    const int total = __shfl_sync(0xffffffffu, pre, 31);
-                    int pos = qlen + pre - cnt;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if ((passm >> k) & 1u) { qt[pos] = (unsigned short)(8 * g + k); qw[pos] = (unsigned short)radius_hi16(a, (uint32_t)k); ++pos; }
-                    qlen += total;
-                    g0 += 32;
-                    __syncwarp();
-                }
-                // evaluate up to 32 queued attempts, lowest attempt index first
-                const int e = qhead + lane;
-                Pose c = {0, 0, 0};
-                bool ok = false;
-                int t = 0;
-                if (lane == 0 && qlen > qhead) { MOTION_STAT(p, 4, 1); MOTION_STAT(p, 7, min(32, qlen - qhead)); }
-                if (e < qlen) {
-                    t = qt[e];
-                    const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
-                    double z0, z1, z2;
-                    normals3_from_words(radius_word((uint32_t)qw[e], o), o, z0, z1, z2);
-                    ok = motion_candidate(p, sx, sy, sth, z0, z1, z2, c);
-                }
-                const unsigned okm = __ballot_sync(0xffffffffu, ok);
-                if (okm) {
-                    const int w = __ffs(okm) - 1;                    // queue order = attempt order: lowest valid attempt
-                    win.x = shfl_d(c.x, w); win.y = shfl_d(c.y, w); win.th = shfl_d(c.th, w);
-                    watt = __shfl_sync(0xffffffffu, t, w) + 1;
-                    found = true;
-                }
-                qhead += 32;
-                if (qhead >= qlen) { qhead = 0; qlen = 0; }          // queue drained: reuse it from the start
-                __syncwarp();
-            }
+            if (lane == src) { out = win; att = watt; }       // watt == 0: keep the old pose (pu:360-361)
+            pending &= pending - 1;
         }
-        if (lane == 0 && watt) MOTION_STAT(p, 5, 1);
-        if (lane == src) { out = win; att = watt; }       // watt == 0: keep the old pose (pu:360-361)
-        pending &= pending - 1;
     }
     if (live) {
-        p.xo[i] = out.x; p.yo[i] = out.y; p.tho[i] = out.th;
+        p.xo[i] = out.x; p.yo[i] = out.y; p.tho[i] = out.th;     // retried particles: the old pose until kernel 2 finds one
         if (p.attempts) p.attempts[i] = att;
+    }
+}
+
+// One block of 32 attempts (32 g .. 32 g + 31, lane k = attempt 32 g + k) of a particle whose threshold is above
+// 2^28: every attempt whose top nibble is <= nmax is evaluated for validity.  a = its MOTION_R block, zbefore = zero
+// nibbles among attempts 1 .. 32 g - 1.  Returns (attempt << 32 | radius word) of this lane's attempt if valid.
+__device__ __forceinline__ unsigned long long dense_block(const MotionParams &p, const uint4 &a, unsigned zbefore, int g,
+                                                          int lane, uint64_t item, double sx, double sy, double sth,
+                                                          unsigned long long T, int nmax, unsigned &zeros) {
+    const int t = 32 * g + lane;
+    const uint32_t nib = (pick_word(a, (uint32_t)lane >> 3) >> (4 * (lane & 7))) & 15u;
+    const bool valid = t >= 1 && t < p.max_attempts;
+    const unsigned zmask = __ballot_sync(0xffffffffu, valid && nib == 0u);
+    zeros = (unsigned)__popc(zmask);
+    uint32_t mid = 0u;
+    if (valid && nib == 0u) {
+        const unsigned c = zbefore + (unsigned)__popc(zmask & ((1u << lane) - 1u));
+        mid = half_word(philox_draw4(p.seed, p.step, item, c >> 3, MCL_STREAM_MOTION_R2), c & 7u);
+    }
+    unsigned long long r = ~0ull;
+    if (valid && (int)nib <= nmax) {
+        const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)t, MCL_STREAM_MOTION);
+        const uint32_t wr = radius_word(nib, mid, o);
+        if ((unsigned long long)wr + 1ull <= T) {
+            double z0, z1;
+            normals2_from_words(wr, o, z0, z1);
+            if (motion_candidate_xy(p, sx, sy, sth, z0, z1)) r = ((unsigned long long)(unsigned)t << 32) | wr;
+        }
+    }
+    if (lane == 0) { MOTION_STAT(p, 3, 1); MOTION_STAT(p, 4, 1); }
+    return r;
+}
+// the accepted attempt in full (called by a whole warp; lane 0 writes)
+__device__ __forceinline__ void retry_commit(const MotionParams &p, int64_t i, uint64_t item, double sx, double sy,
+                                             double sth, unsigned long long best, int lane) {
+    const int watt = (int)(best >> 32) + 1;
+    const uint4 o = philox_draw4(p.seed, p.step, item, (uint32_t)(watt - 1), MCL_STREAM_MOTION);
+    double z0, z1, z2;
+    Pose win;
+    normals3_from_words((uint32_t)best, o, z0, z1, z2);
+    motion_candidate(p, sx, sy, sth, z0, z1, z2, win);
+    if (lane == 0) {
+        MOTION_STAT(p, 5, 1);
+        p.xo[i] = win.x; p.yo[i] = win.y; p.tho[i] = win.th;
+        if (p.attempts) p.attempts[i] = watt;
+    }
+}
+
+// Kernel 2: the retry lists, entries handed out by ticket.  Q = capacity of the candidate queue: 320 in production;
+// the 64-entry instantiation exists so that tests reach the partial-round path (mcl_debug_motion).
+// Dense entries (T > 2^28) first: a warp evaluates the first 64 attempts, which settles most of them.  The others
+// may need every attempt evaluated -- up to 1000 evaluations, 0.08 ms on one warp, which set the duration of the
+// kernel -- so the whole CTA takes them over: warp w evaluates attempt blocks 2 + w, 2 + w + 8, ... and the lowest
+// valid attempt over the CTA wins.  Then the sparse entries (T <= 2^28), a warp each.
+template <int Q>
+__global__ void __launch_bounds__(MOTION_RETRY_BLOCK, MOTION_RETRY_BLOCKS_PER_SM) k_motion_retry(const MotionParams p) {
+    constexpr int NW = MOTION_RETRY_BLOCK / 32;
+    constexpr int WARP_STAGE = 2;                         // attempt blocks a single warp tries before the CTA takes over
+    __shared__ MotionWarpScratch<Q> scratch[NW];
+    __shared__ uint4 sm_nib[MOTION_RETRY_BLOCK];          // MOTION_R blocks of one super-chunk (256 x 32 attempts)
+    __shared__ unsigned sm_zb[MOTION_RETRY_BLOCK];        // zero nibbles before each of them
+    __shared__ unsigned sm_wtot[NW];
+    __shared__ long long sm_heavy[NW];                    // list slots the warps pass on to the CTA (-1: none)
+    __shared__ unsigned long long sm_best;                // (attempt << 32 | radius word) of the lowest valid attempt
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned n_sparse = ((volatile unsigned *)p.retry_count)[0], n_dense = ((volatile unsigned *)p.retry_count)[1];
+    const int nblk = (p.max_attempts + 31) >> 5;
+    __shared__ unsigned sm_ticket;
+    while (n_dense) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm_ticket = atomicAdd(p.retry_ticket, (unsigned)NW);     // one entry per warp
+        __syncthreads();
+        const unsigned e = sm_ticket + (unsigned)warp;
+        if (sm_ticket >= n_dense) break;                               // uniform over the CTA
+        const bool have = e < n_dense;
+        long long heavy = -1;
+        if (have) {
+            const int64_t slot = p.n - 1 - (int64_t)e;
+            const int64_t i = p.retry_idx[slot];
+            const unsigned long long T = p.retry_thr[slot];
+            const int nmax = (int)((T - 1ull) >> 28);                  // nibbles n with (n << 28) + 1 <= T
+            const uint64_t item = p.first_index + (uint64_t)i;
+            const double sx = p.xo[i], sy = p.yo[i], sth = p.tho[i];
+            unsigned zbefore = 0;
+            unsigned long long best = ~0ull;
+            for (int g = 0; g < min(nblk, WARP_STAGE) && best == ~0ull; ++g) {
+                const uint4 a = philox_draw4(p.seed, p.step, item, (uint32_t)g, MCL_STREAM_MOTION_R);
+                unsigned zeros;
+                unsigned long long r = dense_block(p, a, zbefore, g, lane, item, sx, sy, sth, T, nmax, zeros);
+                zbefore += zeros;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, r, o); r = v < r ? v : r; }
+                best = r;
+            }
+            if (best != ~0ull) retry_commit(p, i, item, sx, sy, sth, best, lane);
+            else if (nblk > WARP_STAGE) heavy = slot;
+        }
+        if (lane == 0) sm_heavy[warp] = heavy;
+        __syncthreads();
+        for (int hw = 0; hw < NW; ++hw) {
+            const long long slot = sm_heavy[hw];
+            if (slot < 0) continue;                                    // uniform over the CTA
+            const int64_t i = p.retry_idx[slot];
+            const unsigned long long T = p.retry_thr[slot];
+            const int nmax = (int)((T - 1ull) >> 28);
+            const uint64_t item = p.first_index + (uint64_t)i;
+            const double sx = p.xo[i], sy = p.yo[i], sth = p.tho[i];
+            unsigned carry = 0;                                        // zero nibbles among attempts 1 .. 32 G0 - 1
+            if (threadIdx.x == 0) sm_best = ~0ull;
+            bool found = false;
+            for (int G0 = 0; G0 < nblk && !found; G0 += MOTION_RETRY_BLOCK) {
+                // top nibbles of this super-chunk: thread t draws block G0 + t; ranks of the zero nibbles by a CTA scan
+                const int gmine = G0 + (int)threadIdx.x;
+                uint4 a = make_uint4(0u, 0u, 0u, 0u);
+                int zc = 0;
+                if (gmine < nblk) {
+                    a = philox_draw4(p.seed, p.step, item, (uint32_t)gmine, MCL_STREAM_MOTION_R);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int lo = 32 * gmine + 8 * w;
+                        const int nv = min(8, max(0, p.max_attempts - lo));
+                        uint32_t valid = nv == 8 ? 0x11111111u : (((1u << (4 * nv)) - 1u) & 0x11111111u);
+                        if (lo == 0) valid &= ~1u;
+                        zc += __popc(zero_nibble_flags(pick_word(a, (uint32_t)w)) & valid);
+                    }
+                }
+                int zpre = zc;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, zpre, o); if (lane >= o) zpre += v; }
+                __syncthreads();                                       // previous users of the shared arrays are done
+                if (lane == 31) sm_wtot[warp] = (unsigned)zpre;
+                sm_nib[threadIdx.x] = a;
+                __syncthreads();
+                unsigned before = carry, total = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { if (w < warp) before += sm_wtot[w]; total += sm_wtot[w]; }
+                sm_zb[threadIdx.x] = before + (unsigned)(zpre - zc);
+                carry += total;
+                __syncthreads();
+                const int first = G0 == 0 ? WARP_STAGE : 0;            // the warp stage has tried blocks 0 .. WARP_STAGE - 1
+                const int chunk_blocks = min(MOTION_RETRY_BLOCK, nblk - G0);
+                for (int r0 = first; r0 < chunk_blocks && !found; r0 += NW) {
+                    const int gl = r0 + warp;
+                    if (gl < chunk_blocks) {
+                        unsigned zeros;
+                        const unsigned long long r = dense_block(p, sm_nib[gl], sm_zb[gl], G0 + gl, lane, item, sx, sy, sth, T,
+                                                                 nmax, zeros);
+                        if (r != ~0ull) atomicMin(&sm_best, r);
+                    }
+                    __syncthreads();                                   // the blocks of this round are complete:
+                    found = sm_best != ~0ull;                          // a valid attempt now is the lowest one
+                }
+            }
+            if (found && warp == 0) retry_commit(p, i, item, sx, sy, sth, sm_best, lane);
+            __syncthreads();
+        }
+    }
+    MotionWarpScratch<Q> &ws = scratch[warp];
+    while (n_sparse) {
+        unsigned e = 0;
+        if (lane == 0) e = atomicAdd(p.retry_ticket + 1, 1u);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n_sparse) break;
+        const int64_t i = p.retry_idx[e];
+        const unsigned long long T = p.retry_thr[e];
+        // the source pose: kernel 1 left it in the output arrays as well, so in-place calls (xo == x) see it too
+        const double sx = p.xo[i], sy = p.yo[i], sth = p.tho[i];
+        Pose win = {sx, sy, sth};
+        const int watt = retry_particle<Q>(p, ws, lane, p.first_index + (uint64_t)i, sx, sy, sth, T, win);
+        if (lane == 0 && watt) {
+            MOTION_STAT(p, 5, 1);
+            p.xo[i] = win.x; p.yo[i] = win.y; p.tho[i] = win.th;
+            if (p.attempts) p.attempts[i] = watt;
+        }
+        __syncwarp();
+    }
+    // the last CTA to finish re-arms the lists for the next call
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.retry_done, 1u) == gridDim.x - 1) {
+            p.retry_count[0] = 0u; p.retry_count[1] = 0u; *p.retry_done = 0u; p.retry_ticket[0] = 0u; p.retry_ticket[1] = 0u;
+        }
     }
 }
 
@@ -348,19 +696,38 @@ int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, cons
                                  : (unsigned long long)(4294967296.0 * exp(-0.5 * rho * rho) * (1.0 + 1e-9)) + 2ull;
         p.n_levels = k + 1;
     }
-    static const int block = [] {                        // MCL_MOTION_BLOCK=32|64|128|256 for A/B measurements
-        const char *e = getenv("MCL_MOTION_BLOCK");
-        const int v = e ? atoi(e) : 64;
-        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 64;
-    }();
-    const int blocks = (int)((n + block - 1) / block);
-    switch (block) {
-    case 32:  k_motion<32><<<blocks, 32, 0, h->stream>>>(p); break;
-    case 128: k_motion<128><<<blocks, 128, 0, h->stream>>>(p); break;
-    case 256: k_motion<256><<<blocks, 256, 0, h->stream>>>(p); break;
-    default:  k_motion<64><<<blocks, 64, 0, h->stream>>>(p); break;
+    p.min_thr = h->motion_min_thr;
+    p.retry_idx = nullptr; p.retry_thr = nullptr; p.retry_count = nullptr; p.retry_done = nullptr; p.retry_ticket = nullptr;
+    const bool retry = !d_normals && max_attempts > 1;
+    if (retry) {
+        if (n > 0x7fffffffll) return mcl_fail(h, MCL_ERR_ARG, "mcl_predict: more than 2^31 - 1 particles per call");
+        if (h->retry_cap < n) {                          // retry list: worst case every particle
+            MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_retry_idx); cudaFree(h->d_retry_thr);
+            h->d_retry_idx = nullptr; h->d_retry_thr = nullptr; h->retry_cap = 0;
+            MCL_CUDA(h, cudaMalloc((void **)&h->d_retry_idx, (size_t)n * sizeof(int32_t)));
+            MCL_CUDA(h, cudaMalloc((void **)&h->d_retry_thr, (size_t)n * sizeof(unsigned long long)));
+            h->retry_cap = n;
+        }
+        if (!h->d_retry_ctr) {
+            MCL_CUDA(h, cudaMalloc((void **)&h->d_retry_ctr, 8 * sizeof(unsigned)));
+            MCL_CUDA(h, cudaMemsetAsync(h->d_retry_ctr, 0, 8 * sizeof(unsigned), h->stream));
+        }
+        p.retry_idx = h->d_retry_idx; p.retry_thr = h->d_retry_thr;
+        p.retry_count = h->d_retry_ctr; p.retry_done = h->d_retry_ctr + 2; p.retry_ticket = h->d_retry_ctr + 4;
+    } else if (!d_normals) {
+        p.max_attempts = max_attempts > 0 ? 1 : 0;       // nothing to retry: kernel 1 alone (the list is never touched)
+        p.n_levels = 0;
     }
+    const int blocks = (int)((n + MOTION_BLOCK - 1) / MOTION_BLOCK);
+    k_motion<<<blocks, MOTION_BLOCK, 0, h->stream>>>(p);
     MCL_LAUNCH_CHECK(h);
+    if (retry) {
+        const int rblocks = h->sm_count * MOTION_RETRY_BLOCKS_PER_SM;
+        if (h->motion_small_queue) k_motion_retry<64><<<rblocks, MOTION_RETRY_BLOCK, 0, h->stream>>>(p);
+        else k_motion_retry<320><<<rblocks, MOTION_RETRY_BLOCK, 0, h->stream>>>(p);
+        MCL_LAUNCH_CHECK(h);
+    }
     return MCL_OK;
 }
 
@@ -376,5 +743,16 @@ int mcl_debug_motion_stats(mcl_handle *h, unsigned long long out[16]) {
     MCL_CUDA(h, cudaStreamSynchronize(h->stream));
     MCL_CUDA(h, cudaMemcpy(out, h->d_motion_stats, 16 * 8, cudaMemcpyDeviceToHost));
     MCL_CUDA(h, cudaMemset(h->d_motion_stats, 0, 16 * 8));
+    return MCL_OK;
+}
+
+// Test hook: min_thr raises every screening threshold of the rejection loop below it (a looser screen is still exact:
+// 2^28 makes every zero nibble a candidate, 2^32 disables the screen); small_queue = 1 selects the 64-entry queue so
+// that rounds which do not fit the queue occur.  (0, 0) restores production behaviour.
+int mcl_debug_motion(mcl_handle *h, unsigned long long min_thr, int small_queue) {
+    if (!h) return MCL_ERR_ARG;
+    if (min_thr > (1ull << 32)) return mcl_fail(h, MCL_ERR_ARG, "mcl_debug_motion: min_thr > 2^32");
+    h->motion_min_thr = min_thr;
+    h->motion_small_queue = small_queue != 0;
     return MCL_OK;
 }

@@ -172,7 +172,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* Stream ids (ctr[3] low byte) -- must match mcmh_localization_b200/csrc/philox.cuh */
 enum { ORC_STREAM_MOTION = 1, ORC_STREAM_MH = 2, ORC_STREAM_RESAMPLE = 3, ORC_STREAM_INIT = 4,
-       ORC_STREAM_KLD = 5, ORC_STREAM_MOTION_R = 6 };
+       ORC_STREAM_KLD = 5, ORC_STREAM_MOTION_R = 6, ORC_STREAM_MOTION_R2 = 7 };
 
 static inline void draw4(uint64_t seed, uint64_t step, uint64_t item, uint32_t sub, uint32_t stream,
                          uint32_t out[4]) {
@@ -196,18 +196,23 @@ double orc_uniform53(uint64_t seed, uint64_t step, uint64_t item, uint32_t sub, 
 }
 /* Three standard normals per (particle, attempt t): Box-Muller on 32-bit uniforms, u1 in (0,1],
  * u2 in [0,1):  z0 = R1 cos(2 pi u2), z1 = R1 sin(2 pi u2), z2 = R2 cos(2 pi u4), R = sqrt(-2 ln u).
- * The radius word of attempt t: high half = half-word (t & 7) of the MOTION_R block (particle, step, t >> 3)
- * (eight consecutive attempts share one Philox call, which lets the GPU rejection loop screen eight attempts
- * per call on the high half: |z0|, |z1| <= R1, so a small R1 cannot leave an all-blocked neighbourhood);
- * low half = low half of word 3 of the MOTION block (particle, step, t), whose other three words give the
- * remaining uniforms. */
-static inline void normals3(uint64_t seed, uint64_t step, uint64_t item, uint32_t attempt, double z[3]) {
-    uint32_t a[4], o[4];
-    draw4(seed, step, item, attempt >> 3, ORC_STREAM_MOTION_R, a);
-    draw4(seed, step, item, attempt, ORC_STREAM_MOTION, o);
-    const uint32_t k = attempt & 7u, wk = a[k >> 1];
-    const uint32_t hi16 = (k & 1u) ? (wk >> 16) : (wk & 0xffffu);
-    const uint32_t wr = (hi16 << 16) | (o[3] & 0xffffu);
+ * u2, u3, u4 come from words 0, 1, 2 of the MOTION block (particle, step, t).  The RADIUS WORD (u1) is dealt so that
+ * the GPU rejection loop can screen many attempts per Philox call (|z0|, |z1| <= R1: a small R1 cannot leave an
+ * all-blocked neighbourhood), every bit being used exactly once:
+ *   t = 0 : word 3 of the MOTION block.
+ *   t >= 1: top nibble = nibble (t & 31) of the MOTION_R block (particle, step, t >> 5);
+ *           nibble != 0: low 28 bits = top 28 bits of word 3 of the MOTION block;
+ *           nibble == 0: next 16 bits = half-word (c & 7) of the MOTION_R2 block (particle, step, c >> 3), where
+ *           c = number of attempts 1 <= s < t whose nibble is zero; low 12 bits = low 12 bits of word 3. */
+static inline uint32_t motion_nibble(const uint32_t a[4], uint32_t t) {
+    const uint32_t k = t & 31u;
+    return (a[k >> 3] >> (4u * (k & 7u))) & 15u;
+}
+static inline uint32_t motion_half(const uint32_t b[4], uint32_t c) {
+    const uint32_t k = c & 7u, w = b[k >> 1];
+    return (k & 1u) ? (w >> 16) : (w & 0xffffu);
+}
+static inline void normals3_words(uint32_t wr, const uint32_t o[4], double z[3]) {
     const double u1 = ((double)wr + 1.0) * 2.3283064365386963e-10;
     const double u2 = (double)o[0] * 2.3283064365386963e-10;
     const double u3 = ((double)o[1] + 1.0) * 2.3283064365386963e-10;
@@ -216,8 +221,73 @@ static inline void normals3(uint64_t seed, uint64_t step, uint64_t item, uint32_
     const double a1 = 6.283185307179586 * u2, a2 = 6.283185307179586 * u4;
     z[0] = r1 * cos(a1); z[1] = r1 * sin(a1); z[2] = r2 * cos(a2);
 }
+/* Sequential reader of one particle's attempts 0, 1, 2, ... (what the rejection loop needs). */
+typedef struct {
+    uint64_t seed, step, item;
+    uint32_t next, zeros;          /* next attempt to be read; zero nibbles among attempts 1 .. next - 1 */
+    uint32_t a[4];                 /* MOTION_R block of attempt `next` (valid when next & 31 or next was loaded) */
+    int a_block;
+} MotionDraws;
+static inline void motion_draws_init(MotionDraws *d, uint64_t seed, uint64_t step, uint64_t item) {
+    d->seed = seed; d->step = step; d->item = item; d->next = 0; d->zeros = 0; d->a_block = -1;
+}
+static inline void motion_draws_next(MotionDraws *d, double z[3]) {
+    uint32_t o[4], wr;
+    const uint32_t t = d->next++;
+    draw4(d->seed, d->step, d->item, t, ORC_STREAM_MOTION, o);
+    if (t == 0) {
+        wr = o[3];
+    } else {
+        if (d->a_block != (int)(t >> 5)) {
+            draw4(d->seed, d->step, d->item, t >> 5, ORC_STREAM_MOTION_R, d->a);
+            d->a_block = (int)(t >> 5);
+        }
+        const uint32_t nib = motion_nibble(d->a, t);
+        if (nib) {
+            wr = (nib << 28) | (o[3] >> 4);
+        } else {
+            uint32_t b[4];
+            const uint32_t c = d->zeros++;
+            draw4(d->seed, d->step, d->item, c >> 3, ORC_STREAM_MOTION_R2, b);
+            wr = (motion_half(b, c) << 12) | (o[3] & 0xfffu);
+        }
+    }
+    normals3_words(wr, o, z);
+}
+/* Random access (tests): reads the attempts before it. */
+static inline void normals3(uint64_t seed, uint64_t step, uint64_t item, uint32_t attempt, double z[3]) {
+    uint32_t o[4], wr;
+    draw4(seed, step, item, attempt, ORC_STREAM_MOTION, o);
+    if (attempt == 0) {
+        wr = o[3];
+    } else {
+        uint32_t a[4], c = 0, nib = 0;
+        for (uint32_t g = 0; g <= (attempt >> 5); ++g) {
+            draw4(seed, step, item, g, ORC_STREAM_MOTION_R, a);
+            for (uint32_t t = 32u * g; t < 32u * g + 32u && t <= attempt; ++t) {
+                if (t == 0) continue;
+                nib = motion_nibble(a, t);
+                if (t < attempt && nib == 0) ++c;
+            }
+        }
+        if (nib) {
+            wr = (nib << 28) | (o[3] >> 4);
+        } else {
+            uint32_t b[4];
+            draw4(seed, step, item, c >> 3, ORC_STREAM_MOTION_R2, b);
+            wr = (motion_half(b, c) << 12) | (o[3] & 0xfffu);
+        }
+    }
+    normals3_words(wr, o, z);
+}
 void orc_normals3(uint64_t seed, uint64_t step, uint64_t item, uint32_t attempt, double z[3]) {
     normals3(seed, step, item, attempt, z);
+}
+/* attempts 0 .. n-1 of one particle through the sequential reader (what orc_apply_motion_model uses) */
+void orc_normals3_seq(uint64_t seed, uint64_t step, uint64_t item, int n, double *z_out) {
+    MotionDraws d;
+    motion_draws_init(&d, seed, step, item);
+    for (int t = 0; t < n; ++t) motion_draws_next(&d, z_out + 3 * (size_t)t);
 }
 
 /* pu:332-363 apply_motion_model_parallel.
@@ -242,13 +312,15 @@ void orc_apply_motion_model(const double *particles, int64_t N, const double del
     for (int64_t i = 0; i < N; ++i) {
         const double x = particles[3 * i], y = particles[3 * i + 1], theta = particles[3 * i + 2];
         int success = 0;
+        MotionDraws draws;
+        motion_draws_init(&draws, seed, step, first_index + (uint64_t)i);
         for (int t = 0; t < max_attempts; ++t) {
             double z[3];
             if (normals) {
                 const double *zz = normals + ((size_t)i * A + (size_t)(t % A)) * 3;
                 z[0] = zz[0]; z[1] = zz[1]; z[2] = zz[2];
             } else {
-                normals3(seed, step, first_index + (uint64_t)i, (uint32_t)t, z);
+                motion_draws_next(&draws, z);
             }
             const double r1_hat = rot1 + (0.0 + s1 * z[0]);
             const double t_hat = trans + (0.0 + s2 * z[1]);

@@ -291,6 +291,14 @@ def normals3(seed, step, item, attempt):
     return z
 
 
+def normals3_seq(seed, step, item, n):
+    """attempts 0 .. n-1 of one particle through the oracle's sequential reader -> (n, 3)"""
+    z = np.zeros((int(n), 3), np.float64)
+    lib().orc_normals3_seq(C.c_uint64(int(seed)), C.c_uint64(int(step)), C.c_uint64(int(item)), C.c_int(int(n)),
+                           _p(z, C.c_double))
+    return z
+
+
 # ---- functions the node imports but its callbacks never reach (SURVEY 8(a) row a14) -------------------------
 def compute_valid_indices(particles, map_data, map_resolution, origin_x, origin_y, width, height):
     """pu:369-386 -> int32 indices of the particles on cells with map_data <= 10."""

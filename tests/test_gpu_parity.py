@@ -316,6 +316,44 @@ def test_motion_philox_vs_oracle(pu, orc, oracle_map_world):
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("min_thr,small_queue", [(1 << 28, 0), (1 << 28, 1), (1 << 32, 0), (1 << 32, 1), (3 << 28, 1),
+                                                (1 << 20, 1)])
+def test_motion_rejection_loop_rare_paths_vs_oracle(pu, orc, oracle_map_world, min_thr, small_queue):
+    """The two-level screen of the rejection loop under a loosened threshold (still exact: the threshold is only a
+    necessary condition) and a 64-entry candidate queue: every zero top nibble a candidate (2^28), no screen at all
+    (2^32: dense rounds), rounds that do not fit the queue and are taken block by block.  Accepted attempt index and
+    pose must equal the oracle's plain loop for every particle; max_attempts beyond one screening round as well."""
+    import ctypes as C
+    mp = oracle_map_world
+    rs = np.random.RandomState(11)
+    near = np.flatnonzero((mp["map_data"] == 0) & (mp["distance_map"] <= 0.1001))
+    n = 6000
+    cells = near[rs.randint(0, len(near), n)]
+    my, mx = np.divmod(cells, mp["width"])
+    parts = np.column_stack((mp["origin_np"][0] + (mx + rs.uniform(0, 1, n)) * mp["resolution"],
+                             mp["origin_np"][1] + (my + rs.uniform(0, 1, n)) * mp["resolution"],
+                             rs.uniform(-np.pi, np.pi, n)))
+    alpha = np.array([P["alpha1"], P["alpha2"], P["alpha3"], P["alpha4"]], dtype=np.float32)
+    h = pu._ctx().h
+    h.call("mcl_debug_motion", C.c_ulonglong(min_thr), int(small_queue))
+    try:
+        for k, (delta, max_att) in enumerate([((0.0, 0.02, 0.01), 1000), ((0.3, 0.05, -0.1), 1000),
+                                               ((0.0, 0.02, 0.01), 2500), ((0.0, 0.02, 0.01), 37)]):
+            pu.seed(900 + k)
+            out, att = pu.apply_motion_model_parallel(parts, delta, alpha, mp["map_data"], mp["resolution"],
+                                                      mp["origin_np"][0], mp["origin_np"][1], mp["width"],
+                                                      mp["height"], return_attempts=True, max_attempts=max_att)
+            ref, ratt = orc.apply_motion_model_parallel(parts, delta, alpha, mp["map_data"], mp["resolution"],
+                                                        mp["origin_np"][0], mp["origin_np"][1], mp["width"],
+                                                        mp["height"], seed=900 + k, step=1, return_attempts=True,
+                                                        max_attempts=max_att)
+            assert np.array_equal(att, ratt), (k, int((att != ratt).sum()))
+            np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12)
+            assert (att == 0).sum() > 100 and (max_att < 1000 or (att > 1).sum() > 100)
+    finally:
+        h.call("mcl_debug_motion", C.c_ulonglong(0), 0)
+
+
 def test_motion_wall_hugging_cloud_vs_oracle(pu, orc, oracle_map_world):
     """Soundness of the provably-stuck early exit: 20k particles within 10 cm of a wall, random
     headings, several odometry increments -- accepted attempt index and pose must equal the oracle's

@@ -1,17 +1,19 @@
 """Statistical checks of the product's motion-noise generator (Philox4x32-10 + Box-Muller, common.cuh
-philox_normals3; restated draw for draw in oracle/c/mcl_oracle.c orc_normals3, and the GPU kernel is tested equal to
-that restatement attempt by attempt in test_gpu_parity.py).  Draw-for-draw equality with our own restatement says
-nothing about the DISTRIBUTION, and the radius word of an attempt is assembled from two Philox blocks (its high half
-comes from a block shared by eight consecutive attempts), so: moments, Kolmogorov-Smirnov against N(0,1), independence
-of the three normals of an attempt, and serial correlation between attempts t, t+1 ... t+7 of one particle (inside one
-shared block and across two).  Fixed seeds: the numbers are deterministic; the bounds are ~4.5 standard errors."""
+normals3_from_words; restated draw for draw in oracle/c/mcl_oracle.c, and the GPU kernel is tested equal to that
+restatement attempt by attempt in test_gpu_parity.py).  Draw-for-draw equality with our own restatement says nothing
+about the DISTRIBUTION, and the radius word of an attempt is assembled from up to three Philox blocks (its top nibble
+comes from a block shared by 32 consecutive attempts; after a zero nibble the next 16 bits are dealt by rank from
+another stream), so: moments, Kolmogorov-Smirnov against N(0,1), independence of the three normals of an attempt,
+serial correlation between neighbouring attempts of one particle, and the radius distribution of the zero-nibble
+attempts on their own (the far tail, which is what lets a particle leave a wall).  Fixed seeds: the numbers are
+deterministic; the bounds are ~4.5 standard errors."""
 import numpy as np
 import pytest
 from scipy import stats
 
 from oracle import clib
 
-N_ITEMS, N_ATT = 12000, 16
+N_ITEMS, N_ATT = 12000, 40
 
 
 @pytest.fixture(scope="module")
@@ -61,6 +63,19 @@ def test_no_serial_correlation_between_attempts_sharing_a_radius_block(draws):
     assert abs(np.corrcoef(z0[:-1].ravel(), z0[1:].ravel())[0, 1]) < 4.5 / np.sqrt(z0[:-1].size)
     # the shared HIGH half of the radius word: radii of the same block must not cluster (rank correlation)
     assert abs(stats.spearmanr(rad[:, 2], rad[:, 3]).statistic) < 4.5 / np.sqrt(N_ITEMS)
+
+
+def test_radius_words_are_uniform_including_the_rank_dealt_tail():
+    """u1 = (radius word + 1) / 2^32 recovered from the normals (R1^2 = z0^2 + z1^2 = -2 ln u1): uniform over all
+    attempts >= 1, and uniform on (0, 1/16] for the attempts whose top nibble is zero (dealt by rank from MOTION_R2)."""
+    z = np.array([clib.normals3_seq(77, 3, i, 200)[1:] for i in range(1500)]).reshape(-1, 3)
+    u1 = np.exp(-0.5 * (z[:, 0] ** 2 + z[:, 1] ** 2))
+    assert stats.kstest(u1, "uniform").pvalue > 1e-3
+    tail = u1[u1 <= 1.0 / 16.0] * 16.0
+    assert abs(len(tail) / len(u1) - 1.0 / 16.0) < 4.5 * np.sqrt(15.0 / 256.0 / len(u1))
+    assert stats.kstest(tail, "uniform").pvalue > 1e-3
+    far = np.mean(u1 <= 2.0 ** -12)                               # R1 >= 4.08: one attempt in 4096
+    assert abs(far - 2.0 ** -12) < 4.5 * np.sqrt(2.0 ** -12 / len(u1))
 
 
 def test_mh_and_resampling_uniforms_are_uniform():
