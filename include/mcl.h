@@ -306,7 +306,7 @@ int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]);    
 int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);                       /* node:488-492 */
 /* odom + scan -> predict (delta != NULL), update on pre-staged scan `scan_slot` (or the current scan
  * if < 0), estimate (to d_out18 and/or blocking into h_out16; both nullable), resample.
- * With symmetric MH or plain MCL the step is three launches: motion, likelihood of both particle sets, and the
+ * With symmetric MH or plain MCL the step is four launches: motion, motion retries, likelihood of both particle sets, and the
  * persistent tail kernel (csrc/tail.cu: softmax x2, MH accept, estimate sums, resampling in either arithmetic;
  * on sharded handles also the cross-rank exchanges and the peer push) -- same results bit for bit as the calls
  * above issued one by one.  MCL_NO_TAIL=1 in the environment selects round 1's four fused kernels (fixed point)

@@ -62,6 +62,8 @@ struct mcl_handle {
     int win_rows = 0;            // (major extent + 2) rows of 256 cells
     int32_t *d_win = nullptr;
     size_t win_bytes = 0;
+    int32_t *d_win_skew = nullptr;   // the same window with rows of 264 words (bank-skewed)
+    size_t win_skew_bytes = 0;
     int lik_path = 0;            // 0 auto, 1 global, 2 smem window
     // coded window for maps whose int32 window exceeds shared memory: one byte per cell indexing a
     // table of the (<= 256) distinct values (the value depends only on dist, and an EDT on a grid takes

@@ -293,7 +293,7 @@ __device__ __forceinline__ uint32_t g1_fetch(const G1Ctx &k, int cell) {
 // P slices (rows i0, i0 + row, ...) of one warp; lanes whose particle index is >= end idle on a copy of end - 1
 // PERM: i0 / end are positions in a tile-sorted order and perm[] maps them to particle indices (tiled kernel)
 // PERM: 0 no; 1 tiled kernel with rows of 260 bytes (manual staging); 2 tiled kernel with rows of 272 bytes (bulk copies)
-template <bool SMEM, bool CODED, bool TPOSE, int P, int PERM = 0>
+template <bool SMEM, bool CODED, bool TPOSE, int P, int PERM = 0, bool SKEW = false>
 __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, const double *__restrict__ xs,
                                           const double *__restrict__ ys, const double *__restrict__ ts,
                                           float *__restrict__ score, int64_t i0, int64_t row, int64_t end, float &smax,
@@ -330,6 +330,7 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
             const int ry = __viaddmin_s32_relu(__double2hiint(TY), negK, k.cmy);
             unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
             if (PERM == 1) cell += (cell >> 8) << 2;     // tiled kernel: rows of 260 bytes (see k_likelihood_tiled)
+            if (SKEW) cell += cell >> 5;                 // rows of 264 words: consecutive rows 8 banks apart (k_pack_window)
             if (PERM == 2) return g1_fetch_t2(k, cell);  // rows of 272 bytes (k_likelihood_tiled2)
             return g1_fetch<CODED>(k, (int)cell);
         };
@@ -373,6 +374,7 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
                 const int ry = __viaddmin_s32_relu(hy - min(fy, 0), negK, k.cmy);
                 unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
                 if (PERM == 1) cell += (cell >> 8) << 2;
+                if (SKEW) cell += cell >> 5;
                 const uint32_t v = PERM == 2 ? g1_fetch_t2(k, cell) : g1_fetch<CODED>(k, (int)cell);
                 const bool in = coord_in_map(TX, fx, 8, limx) && coord_in_map(TY, fy, 8, limy);
                 return in ? v : zero_off;
@@ -435,7 +437,7 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
 }
 
 // Tunables (chosen by measurement, see profiles/): threads per CTA and minimum CTAs per SM.
-template <bool SMEM, int G1_THREADS, int MINB, bool CODED = false, bool TPOSE = false>
+template <bool SMEM, int G1_THREADS, int MINB, bool CODED = false, bool TPOSE = false, bool SKEW = false>
 __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
@@ -483,11 +485,11 @@ __global__ void __launch_bounds__(G1_THREADS, MINB) k_likelihood_g1(const LikPar
     float smax0 = -FLT_MAX;
     int64_t i = first + 2 * (threadIdx.x & ~31);
     for (; i < end; i += 2 * G1_THREADS)
-        g1_slices<SMEM, CODED, TPOSE, 2>(p, k, xs, ys, ts, score, i + k.lane, 32, end, smax0);
+        g1_slices<SMEM, CODED, TPOSE, 2, 0, SKEW>(p, k, xs, ys, ts, score, i + k.lane, 32, end, smax0);
     // Never taken (the host rejects n < 0).  With this second, cold copy of the slice code in the kernel
     // ptxas keeps the hot copy above on the uniform datapath; without it the beam constants are fetched with
     // per-thread LDC (found by bisection on the SASS, CUDA 12.9).
-    if (p.n < 0) g1_slices<SMEM, CODED, TPOSE, 1>(p, k, xs, ys, ts, score, i + k.lane, 0, end, smax0);
+    if (p.n < 0) g1_slices<SMEM, CODED, TPOSE, 1, 0, SKEW>(p, k, xs, ys, ts, score, i + k.lane, 0, end, smax0);
     if (p.keymax) {                                        // maximum score of the set (first softmax pass, node:353)
         __shared__ float smx[32];
         smax0 = warp_max(smax0);
@@ -1065,9 +1067,18 @@ static int likelihood_g1_dispatch(mcl_handle *h, const LikParams &p, unsigned lo
         const size_t sm = 16 + 32768 + h->win8_bytes;
         return h->win_tpose ? launch_g1<true, true, true>(h, p, sm) : launch_g1<true, true, false>(h, p, sm);
     }
-    if (use_smem && h->cell_S == 8)
+    if (use_smem && h->cell_S == 8) {
+        static int skew = -1;
+        if (skew < 0) { const char *e = getenv("MCL_LIK_SKEW"); skew = e ? atoi(e) : 0; }
+        if (skew && h->d_win_skew) {
+            LikParams ps = p;
+            ps.win = h->d_win_skew; ps.win_bytes = (uint32_t)h->win_skew_bytes;
+            return h->win_tpose ? launch_lik_kernel(h, k_likelihood_g1<true, 896, 1, false, true, true>, ps, 16 + h->win_skew_bytes, 1, 896, true)
+                                : launch_lik_kernel(h, k_likelihood_g1<true, 896, 1, false, false, true>, ps, 16 + h->win_skew_bytes, 1, 896, true);
+        }
         return h->win_tpose ? launch_g1<true, false, true>(h, p, 16 + h->win_bytes)
                             : launch_g1<true, false, false>(h, p, 16 + h->win_bytes);
+    }
     return launch_g1<false, false, false>(h, p, 16);
 }
 

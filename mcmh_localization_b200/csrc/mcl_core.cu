@@ -69,7 +69,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     cudaFree(h->d_est18); cudaFree(h->d_fused); cudaFree(h->d_code8); cudaFree(h->d_code8p); cudaFree(h->d_tiled);
     cudaFree(h->d_kld);
     cudaFree(h->d_seq);
-    cudaFree(h->d_tail); cudaFree(h->d_tail_prof); cudaFree(h->d_motion_stats); cudaFree(h->d_retry_idx); cudaFree(h->d_retry_thr); cudaFree(h->d_retry_ctr);
+    cudaFree(h->d_tail); cudaFree(h->d_tail_prof); cudaFree(h->d_motion_stats); cudaFree(h->d_retry_idx); cudaFree(h->d_retry_thr); cudaFree(h->d_retry_ctr); cudaFree(h->d_win_skew);
     if (h->ev_est) cudaEventDestroy(h->ev_est);
     cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
     cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch); cudaFree(h->d_win8); cudaFree(h->d_lut);
@@ -199,7 +199,7 @@ __global__ void k_build_logtab(const float *__restrict__ dist, int32_t *__restri
 
 // window cell (ix, iy) <-> map cell (ix + ofx, iy + ofy); see mcl_handle::win_edge for the EDGE sides
 __global__ void k_pack_window(const int32_t *__restrict__ logtab, int32_t *__restrict__ win, int W, int H, int ofx, int ofy,
-                              int edge, int rows, int tpose, int32_t c0, int32_t voff) {
+                              int edge, int rows, int tpose, int32_t c0, int32_t voff, int skew) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * 256; i += gridDim.x * blockDim.x) {
         const int major = i >> 8, minor = i & 255;
         const int ix = tpose ? major : minor, iy = tpose ? minor : major;
@@ -211,7 +211,7 @@ __global__ void k_pack_window(const int32_t *__restrict__ logtab, int32_t *__res
         int32_t v = c0;                               // in-map cells outside the free-space box
         if (outside) v = 0;                           // beyond the map: the beam is skipped (pu:131-132), adds 0
         else if (mx >= 0 && mx < W && my >= 0 && my < H) v = logtab[(size_t)my * W + mx];
-        win[i] = v - voff;     // >= 0: see mcl_handle::voff
+        win[skew ? i + (i >> 5) : i] = v - voff;     // >= 0: see mcl_handle::voff; skew: rows of 264 words
     }
 }
 
@@ -289,8 +289,19 @@ int mcl_prepare_table(mcl_handle *h) {
         const int n = h->win_rows * 256;
         k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
             h->d_logtab, h->d_win, h->W, h->H, h->win_ofx, h->win_ofy, h->win_edge, h->win_rows, h->win_tpose ? 1 : 0,
-            h->c0, h->voff);
+            h->c0, h->voff, 0);
         MCL_LAUNCH_CHECK(h);
+        // skewed copy (rows of 264 words: consecutive rows start 8 banks apart)
+        cudaFree(h->d_win_skew); h->d_win_skew = nullptr;
+        h->win_skew_bytes = ((size_t)n + ((size_t)n >> 5) + 8) * sizeof(int32_t);
+        if (16 + h->win_skew_bytes <= (size_t)h->smem_optin - 512) {
+            MCL_CUDA(h, cudaMalloc((void **)&h->d_win_skew, h->win_skew_bytes));
+            MCL_CUDA(h, cudaMemsetAsync(h->d_win_skew, 0, h->win_skew_bytes, h->stream));
+            k_pack_window<<<std::max(1, std::min((n + 255) / 256, h->sm_count * 8)), 256, 0, h->stream>>>(
+                h->d_logtab, h->d_win_skew, h->W, h->H, h->win_ofx, h->win_ofy, h->win_edge, h->win_rows, h->win_tpose ? 1 : 0,
+                h->c0, h->voff, 1);
+            MCL_LAUNCH_CHECK(h);
+        }
         // coded window (uint8 + table of distinct values) when the int32 window does not fit in shared memory
         const size_t limit = (size_t)h->smem_optin - 512;
         if (16 + h->win_bytes > limit && (size_t)n + 16 + 32768 + 64 <= limit) {
