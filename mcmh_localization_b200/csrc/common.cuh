@@ -128,6 +128,7 @@ struct mcl_handle {
     int coop_launch = -1;        // cudaDevAttrCooperativeLaunch (-1: not queried yet)
     double *d_est18 = nullptr;   // device staging of the estimate sums (mcl_filter_step)
     cudaEvent_t ev_est = nullptr;
+    cudaEvent_t ev_beams = nullptr;      // after the last copy out of the pinned beam staging buffer (mcl_set_scan)
 
     // timing of likelihood launches
     bool timing = false;

@@ -71,6 +71,7 @@ extern "C" int mcl_destroy(mcl_handle *h) {
     cudaFree(h->d_seq);
     cudaFree(h->d_tail); cudaFree(h->d_tail_prof); cudaFree(h->d_motion_stats); cudaFree(h->d_retry_idx); cudaFree(h->d_retry_thr); cudaFree(h->d_retry_ctr); cudaFree(h->d_win_skew);
     if (h->ev_est) cudaEventDestroy(h->ev_est);
+    if (h->ev_beams) cudaEventDestroy(h->ev_beams);
     cudaFree(h->d_occ); cudaFree(h->d_dist); cudaFree(h->d_logtab); cudaFree(h->d_win);
     cudaFree(h->d_beams); cudaFree(h->d_batch); cudaFree(h->d_scratch); cudaFree(h->d_win8); cudaFree(h->d_lut);
     cudaFreeHost(h->h_beams); cudaFreeHost(h->h_pinned);
@@ -426,17 +427,21 @@ extern "C" int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h
         MCL_CUDA(h, cudaMalloc((void **)&h->d_beams, (size_t)cap * sizeof(BeamTable)));
         MCL_CUDA(h, cudaMallocHost((void **)&h->h_beams, (size_t)cap * sizeof(BeamTable)));
         h->beams_cap = cap;
-    } else {
-        // the pinned staging buffer may still be the source of an in-flight copy
-        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else if (h->ev_beams) {
+        // the pinned staging buffer may still be the source of an in-flight copy: wait for THAT copy only, so that
+        // the table of the next scan is built while kernels enqueued since (the motion kernels of the step) run
+        MCL_CUDA(h, cudaEventSynchronize(h->ev_beams));
     }
+    if (!h->ev_beams) MCL_CUDA(h, cudaEventCreateWithFlags(&h->ev_beams, cudaEventDisableTiming));
     int n_pos = 0, n_neg = 0;
     double rmax = 0;
     build_beam_table(h, h_ranges, h_angles, M, h->h_beams, n_pos, n_neg, rmax);
     h->n_pos = n_pos; h->n_neg = n_neg; h->rmax_cells = rmax;
-    if (n_pos + n_neg > 0)
+    if (n_pos + n_neg > 0) {
         MCL_CUDA(h, cudaMemcpyAsync(h->d_beams, h->h_beams, (size_t)(n_pos + n_neg) * sizeof(BeamTable),
                                     cudaMemcpyHostToDevice, h->stream));
+        MCL_CUDA(h, cudaEventRecord(h->ev_beams, h->stream));
+    }
     h->d_beams_active = h->d_beams;
     h->scan_gen = mcl_next_scan_uid();
     h->scan_set = true;

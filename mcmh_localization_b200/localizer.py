@@ -223,7 +223,9 @@ class Localizer:
             angles = np.linspace(angle_min, angle_max, len(r), dtype=np.float32)  # node:346-348
         a = np.ascontiguousarray(angles, dtype=np.float32)
         self._bind_stream()
-        self.h.call("mcl_set_scan", C.c_void_p(r.ctypes.data), C.c_void_p(a.ctypes.data), len(r))
+        # (__array_interface__ instead of .ctypes: 4 us less per scan)
+        self.h.call("mcl_set_scan", C.c_void_p(r.__array_interface__["data"][0]),
+                    C.c_void_p(a.__array_interface__["data"][0]), len(r))
 
     def update(self, ranges, angle_min=None, angle_max=None, angles=None, uniforms=None):
         """node:296-322: update_scans, update_weights (both particle sets), MH accept by mode."""
@@ -362,6 +364,12 @@ class Localizer:
                 self.delta = compute_motion(self.last_odom, cur_odom)
                 d = _dbl3(self.delta)
             self.last_odom = cur_odom
+            if d is not None and not self.use_adaptive and not self.assym:
+                # the motion kernels do not need the scan: enqueue them first and build the beam table of the scan
+                # on the host while they run (same calls, same results as mcl_filter_step(d, ...))
+                self._bind_stream()
+                self.h.call("mcl_filter_predict", d, None, 0)
+                d = None
             self.set_scan(ranges, angle_min, angle_max, angles)
             if self.use_adaptive:                 # N changes per scan: sequence the stages from the host
                 if d is not None:
@@ -471,11 +479,22 @@ def compute_motion(odom1, odom2):
 
 
 def assemble_estimate(o):
-    """np.average / np.cov(aweights) from the 16 numbers of mcl_estimate (include/mcl.h)."""
+    """np.average / np.cov(aweights) from the 16 numbers of mcl_estimate (include/mcl.h).  Scalar arithmetic in the
+    order of (sdd - np.outer(sd, sd) / v1) / fact: the same IEEE operations without 17 us of small-array overhead
+    per step."""
     v1, v2 = o[0], o[1]
-    mean = np.array([o[2], o[3], o[4]])
-    sd = np.array(o[5:8])
-    sdd = np.array([[o[8], o[9], o[10]], [o[9], o[11], o[12]], [o[10], o[12], o[13]]])
+    s0, s1, s2 = o[5], o[6], o[7]
     fact = v1 - v2 / v1                       # np.cov: w_sum - ddof * sum(w * aweights) / w_sum
-    cov = (sdd - np.outer(sd, sd) / v1) / fact
-    return mean[0], mean[1], mean[2], cov
+    if fact == 0.0 or v1 == 0.0:              # one effective particle: np.cov divides by zero (nan / inf entries)
+        sd = np.array([s0, s1, s2])
+        sdd = np.array([[o[8], o[9], o[10]], [o[9], o[11], o[12]], [o[10], o[12], o[13]]])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return o[2], o[3], o[4], (sdd - np.outer(sd, sd) / v1) / fact
+    c00 = (o[8] - s0 * s0 / v1) / fact
+    c01 = (o[9] - s0 * s1 / v1) / fact
+    c02 = (o[10] - s0 * s2 / v1) / fact
+    c11 = (o[11] - s1 * s1 / v1) / fact
+    c12 = (o[12] - s1 * s2 / v1) / fact
+    c22 = (o[13] - s2 * s2 / v1) / fact
+    cov = np.array(((c00, c01, c02), (c01, c11, c12), (c02, c12, c22)))
+    return o[2], o[3], o[4], cov
