@@ -118,6 +118,7 @@ struct mcl_handle {
     unsigned long long tail_bar = 0;   // grid-barrier arrivals consumed so far (base of the next launch)
     void *d_tail_prof = nullptr; // MCL_TAIL_PROF=1: stage time stamps of the tail kernel
     int tail_prof_grid = 0;
+    int64_t tail_drift_n = -1;   // particle count the tail kernel's drift hints belong to
     void *d_motion_stats = nullptr; // MCL_MOTION_STATS=1: counters of the motion kernel's rejection loop
     unsigned long long motion_min_thr = 0;   // mcl_debug_motion (tests)
     bool motion_small_queue = false;

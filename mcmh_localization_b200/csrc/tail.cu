@@ -80,6 +80,7 @@ struct TailArgs {
     void *tend;                  // [nt] value of C at the end of every tile
     unsigned long long *ttot;    // [nt] fixed: tile totals
     double *est18;
+    double *drift;               // [nt] relative drift (exact sequential sum / fp64 sum - 1) at the end of every tile, last step
     double r, rstep;
     int32_t *idx;
     double *gx, *gy, *gt;
@@ -707,7 +708,22 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
         double ttot;
         const double pe = tl_block_excl_scan_d(ls, ttot, sh);     // predicted (fp64) sum entering this thread's weights
         if (rd == 0) tl_stamp(a, P2 ? 27 : 30);
-        const double lo_v = sh.ownP[rd] * invS, hi_v = lo_v + ttot;
+        // Where the tile's sums will lie.  The fp64 sums of S2 know nothing of the DRIFT of the sequential f32 sum,
+        // which in a converged filter (long runs of equal weights, every addition rounding the same way) reaches
+        // ~1 % -- more than the 2^-9 margin, so the last tiles (sum near 1 = a binade boundary) were misclassified
+        // and fell back to the restart loop, 12 us per pass.  Pass 2 therefore predicts from the EXACT sums of
+        // pass 1 (its records, divided by S: the same weights up to the scale), and pass 1 corrects the fp64 sums
+        // by the relative drift the previous step saw at the same tile.  Predictions only: every result is checked.
+        const double p_lo = sh.ownP[rd] * invS, p_hi = p_lo + ttot;
+        double lo_v = p_lo, hi_v = p_hi;
+        if (P2) {
+            if (v > 0) lo_v = (double)__uint_as_float((unsigned)__ldcg(a.st1 + v - 1)) * invS;
+            hi_v = (double)__uint_as_float((unsigned)__ldcg(a.st1 + v)) * invS;
+        } else if (a.drift) {
+            if (v > 0) lo_v = p_lo * (1.0 + __ldcg(a.drift + v - 1));
+            hi_v = p_hi * (1.0 + __ldcg(a.drift + v));
+        }
+        if (!(hi_v >= lo_v)) { lo_v = p_lo; hi_v = p_hi; }
         int kind = TL_KIND_MULTI, e1 = 0;
         if (lo_v > 0.0 && hi_v < 1e38) {
             const int ea = ilogb(lo_v * (1.0 - TL_DELTA_TILE)), eb = ilogb(hi_v * (1.0 + TL_DELTA_TILE));
@@ -954,6 +970,7 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
             if (t == 0 && a.prof) a.prof[(size_t)blockIdx.x * 32 + (P2 ? 25 : 24)] = (unsigned long long)(failed * 1000 + kind * 100000 + nitems);
         }
         if (t == 0) {
+            if (!P2 && a.drift) a.drift[v] = p_hi > 0.0 ? (double)c_out / p_hi - 1.0 : 0.0;      // for the next step's pass 1
             if (P2) ((float *)a.tend)[v] = c_out;
             else if (v == a.nt - 1) a.hd->S = c_out;
             if (xk && v == a.nt - 1) tl_publish_one(a, xk, (unsigned long long)__float_as_uint(c_out));   // to the next rank
@@ -1528,7 +1545,7 @@ static size_t tl_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct TailPlan {
     int ipt, tile, nt, grid;
-    size_t o_q, o_m, o_c, o_st1, o_st2, o_C, o_tend, o_ttot, bytes;
+    size_t o_drift, o_q, o_m, o_c, o_st1, o_st2, o_C, o_tend, o_ttot, bytes;
 };
 static TailPlan tail_plan(const mcl_handle *h, int64_t n) {
     TailPlan p;
@@ -1539,6 +1556,7 @@ static TailPlan tail_plan(const mcl_handle *h, int64_t n) {
     p.nt = (int)((n + p.tile - 1) / p.tile);
     p.grid = std::min(p.nt, h->sm_count);
     size_t off = tl_align(sizeof(TailHeader));
+    p.o_drift = off; off += tl_align((size_t)h->sm_count * TL_MAX_ROUNDS * 8);     // fixed place: survives a re-plan
     p.o_q = off; off += tl_align((size_t)2 * h->sm_count * 8);
     p.o_m = off; off += tl_align((size_t)p.nt * 8 * 8);
     p.o_c = off; off += tl_align((size_t)p.nt * 9 * 8);
@@ -1579,7 +1597,7 @@ static int tail_prepare(mcl_handle *h, int64_t n) {
     cudaFree(h->d_tail);
     h->d_tail = nullptr; h->tail_bytes = 0;
     MCL_CUDA(h, cudaMalloc(&h->d_tail, p.bytes + p.bytes / 4));
-    MCL_CUDA(h, cudaMemset(h->d_tail, 0, tl_align(sizeof(TailHeader))));
+    MCL_CUDA(h, cudaMemset(h->d_tail, 0, p.o_q));      // header + drift hints (0 = no drift known)
     h->tail_bytes = p.bytes + p.bytes / 4;
     h->tail_bar = 0;
     return MCL_OK;
@@ -1623,6 +1641,11 @@ int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keyma
     a.st1 = (unsigned long long *)(b + p.o_st1); a.st2 = (unsigned long long *)(b + p.o_st2);
     a.C = b + p.o_C; a.tend = b + p.o_tend; a.ttot = (unsigned long long *)(b + p.o_ttot);
     a.est18 = u.est18;
+    a.drift = (double *)(b + p.o_drift);
+    if (h->tail_drift_n != u.n) {                    // another particle count: the tiles are other tiles
+        MCL_CUDA(h, cudaMemsetAsync(a.drift, 0, (size_t)h->sm_count * TL_MAX_ROUNDS * 8, h->stream));
+        h->tail_drift_n = u.n;
+    }
     a.r = r; a.rstep = 1.0 / (double)(comm ? comm->n_global : u.n);     // pu:434
     if (comm) {
         a.rank = comm->rank; a.world = comm->world; a.n_global = comm->n_global;
