@@ -28,7 +28,7 @@ def launches(path, out):
     rows = [r for r in csv.DictReader(lines) if r["Metric Name"] == "gpu__time_duration.sum"]
     names = [(re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", ""), float(r["Metric Value"].replace(",", "")) / 1e3,
               r["Grid Size"], r["Block Size"]) for r in rows]
-    idx = [i for i, n in enumerate(names) if n[0].startswith("k_motion")]
+    idx = [i for i, n in enumerate(names) if n[0] == "k_motion"]
     out.write("ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
     out.write("launches captured: %d; k_motion launches at %s\n\n" % (len(names), idx))
     if len(idx) >= 2:
@@ -94,7 +94,7 @@ if __name__ == "__main__":
         traffic_json(rep, tag, int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 2)
     os.makedirs("profiles", exist_ok=True)
     with open("profiles/%s_summary.txt" % tag, "w") as out:
-        out.write("profile summary %s  (command: python bench.py --steps 3 --warmup 10 --quick, 1M particles x 360 beams)\n\n" % tag)
+        out.write("profile summary %s  (command: python bench.py --steps 30 --warmup 10 --quick, 1M particles x 360 beams)\n\n" % tag)
         launches(lpath, out)
         full(rep, out)
     print(open("profiles/%s_summary.txt" % tag).read())
