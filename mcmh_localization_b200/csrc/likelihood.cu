@@ -588,18 +588,35 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(int *hist, int ntiles, in
             const int first = c0 + woff + inc - v;
             offsets[i] = first;
             hist[i] = 0;
-            int it = c2 + woff2 + inc2 - np;
-            for (int j = 0; j < np; ++j, ++it) {
-                items[3 * it] = i;
-                items[3 * it + 1] = first + j * piece;
-                items[3 * it + 2] = min(first + v, first + (j + 1) * piece);
-            }
         }
         __syncthreads();
         if (threadIdx.x == 1023) { carry = c0 + woff + inc; carry2 = c2 + woff2 + inc2; }
         __syncthreads();
     }
     if (threadIdx.x == 0) { offsets[ntiles] = carry; counters[0] = carry2; counters[1] = 0; }
+    // Work items, LARGEST FIRST (four size classes; the order inside a class is irrelevant): the CTAs of the tiled
+    // kernel take items from a counter and the kernel ends with the slowest CTA, so the small pieces must come last.
+    __shared__ int ccount[4], cbase[4], ccur[4];
+    if (threadIdx.x < 4) { ccount[threadIdx.x] = 0; ccur[threadIdx.x] = 0; }
+    __syncthreads();                                    // also: offsets[] written above are visible to the block
+    auto size_class = [piece](int size) { return size >= piece ? 0 : 1 + min(2, (3 * (piece - size)) / piece); };
+    for (int i = threadIdx.x; i < ntiles; i += 1024) {
+        const int v = offsets[i + 1] - offsets[i];
+        for (int j = 0; j * piece < v; ++j) atomicAdd(&ccount[size_class(min(piece, v - j * piece))], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { cbase[0] = 0; for (int c = 1; c < 4; ++c) cbase[c] = cbase[c - 1] + ccount[c - 1]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntiles; i += 1024) {
+        const int first = offsets[i], v = offsets[i + 1] - first;
+        for (int j = 0; j * piece < v; ++j) {
+            const int size = min(piece, v - j * piece), c = size_class(size);
+            const int it = cbase[c] + atomicAdd(&ccur[c], 1);
+            items[3 * it] = i;
+            items[3 * it + 1] = first + j * piece;
+            items[3 * it + 2] = first + j * piece + size;
+        }
+    }
 }
 // perm[first position of the tile + rank inside the tile] = particle.  SH: the block counts its share per tile in
 // shared memory, reserves one range per tile with a single global atomic, then ranks its particles locally.
@@ -917,7 +934,15 @@ static int launch_tiled(mcl_handle *h, LikParams p, unsigned long long *keymax) 
     const size_t o_tile = 0, o_perm = o_tile + (((size_t)p.n * 4 + 255) & ~(size_t)255);
     const size_t o_hist = o_perm + (((size_t)p.n * 4 + 255) & ~(size_t)255);
     const size_t o_off = o_hist + (((size_t)(ntiles + 1) * 4 + 255) & ~(size_t)255);
-    constexpr int PIECE = 16 * 448;                                   // particles per work item at most
+    // particles per work item at most (MCL_TILED_PIECE for A/B).  An item costs a CTA ~27 us per 1000 particles and
+    // the kernel ends with the slowest CTA: in tile order 7168 left the SMs idle 16 % of the time (ncu:
+    // sm__cycles_active vs elapsed), and smaller pieces pay for more staging; with the items handed out largest
+    // first (k_tile_offsets) 7168 and 3584 measure the same, 11 % faster.
+    static const int PIECE = [] {
+        const char *e = getenv("MCL_TILED_PIECE");
+        const int v = e ? atoi(e) : 0;
+        return v >= 64 && v <= 16 * 448 ? (v & ~63) : 16 * 448;
+    }();
     const size_t max_items = (size_t)ntiles + (size_t)(p.n / PIECE) + 2;
     const size_t o_items = o_off + (((size_t)(ntiles + 1) * 4 + 255) & ~(size_t)255);
     const size_t o_cnt = o_items + ((max_items * 12 + 255) & ~(size_t)255);
