@@ -771,18 +771,24 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
             if (warp == 0) {
                 const float c_in = tl_lookback(st, v, &a.hd->err, a, xk);
                 if (rd == 0) tl_stamp(a, P2 ? 21 : 17);
+                // first thread whose last sum leaves the binade (the sums are monotone): two 32-way steps by the whole
+                // warp instead of ten dependent ones by one lane -- this sits on the serial chain of the pass
+                const long long K0 = seq_K(c_in);
+                const int ec = seq_exponent(c_in);
+                int ts_w = TL_THREADS;
+                if (ec == e1) {
+                    const unsigned m1 = __ballot_sync(TL_FULL, tl_apply(K0, pfs[32 * lane + 31]) >= (1ll << 24));
+                    if (m1) {
+                        const int ch = __ffs(m1) - 1;
+                        const unsigned m2 = __ballot_sync(TL_FULL, tl_apply(K0, pfs[32 * ch + lane]) >= (1ll << 24));
+                        ts_w = 32 * ch + __ffs(m2) - 1;
+                    }
+                }
                 if (lane == 0) {
-                    const long long K0 = seq_K(c_in);
-                    const int ec = seq_exponent(c_in);
                     int fail = 1, ts = TL_THREADS;
                     float c = c_in, cp = c_in;
                     if (ec == e1) {
-                        int lo = 0, hi = TL_THREADS;     // first thread whose last sum leaves the binade
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (tl_apply(K0, pfs[mid]) >= (1ll << 24)) hi = mid; else lo = mid + 1;
-                        }
-                        ts = lo;
+                        ts = ts_w;
                         if (ts == TL_THREADS) { c = seq_value(tl_apply(K0, pfs[TL_THREADS - 1]), e1); fail = 0; }
                         else {
                             cp = seq_value(ts ? tl_apply(K0, pfs[ts - 1]) : K0, e1);
