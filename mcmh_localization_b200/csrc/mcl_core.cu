@@ -396,13 +396,17 @@ int mcl_prepare_table(mcl_handle *h) {
 // pu:119-129: beams j = 0, step, 2 step, ...; valid iff isfinite(r) and r < max_range.
 // endpoint offset r*(cos a, sin a) with a = (double)angles[j], scaled to cells.
 // Valid beams with r >= 0 first ("0 <= r <= max_range", pu:139), then negative finite ranges (p_rand = 0).
-static void build_beam_table(const mcl_handle *h, const float *h_ranges, const float *h_angles, int M,
+// A finite range <= -max_range also passes the reference's test (pu:123 has no lower bound), but its endpoint lies
+// further from the particle than the cell arithmetic is sized for (mcl_prepare_table: map extent + 2 max_range):
+// such a scan is refused (returns false) instead of scored wrongly.  No LaserScan holds negative ranges.
+static bool build_beam_table(const mcl_handle *h, const float *h_ranges, const float *h_angles, int M,
                              BeamTable *out, int &n_pos, int &n_neg, double &rmax) {
     n_pos = 0; n_neg = 0; rmax = 0;
     std::vector<BeamTable> neg;
     for (int j = 0; j < M; j += h->step) {
         const double r = (double)h_ranges[j];
         if (!(isfinite(r) && r < h->max_range)) continue;
+        if (r <= -h->max_range) return false;
         const double a = (double)h_angles[j];
         BeamTable b;
         b.bx = r * cos(a) / h->res;
@@ -412,6 +416,7 @@ static void build_beam_table(const mcl_handle *h, const float *h_ranges, const f
         else neg.push_back(b);
     }
     for (auto &b : neg) out[n_pos + n_neg++] = b;
+    return true;
 }
 
 extern "C" int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h_angles, int M) {
@@ -435,7 +440,8 @@ extern "C" int mcl_set_scan(mcl_handle *h, const float *h_ranges, const float *h
     if (!h->ev_beams) MCL_CUDA(h, cudaEventCreateWithFlags(&h->ev_beams, cudaEventDisableTiming));
     int n_pos = 0, n_neg = 0;
     double rmax = 0;
-    build_beam_table(h, h_ranges, h_angles, M, h->h_beams, n_pos, n_neg, rmax);
+    if (!build_beam_table(h, h_ranges, h_angles, M, h->h_beams, n_pos, n_neg, rmax))
+        return mcl_fail(h, MCL_ERR_ARG, "mcl_set_scan: a range <= -max_range (the cell arithmetic covers |r| < max_range)");
     h->n_pos = n_pos; h->n_neg = n_neg; h->rmax_cells = rmax;
     if (n_pos + n_neg > 0) {
         MCL_CUDA(h, cudaMemcpyAsync(h->d_beams, h->h_beams, (size_t)(n_pos + n_neg) * sizeof(BeamTable),
@@ -461,8 +467,9 @@ extern "C" int mcl_set_scan_batch(mcl_handle *h, const float *h_ranges, const fl
     std::vector<BeamTable> host((size_t)M * K);
     for (int k = 0; k < K; ++k) {
         mcl_handle::ScanMeta m;
-        build_beam_table(h, h_ranges + (size_t)k * M, h_angles, M, host.data() + (size_t)k * M, m.n_pos, m.n_neg,
-                         m.rmax_cells);
+        if (!build_beam_table(h, h_ranges + (size_t)k * M, h_angles, M, host.data() + (size_t)k * M, m.n_pos, m.n_neg,
+                              m.rmax_cells))
+            return mcl_fail(h, MCL_ERR_ARG, "mcl_set_scan_batch: a range <= -max_range (the cell arithmetic covers |r| < max_range)");
         h->batch_meta.push_back(m);
     }
     MCL_CUDA(h, cudaMalloc((void **)&h->d_batch, host.size() * sizeof(BeamTable)));

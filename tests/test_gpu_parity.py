@@ -1093,6 +1093,20 @@ def test_c_abi_error_behaviour():
     with pytest.raises(MclError):
         _lib.Handle(10_000)                 # no such device
     h.close()
+    # a range <= -max_range passes pu:123 in the reference, but its endpoint is beyond what the cell arithmetic is
+    # sized for: the scan is refused, not scored wrongly (negative ranges above -max_range are supported)
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    import os
+    from conftest import GOLDEN
+    loc = Localizer(params=P, mode="MCL")
+    loc.load_map(load_npz(os.path.join(GOLDEN, "map_world.npz")))
+    ang = np.linspace(0, 2 * np.pi, 8, endpoint=False).astype(np.float32)
+    loc.set_scan(np.array([1, 2, -1.5, 3, 1, 1, 1, 1], np.float32), angles=ang)
+    with pytest.raises(MclError) as e:
+        loc.set_scan(np.array([1, 2, -float(P["max_range"]) - 0.5, 3, 1, 1, 1, 1], np.float32), angles=ang)
+    assert e.value.code == -1
+    loc.close()
 
 
 def test_gpu_edt_bit_identical_to_scipy():
