@@ -723,7 +723,9 @@ int mcl_predict_cached(mcl_handle *h, const double *d_x, const double *d_y, cons
     k_motion<<<blocks, MOTION_BLOCK, 0, h->stream>>>(p);
     MCL_LAUNCH_CHECK(h);
     if (retry) {
-        const int rblocks = h->sm_count * MOTION_RETRY_BLOCKS_PER_SM;
+        // one warp per entry at most: small clouds (the reference's own 1 k particles) launch a few CTAs only
+        const int rblocks = (int)std::min<int64_t>((int64_t)h->sm_count * MOTION_RETRY_BLOCKS_PER_SM,
+                                                   (n + MOTION_RETRY_BLOCK / 32 - 1) / (MOTION_RETRY_BLOCK / 32));
         if (h->motion_small_queue) k_motion_retry<64><<<rblocks, MOTION_RETRY_BLOCK, 0, h->stream>>>(p);
         else k_motion_retry<320><<<rblocks, MOTION_RETRY_BLOCK, 0, h->stream>>>(p);
         MCL_LAUNCH_CHECK(h);

@@ -652,6 +652,8 @@ __device__ __forceinline__ Pair64 tl_block_suffix_scan_pair(const Pair64 &mine, 
 #define TL_KIND_CLEAN 0
 #define TL_KIND_TWO 1
 #define TL_KIND_MULTI 2
+#define TL_KIND_SEQ 3                      // one small tile: the plain sequential loop on one thread
+#define TL_SEQ_MAX 2048                    // ... up to this many weights (2 ns per addition beats the walk of a MULTI tile)
 #define TL_WSM_BYTES (TL_THREADS * TL_WSTRIDE * 4)
 
 // One exact pass over the tiles this CTA owns (v = blockIdx.x, + gridDim.x, ...).  P2: the weights are divided
@@ -729,6 +731,10 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
             const int ea = ilogb(lo_v * (1.0 - TL_DELTA_TILE)), eb = ilogb(hi_v * (1.0 + TL_DELTA_TILE));
             if (ea >= -126 && eb < 127) { e1 = ea; kind = eb == ea ? TL_KIND_CLEAN : (eb == ea + 1 ? TL_KIND_TWO : TL_KIND_MULTI); }
         }
+        // The reference's own scale (a few thousand particles): the whole population is one tile whose sum runs through
+        // ~20 binades.  The definition itself -- one thread adding in order, pu:430 / pu:436-443 -- takes 2 ns per
+        // weight there, less than preparing and walking a MULTI tile.
+        if (a.nt == 1 && xk == 0 && a.n <= TL_SEQ_MAX) kind = TL_KIND_SEQ;
         // per-kind state that the write phase needs
         Pair64 EX; EX.a0 = 0; EX.a1 = 0;                 // CLEAN / TWO: map of the threads before me (under e1); MULTI: inside my run
         Pair64 G; G.a0 = 0; G.a1 = 0;                    // TWO: my map under e1 + 1
@@ -810,6 +816,36 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
                 }
                 if (rd == 0) tl_stamp(a, P2 ? 22 : 18);
             }
+        } else if (kind == TL_KIND_SEQ) {
+            float *dn = (float *)pfs;                    // dense copy of the weights (TL_SEQ_MAX floats fit the map arrays)
+            const int cnt = (int)(end - tile_lo);
+#pragma unroll
+            for (int k = 0; k < TL_MAX_IPT; ++k) {
+                const int j = t * a.ipt + k;
+                if (k < a.ipt && j < TL_SEQ_MAX) dn[j] = j < cnt ? wt[k] : 0.0f;      // + 0 changes no sum
+            }
+            __syncthreads();
+            if (t == 0) {
+                float c = 0.0f;
+                float4 *d4 = (float4 *)dn;
+                for (int q = 0; q < (cnt + 7) / 8; ++q) {          // eight additions per trip, operands loaded ahead
+                    float4 u = d4[2 * q], w = d4[2 * q + 1];
+                    u.x = c = __fadd_rn(c, u.x); u.y = c = __fadd_rn(c, u.y); u.z = c = __fadd_rn(c, u.z); u.w = c = __fadd_rn(c, u.w);
+                    w.x = c = __fadd_rn(c, w.x); w.y = c = __fadd_rn(c, w.y); w.z = c = __fadd_rn(c, w.z); w.w = c = __fadd_rn(c, w.w);
+                    if (P2) { d4[2 * q] = u; d4[2 * q + 1] = w; }
+                }
+                tl_st_release(st + v, tl_rec_inc(c));
+                sh.c_in = 0.0f; sh.c_out = c; sh.fail = 0;
+            }
+            __syncthreads();
+            if (P2) {
+#pragma unroll
+                for (int k = 0; k < TL_MAX_IPT; ++k) {
+                    const int j = t * a.ipt + k;
+                    if (k < a.ipt && j < cnt) C[tile_lo + j] = dn[j];
+                }
+            }
+            if (!P2 && central && rd == 0) tl_central_sums(a, sh, mx, my, mt);
         } else {
             // ---- MULTI: per-thread prediction; threads within 2^-13 of a power of two are replayed -------------
             const double Pt = lo_v + pe, Qt = Pt + ls;
@@ -924,7 +960,7 @@ __device__ __forceinline__ void tl_exact_pass(const TailArgs &a, TlShared &sh, f
         if (failed) {                                    // a check failed (or too many pieces): general path
             c_out = tl_tile_general(P2, wt, a.ipt, first, tile_lo, end, sh.c_in, C, sh);
             if (t == 0) tl_st_release(st + v, tl_rec_inc(c_out));
-        } else if (P2) {
+        } else if (P2 && kind != TL_KIND_SEQ) {
             // ---- every running sum of the tile, from the exact sum that enters it --------------------------------
             bool replay = false;
             float cs = sh.c_in;
@@ -1558,6 +1594,8 @@ static TailPlan tail_plan(const mcl_handle *h, int64_t n) {
     p.ipt = TL_MAX_IPT;
     for (int k = 1; k <= TL_MAX_IPT; ++k)
         if ((n + (int64_t)TL_THREADS * k - 1) / ((int64_t)TL_THREADS * k) <= h->sm_count) { p.ipt = k; break; }
+    // a few thousand particles (the reference's own scale): ONE tile, whose exact sums a single thread adds in order
+    if (n <= TL_SEQ_MAX) p.ipt = (int)std::max<int64_t>(1, (n + TL_THREADS - 1) / TL_THREADS);
     p.tile = TL_THREADS * p.ipt;
     p.nt = (int)((n + p.tile - 1) / p.tile);
     p.grid = std::min(p.nt, h->sm_count);
