@@ -1471,37 +1471,56 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
                 for (int64_t j = t; j < cnt; j += TL_THREADS) stage[j] = __ldcg(C + i_lo + j);
                 __syncthreads();
             }
-            for (int k = 0; k < a.ipt; ++k) {
-                const int64_t m = m0 + (int64_t)k * TL_THREADS + t;
-                if (m >= m1) break;
-                KeyT key = tl_key<REF>(m, a.r, a.rstep, totd);
-                if (SH && !REF) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
-                int64_t src;
-                if (staged) {
-                    int lo = 0, hi = (int)cnt - 1;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (TlCum<REF>::gt(key, stage[mid])) lo = mid + 1; else hi = mid;
+            // four output slots at a time: the searches first, then all twelve gather loads in flight together, then
+            // the stores (slot by slot the loads of one slot waited for the stores of the one before)
+            for (int k0 = 0; k0 < a.ipt; k0 += 4) {
+                int64_t src[4], mm[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u;
+                    const int64_t m = m0 + (int64_t)k * TL_THREADS + t;
+                    mm[u] = m; ok[u] = k < a.ipt && m < m1; src[u] = 0;
+                    if (!ok[u]) continue;
+                    KeyT key = tl_key<REF>(m, a.r, a.rstep, totd);
+                    if (SH && !REF) key = (KeyT)((unsigned long long)key > koff ? (unsigned long long)key - koff : 0ull);
+                    if (staged) {
+                        int lo = 0, hi = (int)cnt - 1;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (TlCum<REF>::gt(key, stage[mid])) lo = mid + 1; else hi = mid;
+                        }
+                        src[u] = i_lo + lo;
+                    } else {
+                        int64_t lo = i_lo, hi = i_hi;
+                        while (lo < hi) {
+                            const int64_t mid = (lo + hi) >> 1;
+                            if (TlCum<REF>::gt(key, __ldcg(C + mid))) lo = mid + 1; else hi = mid;
+                        }
+                        src[u] = lo;
                     }
-                    src = i_lo + lo;
-                } else {
-                    int64_t lo = i_lo, hi = i_hi;
-                    while (lo < hi) {
-                        const int64_t mid = (lo + hi) >> 1;
-                        if (TlCum<REF>::gt(key, __ldcg(C + mid))) lo = mid + 1; else hi = mid;
-                    }
-                    src = lo;
                 }
-                if (SH) {
-                    int64_t d = m / n_per_rank;
-                    if (d > a.world - 1) d = a.world - 1;
-                    const int64_t j = m - d * n_per_rank;
-                    reinterpret_cast<double *>(sh.xch[d])[j] = a.nx[src];
-                    reinterpret_cast<double *>(sh.xch[a.world + d])[j] = a.ny[src];
-                    reinterpret_cast<double *>(sh.xch[2 * a.world + d])[j] = a.nth[src];
-                } else {
-                    a.idx[m] = (int32_t)src;
-                    if (!raw) { a.gx[m] = a.nx[src]; a.gy[m] = a.ny[src]; a.gt[m] = a.nth[src]; }
+                double vx[4], vy[4], vt[4];
+                if (SH || !raw) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (ok[u]) { vx[u] = a.nx[src[u]]; vy[u] = a.ny[src[u]]; vt[u] = a.nth[src[u]]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!ok[u]) continue;
+                    const int64_t m = mm[u];
+                    if (SH) {
+                        int64_t d = m / n_per_rank;
+                        if (d > a.world - 1) d = a.world - 1;
+                        const int64_t j = m - d * n_per_rank;
+                        reinterpret_cast<double *>(sh.xch[d])[j] = vx[u];
+                        reinterpret_cast<double *>(sh.xch[a.world + d])[j] = vy[u];
+                        reinterpret_cast<double *>(sh.xch[2 * a.world + d])[j] = vt[u];
+                    } else {
+                        a.idx[m] = (int32_t)src[u];
+                        if (!raw) { a.gx[m] = vx[u]; a.gy[m] = vy[u]; a.gt[m] = vt[u]; }
+                    }
                 }
             }
             __syncthreads();
