@@ -759,90 +759,91 @@ __global__ void __launch_bounds__((NCONS + 1) * 32, 1) k_likelihood_tiled2(const
     const int lpad = (16 - (t.margin & 15)) & 15;                     // bytes in front of column 0: 16-byte aligned sources
     if (threadIdx.x == 0) {
         mbar_init(full, 1); mbar_init(full + 1, 1);
-        mbar_init(empty, NCONS); mbar_init(empty + 1, NCONS);
+        mbar_init(empty, NCONS + 1); mbar_init(empty + 1, NCONS + 1);
     }
     for (int e = threadIdx.x; e < 256 * 32; e += (NCONS + 1) * 32) slut[e] = __ldg(t.lut + (e >> 5));
     __syncthreads();
     const int nitems = t.counters[0];
     float smax = -FLT_MAX;
-    if (warp == NCONS) {
-        // ------------------------------------------------------------------ producer
-        for (int s = 0;; ++s) {
-            const int b = s & 1;
-            if (s >= 2) mbar_wait(empty + b, ((s >> 1) - 1) & 1);      // every consumer warp is done with use s - 2
-            int item = 0;
-            if (lane == 0) item = atomicAdd(t.counters + 1, 1);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= nitems) {
-                if (lane == 0) { ring[b * 4] = -1; mbar_arrive(full + b); }
-                break;
-            }
-            const int tile = __ldg(t.items + 3 * item);
-            const int sub_x0 = (tile % t.tiles_x) * t.tile_w - t.margin, sub_y0 = (tile / t.tiles_x) * t.tile_h - t.margin;
-            unsigned char *dst = bufs + (size_t)b * buf_bytes;
-            // columns [xs, xe) of every row come from the padded map (x >= -16, y >= -1; 16-byte aligned), the rest is
-            // zero-filled
-            const int x_start = sub_x0 - lpad;
-            const int xs = max(x_start, -16), xe = min(x_start + T2_PITCH, p.W);
-            const int y_lo = max(sub_y0, -1), y_hi = min(sub_y0 + t.sub_rows, p.H);
-            const uint32_t row_bytes = xe > xs ? (uint32_t)(xe - xs) : 0u;
-            const uint32_t total = row_bytes * (uint32_t)max(y_hi - y_lo, 0);
-            if (row_bytes < T2_PITCH || y_lo > sub_y0 || y_hi < sub_y0 + t.sub_rows) {
-                // edge tile: zero what the copies will not write (whole rows above / below, strips left / right)
-                for (int r = 0; r < t.sub_rows; ++r) {
-                    const int my = sub_y0 + r;
-                    uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)r * T2_PITCH);
-                    if (my < y_lo || my >= y_hi || row_bytes == 0) {
-                        for (int w = lane; w < T2_PITCH / 4; w += 32) row[w] = 0u;
-                    } else {
-                        const int a = (xs - x_start) >> 2, z = (xe - x_start) >> 2;
-                        for (int w = lane; w < T2_PITCH / 4; w += 32)
-                            if (w < a || w >= z) row[w] = 0u;
-                    }
+    // Every warp consumes; the last one also stages: before it turns to use s it stages use s + 1 into the other
+    // buffer (as soon as every warp is done with use s - 1, which held that buffer).  With a warp that only staged,
+    // one of the four schedulers carried six consumers instead of seven.
+    auto stage_use = [&](int s) {                                      // producer warp only; s = use to be staged
+        const int b = s & 1;
+        if (s >= 2) mbar_wait(empty + b, ((s >> 1) - 1) & 1);          // every warp is done with use s - 2
+        int item = 0;
+        if (lane == 0) item = atomicAdd(t.counters + 1, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) {
+            if (lane == 0) { ring[b * 4] = -1; mbar_arrive(full + b); }
+            return;
+        }
+        const int tile = __ldg(t.items + 3 * item);
+        const int sub_x0 = (tile % t.tiles_x) * t.tile_w - t.margin, sub_y0 = (tile / t.tiles_x) * t.tile_h - t.margin;
+        unsigned char *dst = bufs + (size_t)b * buf_bytes;
+        // columns [xs, xe) of every row come from the padded map (x >= -16, y >= -1; 16-byte aligned), the rest is
+        // zero-filled
+        const int x_start = sub_x0 - lpad;
+        const int xs = max(x_start, -16), xe = min(x_start + T2_PITCH, p.W);
+        const int y_lo = max(sub_y0, -1), y_hi = min(sub_y0 + t.sub_rows, p.H);
+        const uint32_t row_bytes = xe > xs ? (uint32_t)(xe - xs) : 0u;
+        const uint32_t total = row_bytes * (uint32_t)max(y_hi - y_lo, 0);
+        if (row_bytes < T2_PITCH || y_lo > sub_y0 || y_hi < sub_y0 + t.sub_rows) {
+            // edge tile: zero what the copies will not write (whole rows above / below, strips left / right)
+            for (int r = 0; r < t.sub_rows; ++r) {
+                const int my = sub_y0 + r;
+                uint32_t *row = reinterpret_cast<uint32_t *>(dst + (size_t)r * T2_PITCH);
+                if (my < y_lo || my >= y_hi || row_bytes == 0) {
+                    for (int w = lane; w < T2_PITCH / 4; w += 32) row[w] = 0u;
+                } else {
+                    const int a = (xs - x_start) >> 2, z = (xe - x_start) >> 2;
+                    for (int w = lane; w < T2_PITCH / 4; w += 32)
+                        if (w < a || w >= z) row[w] = 0u;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            __syncwarp();
-            if (lane == 0) {
-                ring[b * 4] = tile; ring[b * 4 + 1] = __ldg(t.items + 3 * item + 1); ring[b * 4 + 2] = __ldg(t.items + 3 * item + 2);
-                sctr[b] = 0;
-                if (total) mbar_expect_tx(full + b, total); else mbar_arrive(full + b);
-            }
-            __syncwarp();
-            if (row_bytes)
-                for (int my = y_lo + lane; my < y_hi; my += 32)
-                    bulk_g2s(dst + (size_t)(my - sub_y0) * T2_PITCH + (xs - x_start),
-                             t.code8p + (size_t)(my + 1) * (p.W + 16) + (xs + 16), row_bytes, full + b);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-    } else {
-        // ------------------------------------------------------------------ consumers
-        G1Ctx k;
-        k.swin = nullptr; k.slut = slut;
-        k.lane = lane;
-        k.nb = p.n_pos + p.n_neg;
-        k.cmx = (255 << 8) | 255; k.cmy = ((t.sub_rows - 1) << 8) | 255;
-        k.slut_s = smem_u32(slut) + 4u * (uint32_t)lane;
-        for (int s = 0;; ++s) {
-            const int b = s & 1;
-            mbar_wait(full + b, (s >> 1) & 1);
-            const int tile = __reduce_min_sync(0xffffffffu, ring[b * 4]);
-            if (tile < 0) break;
-            const int seg_lo = __reduce_min_sync(0xffffffffu, ring[b * 4 + 1]), seg_hi = __reduce_min_sync(0xffffffffu, ring[b * 4 + 2]);
-            k.swin8 = bufs + (size_t)b * buf_bytes + lpad;
-            k.swin8_s = smem_u32(k.swin8);
-            k.wofx = (tile % t.tiles_x) * t.tile_w - t.margin; k.wofy = (tile / t.tiles_x) * t.tile_h - t.margin;
-            int pos = 0;
-            for (;;) {                                    // pairs of adjacent 32-particle slices from the shared counter
-                const int sl = __reduce_max_sync(0xffffffffu, lane == 0 ? atomicAdd(sctr + b, 2) : 0);
-                pos = seg_lo + 32 * sl;
-                if (pos >= seg_hi) break;
-                g1_slices<true, true, false, 2, 2>(p, k, p.x, p.y, p.th, p.score, (int64_t)pos + lane, 32, (int64_t)seg_hi, smax, t.perm);
-            }
-            // never taken: keeps the hot copy of the slice code on the uniform datapath (see k_likelihood_g1)
-            if (p.n < 0) g1_slices<true, true, false, 1, 2>(p, k, p.x, p.y, p.th, p.score, (int64_t)pos + lane, 0, (int64_t)seg_hi, smax, t.perm);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + b);
+        __syncwarp();
+        if (lane == 0) {
+            ring[b * 4] = tile; ring[b * 4 + 1] = __ldg(t.items + 3 * item + 1); ring[b * 4 + 2] = __ldg(t.items + 3 * item + 2);
+            sctr[b] = 0;
+            if (total) mbar_expect_tx(full + b, total); else mbar_arrive(full + b);
         }
+        __syncwarp();
+        if (row_bytes)
+            for (int my = y_lo + lane; my < y_hi; my += 32)
+                bulk_g2s(dst + (size_t)(my - sub_y0) * T2_PITCH + (xs - x_start),
+                         t.code8p + (size_t)(my + 1) * (p.W + 16) + (xs + 16), row_bytes, full + b);
+    };
+    const bool producer = warp == NCONS;                               // (uniform: warp comes out of a REDUX)
+    if (producer) stage_use(0);
+    G1Ctx k;
+    k.swin = nullptr; k.slut = slut;
+    k.lane = lane;
+    k.nb = p.n_pos + p.n_neg;
+    k.cmx = (255 << 8) | 255; k.cmy = ((t.sub_rows - 1) << 8) | 255;
+    k.slut_s = smem_u32(slut) + 4u * (uint32_t)lane;
+    for (int s = 0;; ++s) {
+        const int b = s & 1;
+        if (producer) stage_use(s + 1);
+        mbar_wait(full + b, (s >> 1) & 1);
+        const int tile = __reduce_min_sync(0xffffffffu, ring[b * 4]);
+        if (tile < 0) break;
+        const int seg_lo = __reduce_min_sync(0xffffffffu, ring[b * 4 + 1]), seg_hi = __reduce_min_sync(0xffffffffu, ring[b * 4 + 2]);
+        k.swin8 = bufs + (size_t)b * buf_bytes + lpad;
+        k.swin8_s = smem_u32(k.swin8);
+        k.wofx = (tile % t.tiles_x) * t.tile_w - t.margin; k.wofy = (tile / t.tiles_x) * t.tile_h - t.margin;
+        int pos = 0;
+        for (;;) {                                        // pairs of adjacent 32-particle slices from the shared counter
+            const int sl = __reduce_max_sync(0xffffffffu, lane == 0 ? atomicAdd(sctr + b, 2) : 0);
+            pos = seg_lo + 32 * sl;
+            if (pos >= seg_hi) break;
+            g1_slices<true, true, false, 2, 2>(p, k, p.x, p.y, p.th, p.score, (int64_t)pos + lane, 32, (int64_t)seg_hi, smax, t.perm);
+        }
+        // never taken: keeps the hot copy of the slice code on the uniform datapath (see k_likelihood_g1)
+        if (p.n < 0) g1_slices<true, true, false, 1, 2>(p, k, p.x, p.y, p.th, p.score, (int64_t)pos + lane, 0, (int64_t)seg_hi, smax, t.perm);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + b);
     }
     if (p.keymax) {
         __shared__ float smx[32];
