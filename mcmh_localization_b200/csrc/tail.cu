@@ -1466,11 +1466,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             __syncthreads();
             const int64_t i_lo = sh.irange[0], i_hi = sh.irange[1];
             const int64_t cnt = i_hi - i_lo + 1;
+            // the running sums of the source range go to shared memory; a range that does not fit (very uneven
+            // weights: a freshly initialised cloud) is staged as every stride-th sum -- the last of each block of
+            // `stride` sources, i.e. the block's largest -- and the search ends inside one block in global memory
             const bool staged = cnt <= stage_cap;
-            if (staged) {
-                for (int64_t j = t; j < cnt; j += TL_THREADS) stage[j] = __ldcg(C + i_lo + j);
-                __syncthreads();
-            }
+            const int64_t stride = staged ? 1 : (cnt + stage_cap - 1) / stage_cap;
+            const int nblocks = (int)((cnt + stride - 1) / stride);
+            for (int64_t j = t; j < nblocks; j += TL_THREADS) stage[j] = __ldcg(C + i_lo + min(cnt - 1, (j + 1) * stride - 1));
+            __syncthreads();
             // four output slots at a time: the searches first, then all twelve gather loads in flight together, then
             // the stores (slot by slot the loads of one slot waited for the stores of the one before)
             for (int k0 = 0; k0 < a.ipt; k0 += 4) {
@@ -1492,7 +1495,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
                         }
                         src[u] = i_lo + lo;
                     } else {
-                        int64_t lo = i_lo, hi = i_hi;
+                        int bl = 0, bh = nblocks - 1;                  // first block whose last sum reaches the key
+                        while (bl < bh) {
+                            const int mid = (bl + bh) >> 1;
+                            if (TlCum<REF>::gt(key, stage[mid])) bl = mid + 1; else bh = mid;
+                        }
+                        int64_t lo = i_lo + (int64_t)bl * stride, hi = min(i_hi, lo + stride - 1);
                         while (lo < hi) {
                             const int64_t mid = (lo + hi) >> 1;
                             if (TlCum<REF>::gt(key, __ldcg(C + mid))) lo = mid + 1; else hi = mid;
