@@ -308,8 +308,7 @@ def run_native(args):
             loc.predict(poses[k])
             loc.h.call("mcl_use_scan", int(k))
             loc.update_chain(None, iters=iters)
-            loc.estimate_async(est_buf[k])
-            loc.resample()
+            loc.finish_async(est_buf[k])
 
     for k in range(1, W + 1):
         staged_step(k)
@@ -355,7 +354,7 @@ def run_native(args):
         if iters == 1:
             loc.step(poses[k], scans[k], angles=angles)
         else:
-            loc.predict(poses[k]); loc.update_chain(scans[k], angles=angles, iters=iters); loc.estimate(); loc.resample()
+            loc.step_chain(poses[k], scans[k], angles=angles, iters=iters)
         torch.cuda.synchronize(dev)
         e2e_t += time.perf_counter() - t0
         h2d += int(valid[k]) * 16 + 0      # the per-scan beam table (fp64 pairs) is what crosses PCIe
@@ -545,8 +544,7 @@ def run_extras(args, loc, world, rank, local, dev, poses, scans, angles, valid, 
             loc.predict(poses[k])
             loc.h.call("mcl_use_scan", int(k))
             loc.update_chain(None, iters=32)
-            loc.estimate_async(loc.est18)
-            loc.resample()
+            loc.finish_async(loc.est18)
         ms = timed(chain_step)
         mv = float(np.mean(valid[W + 1:W + 1 + K]))
         out["configs[3] MH x32"] = {"ms_per_scan": ms, "particles_per_gpu": n, "n_gpus": world, "mh_iterations": 32,

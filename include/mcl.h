@@ -304,6 +304,11 @@ int mcl_filter_update(mcl_handle *h, const double *d_uniforms);                 
 int mcl_filter_update_chain(mcl_handle *h, int iters);
 int mcl_filter_estimate(mcl_handle *h, double *d_out18, double h_out16[16]);                   /* node:586-597 */
 int mcl_filter_resample(mcl_handle *h, double r /* < 0: Philox draw */);                       /* node:488-492 */
+/* estimate (node:586-597; to d_out18 and/or blocking into h_out16, both nullable) followed by resample_lvr
+ * (node:488-492, Philox offset) of the particles and weights as they are -- what follows mcl_filter_update or
+ * mcl_filter_update_chain in lidar_callback.  One launch of the persistent tail kernel on one GPU; same results as
+ * mcl_filter_estimate + mcl_filter_resample(-1). */
+int mcl_filter_finish(mcl_handle *h, double *d_out18, double h_out16[16]);
 /* odom + scan -> predict (delta != NULL), update on pre-staged scan `scan_slot` (or the current scan
  * if < 0), estimate (to d_out18 and/or blocking into h_out16; both nullable), resample.
  * With symmetric MH or plain MCL the step is four launches: motion, motion retries, likelihood of both particle sets, and the

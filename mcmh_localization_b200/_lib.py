@@ -86,6 +86,7 @@ SIGNATURES = {
     "mcl_filter_update_chain": (_i, [_vp, _i]),
     "mcl_filter_estimate": (_i, [_vp, _vp, _pd]),
     "mcl_filter_resample": (_i, [_vp, _d]),
+    "mcl_filter_finish": (_i, [_vp, _vp, _vp]),
     "mcl_filter_step": (_i, [_vp, _pd, _i, _vp, _pd]),
     "mcl_comm_init": (_i, [_vp, _i, _i, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "mcl_comm_status": (_i, [_vp, _pi]),

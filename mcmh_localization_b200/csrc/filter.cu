@@ -697,6 +697,40 @@ extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
     return MCL_OK;
 }
 
+// node:586-597 estimate, then node:488-492 resample_lvr, of the particles and weights as they are (after
+// mcl_filter_update / mcl_filter_update_chain): one launch of the tail kernel without its softmax / accept stages on
+// one GPU; else the two calls one after the other.  Same results as mcl_filter_estimate + mcl_filter_resample(-1).
+extern "C" int mcl_filter_finish(mcl_handle *h, double *d_out18, double h_out16[16]) {
+    FILTER_OR_FAIL("mcl_filter_finish");
+    const bool arith_ok = f->resample_mode == MCL_RESAMPLE_FIXED_POINT || f->resample_mode == MCL_RESAMPLE_REFERENCE_F32;
+    if (f->comm || !arith_ok || !mcl_tail_available(h, f->n)) {
+        if (d_out18 || h_out16) { const int rc = mcl_filter_estimate(h, d_out18, h_out16); if (rc) return rc; }
+        return mcl_filter_resample(h, -1.0);
+    }
+    DeviceGuard guard(h->device);
+    f->tick++;                                       // node:488-492 resample_lvr draws r
+    const double r = mcl_resample_offset(f->seed, f->tick, f->n);
+    double *est = h->d_est18;
+    int rc = mcl_tail_finish(h, f->n, f->w[f->wslot], f->x[f->cur], f->y[f->cur], f->th[f->cur], est, f->resample_mode, r,
+                             f->idx, f->x[f->spare], f->y[f->spare], f->th[f->spare]);
+    if (rc) return rc;
+    const int t = f->cur; f->cur = f->spare; f->spare = t;
+    if (d_out18) MCL_CUDA(h, cudaMemcpyAsync(d_out18, est, 18 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (h_out16) {
+        MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned, est, 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        MCL_CUDA(h, cudaMemcpyAsync(h->h_pinned + 20, mcl_tail_err_ptr(h), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        MCL_CUDA(h, cudaStreamSynchronize(h->stream));
+        int terr = 0;
+        memcpy(&terr, h->h_pinned + 20, sizeof(int));
+        if (terr) return mcl_fail(h, MCL_ERR_CUDA, "step tail: a grid barrier / look-back wait timed out (mcl_tail_status)");
+        const double *o = h->h_pinned;
+        h_out16[0] = o[0]; h_out16[1] = o[1]; h_out16[2] = o[6]; h_out16[3] = o[7]; h_out16[4] = o[8];
+        for (int k = 0; k < 9; ++k) h_out16[5 + k] = o[9 + k];
+        h_out16[14] = 0; h_out16[15] = 0;
+    }
+    return MCL_OK;
+}
+
 // update -> estimate -> resample through the fused kernels (fused.cu) when the configuration allows it:
 // symmetric MH or plain MCL, fixed-point resampling.  Sharded (f->comm): the same four kernels with the peer-memory exchanges between them (score maxima,
 // softmax sums, raw estimate sums + weight maximum, central sums, totals) and the peer-push gather.

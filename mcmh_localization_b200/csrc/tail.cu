@@ -66,7 +66,8 @@ struct TailArgs {
     int nt, ipt, tile, use_mh;
     unsigned long long *prof;    // debug: [grid][32] globaltimer stamps of the stage boundaries (nullable)
     int stop;                    // debug: return after stage `stop` (0 = run everything)
-    int raw;                     // test hook: w_out holds the weights already, no poses (S1, estimate, gather skipped)
+    int raw;                     // 1 (test hook): w_out holds the weights already, no poses (S1, estimate, gather skipped)
+                                 // 2: w_out holds the weights and (nx, ny, nth) the particles (MH chain: estimate + resampling)
     const float *s_post, *s_pre;
     float *w_out;
     const double *px, *py, *pt, *ox, *oy, *ot;
@@ -1092,9 +1093,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     for (int v = b; v < a.nt; v += G) {                  // look-back records of both passes start empty
         if (t == 0) { a.st1[v] = 0ull; a.st2[v] = 0ull; }
     }
-    const bool raw = a.raw != 0;
+    const bool raw = a.raw == 1, given = a.raw == 2;
     tl_stamp(a, 0);
-    if (!raw) {
+    if (!raw && !given) {
         unsigned long long acc0 = 0, acc1 = 0;
         for (int v = b; v < a.nt; v += G) {
             const int64_t base = (int64_t)v * a.tile + t;
@@ -1114,7 +1115,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
     tl_grid_barrier(a, 1);
     tl_stamp(a, 2);
     float sum_post = 1.0f, sum_pre = 1.0f;
-    if (!raw) {
+    if (!raw && !given) {
         unsigned long long q0 = 0, q1 = 0;
         for (int u = t; u < G; u += TL_THREADS) { q0 += __ldcg(a.part_q + u); q1 += __ldcg(a.part_q + G + u); }
         tl_block_sum_u64x2(q0, q1, sh);
@@ -1142,6 +1143,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
             if (raw) {
                 const float w = a.w_out[i];
                 s6[0] += (double)w;
+                wmax = fmaxf(wmax, w);
+                continue;
+            }
+            if (given) {                                 // weights and particles are there: estimate sums only
+                const float w = a.w_out[i];
+                const double wi = (double)w, x = a.nx[i], y = a.ny[i];
+                double sn, cs;
+                sincos(a.nth[i], &sn, &cs);
+                s6[0] += wi; s6[1] += wi * wi; s6[2] += wi * x; s6[3] += wi * y; s6[4] += wi * cs; s6[5] += wi * sn;
                 wmax = fmaxf(wmax, w);
                 continue;
             }
@@ -1736,6 +1746,19 @@ int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keyma
     h->launches++;
     h->tail_bar += (unsigned long long)(comm ? TL_NBAR + 1 : TL_NBAR) * p.grid;
     return MCL_OK;
+}
+
+// estimate sums + resampling of particles whose weights are there already (the MH chain's result): the tail kernel
+// without its softmax / accept stages.  One GPU.
+int mcl_tail_finish(mcl_handle *h, int64_t n, float *d_w, double *d_x, double *d_y, double *d_th, double *d_est18,
+                    int resample_mode, double r, int32_t *idx, double *gx, double *gy, double *gt) {
+    FusedStep u;
+    memset(&u, 0, sizeof(u));
+    u.n = n; u.n_global = n; u.use_mh = 0; u.w_out = d_w; u.nx = d_x; u.ny = d_y; u.nth = d_th; u.est18 = d_est18;
+    g_tail_raw = 2;
+    const int rc = mcl_tail_step(h, u, mcl_fused_keymax(h), resample_mode, r, idx, gx, gy, gt, nullptr);
+    g_tail_raw = 0;
+    return rc;
 }
 
 // device address of the sticky error word of the tail kernel (0 = ok), or NULL before the first tail step

@@ -354,6 +354,38 @@ class Localizer:
             self.h.call("mcl_filter_resample", -1.0 if r is None else float(r))
             # self.weights keeps the pre-resampling values (node:490 discards the uniform weights)
 
+    def finish(self):
+        """estimate() followed by resample() -- what lidar_callback does after the weights are updated (node:324-331)
+        -- as one library call (fixed-N modes on one GPU: one launch of the tail kernel); returns the estimate."""
+        if self.use_adaptive:
+            est = self.estimate()
+            self.resample()
+            return est
+        with self._lock:
+            self._bind_stream()
+            out = (C.c_double * 16)()
+            self.h.call("mcl_filter_finish", None, out)
+        if self.n < 2:
+            return None
+        return assemble_estimate(list(out))
+
+    def finish_async(self, out18):
+        """finish() with the estimate left in a device tensor of 18 float64 (no host round trip)."""
+        with self._lock:
+            self._bind_stream()
+            if self.use_adaptive:
+                self.h.call("mcl_filter_estimate", _ptr(out18), None)
+                self._resample_amcl_kld(None)
+                return
+            self.h.call("mcl_filter_finish", _ptr(out18), None)
+
+    def step_chain(self, odom, ranges, angle_min=None, angle_max=None, angles=None, iters=32):
+        """One odom message followed by one scan with `iters` MH iterations per particle (BASELINE config 4):
+        predict -> update_chain -> estimate -> resample."""
+        self.predict(odom)
+        self.update_chain(ranges, angle_min, angle_max, angles, iters=iters)
+        return self.finish()
+
     def step(self, odom, ranges, angle_min=None, angle_max=None, angles=None):
         """One odom message followed by one scan: predict -> update -> estimate -> resample, enqueued by
         ONE library call; returns the host estimate while the resampling kernels are still running."""

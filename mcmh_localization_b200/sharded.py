@@ -264,6 +264,19 @@ class ShardedLocalizer(Localizer):
             out18[:9].copy_(self.m9)
             out18[9:].copy_(self.c9)
 
+    def finish(self):
+        if self.native:
+            return Localizer.finish(self)        # the library sequences estimate + resample with its own exchanges
+        est = self.estimate()
+        self.resample()
+        return est
+
+    def finish_async(self, out18):
+        if self.native:
+            return Localizer.finish_async(self, out18)
+        self.estimate_async(out18)
+        self.resample()
+
     # -- resample ----------------------------------------------------------------------------
     def resample(self, r=None):
         if self.native:

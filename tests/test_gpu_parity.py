@@ -1062,6 +1062,47 @@ def test_sharded_two_gpus_equals_single_gpu():
         assert "DIST_CHECK OK" in r.stdout, ("native/reference arithmetic", n_local, r.stdout[-2000:] + r.stderr[-2000:])
 
 
+@pytest.mark.parametrize("resample_mode", ["reference", "fixed"])
+@pytest.mark.parametrize("n", [1, 777, 2500, 300_001])
+def test_finish_equals_estimate_then_resample(resample_mode, n):
+    """Localizer.finish() -- the tail kernel without its softmax / accept stages, what follows the MH chain -- equals
+    estimate() followed by resample(): particles (i.e. indices) bit for bit, estimate to fp64 rounding, in both arithmetics."""
+    _need_gpu()
+    import os
+    from conftest import GOLDEN
+    from mcmh_localization_b200 import Localizer
+    from mcmh_localization_b200.maps import load_npz
+    from mcmh_localization_b200.synth import free_space_particles, raycast_scan
+    gm = load_npz(os.path.join(GOLDEN, "map_world.npz"))
+    parts = free_space_particles(gm, n, seed=21)
+    pose = np.array([-2.0, -0.5, 0.0])
+    locs = []
+    for _ in range(2):
+        loc = Localizer(params=P, mode="MHMCL", seed=5, resample_mode=resample_mode)
+        loc.load_map(gm)
+        loc.set_particles(parts)
+        locs.append(loc)
+    a, b = locs
+    for k in range(3):
+        pose = pose + np.array([0.02, 0.0, 0.01])
+        scan, angles = raycast_scan(gm, pose)
+        for loc in locs:
+            loc.predict(pose)
+            loc.update_chain(scan, angles=angles, iters=3)
+        ea = a.finish()
+        eb = b.estimate()
+        b.resample()
+        if n >= 2:
+            # (fp64 sums in another order than the stand-alone estimate kernels: equal to rounding)
+            np.testing.assert_allclose(ea[:3], eb[:3], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(ea[3], eb[3], rtol=1e-9, atol=1e-16)
+        else:
+            assert ea is None and eb is None
+        assert np.array_equal(a.particles(), b.particles())
+    for loc in locs:
+        loc.close()
+
+
 def test_c_abi_error_behaviour():
     """Every export returns a negative mcl_status with a message instead of crashing (SURVEY 8(b) errors)."""
     _need_gpu()
