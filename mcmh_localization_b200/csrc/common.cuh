@@ -164,8 +164,10 @@ struct FusedStep {
     double *est18;
 };
 struct FusedPtrs { unsigned long long *keymax, *sumq, *total; double *msum, *csum; };
-int mcl_tail_finish(mcl_handle *h, int64_t n, float *d_w, double *d_x, double *d_y, double *d_th, double *d_est18,
-                    int resample_mode, double r, int32_t *idx, double *gx, double *gy, double *gt);
+struct TailComm;
+int mcl_tail_finish(mcl_handle *h, int64_t n, int64_t n_global, float *d_w, double *d_x, double *d_y, double *d_th,
+                    double *d_est18, int resample_mode, double r, int32_t *idx, double *gx, double *gy, double *gt,
+                    const TailComm *comm);
 int mcl_fused_prepare(mcl_handle *h, int64_t n);
 unsigned long long *mcl_fused_keymax(mcl_handle *h);
 void mcl_fused_exchange_ptrs(mcl_handle *h, FusedPtrs *out);

@@ -699,20 +699,32 @@ extern "C" int mcl_filter_resample(mcl_handle *h, double r) {
 
 // node:586-597 estimate, then node:488-492 resample_lvr, of the particles and weights as they are (after
 // mcl_filter_update / mcl_filter_update_chain): one launch of the tail kernel without its softmax / accept stages on
-// one GPU; else the two calls one after the other.  Same results as mcl_filter_estimate + mcl_filter_resample(-1).
+// (sharded: with the exchanges and the peer push inside, in either arithmetic); else the two calls one after the
+// other.  Same results as mcl_filter_estimate + mcl_filter_resample(-1).
 extern "C" int mcl_filter_finish(mcl_handle *h, double *d_out18, double h_out16[16]) {
     FILTER_OR_FAIL("mcl_filter_finish");
     const bool arith_ok = f->resample_mode == MCL_RESAMPLE_FIXED_POINT || f->resample_mode == MCL_RESAMPLE_REFERENCE_F32;
-    if (f->comm || !arith_ok || !mcl_tail_available(h, f->n)) {
+    if (!arith_ok || !mcl_tail_available(h, f->n)) {
         if (d_out18 || h_out16) { const int rc = mcl_filter_estimate(h, d_out18, h_out16); if (rc) return rc; }
         return mcl_filter_resample(h, -1.0);
     }
     DeviceGuard guard(h->device);
+    int rc = mcl_fused_prepare(h, f->n);             // (the key words the kernel reads at its start live there)
+    if (rc) return rc;
     f->tick++;                                       // node:488-492 resample_lvr draws r
-    const double r = mcl_resample_offset(f->seed, f->tick, f->n);
+    const double r = mcl_resample_offset(f->seed, f->tick, f->comm ? f->n_global : f->n);
     double *est = h->d_est18;
-    int rc = mcl_tail_finish(h, f->n, f->w[f->wslot], f->x[f->cur], f->y[f->cur], f->th[f->cur], est, f->resample_mode, r,
-                             f->idx, f->x[f->spare], f->y[f->spare], f->th[f->spare]);
+    const int dst = f->spare;
+    TailComm tc;
+    if (f->comm) {                                   // sharded: the exchanges and the peer push run inside the kernel
+        tc.rank = f->rank; tc.world = f->world; tc.n_global = f->n_global; tc.mailbox = f->mailbox;
+        for (int d = 0; d < 16; ++d) tc.peers[d] = f->peer_mailbox[d];
+        tc.epoch0 = f->epoch; tc.d_err = f->d_comm_err;
+        tc.d_peer_pose_dst = (const unsigned long long *)(f->d_peer_pose + (size_t)dst * 3 * f->world);
+        f->epoch += f->resample_mode == MCL_RESAMPLE_REFERENCE_F32 ? TAIL_EXCHANGES_REF : TAIL_EXCHANGES;
+    }
+    rc = mcl_tail_finish(h, f->n, f->comm ? f->n_global : f->n, f->w[f->wslot], f->x[f->cur], f->y[f->cur], f->th[f->cur], est,
+                         f->resample_mode, r, f->idx, f->x[dst], f->y[dst], f->th[dst], f->comm ? &tc : nullptr);
     if (rc) return rc;
     const int t = f->cur; f->cur = f->spare; f->spare = t;
     if (d_out18) MCL_CUDA(h, cudaMemcpyAsync(d_out18, est, 18 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -723,6 +735,7 @@ extern "C" int mcl_filter_finish(mcl_handle *h, double *d_out18, double h_out16[
         int terr = 0;
         memcpy(&terr, h->h_pinned + 20, sizeof(int));
         if (terr) return mcl_fail(h, MCL_ERR_CUDA, "step tail: a grid barrier / look-back wait timed out (mcl_tail_status)");
+        if (f->comm) { rc = comm_check(h, f); if (rc) return rc; }
         const double *o = h->h_pinned;
         h_out16[0] = o[0]; h_out16[1] = o[1]; h_out16[2] = o[6]; h_out16[3] = o[7]; h_out16[4] = o[8];
         for (int k = 0; k < 9; ++k) h_out16[5 + k] = o[9 + k];

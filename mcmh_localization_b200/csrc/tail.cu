@@ -1129,6 +1129,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) k_tail(const TailArgs a) {
         sum_post = (float)((double)q0 / TL_SOFTMAX_FIX);
         sum_pre = MH ? (float)((double)q1 / TL_SOFTMAX_FIX) : 1.0f;
         if (b == 0 && t == 0) { a.keymax[0] = 0ull; a.keymax[1] = 0ull; }    // every CTA has read the keys
+    } else if (SH) {
+        tl_exchange(a, sh, 2, 0, true);                  // given weights: the exchange is made empty (parities stay in step)
     }
 
     // ---- S2: weights (node:356-357), MH accept (pu:229-233), raw estimate sums (node:586-589), weight maximum ---
@@ -1749,14 +1751,16 @@ int mcl_tail_step(mcl_handle *h, const FusedStep &u, unsigned long long *d_keyma
 }
 
 // estimate sums + resampling of particles whose weights are there already (the MH chain's result): the tail kernel
-// without its softmax / accept stages.  One GPU.
-int mcl_tail_finish(mcl_handle *h, int64_t n, float *d_w, double *d_x, double *d_y, double *d_th, double *d_est18,
-                    int resample_mode, double r, int32_t *idx, double *gx, double *gy, double *gt) {
+// without its softmax / accept stages (sharded: the exchanges of those stages are still made, empty, so that the
+// mailbox protocol stays in step).
+int mcl_tail_finish(mcl_handle *h, int64_t n, int64_t n_global, float *d_w, double *d_x, double *d_y, double *d_th,
+                    double *d_est18, int resample_mode, double r, int32_t *idx, double *gx, double *gy, double *gt,
+                    const TailComm *comm) {
     FusedStep u;
     memset(&u, 0, sizeof(u));
-    u.n = n; u.n_global = n; u.use_mh = 0; u.w_out = d_w; u.nx = d_x; u.ny = d_y; u.nth = d_th; u.est18 = d_est18;
+    u.n = n; u.n_global = n_global; u.use_mh = 0; u.w_out = d_w; u.nx = d_x; u.ny = d_y; u.nth = d_th; u.est18 = d_est18;
     g_tail_raw = 2;
-    const int rc = mcl_tail_step(h, u, mcl_fused_keymax(h), resample_mode, r, idx, gx, gy, gt, nullptr);
+    const int rc = mcl_tail_step(h, u, mcl_fused_keymax(h), resample_mode, r, idx, gx, gy, gt, comm);
     g_tail_raw = 0;
     return rc;
 }
