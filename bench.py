@@ -460,19 +460,20 @@ def run_native(args):
         gl = {"error": str(e)}
 
     # The ceiling that actually binds the likelihood kernel: the warp schedulers.  An evaluation costs
-    # 11.06 instructions of which 4 are DFMA, and a DFMA holds its scheduler for two cycles (scripts/ubench/dmma.cu;
-    # the mix is pinned on the built library by tests/test_abi_host.py) = 15.06 issue cycles per warp and evaluation.
+    # 10.06 instructions of which 4 are DFMA (11.06 for particles whose beams can leave the window's 256 columns: one
+    # more clamp), and a DFMA holds its scheduler for two cycles (scripts/ubench/dmma.cu; the mix is pinned on the
+    # built library by tests/test_abi_host.py) = 14.06 issue cycles per warp and evaluation.
     issue = {}
     try:
         props = torch.cuda.get_device_properties(dev)
         sm_hz = float((clocks or {}).get("sm_mhz") or 0.0) * 1e6
         if sm_hz > 0 and iters == 1:
-            cyc = 15.06
+            cyc = 14.06
             peak_issue = props.multi_processor_count * 4 * sm_hz * 32.0 / cyc
             lik_rate_i = n * mv * sets_per_launch / (lik_launch_ms * 1e-3)
             issue = {"bound": "warp-scheduler issue cycles", "achieved": lik_rate_i, "peak": peak_issue, "unit": "evals/s",
                      "frac": lik_rate_i / peak_issue, "issue_cycles_per_evaluation": cyc, "sm_mhz": sm_hz / 1e6,
-                     "how": "SMs x 4 schedulers x SM clock under load x 32 lanes / (7.06 single-cycle instructions + 4 DFMA "
+                     "how": "SMs x 4 schedulers x SM clock under load x 32 lanes / (6.06 single-cycle instructions + 4 DFMA "
                             "x 2 cycles per evaluation: SASS of the beam loop)"}
     except Exception as e:  # explanatory figure only
         issue = {"error": str(e)}

@@ -31,6 +31,8 @@
 
 #include <algorithm>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 #define LIK_THREADS 512
@@ -109,6 +111,8 @@ struct Pose {          // one particle, ready for the beam loop
     double s, c;
     bool interior;     // no endpoint can leave the map (coordinates >= 1: trunc == floor, no bounds test)
     bool far;          // outside the range of the arithmetic: no endpoint can be inside the map
+    bool mfree;        // no endpoint can leave the 256 columns of the window's minor axis: no clamp on that coordinate
+    bool inmap;        // the particle lies on the map (tiled kernel: inside the tile it was binned to)
 };
 
 __device__ __forceinline__ Pose load_pose(const LikParams &p, const double *__restrict__ xs, const double *__restrict__ ys,
@@ -123,6 +127,9 @@ __device__ __forceinline__ Pose load_pose(const LikParams &p, const double *__re
     q.PX = __dadd_rn(q.far ? 0.0 : wx, p.M);
     q.PY = __dadd_rn(q.far ? 0.0 : wy, p.M);
     q.interior = !q.far && (px >= p.ilox) && (px <= p.ihix) && (py >= p.iloy) && (py <= p.ihiy);
+    const double wm = p.tpose ? wy : wx;                               // (tiled kernels pass their own origin: unused there)
+    q.mfree = (wm >= p.margin) && (wm + p.margin < 256.0);
+    q.inmap = (px >= 0.0) && (px < (double)p.W) && (py >= 0.0) && (py < (double)p.H);
     return q;
 }
 
@@ -302,7 +309,7 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
     int64_t idx[P];
     int64_t pidx[P];
     Pose q[P];
-    bool interior = true, any_near = false;
+    bool interior = true, any_near = false, mfree = true, inmap = true;
 #pragma unroll
     for (int u = 0; u < P; ++u) {
         idx[u] = i0 + u * row;
@@ -310,6 +317,8 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
         pidx[u] = PERM ? (int64_t)perm[il] : il;
         q[u] = load_pose(p, xs, ys, ts, pidx[u], wofx, wofy);
         interior = interior && q[u].interior;
+        mfree = mfree && q[u].mfree;
+        inmap = inmap && q[u].inmap;
         any_near = any_near || !q[u].far;
     }
     long long acc[P];
@@ -324,35 +333,46 @@ __device__ __forceinline__ void g1_slices(const LikParams &p, const G1Ctx &k, co
 #pragma unroll
         for (int u = 0; u < P; ++u) { PX[u] = q[u].PX; PY[u] = q[u].PY; ss[u] = q[u].s; cc[u] = q[u].c; }
         const int negK = -p.K;
-        auto eval = [&](int u, const double2 b) -> uint32_t {
-            const double TX = fma(cc[u], b.x, fma(-ss[u], b.y, PX[u])), TY = fma(ss[u], b.x, fma(cc[u], b.y, PY[u]));
-            const int rx = __viaddmin_s32_relu(__double2hiint(TX), negK, k.cmx);
-            const int ry = __viaddmin_s32_relu(__double2hiint(TY), negK, k.cmy);
-            unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
-            if (PERM == 1) cell += (cell >> 8) << 2;     // tiled kernel: rows of 260 bytes (see k_likelihood_tiled)
-            if (SKEW) cell += cell >> 5;                 // rows of 264 words: consecutive rows 8 banks apart (k_pack_window)
-            if (PERM == 2) return g1_fetch_t2(k, cell);  // rows of 272 bytes (k_likelihood_tiled2)
-            return g1_fetch<CODED>(k, (int)cell);
-        };
-        int j = 0;
-        for (; j + MCL_ACC_TERMS <= p.n_pos; j += MCL_ACC_TERMS) {
-            uint32_t part[P];
+        // MF: no endpoint of these particles leaves the 256 columns of the minor axis, so that coordinate needs no
+        // clamp: the byte permute takes byte 1 of the raw high word (the low 16 bits of K are zero) -- one issue cycle
+        // in 15.  (Windowed kernels: particles whose beam footprint lies inside the columns; tiled kernel: particles
+        // inside the tile they were binned to -- the staged sub-window covers every endpoint.  Its 304 rows need nine
+        // bits, which a raw high word does not deliver cleanly, so the row coordinate keeps its clamp.)
+        auto beam_loop = [&](auto mf_tag) {
+            constexpr bool MF = decltype(mf_tag)::value;
+            auto eval = [&](int u, const double2 b) -> uint32_t {
+                const double TX = fma(cc[u], b.x, fma(-ss[u], b.y, PX[u])), TY = fma(ss[u], b.x, fma(cc[u], b.y, PY[u]));
+                const int rx = (MF && !TPOSE) ? __double2hiint(TX) : __viaddmin_s32_relu(__double2hiint(TX), negK, k.cmx);
+                const int ry = (MF && TPOSE) ? __double2hiint(TY) : __viaddmin_s32_relu(__double2hiint(TY), negK, k.cmy);
+                unsigned cell = TPOSE ? __byte_perm(ry, rx, 0x7651) : __byte_perm(rx, ry, 0x7651);
+                if (PERM == 1) cell += (cell >> 8) << 2;     // tiled kernel: rows of 260 bytes (see k_likelihood_tiled)
+                if (SKEW) cell += cell >> 5;                 // rows of 264 words: consecutive rows 8 banks apart (k_pack_window)
+                if (PERM == 2) return g1_fetch_t2(k, cell);  // rows of 272 bytes (k_likelihood_tiled2)
+                return g1_fetch<CODED>(k, (int)cell);
+            };
+            int j = 0;
+            for (; j + MCL_ACC_TERMS <= p.n_pos; j += MCL_ACC_TERMS) {
+                uint32_t part[P];
 #pragma unroll
-            for (int u = 0; u < P; ++u) part[u] = 0;
+                for (int u = 0; u < P; ++u) part[u] = 0;
 #pragma unroll
-            for (int t = 0; t < MCL_ACC_TERMS; ++t) {
-                const double2 b = c_beams[j + t];
+                for (int t = 0; t < MCL_ACC_TERMS; ++t) {
+                    const double2 b = c_beams[j + t];
 #pragma unroll
-                for (int u = 0; u < P; ++u) part[u] += eval(u, b);
+                    for (int u = 0; u < P; ++u) part[u] += eval(u, b);
+                }
+#pragma unroll
+                for (int u = 0; u < P; ++u) uacc[u] += part[u];
             }
+            for (; j < p.n_pos; ++j) {
+                const double2 b = c_beams[j];
 #pragma unroll
-            for (int u = 0; u < P; ++u) uacc[u] += part[u];
-        }
-        for (; j < p.n_pos; ++j) {
-            const double2 b = c_beams[j];
-#pragma unroll
-            for (int u = 0; u < P; ++u) uacc[u] += eval(u, b);
-        }
+                for (int u = 0; u < P; ++u) uacc[u] += eval(u, b);
+            }
+        };
+        const bool mf = PERM == 0 ? mfree : inmap;
+        if ((PERM == 0 || (PERM == 2 && !TPOSE)) && !SKEW && __reduce_and_sync(0xffffffffu, mf ? 1u : 0u)) beam_loop(std::true_type{});
+        else beam_loop(std::false_type{});
 #pragma unroll
         for (int u = 0; u < P; ++u) acc[u] = (long long)uacc[u] + (long long)p.n_pos * p.voff;
     } else if (__any_sync(0xffffffffu, any_near)) {

@@ -179,6 +179,10 @@ def test_likelihood_hot_loop_stays_on_the_uniform_datapath():
         assert ops.count("LDCU") >= n_ev // 2 and ops.count("LDC") <= 1, (name, ops.count("LDCU"), ops.count("LDC"))
         assert ops.count("DFMA") == 4 * n_ev, name
         assert "F2I" not in ops and "DADD" not in ops, name
+        if name.startswith("_Z15k_likelihood_g1ILb1ELi896ELi1ELb0ELb0ELb0E"):
+            # the production variant: the first copy of the loop is the one without a clamp on the minor-axis
+            # coordinate (particles whose beams stay inside the 256 columns of the window): one clamp per evaluation
+            assert ops.count("VIADDMNMX") == n_ev, (name, ops.count("VIADDMNMX"), n_ev)
     assert checked >= 5
     # the double-buffered tiled kernel stages its sub-windows with the TMA engine's bulk copies (UBLKCP) handed over
     # by mbarriers (SYNCS), not with per-thread LDGSTS copies and __syncthreads pairs
