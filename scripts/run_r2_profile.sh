@@ -1,6 +1,6 @@
 # round-2 ncu evidence (1 GPU): launch list of a short bench run + --set full of the four kernels of a step
 cd $GRAFT_REPO_ROOT
-TAG=${1:-r2c}
+TAG=${1:-r2d}
 python bench.py --steps 30 --warmup 10 --quick > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 30 --warmup 10 --quick > gpurun_out/ncu_${TAG}_1.log 2>&1
 echo "launch list rc $?"
