@@ -417,8 +417,10 @@ __global__ void __launch_bounds__(MOTION_BLOCK, 1024 / MOTION_BLOCK) k_motion(co
                 const bool isd = (dense >> lane) & 1u;
                 const int64_t slot = isd ? p.n - 1 - (int64_t)(bd + (unsigned)__popc(dense & below))
                                          : (int64_t)(bs + (unsigned)__popc(sparse & below));
-                p.retry_idx[slot] = (int32_t)i;
-                p.retry_thr[slot] = thr;
+                if (slot >= 0 && slot < p.n) {           // (always, unless an earlier call's second kernel never ran)
+                    p.retry_idx[slot] = (int32_t)i;
+                    p.retry_thr[slot] = thr;
+                }
             }
         }
     } else {
@@ -513,7 +515,8 @@ __global__ void __launch_bounds__(MOTION_RETRY_BLOCK, MOTION_RETRY_BLOCKS_PER_SM
     __shared__ long long sm_heavy[NW];                    // list slots the warps pass on to the CTA (-1: none)
     __shared__ unsigned long long sm_best;                // (attempt << 32 | radius word) of the lowest valid attempt
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned n_sparse = ((volatile unsigned *)p.retry_count)[0], n_dense = ((volatile unsigned *)p.retry_count)[1];
+    unsigned n_sparse = ((volatile unsigned *)p.retry_count)[0], n_dense = ((volatile unsigned *)p.retry_count)[1];
+    if ((int64_t)n_sparse + (int64_t)n_dense > p.n) { n_sparse = 0; n_dense = 0; }     // stale counters: nothing trustworthy
     const int nblk = (p.max_attempts + 31) >> 5;
     __shared__ unsigned sm_ticket;
     while (n_dense) {
