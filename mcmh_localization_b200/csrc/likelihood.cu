@@ -942,7 +942,9 @@ static int launch_g1(mcl_handle *h, const LikParams &p, size_t smem_bytes) {
         case 2: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 768, 1, CODED, TPOSE>, p, smem_bytes, 1, 768, true);
         case 3: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 896, 1, CODED, TPOSE>, p, smem_bytes, 1, 896, true);
         case 4: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 1024, 1, CODED, TPOSE>, p, smem_bytes, 1, 1024, true);
-        // measured at 1 M x 351 (two sets per launch): 896 threads 0.310 ms, 960 (64 registers) 0.329, 1024 0.328, 832 0.343
+        // measured at 1 M x 351 (two sets per launch): 896 threads 0.310 ms, 960 (64 registers) 0.329, 1024 0.328, 832 0.343;
+        // three / four particles per thread (9.6 / 9.4 instructions per evaluation instead of 10.06, but 640 / 512 threads
+        // at 96 / 128 registers): 0.278 / 0.295 ms against 0.274 -- fewer warps cost more than fewer instructions save
         case 5: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 960, 1, CODED, TPOSE>, p, smem_bytes, 1, 960, true);
         case 6: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 832, 1, CODED, TPOSE>, p, smem_bytes, 1, 832, true);
         default: return launch_lik_kernel(h, k_likelihood_g1<SMEM, 896, 1, CODED, TPOSE>, p, smem_bytes, 1, 896, true);   // 72 registers: fastest measured
